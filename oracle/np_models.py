@@ -1,0 +1,177 @@
+"""TEST INFRASTRUCTURE ONLY -- float64 restatement of my_model's four sub-networks and of one
+`Model.train` / `Model.predict` call, built on `oracle/np_oracle.py`.
+
+Follows (paths relative to /root/reference/web_app/components/):
+  my_model/model.py:37-57   make_conv / make_conv_block (L2(0.01) on every conv, LeakyRelu(0.01),
+                            optional last Sigmoid)
+  my_model/model.py:75-85   make_single_up (Upsample2D(2) + conv block)
+  my_model/model.py:108-134 make_monochrome     :137-191 make_paragraph
+  my_model/model.py:194-248 make_line           :251-304 make_dense_block / make_char
+  nn/models.py:232-254      compute_loss_and_gradients + train
+                            (forward -> loss -> backward -> regularize -> update -> clear)
+All four nets are linear chains, so a net is a list of (key, kind, cfg) steps; `key` is the
+flattened layer path used by model_weights.json ("Paragraph/up_2/conv_block/conv_1", ...).
+"""
+import numpy as np
+
+from . import np_oracle as O
+
+N_CHARS = 162            # len(primitives.CHARS), primitives/__init__.py:13-50
+CHAR_FIXED_WIDTH = 8     # my_model/model.py:23
+CHAR_INPUT_HEIGHT = 32   # my_model/model.py:22
+L2_STRENGTH = 0.01       # my_model/model.py:39
+LEAKY_ALPHA = 0.01       # my_model/model.py:53,261
+
+
+def _conv(key, cin, cout, ks, pad, stride=1):
+    return (key, 'conv', dict(cin=cin, cout=cout, ks=ks, pad=pad, stride=stride))
+
+
+def _unet(prefix, ch, out_ch):
+    """make_paragraph / make_line: down_1, down_2 (stride 2), up_2, up_1 (upsample x2 + conv),
+    end (conv + sigmoid); all 5x5, padding 2."""
+    steps, cin = [], 1
+    for i in (1, 2):
+        steps += [_conv(f'{prefix}/down_{i}/conv_1', cin, ch, (5, 5), 2, 2),
+                  (f'{prefix}/down_{i}/leaky_relu_1', 'lrelu', {})]
+        cin = ch
+    for i in (2, 1):
+        steps += [(f'{prefix}/up_{i}/upsample', 'upsample', dict(scale=2)),
+                  _conv(f'{prefix}/up_{i}/conv_block/conv_1', cin, ch, (5, 5), 2),
+                  (f'{prefix}/up_{i}/conv_block/leaky_relu_1', 'lrelu', {})]
+    steps += [_conv(f'{prefix}/end/conv_1', ch, out_ch, (5, 5), 2),
+              (f'{prefix}/end/sigmoid', 'sigmoid', {})]
+    return steps
+
+
+def net_spec(name):
+    if name == 'monochrome':
+        return [_conv('Monochrome/conv_1', 1, 16, (3, 3), 1),
+                ('Monochrome/leaky_relu_1', 'lrelu', {}),
+                _conv('Monochrome/conv_2', 16, 1, (3, 3), 1),
+                ('Monochrome/sigmoid', 'sigmoid', {})]
+    if name == 'paragraph':
+        return _unet('Paragraph', 1, 1)
+    if name == 'line':
+        return _unet('Line', 4, 2)
+    if name == 'char':
+        steps, cin = [], 1
+        for i in (1, 2, 3):
+            steps += [_conv(f'Char/conv_block/conv_{i}', cin, 64, (5, 3), (0, 1), (2, 1)),
+                      (f'Char/conv_block/leaky_relu_{i}', 'lrelu', {})]
+            cin = 64
+        steps += [('Char/fixed_width', 'window', dict(width=CHAR_FIXED_WIDTH)),
+                  ('Char/flatten', 'flatten', {})]
+        n_in = 64 * CHAR_FIXED_WIDTH
+        for i, n_out in enumerate((1024, 128, N_CHARS), start=1):
+            steps.append((f'Char/dense_block/dense_{i}', 'fc', dict(n_in=n_in, n_out=n_out)))
+            if i < 3:
+                steps.append((f'Char/dense_block/leaky_relu_{i}', 'lrelu', {}))
+            n_in = n_out
+        return steps
+    raise KeyError(name)
+
+
+def loss_kind(name):
+    return 'softmax_ce' if name == 'char' else 'dice'
+
+
+def init_weights(spec, rng):
+    """kaiming_uniform as the reference draws it (initializers.py:22-25: a * U[0,1), all
+    positive), bias = last row (layers/convolutional.py:39-45), from a seeded Generator."""
+    weights = {}
+    for key, kind, cfg in spec:
+        if kind == 'conv':
+            kh, kw = cfg['ks']
+            n_in = kh * kw * cfg['cin'] + 1
+            wb = rng.uniform(size=(n_in, cfg['cout'])) / np.sqrt(n_in / 2)
+            weights[key] = {'w': wb[:-1].reshape(kh, kw, cfg['cin'], cfg['cout']).copy(),
+                            'b': wb[-1].copy()}
+        elif kind == 'fc':
+            n_in = cfg['n_in'] + 1
+            weights[key] = {'w': rng.uniform(size=(n_in, cfg['n_out'])) / np.sqrt(n_in / 2)}
+    return weights
+
+
+def forward(spec, weights, X, keep=False, loop=False):
+    """Model.predict (nn/models.py:270-271).  With keep=True also returns the per-step inputs
+    needed by `backward`."""
+    conv_f = O.conv2d_fwd_loop if loop else O.conv2d_fwd
+    saved = []
+    for key, kind, cfg in spec:
+        saved.append(X)
+        if kind == 'conv':
+            p = weights[key]
+            X = conv_f(X, p['w'], p['b'], cfg['pad'], 0.0, cfg['stride'])
+        elif kind == 'lrelu':
+            X = O.leaky_relu_fwd(X, LEAKY_ALPHA)
+        elif kind == 'sigmoid':
+            X = O.sigmoid_fwd(X)
+        elif kind == 'upsample':
+            X = O.upsample2d_fwd(X, cfg['scale'])
+        elif kind == 'window':
+            X = O.window_batch_fwd(X, cfg['width'])
+        elif kind == 'flatten':
+            X = X.reshape(X.shape[0], -1)
+        elif kind == 'fc':
+            X = O.fc_fwd(X, weights[key]['w'])
+        else:
+            raise KeyError(kind)
+    return (X, saved) if keep else X
+
+
+def backward(spec, weights, saved, grad, loop=False):
+    """Model.backward for a chain -> (dX, {key: {'w': dW, 'b': db}})."""
+    conv_b = O.conv2d_bwd_loop if loop else O.conv2d_bwd
+    ups_b = O.upsample2d_bwd_loop if loop else O.upsample2d_bwd
+    grads = {}
+    for (key, kind, cfg), X in zip(reversed(spec), reversed(saved)):
+        if kind == 'conv':
+            p = weights[key]
+            grad, dW, db = conv_b(X, p['w'], grad, cfg['pad'], 0.0, cfg['stride'])
+            grads[key] = {'w': dW, 'b': db}
+        elif kind == 'lrelu':
+            grad = O.leaky_relu_bwd(X, grad, LEAKY_ALPHA)
+        elif kind == 'sigmoid':
+            grad = O.sigmoid_bwd(X, grad)
+        elif kind == 'upsample':
+            grad = ups_b(grad, cfg['scale'])
+        elif kind == 'window':
+            grad = O.window_batch_bwd(grad, X.shape, cfg['width'])
+        elif kind == 'flatten':
+            grad = grad.reshape(X.shape)
+        elif kind == 'fc':
+            grad, dW = O.fc_bwd(X, weights[key]['w'], grad)
+            grads[key] = {'w': dW}
+    return grad, grads
+
+
+def loss_and_grad(kind, pred, y):
+    return O.dice_loss(pred, y) if kind == 'dice' else O.softmax_ce_loss(pred, y)
+
+
+def new_adam_state(weights):
+    return {k: {n: (np.zeros_like(v), np.zeros_like(v)) for n, v in p.items()}
+            for k, p in weights.items()}
+
+
+def train_step(spec, kind, weights, state, X, y, lr, loop=False):
+    """One `Model.train(X, y)` (nn/models.py:250-254) with the shared Adam optimiser
+    (my_model/train.py:127).  Returns (losses dict, grads incl. L2 term, dX); `weights` and
+    `state` are updated in place (new arrays are bound, inputs are not mutated)."""
+    pred, saved = forward(spec, weights, X, keep=True, loop=loop)
+    loss, grad = loss_and_grad(kind, pred, y)
+    dX, grads = backward(spec, weights, saved, grad, loop=loop)
+    reg_loss = 0
+    for key, step_kind, _ in spec:
+        if step_kind == 'conv':                       # L2 on w *and* b (layers.py:147-155)
+            for n in ('w', 'b'):
+                l, g = O.l2_reg(weights[key][n], L2_STRENGTH)
+                grads[key][n] = grads[key][n] + g
+                reg_loss += l
+    for key, p in grads.items():
+        for n, g in p.items():
+            v, a = state[key][n]
+            weights[key][n], v, a = O.adam_update(weights[key][n], g, v, a, lr)
+            state[key][n] = (v, a)
+    return {'output_losses': [loss], 'regularization_loss': reg_loss}, grads, dX, pred

@@ -1,0 +1,206 @@
+"""Pins oracle/np_oracle.py + oracle/np_models.py to the reference.
+
+1. Against the committed golden vectors (tests/golden/*.npz, produced by running the
+   unmodified reference -- see tests/golden/make_golden.py).  Runs everywhere.
+2. Live, against the reference imported from /root/reference, on fresh random inputs
+   (`-m reference`-style tests; auto-skipped where the tree is absent, e.g. the GPU box).
+
+Tolerance: both sides are float64, only summation order differs -> rtol 1e-10.
+"""
+import numpy as np
+import pytest
+
+from oracle import np_models, np_oracle as O, ref_loader
+from tests.cases import CONV_CASES, MODEL_SHAPES, POOL_CASES
+
+RTOL, ATOL = 1e-10, 1e-12
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    np.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+@pytest.mark.parametrize('loop', [False, True], ids=['vec', 'loop'])
+def test_conv_golden(golden, case, loop):
+    name, _, cin, cout, ks, pad, pv, st = case
+    g = golden('conv2d').case(name)
+    fwd = O.conv2d_fwd_loop if loop else O.conv2d_fwd
+    bwd = O.conv2d_bwd_loop if loop else O.conv2d_bwd
+    close(fwd(g['X'], g['w'], g['b'], pad, pv, st), g['y'])
+    dX, dW, db = bwd(g['X'], g['w'], g['dy'], pad, pv, st)
+    close(dX, g['dX'])
+    close(dW, g['dW'])
+    close(db, g['db'])
+
+
+def test_conv_out_shape_and_channel_assert():
+    assert O.conv2d_out_hw(13, 11, 5, 2, 2) == (7, 6)
+    assert O.conv2d_out_hw(32, 10, (5, 3), (0, 1), (2, 1)) == (14, 10)
+    with pytest.raises(AssertionError):
+        O.conv2d_fwd(np.zeros((1, 4, 4, 3)), np.zeros((2, 2, 2, 1)), np.zeros(1))
+
+
+@pytest.mark.parametrize('case', POOL_CASES, ids=[c[0] for c in POOL_CASES])
+def test_maxpool_golden(golden, case):
+    name, shape, k, pad, st, ceil = case
+    g = golden('maxpool2d').case(name)
+    y, mask = O.maxpool2d_fwd(g['X'], k, pad, st, ceil)
+    assert np.array_equal(y, g['y'])                     # max is exact
+    assert np.array_equal(mask.astype(np.uint8), g['mask'])   # tie mask bit-exact
+    close(O.maxpool2d_bwd(g['dy'], mask, g['X'].shape, k, pad, st), g['dX'])
+
+
+def test_maxpool_known_answer(golden):
+    """nn/test/test_gradients.py:171-177 prints [[1,2],[-1,1]] for this input."""
+    g = golden('maxpool2d').case('kat')
+    y, _ = O.maxpool2d_fwd(g['X'], 2, ceil_mode=True)
+    assert np.array_equal(y[0, :, :, 0], np.array([[1., 2.], [-1., 1.]]))
+    assert np.array_equal(y, g['y'])
+
+
+def test_upsample_golden(golden):
+    g = golden('upsample2d')
+    k = g.case('kat')
+    y = O.upsample2d_fwd(k['X'], (2, 3))
+    assert np.array_equal(y, k['y'])
+    close(O.upsample2d_bwd(y, (2, 3)), k['dX'])
+    close(O.upsample2d_bwd(y, (2, 3))[0, :, :, 0], np.array([[0.6, 1.2], [1.8, 2.4]]))   # :181-188
+    for name, sf in (('s2', 2), ('s5', 5), ('s23', (2, 3))):
+        c = g.case(name)
+        assert np.array_equal(O.upsample2d_fwd(c['X'], sf), c['y'])
+        close(O.upsample2d_bwd(c['dy'], sf), c['dX'])
+        close(O.upsample2d_bwd_loop(c['dy'], sf), c['dX'])
+
+
+def test_elementwise_fc_window_concat_golden(golden):
+    g = golden('layers')
+    X, dy = g['act__X'], g['act__dy']
+    for name, alpha in (('relu', 0.0), ('lrelu', 0.01), ('lrelu_a', 0.2)):
+        close(O.leaky_relu_fwd(X, alpha), g[f'{name}__y'])
+        close(O.leaky_relu_bwd(X, dy, alpha), g[f'{name}__dX'])
+    close(O.sigmoid_fwd(X), g['sigmoid__y'])
+    close(O.sigmoid_bwd(X, dy), g['sigmoid__dX'])
+    close(O.fc_fwd(g['fc__X'], g['fc__W']), g['fc__y'])
+    dX, dW = O.fc_bwd(g['fc__X'], g['fc__W'], g['fc__dy'])
+    close(dX, g['fc__dX'])
+    close(dW, g['fc__dW'])
+    for name, width in (('w3', 3), ('w8', 8), ('w8min', 8)):
+        c = g.case(f'win_{name}')
+        assert np.array_equal(O.window_batch_fwd(c['X'], width), c['y'])
+        close(O.window_batch_bwd(c['dy'], c['X'].shape, width), c['dX'])
+    y = O.concat_fwd([g['cat__a'], g['cat__b']])
+    assert np.array_equal(y, g['cat__y'])
+    ga, gb = O.concat_bwd(y, [g['cat__a'].shape, g['cat__b'].shape])
+    assert np.array_equal(ga, g['cat__ga']) and np.array_equal(gb, g['cat__gb'])
+
+
+def test_losses_regs_optimisers_golden(golden):
+    g = golden('losses_opt')
+    for name, fn in (('dice', O.dice_loss), ('jaccard', O.jaccard_loss)):
+        loss, grad = fn(g['seg__pred'], g['seg__gt'])
+        close(loss, g[f'{name}__loss'])
+        close(grad, g[f'{name}__grad'])
+    loss, grad = O.softmax_ce_loss(g['sce__logits'], g['sce__gt'])
+    close(loss, g['sce__loss'])
+    close(grad, g['sce__grad'])
+    loss, grad = O.softmax_ce_loss(g['sce_nan__logits'], g['sce__gt'])
+    assert np.isnan(loss) and np.isnan(g['sce_nan__loss'])          # 0 * log 0, losses.py:71
+    close(grad, g['sce_nan__grad'])
+    loss, grad = O.sigmoid_ce_loss(g['bce__logits'], g['bce__gt'])
+    close(loss, g['bce__loss'])
+    close(grad, g['bce__grad'])
+    for name, fn, s in (('l1', O.l1_reg, 0.1), ('l2', O.l2_reg, 0.01)):
+        loss, grad = fn(g['reg__w'], s)
+        close(loss, g[f'{name}__loss'])
+        close(grad, g[f'{name}__grad'])
+    w, v, a = g['reg__w'], 0.0, 0.0
+    for i, gr in enumerate((g['opt__g1'], g['opt__g2']), start=1):
+        w, v, a = O.adam_update(w, gr, v, a, lr=0.0015)
+        close(w, g[f'adam__w{i}'])
+    w, v = g['reg__w'], 0.0
+    for i, gr in enumerate((g['opt__g1'], g['opt__g2']), start=1):
+        w, v = O.momentum_update(w, gr, v, 0.01, 0.9)
+        close(w, g[f'momentum__w{i}'])
+    w, a = g['reg__w'], 0.0
+    for i, gr in enumerate((g['opt__g1'], g['opt__g2']), start=1):
+        w, a = O.rmsprop_update(w, gr, a, 0.01)
+        close(w, g[f'rmsprop__w{i}'])
+
+
+@pytest.mark.parametrize('name', list(MODEL_SHAPES))
+def test_submodel_train_golden(golden, name):
+    """Two Model.train steps of each my_model sub-network + predict before/after."""
+    g = golden('models').case(name)
+    spec, kind = np_models.net_spec(name), np_models.loss_kind(name)
+    w = np_models.init_weights(spec, np.random.default_rng(int(g['seed'])))
+    w = {k: {n: v.astype(np.float32).astype(np.float64) for n, v in p.items()} for k, p in w.items()}
+    state = np_models.new_adam_state(w)
+    close(np_models.forward(spec, w, g['X']), g['pred0'])
+    for step in (1, 2):
+        losses, _, _, _ = np_models.train_step(spec, kind, w, state, g['X'], g['y'], lr=0.0015)
+        close(losses['output_losses'][0], g[f'loss{step}'], rtol=1e-9)
+        close(losses['regularization_loss'], g[f'reg{step}'], rtol=1e-9)
+    for key, p in w.items():
+        for n, v in p.items():
+            tag = f'after__{key.replace("/", ".")}/{n}'.replace('/', '.')
+            close(v.ravel()[g[f'{tag}__idx']], g[f'{tag}__val'], rtol=1e-8, atol=1e-11)
+            close(v.sum(), g[f'{tag}__sum'], rtol=1e-8)
+    close(np_models.forward(spec, w, g['X']), g['pred2'], rtol=1e-8)
+
+
+def test_make_divisible_and_pred_ids():
+    a = np.arange(2 * 16 * 30 * 1, dtype=np.float64).reshape(2, 16, 30, 1)
+    out = O.make_divisible_by(a, 16, 16)
+    assert out.shape == (2, 32, 32, 1)                    # full 16 added when already aligned
+    assert np.array_equal(out[:, 8:24, 1:31, :], a)
+    pred = np.array([[0.1, 0.7, 0.7], [0.0, 0.0, 0.0], [-1.0, -2.0, -1.5], [0.3, 0.2, 0.1]])
+    assert O.pred_to_ids(pred).tolist() == [1, 2, 0, 0]   # ties keep all; all-zero row dropped
+
+
+# ------------------------------------------------------------------ live reference diffs
+
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason='/root/reference not present')
+
+
+@needs_ref
+@pytest.mark.reference
+@pytest.mark.parametrize('seed', [1, 2])
+def test_live_conv_pool_against_reference(seed):
+    nn = ref_loader.load_nn()
+    rng = np.random.default_rng(seed)
+    for ks, pad, pv, st in (((3, 3), 1, 0.5, 1), ((5, 5), 2, 0.0, 2), ((5, 3), (0, 1), 0.0, (2, 1)),
+                            ((2, 4), (1, 2), -1.0, (3, 1))):
+        X = rng.standard_normal((2, 11, 9, 3))
+        w = rng.standard_normal((*ks, 3, 4))
+        b = rng.standard_normal(4)
+        layer = nn.layers.Convolutional2D(ks, 3, 4, padding=pad, padding_value=pv, stride=st,
+                                          w=w.copy(), b=b.copy())
+        y = layer.forward(X)[0]
+        close(O.conv2d_fwd(X, w, b, pad, pv, st), y)
+        dy = rng.standard_normal(y.shape)
+        dX = layer.backward(dy)[0]
+        odX, odW, odb = O.conv2d_bwd(X, w, dy, pad, pv, st)
+        close(odX, dX), close(odW, layer.w.grad), close(odb, layer.b.grad)
+    for k, pad, st, ceil in ((2, 0, None, False), (3, 1, 2, True), ((2, 3), (1, 1), (1, 2), False)):
+        X = np.round(rng.standard_normal((2, 9, 10, 2)) * 2) / 2
+        layer = nn.layers.MaxPool2D(k, padding=pad, stride=st, ceil_mode=ceil)
+        y = layer.forward(X)[0]
+        oy, mask = O.maxpool2d_fwd(X, k, pad, st, ceil)
+        assert np.array_equal(oy, y)
+        assert np.array_equal(mask, layer._mem[0][0])
+        dy = rng.standard_normal(y.shape)
+        close(O.maxpool2d_bwd(dy, mask, X.shape, k, pad, st), layer.backward(dy)[0])
+
+
+@needs_ref
+@pytest.mark.reference
+def test_live_reference_gradient_suite_subset():
+    """The reference's own numeric-gradient check (nn/gradient_check.py) run on its own conv
+    layer -- confirms the shimmed reference behaves (full suite: 35/35)."""
+    nn = ref_loader.load_nn()
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((2, 5, 5, 3))
+    layer = nn.layers.Convolutional2D((3, 3), 3, 2, padding=1, padding_value=0.5, stride=2)
+    assert nn.gradient_check.check_layer_gradient(layer, X)
+    assert nn.gradient_check.check_layer_param_gradient(layer, X, 'w')
