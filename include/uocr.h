@@ -1,0 +1,259 @@
+/*
+ * uocr.h -- C ABI of libuocr.so: the B200 (sm_100a) implementation of the layer stack of
+ * KerkDovan/univer-ocr's self-written deep-learning framework (web_app/components/nn).
+ *
+ * The reference has NO native boundary: its seam is the Python layer protocol
+ * (`BaseLayerGPU._make_forward_gpu/_make_backward_gpu`, nn/layers/layers.py:169-237), whose
+ * Numba kernels receive CuPy arrays through __cuda_array_interface__
+ * (nn/layers/convolutional.py:185-193).  Every entry point below replaces one of those Python
+ * call sites; the `replaces:` note of each function cites it (paths relative to
+ * web_app/components/nn/ of the reference).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative UOCR_ERR_* otherwise;
+ *     uocr_last_error() returns a thread-local message for the last failure.
+ *   - all array arguments are RAW DEVICE POINTERS (float32 unless noted), NHWC, densely
+ *     packed; conv weights are (kh, kw, Cin, Cout), FC weights (n_in + 1, n_out) with the
+ *     bias as last row -- the reference's layouts (convolutional.py:41-44, layers.py:324-329).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - asynchronous: nothing synchronises the device except the functions that say so.
+ *   - no ownership transfer: the library never frees or retains a caller pointer.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     UOCR_ERR_CUDA.
+ */
+#ifndef UOCR_H_
+#define UOCR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UOCR_VERSION 100
+
+#define UOCR_OK               0
+#define UOCR_ERR_INVALID     -1   /* bad argument (null pointer, non-positive dim, ...)   */
+#define UOCR_ERR_CUDA        -2   /* CUDA runtime error, see uocr_last_error()             */
+#define UOCR_ERR_UNSUPPORTED -3   /* valid request this build has no kernel for           */
+#define UOCR_ERR_WORKSPACE   -4   /* workspace too small                                   */
+
+/* activation fused into a producing kernel / undone in a consuming one */
+#define UOCR_ACT_NONE     0
+#define UOCR_ACT_LEAKY    1       /* y = x >= 0 ? x : alpha * x   (layers.py:390-401)      */
+#define UOCR_ACT_SIGMOID  2       /* y = 1 / (1 + exp(-x))        (layers.py:407-415)      */
+
+/* arithmetic of the contraction kernels */
+#define UOCR_MATH_FP32   0        /* FP32 FFMA everywhere ("check mode")                   */
+#define UOCR_MATH_TF32   1        /* tcgen05 kind::tf32, FP32 accumulate in TMEM, where a   */
+                                  /* tensor-core kernel exists for the shape; else FP32    */
+
+/* ------------------------------------------------------------------ runtime / plumbing */
+
+int         uocr_version(void);
+const char* uocr_last_error(void);
+
+int uocr_device_count(int* count);
+int uocr_set_device(int device);
+int uocr_get_device(int* device);
+/* name: caller buffer of name_len bytes; any out pointer may be NULL */
+int uocr_device_info(int device, char* name, size_t name_len, int* sm_count,
+                     int* cc_major, int* cc_minor, size_t* total_mem, size_t* free_mem);
+
+/* stream-ordered pooled allocation (cudaMallocAsync on the device's default mempool with the
+ * release threshold lifted): replaces CuPy's memory pool behind cupy.asarray / cp.zeros
+ * (gpu.py:18-22, layers.py:12-13). */
+int uocr_malloc(void** ptr, size_t bytes, void* stream);
+int uocr_free(void* ptr, void* stream);
+int uocr_host_alloc(void** ptr, size_t bytes);      /* pinned host memory */
+int uocr_host_free(void* ptr);
+int uocr_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);   /* CP.copy     gpu.py:18-22 */
+int uocr_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream);   /* CP.asnumpy  gpu.py:24-28 */
+int uocr_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream);
+int uocr_memset(void* dst, int byte_value, size_t bytes, void* stream);        /* cp.zeros_like, layers.py:13,21 */
+
+int uocr_stream_create(void** stream);
+int uocr_stream_destroy(void* stream);
+int uocr_stream_sync(void* stream);                 /* blocks the host   */
+int uocr_device_sync(void);                         /* blocks the host; replaces cuda.synchronize(), convolutional.py:192 */
+int uocr_event_create(void** event);
+int uocr_event_destroy(void* event);
+int uocr_event_record(void* event, void* stream);
+int uocr_event_sync(void* event);                   /* blocks the host   */
+int uocr_event_elapsed_ms(void* start, void* stop, float* ms);
+int uocr_stream_wait_event(void* stream, void* event);
+
+/* CUDA-graph capture of a launch sequence (one inference or train step) */
+int uocr_graph_begin(void* stream);
+int uocr_graph_end(void* stream, void** graph_exec);
+int uocr_graph_launch(void* graph_exec, void* stream);
+int uocr_graph_destroy(void* graph_exec);
+
+/* number of kernels this library has launched in this process (all threads) */
+int uocr_launch_count(uint64_t* count);
+
+/* ------------------------------------------------------------------ array helpers
+ * the whole-array NumPy/CuPy expressions the reference's graph executor and Param use */
+int uocr_fill_f32(float* dst, float value, int64_t n, void* stream);
+int uocr_f64_to_f32(float* dst, const double* src, int64_t n, void* stream);
+int uocr_f32_to_f64(double* dst, const float* src, int64_t n, void* stream);
+int uocr_u8_to_f32(float* dst, const uint8_t* src, float scale, int64_t n, void* stream); /* encode_layers: /255, train_data_generator.py:24-37 */
+/* y = a * x + b * y   (fan-out gradient sum models.py:218; `param.grad += grad` layers.py:153) */
+int uocr_axpby_f32(float* y, const float* x, float a, float b, int64_t n, void* stream);
+int uocr_mul_f32(float* out, const float* a, const float* b, int64_t n, void* stream);
+/* *flag (int32 on device) |= any(isnan(x))   (BaseLayer.nan_weights, layers.py:139-140) */
+int uocr_nan_flag_f32(const float* x, int64_t n, int32_t* flag, void* stream);
+/* out[0] (+)= sum(x)  (float64 accumulation inside, float32 result) */
+int uocr_sum_f32(const float* x, int64_t n, float* out, int accumulate, void* stream);
+/* rows x cols strided 2-D copy, pitches in elements (Concat fwd/bwd, layers.py:240-269) */
+int uocr_copy2d_f32(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch,
+                    int64_t rows, int64_t cols, void* stream);
+/* zero-pad H and W (make_divisible_by, my_model/model.py:26-34; conv padding)            */
+int uocr_pad_hw_f32(float* dst, const float* src, int64_t n, int64_t h, int64_t w, int64_t c,
+                    int64_t top, int64_t bottom, int64_t left, int64_t right, float value,
+                    void* stream);
+
+/* ------------------------------------------------------------------ Convolutional2D
+ * geometry shared by the three conv entry points */
+typedef struct uocr_conv2d_desc {
+    int64_t n, h, w, cin;        /* input  (N, H, W, Cin)                          */
+    int64_t cout;                /* output (N, Ho, Wo, Cout)                       */
+    int32_t kh, kw;              /* kernel_size                                     */
+    int32_t ph, pw;              /* padding                                         */
+    int32_t sh, sw;              /* stride                                          */
+    float   padding_value;       /* constant the border is filled with              */
+    int32_t bias;                /* reference's `bias` flag (b is multiplied by it) */
+    int32_t math_mode;           /* UOCR_MATH_*                                     */
+} uocr_conv2d_desc;
+
+/* Ho = floor((H + 2ph - kh) / sh) + 1 ...   replaces: Convolutional2D.get_output_shapes,
+ * convolutional.py:290-301 */
+int uocr_conv2d_out_hw(const uocr_conv2d_desc* d, int64_t* ho, int64_t* wo);
+
+/* y = act(conv(x, w) + bias * b).   replaces: Convolutional2D._forward_cpu / _forward_gpu,
+ * convolutional.py:62-99 / :147-195 (+ the following LeakyRelu/Sigmoid layer when act != NONE,
+ * layers.py:390-415).  x is the UNPADDED input; the border is synthesised from padding_value. */
+int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, const float* b,
+                    float* y, int act, float alpha, void* stream);
+
+/* dx = dgrad(dy, w) (overwrites dx).   replaces: _backward_gpu_kernel_dx + the crop of
+ * convolutional.py:141-142 / :203-219,239-250. */
+int uocr_conv2d_dgrad(const uocr_conv2d_desc* d, const float* dy, const float* w, float* dx,
+                      void* stream);
+
+/* dw (+)= wgrad(x_padded_with_padding_value, dy), db (+)= bias * sum(dy).
+ * replaces: _backward_gpu_kernel_dw_db + cp.sum + `w.grad += dw_total`,
+ * convolutional.py:221-237,252-265,274-283 (CPU :121-139).  `accumulate` != 0 adds into dw/db
+ * (the reference's `+=`), 0 overwrites.  Deterministic two-stage reduction through
+ * `workspace` (uocr_conv2d_wgrad_workspace bytes; may be NULL when that is 0). */
+int uocr_conv2d_wgrad_workspace(const uocr_conv2d_desc* d, size_t* bytes);
+int uocr_conv2d_wgrad(const uocr_conv2d_desc* d, const float* x, const float* dy, float* dw,
+                      float* db, int accumulate, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* (N, H, W, C) -> (N*W, H, width, C): every width-`width` window of the W axis (zero padded
+ * by width, width/2 on the left) becomes a batch row.   replaces:
+ * Conv2DToBatchedFixedWidthed._forward/_backward, convolutional.py:335-360. */
+int uocr_window_batch_fwd(const float* x, float* y, int64_t n, int64_t h, int64_t w, int64_t c,
+                          int32_t width, void* stream);
+int uocr_window_batch_bwd(const float* dy, float* dx, int64_t n, int64_t h, int64_t w, int64_t c,
+                          int32_t width, void* stream);
+
+/* ------------------------------------------------------------------ MaxPool2D / Upsample2D */
+
+/* Ho/Wo with the reference's floor / ceil rule.  replaces: maxpool.py:204-216 */
+int uocr_maxpool2d_out_hw(int64_t h, int64_t w, int32_t kh, int32_t kw, int32_t ph, int32_t pw,
+                          int32_t sh, int32_t sw, int32_t ceil_mode, int64_t* ho, int64_t* wo);
+/* y = window max over the zero-padded input (padding taps take part with value 0; taps
+ * beyond the padded array are skipped); mask (uint8, (N, kh*Ho, kw*Wo, C)) = 1 where a tap
+ * -- padding taps included -- equals the max: the reference's CPU semantics, maxpool.py:24-57.
+ * Bit-exact outputs. */
+int uocr_maxpool2d_fwd(const float* x, float* y, uint8_t* mask, int64_t n, int64_t h, int64_t w,
+                       int64_t c, int32_t kh, int32_t kw, int32_t ph, int32_t pw, int32_t sh,
+                       int32_t sw, int64_t ho, int64_t wo, void* stream);
+/* dx[p] = sum over windows covering p of mask ? dy / tie_count : 0.  replaces: maxpool.py:61-88 */
+int uocr_maxpool2d_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, int64_t h,
+                       int64_t w, int64_t c, int32_t kh, int32_t kw, int32_t ph, int32_t pw,
+                       int32_t sh, int32_t sw, int64_t ho, int64_t wo, void* stream);
+
+/* nearest-neighbour repeat by (sy, sx) and its adjoint (block sum); h, w are the SMALL
+ * (un-upsampled) sizes.   replaces: upsample.py:21-39 / :41-110 */
+int uocr_upsample2d_fwd(const float* x, float* y, int64_t n, int64_t h, int64_t w, int64_t c,
+                        int32_t sy, int32_t sx, void* stream);
+int uocr_upsample2d_bwd(const float* dy, float* dx, int64_t n, int64_t h, int64_t w, int64_t c,
+                        int32_t sy, int32_t sx, void* stream);
+
+/* ------------------------------------------------------------------ activations
+ * Relu is Leaky with alpha = 0 (layers.py:377-384).  The backward recomputes the mask from the
+ * saved INPUT x, as the reference's stored mask is a function of x only. */
+int uocr_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, void* stream);
+int uocr_leaky_relu_bwd(const float* x, const float* dy, float* dx, int64_t n, float alpha,
+                        void* stream);
+int uocr_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream);
+int uocr_sigmoid_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* dx = dy * act'(.) expressed through the activation OUTPUT y (for fused conv+act chains:
+ * leaky (alpha > 0): y >= 0 ? 1 : alpha;  sigmoid: y * (1 - y)) */
+int uocr_act_bwd_from_output(const float* y, const float* dy, float* dx, int64_t n, int act,
+                             float alpha, void* stream);
+
+/* ------------------------------------------------------------------ FullyConnected
+ * y = act([x, 1] . W), W (n_in + 1, n_out).   replaces: layers.py:335-339 */
+int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t n_in,
+                int64_t n_out, int act, float alpha, int math_mode, void* stream);
+/* dx = dy . W[:-1]^T (skipped when dx == NULL); dw (+)= [x, 1]^T . dy.  replaces: layers.py:341-347 */
+int uocr_fc_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw,
+                int64_t batch, int64_t n_in, int64_t n_out, int accumulate, int math_mode,
+                void* stream);
+
+/* ------------------------------------------------------------------ losses
+ * Each writes the gradient w.r.t. `pred` (may be NULL: loss only, Model.test) and ADDS nothing:
+ * loss[0] (device float32) is overwritten.  One D2H read per step fetches it. */
+#define UOCR_SEG_DICE     0      /* losses.py:9-25   */
+#define UOCR_SEG_JACCARD  1      /* losses.py:28-42  */
+/* pred, gt: (N, H*W, C).  workspace: uocr_seg_loss_workspace(n, c) bytes, 8-byte aligned. */
+int uocr_seg_loss_workspace(int64_t n, int64_t c, size_t* bytes);
+int uocr_seg_loss(int kind, const float* pred, const float* gt, float* grad, float* loss,
+                  int64_t n, int64_t hw, int64_t c, void* workspace, void* stream);
+/* row softmax cross-entropy, (B, C); loss = -sum(gt * log p) / B, grad = (p - gt) / B;
+ * 0 * log 0 -> NaN as in the reference.   replaces: losses.py:60-73 */
+int uocr_softmax_ce(const float* logits, const float* gt, float* grad, float* loss, int64_t batch,
+                    int64_t classes, float* workspace /* batch floats */, void* stream);
+/* replaces: losses.py:45-57 */
+int uocr_sigmoid_ce(const float* logits, const float* gt, float* grad, float* loss, int64_t batch,
+                    int64_t classes, void* stream);
+
+/* ------------------------------------------------------------------ regularisers + optimisers */
+#define UOCR_REG_L1 1            /* regularizations.py:15-19 */
+#define UOCR_REG_L2 2            /* regularizations.py:22-26 */
+/* grad += d/dw strength * |w| or w^2 ; loss[0] += strength * sum(...)   (BaseLayer.regularize,
+ * layers.py:147-155).  grad or loss may be NULL. */
+int uocr_regularize(int kind, const float* w, float* grad, float* loss, int64_t n, float strength,
+                    void* stream);
+
+/* v = b1 v + (1-b1) g; a = b2 a + (1-b2) g^2; w -= lr / (sqrt(a) + eps) * v -- no bias
+ * correction.   replaces: Adam.update, optimizers.py:56-61.
+ * Fused extras (0 / 1 reproduce the reference exactly): g is first scaled by grad_scale
+ * (1/world for averaged data-parallel gradients) and l2 * 2 * w is added (L2 regulariser folded
+ * into the update; the regulariser's gradient is a function of w only).  When `reg_loss` is
+ * non-NULL, l2 * sum(w^2) of the PRE-update weights is added to reg_loss[0]. */
+int uocr_adam_update(float* w, const float* g, float* v, float* a, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float grad_scale, float l2, float* reg_loss,
+                     void* stream);
+/* v = m v - lr g; w += v.   replaces: optimizers.py:77-79 */
+int uocr_momentum_update(float* w, const float* g, float* v, int64_t n, float lr, float momentum,
+                         void* stream);
+/* a = rho a + (1-rho) g^2; w -= lr / (sqrt(a) + eps) * g.   replaces: optimizers.py:93-96 */
+int uocr_rmsprop_update(float* w, const float* g, float* a, int64_t n, float lr, float rho,
+                        float eps, void* stream);
+
+/* ------------------------------------------------------------------ exact-index output
+ * hits[r, c] (uint8) = pred[r, c] == max(pred[r, :]) && max != 0   -- the index part of
+ * PredToText._func1, interpreter/interpreter.py:596-602 (ties keep every column). */
+int uocr_row_max_hits(const float* pred, uint8_t* hits, int64_t rows, int64_t cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UOCR_H_ */

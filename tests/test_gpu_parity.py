@@ -1,0 +1,381 @@
+"""Parity of the CUDA path (through the C ABI, via the host mirror `univer_ocr_b200.nn`) with
+
+  1. the golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+  2. the float64 oracle (oracle/np_oracle.py) on fresh seeded inputs at larger sizes.
+
+Tolerances (stated per test): the CUDA path stores float32 and accumulates in FP32 FFMA
+("check mode", CP.math_mode = fp32); inputs are float32-representable so both sides see the
+same numbers.  Max pooling outputs and tie masks, upsampling, window batching and concat are
+pure selections/copies and must be BIT-EXACT.
+"""
+import numpy as np
+import pytest
+
+from oracle import np_models, np_oracle as O
+from tests.cases import CONV_CASES, MODEL_SHAPES, POOL_CASES
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nn():
+    import univer_ocr_b200.nn as nn_
+    nn_.CP.use_gpu()
+    nn_.CP.set_math_mode('fp32')
+    return nn_
+
+
+def host(a):
+    return np.asarray(a.get() if hasattr(a, 'get') else a, dtype=np.float64)
+
+
+def close(got, want, rtol=1e-4, atol_scale=2e-6, what=''):
+    """|got - want| <= rtol * |want| + atol_scale * max|want| (FP32 accumulate vs float64)."""
+    got, want = host(got), np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f'{what}: shape {got.shape} != {want.shape}'
+    atol = atol_scale * max(float(np.max(np.abs(want))) if want.size else 0.0, 1e-30)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol, err_msg=what)
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+# ----------------------------------------------------------------------------- convolution
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv2d_golden(nn, golden, case):
+    """Convolutional2D fwd / dX / dW / db vs the reference.  rtol 1e-4, atol 2e-6*max."""
+    name, _, cin, cout, ks, pad, pv, st = case
+    g = golden('conv2d').case(name)
+    layer = nn.layers.Convolutional2D(ks, cin, cout, padding=pad, padding_value=pv, stride=st,
+                                      w=g['w'], b=g['b'])
+    y = layer.forward(g['X'])[0]
+    close(y, g['y'], what='y')
+    dX = layer.backward(g['dy'])[0]
+    close(dX, g['dX'], what='dX')
+    close(layer.w.grad, g['dW'], what='dW')
+    close(layer.b.grad, g['db'], what='db')
+
+
+def test_conv2d_grad_accumulates_and_bias_flag(nn, golden):
+    """`w.grad += dw` (convolutional.py:138-139) and bias=False (b multiplied by 0, :87,:117)."""
+    g = golden('conv2d').case('padval')
+    layer = nn.layers.Convolutional2D((4, 4), 6, 7, padding=1, padding_value=0.5, w=g['w'], b=g['b'])
+    for _ in range(2):
+        layer.forward(g['X'])
+        layer.backward(g['dy'])
+    close(layer.w.grad, 2 * g['dW'], what='dW x2')
+    close(layer.b.grad, 2 * g['db'], what='db x2')
+    nob = nn.layers.Convolutional2D((4, 4), 6, 7, padding=1, padding_value=0.5, w=g['w'], b=g['b'],
+                                    bias=False)
+    close(nob.forward(g['X'])[0], O.conv2d_fwd(g['X'], g['w'], g['b'], 1, 0.5, 1, bias=False), what='y')
+    nob.backward(g['dy'])
+    assert np.all(host(nob.b.grad) == 0.0)
+
+
+def test_conv2d_channel_mismatch_raises(nn):
+    layer = nn.layers.Convolutional2D((3, 3), 3, 2)
+    with pytest.raises(AssertionError):
+        layer.forward(np.zeros((1, 5, 5, 4)))
+
+
+@pytest.mark.parametrize('shape,cin,cout,ks,pad,st', [
+    ((3, 62, 92), 1, 16, (3, 3), 1, 1), ((3, 62, 92), 16, 1, (3, 3), 1, 1),
+    ((2, 124, 92), 1, 1, (5, 5), 2, 2), ((2, 61, 47), 4, 4, (5, 5), 2, 2),
+    ((2, 64, 128), 4, 2, (5, 5), 2, 1), ((3, 32, 70), 1, 64, (5, 3), (0, 1), (2, 1)),
+    ((3, 14, 70), 64, 64, (5, 3), (0, 1), (2, 1)), ((2, 33, 35), 5, 3, (4, 2), (2, 1), (3, 2)),
+], ids=['mono1', 'mono2', 'para_s2', 'line_s2_odd', 'line_end', 'char1', 'char2', 'odd'])
+def test_conv2d_vs_oracle_medium(nn, shape, cin, cout, ks, pad, st):
+    """Larger seeded cases against the float64 oracle (rtol 2e-4, atol 4e-6*max)."""
+    rng = np.random.default_rng(hash((shape, cin, cout)) % (2 ** 32))
+    n, h, w = shape
+    X = f32(rng.standard_normal((n, h, w, cin)))
+    wt = f32(rng.standard_normal((*ks, cin, cout)) / np.sqrt(ks[0] * ks[1] * cin))
+    b = f32(rng.standard_normal(cout))
+    layer = nn.layers.Convolutional2D(ks, cin, cout, padding=pad, stride=st, w=wt, b=b)
+    y = layer.forward(X)[0]
+    want = O.conv2d_fwd(X, wt, b, pad, 0.0, st)
+    close(y, want, 2e-4, 4e-6, 'y')
+    dy = f32(rng.standard_normal(want.shape))
+    dX = layer.backward(dy)[0]
+    odX, odW, odb = O.conv2d_bwd(X, wt, dy, pad, 0.0, st)
+    close(dX, odX, 2e-4, 4e-6, 'dX')
+    close(layer.w.grad, odW, 2e-4, 4e-6, 'dW')
+    close(layer.b.grad, odb, 2e-4, 4e-6, 'db')
+
+
+# ----------------------------------------------------------------------------- pooling etc.
+
+@pytest.mark.parametrize('case', POOL_CASES, ids=[c[0] for c in POOL_CASES])
+def test_maxpool_golden_bit_exact(nn, golden, case):
+    name, shape, k, pad, st, ceil = case
+    g = golden('maxpool2d').case(name)
+    layer = nn.layers.MaxPool2D(k, padding=pad, stride=st, ceil_mode=ceil)
+    y = layer.forward(g['X'])[0]
+    assert np.array_equal(host(y), g['y'])                                   # bit-exact max
+    assert np.array_equal(layer._mem[0][0].get(), g['mask'])                 # bit-exact tie mask
+    close(layer.backward(g['dy'])[0], g['dX'], 1e-6, 1e-7, 'dX')
+
+
+def test_maxpool_known_answer(nn, golden):
+    g = golden('maxpool2d').case('kat')
+    y = nn.layers.MaxPool2D(2, ceil_mode=True).forward(g['X'])[0]
+    assert np.array_equal(host(y)[0, :, :, 0], np.array([[1., 2.], [-1., 1.]]))
+
+
+def test_maxpool_vs_oracle_identity_shape(nn):
+    """test_identity.py:81-85 shape family: (5, 240, 320, 6) is scaled to (2, 60, 80, 6)."""
+    rng = np.random.default_rng(5)
+    X = f32(np.round(rng.standard_normal((2, 60, 80, 6)) * 4) / 4)
+    for k, pad, st in ((2, 0, None), (2, 1, None), (2, 0, 1), (2, 1, 1), (3, 1, 2)):
+        layer = nn.layers.MaxPool2D(k, padding=pad, stride=st)
+        y = layer.forward(X)[0]
+        oy, mask = O.maxpool2d_fwd(X, k, pad, st)
+        assert np.array_equal(host(y), oy)
+        assert np.array_equal(layer._mem[0][0].get(), mask.astype(np.uint8))
+        dy = f32(rng.standard_normal(oy.shape))
+        close(layer.backward(dy)[0], O.maxpool2d_bwd(dy, mask, X.shape, k, pad, st), 1e-5, 1e-6)
+
+
+def test_upsample_golden(nn, golden):
+    g = golden('upsample2d')
+    k = g.case('kat')
+    up = nn.layers.Upsample2D((2, 3))
+    y = up.forward(k['X'])[0]
+    assert np.array_equal(host(y), f32(k['y']))
+    close(up.backward(y)[0], k['dX'], 1e-6, 1e-7)
+    for name, sf in (('s2', 2), ('s5', 5), ('s23', (2, 3))):
+        c = g.case(name)
+        up = nn.layers.Upsample2D(sf)
+        assert np.array_equal(host(up.forward(c['X'])[0]), c['y'])           # pure copy: exact
+        close(up.backward(c['dy'])[0], c['dX'], 1e-6, 1e-6)
+
+
+def test_elementwise_fc_window_concat_golden(nn, golden):
+    g = golden('layers')
+    X, dy = g['act__X'], g['act__dy']
+    for name, layer in (('relu', nn.layers.Relu()), ('lrelu', nn.layers.LeakyRelu(0.01)),
+                        ('lrelu_a', nn.layers.LeakyRelu(0.2)), ('sigmoid', nn.layers.Sigmoid())):
+        close(layer.forward(X)[0], g[f'{name}__y'], 2e-6, 1e-7, name)
+        close(layer.backward(dy)[0], g[f'{name}__dX'], 2e-6, 1e-7, name)
+    fc = nn.layers.FullyConnected(9, 6, w=g['fc__W'])
+    close(fc.forward(g['fc__X'])[0], g['fc__y'], 1e-5, 1e-6)
+    close(fc.backward(g['fc__dy'])[0], g['fc__dX'], 1e-5, 1e-6)
+    close(fc.w.grad, g['fc__dW'], 1e-5, 1e-6)
+    for name, width in (('w3', 3), ('w8', 8), ('w8min', 8)):
+        c = g.case(f'win_{name}')
+        wl = nn.layers.Conv2DToBatchedFixedWidthed(width)
+        assert np.array_equal(host(wl.forward(c['X'])[0]), c['y'])            # pure copy: exact
+        close(wl.backward(c['dy'])[0], c['dX'], 1e-6, 1e-6)
+    cat = nn.layers.Concat()
+    y = cat.forward([g['cat__a'], g['cat__b']])[0]
+    assert np.array_equal(host(y), g['cat__y'])
+    ga, gb = cat.backward([y])
+    assert np.array_equal(host(ga), g['cat__ga']) and np.array_equal(host(gb), g['cat__gb'])
+
+
+def test_fc_vs_oracle_char_head(nn):
+    """The three Char FC shapes (513x1024, 1025x128, 129x162) at batch 300."""
+    rng = np.random.default_rng(11)
+    for n_in, n_out in ((512, 1024), (1024, 128), (128, 162)):
+        X = f32(rng.standard_normal((300, n_in)))
+        W = f32(rng.uniform(size=(n_in + 1, n_out)) / np.sqrt((n_in + 1) / 2))
+        dy = f32(rng.standard_normal((300, n_out)))
+        fc = nn.layers.FullyConnected(n_in, n_out, w=W)
+        close(fc.forward(X)[0], O.fc_fwd(X, W), 2e-4, 4e-6, 'y')
+        odX, odW = O.fc_bwd(X, W, dy)
+        close(fc.backward(dy)[0], odX, 2e-4, 4e-6, 'dX')
+        close(fc.w.grad, odW, 2e-4, 4e-6, 'dW')
+
+
+# ----------------------------------------------------------------------------- losses / opt
+
+def test_losses_golden(nn, golden):
+    g = golden('losses_opt')
+    for name, fn in (('dice', nn.losses.SegmentationDice2D()), ('jaccard', nn.losses.SegmentationJaccard2D())):
+        loss, grad = fn(g['seg__pred'], g['seg__gt'])
+        assert abs(float(loss) - float(g[f'{name}__loss'])) <= 1e-5 * abs(float(g[f'{name}__loss']))
+        close(grad, g[f'{name}__grad'], 1e-5, 1e-6, name)
+    loss, grad = nn.losses.SoftmaxCrossEntropy()(g['sce__logits'], g['sce__gt'])
+    assert abs(float(loss) - float(g['sce__loss'])) <= 1e-5 * abs(float(g['sce__loss']))
+    close(grad, g['sce__grad'], 1e-4, 1e-6)
+    loss, grad = nn.losses.SoftmaxCrossEntropy()(g['sce_nan__logits'], g['sce__gt'])
+    assert np.isnan(float(loss))                       # 0 * log 0 -> NaN as in the reference
+    close(grad, g['sce_nan__grad'], 1e-4, 1e-6)
+    loss, grad = nn.losses.SigmoidCrossEntropy()(g['bce__logits'], g['bce__gt'])
+    assert abs(float(loss) - float(g['bce__loss'])) <= 1e-5 * abs(float(g['bce__loss']))
+    close(grad, g['bce__grad'], 1e-5, 1e-6)
+
+
+def test_regularisers_and_optimisers_golden(nn, golden):
+    g = golden('losses_opt')
+    for name, reg in (('l1', nn.regularizations.L1(0.1)), ('l2', nn.regularizations.L2(0.01))):
+        loss, grad = reg(g['reg__w'])
+        assert abs(float(loss) - float(g[f'{name}__loss'])) <= 1e-6 * abs(float(g[f'{name}__loss']))
+        close(grad, g[f'{name}__grad'], 1e-6, 1e-7)
+    for name, opt in (('adam', nn.optimizers.Adam(lr=0.0015)),
+                      ('momentum', nn.optimizers.Momentum(lr=0.01, momentum=0.9)),
+                      ('rmsprop', nn.optimizers.RMSProp(lr=0.01))):
+        p = nn.layers.Param(g['reg__w'], optimizer=opt)
+        for i, gr in enumerate((g['opt__g1'], g['opt__g2']), start=1):
+            p.grad = nn.CP.copy(gr)
+            p.update_grad()
+            # Adam's first steps are ~3.16*lr*sign(g): compare with an absolute floor
+            close(p.value, g[f'{name}__w{i}'], 1e-5, 1e-6, f'{name} step {i}')
+
+
+def test_dice_large_tile(nn):
+    """Dice on a full 496x736 tile: two-pass reduction vs float64 (loss rel 1e-5)."""
+    rng = np.random.default_rng(3)
+    pred = f32(rng.uniform(0.01, 0.99, size=(2, 496, 736, 1)))
+    gt = (rng.uniform(size=pred.shape) < 0.2).astype(np.float64)
+    loss, grad = nn.losses.SegmentationDice2D()(pred, gt)
+    ol, og = O.dice_loss(pred, gt)
+    assert abs(float(loss) - ol) <= 1e-5 * abs(ol)
+    close(grad, og, 1e-4, 1e-6)
+
+
+# ----------------------------------------------------------------------------- whole sub-models
+
+@pytest.mark.parametrize('name', list(MODEL_SHAPES))
+def test_submodel_train_golden(nn, golden, name):
+    """Two Model.train steps of each my_model sub-network (fwd + loss + bwd + L2 + Adam) vs the
+    reference.  Predictions rtol 1e-4; updated weights rtol 1e-3 with an absolute floor of
+    1e-5 (Adam without bias correction amplifies sign flips of near-zero gradients)."""
+    from univer_ocr_b200 import my_model
+    g = golden('models').case(name)
+    spec = np_models.net_spec(name)
+    w0 = np_models.init_weights(spec, np.random.default_rng(int(g['seed'])))
+    opt = nn.optimizers.Adam(lr=0.0015)
+    model = my_model.MAKERS[name](MODEL_SHAPES[name], optimizer=opt)
+    model.set_weights({k: {n: f32(v).tolist() for n, v in p.items()} for k, p in w0.items()})
+    close(model.predict(g['X'])[0], g['pred0'], 1e-4, 2e-6, 'pred0')
+    for step in (1, 2):
+        losses = model.train(g['X'], g['y'])
+        got = float(losses['output_losses'][0])
+        assert abs(got - float(g[f'loss{step}'])) <= 2e-5 * abs(float(g[f'loss{step}'])), (got, g[f'loss{step}'])
+        reg = float(losses['regularization_loss'])
+        assert abs(reg - float(g[f'reg{step}'])) <= 2e-5 * abs(float(g[f'reg{step}']))
+    for key, param in model.params().items():
+        tag = f'after__{key.replace("/", ".")}'
+        v = host(param.value).ravel()
+        np.testing.assert_allclose(v[g[f'{tag}__idx']], g[f'{tag}__val'], rtol=1e-3, atol=1e-5,
+                                   err_msg=key)
+    close(model.predict(g['X'])[0], g['pred2'], 1e-3, 1e-5, 'pred2')
+
+
+def test_weights_json_roundtrip(nn, tmp_path):
+    """model_weights.json: same keys / nesting as the reference, values survive a
+    save -> load cycle bit-exactly (float32 -> float64 repr -> float32)."""
+    import json
+    from univer_ocr_b200 import my_model
+    np.random.seed(0)
+    models = [my_model.make_monochrome((1, 16, 16, 1)), my_model.make_line((1, 16, 16, 1))]
+    path = tmp_path / 'model_weights.json'
+    my_model.save_weights(models, path)
+    data = json.load(open(path))
+    assert set(data) == {'Monochrome/conv_1', 'Monochrome/conv_2', 'Line/down_1/conv_1',
+                         'Line/down_2/conv_1', 'Line/up_1/conv_block/conv_1',
+                         'Line/up_2/conv_block/conv_1', 'Line/end/conv_1'}
+    assert np.array(data['Monochrome/conv_1']['w']).shape == (3, 3, 1, 16)
+    assert np.array(data['Line/end/conv_1']['b']).shape == (2,)
+    fresh = [my_model.make_monochrome((1, 16, 16, 1)), my_model.make_line((1, 16, 16, 1))]
+    my_model.load_weights(fresh, path)
+    for a, b in zip(models, fresh):
+        for key in a.params():
+            assert np.array_equal(a.params()[key].value.get(), b.params()[key].value.get())
+    # NaN / shape-mismatch tensors are skipped with a message (layers.py:129-136)
+    bad = {'Monochrome/conv_1': {'w': np.full((3, 3, 1, 16), np.nan).tolist(), 'b': [0.0] * 3}}
+    before = fresh[0].params()['Monochrome/conv_1/w'].value.get().copy()
+    fresh[0].set_weights(bad)
+    assert np.array_equal(fresh[0].params()['Monochrome/conv_1/w'].value.get(), before)
+    assert not fresh[0].nan_weights()
+
+
+def test_dag_model_fanout_and_multi_io(nn):
+    """Multi-input / multi-output DAG with fan-out (test_gradients.py:225-259 topology), checked
+    against the oracle composed by hand: y1 = fc1(flat(pool(cat(c1(x0), c2(x1), c3(x2)))))."""
+    rng = np.random.default_rng(21)
+    L = nn.layers
+    X = [f32(rng.standard_normal((5, 5, 5, 1))) for _ in range(3)]
+    ws = [f32(rng.standard_normal((2, 2, 1, 3)) * 0.5) for _ in range(3)]
+    bs = [f32(rng.standard_normal(3)) for _ in range(3)]
+    W1 = f32(rng.standard_normal((2 * 2 * 9 + 1, 3)) * 0.3)
+    W2 = f32(rng.standard_normal((4, 3)) * 0.3)
+    layers = {f'conv{i + 1}': L.Convolutional2D((2, 2), out_channels=3, w=ws[i], b=bs[i], in_channels=1)
+              for i in range(3)}
+    layers.update({'concat': L.Concat(), 'pool': L.MaxPool2D(2), 'flatten': L.Flatten(),
+                   'dense1': L.FullyConnected(n_output=3, w=W1, n_input=36),
+                   'dense2': L.FullyConnected(n_output=3, w=W2, n_input=3)})
+    relations = {'conv1': 0, 'conv2': 1, 'conv3': 2, 'concat': ['conv1', 'conv2', 'conv3'],
+                 'pool': 'concat', 'flatten': 'pool', 'dense1': 'flatten', 'dense2': 'dense1',
+                 0: 'dense1', 1: 'dense2'}
+    model = nn.models.Model(layers, relations, loss=nn.losses.SigmoidCrossEntropy())
+    model.initialize_from_X(X)
+    y = [(rng.uniform(size=(5, 3)) < 0.5).astype(np.float64) for _ in range(2)]
+    out = model.compute_loss_and_gradients(X, y)
+    # oracle
+    convs = [O.conv2d_fwd(X[i], ws[i], bs[i]) for i in range(3)]
+    cat = np.concatenate(convs, axis=-1)
+    pooled, mask = O.maxpool2d_fwd(cat, 2)
+    flat = pooled.reshape(5, -1)
+    d1 = O.fc_fwd(flat, W1)
+    d2 = O.fc_fwd(d1, W2)
+    l1, g1 = O.sigmoid_ce_loss(d1, y[0])
+    l2, g2 = O.sigmoid_ce_loss(d2, y[1])
+    assert abs(float(out['output_losses'][0]) - l1) < 1e-5 * abs(l1)
+    assert abs(float(out['output_losses'][1]) - l2) < 1e-5 * abs(l2)
+    gd1_from2, dW2 = O.fc_bwd(d1, W2, g2)
+    gflat, dW1 = O.fc_bwd(flat, W1, g1 + gd1_from2)                 # fan-out: two consumers of dense1
+    close(model.layers['dense2'].w.grad, dW2, 1e-4, 2e-6, 'dW2')
+    close(model.layers['dense1'].w.grad, dW1, 1e-4, 2e-6, 'dW1')
+    gcat = O.maxpool2d_bwd(gflat.reshape(pooled.shape), mask, cat.shape, 2)
+    for i in range(3):
+        dXi, dWi, _ = O.conv2d_bwd(X[i], ws[i], gcat[..., 3 * i:3 * i + 3])
+        close(model.input_grads[i], dXi, 1e-4, 2e-6, f'dX{i}')
+        close(model.layers[f'conv{i + 1}'].w.grad, dWi, 1e-4, 2e-6, f'dWconv{i}')
+
+
+# ----------------------------------------------------------------------------- full-size properties
+
+def test_full_size_adjoint_identities(nn):
+    """At BASELINE.json's tile size (496x736; batch 4 here, the identities are batch-independent)
+    the oracle is too slow, so check size-independent properties that tie the three conv kernels
+    together:  <conv(x) - bias, dy> == <x, dgrad(dy)> == <w, wgrad(x, dy)>  (bilinearity /
+    adjointness), and the same adjoint identity for Upsample2D."""
+    rng = np.random.default_rng(8)
+    for cin, cout, ks, pad, st, hw in ((1, 16, (3, 3), 1, 1, (496, 736)), (16, 1, (3, 3), 1, 1, (496, 736)),
+                                       (1, 1, (5, 5), 2, 2, (496, 736)), (4, 4, (5, 5), 2, 1, (128, 256)),
+                                       (64, 64, (5, 3), (0, 1), (2, 1), (14, 256))):
+        X = f32(rng.standard_normal((4, *hw, cin)))
+        wt = f32(rng.standard_normal((*ks, cin, cout)) / np.sqrt(ks[0] * ks[1] * cin))
+        layer = nn.layers.Convolutional2D(ks, cin, cout, padding=pad, stride=st, w=wt, b=np.zeros(cout))
+        y = host(layer.forward(X)[0])
+        dy = f32(rng.standard_normal(y.shape))
+        dX = host(layer.backward(dy)[0])
+        lhs = float(np.sum(y * dy))
+        scale = float(np.sqrt(np.sum(y * y) * np.sum(dy * dy)))
+        assert abs(lhs - float(np.sum(X * dX))) <= 2e-5 * scale, (cin, cout, 'dgrad adjoint')
+        assert abs(lhs - float(np.sum(wt * host(layer.w.grad)))) <= 2e-5 * scale, (cin, cout, 'wgrad adjoint')
+        assert abs(float(np.sum(dy)) - float(np.sum(host(layer.b.grad)))) <= 1e-4 * np.sqrt(dy.size)
+    up = nn.layers.Upsample2D(2)
+    X = f32(rng.standard_normal((4, 248, 368, 1)))
+    y = host(up.forward(X)[0])
+    dy = f32(rng.standard_normal(y.shape))
+    assert abs(np.sum(y * dy) - np.sum(X * host(up.backward(dy)[0]))) <= 1e-5 * np.sqrt(np.sum(y * y) * np.sum(dy * dy))
+
+
+def test_row_max_hits_bit_exact(nn):
+    """PredToText index rule (interpreter.py:596-602): ties keep all columns, all-zero rows drop."""
+    import ctypes
+    from univer_ocr_b200._lib import lib
+    rng = np.random.default_rng(4)
+    pred = f32(np.round(rng.standard_normal((300, 162)) * 2) / 2)
+    pred[7, :] = 0.0
+    pred[9, :] = -1.0
+    d = nn.CP.copy(pred)
+    hits = nn.DeviceArray((300, 162), np.uint8)
+    lib.uocr_row_max_hits(d.ptr, hits.ptr, 300, 162, nn.CP.stream())
+    got = np.argwhere(hits.get() != 0)[:, 1]
+    assert np.array_equal(got, O.pred_to_ids(pred))

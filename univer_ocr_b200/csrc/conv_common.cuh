@@ -1,0 +1,34 @@
+// Geometry shared by the convolution kernels + the dispatch seams between the general path
+// (conv.cu) and the shape-specialised paths (conv_fast.cu).
+#pragma once
+#include "common.cuh"
+
+namespace uocr {
+
+struct ConvGeom {
+    int n, h, w, cin, cout;
+    int kh, kw, ph, pw, sh, sw;
+    int ho, wo;
+    float padding_value;
+    int bias;
+};
+
+// Shape-specialised kernels.  Each returns UOCR_ERR_UNSUPPORTED when it has no kernel for the
+// geometry / math mode, in which case the caller runs the general kernel.
+int conv_fwd_fast(const ConvGeom& g, int math_mode, const float* x, const float* w, const float* b,
+                  float* y, int act, float alpha, cudaStream_t st);
+int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const float* w, float* dx,
+                    cudaStream_t st);
+size_t conv_wgrad_fast_workspace(const ConvGeom& g, int math_mode);
+int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const float* dy, float* dw,
+                    float* db, int accumulate, float* ws, cudaStream_t st);
+
+// General kernels (conv.cu), exposed so the fast paths can delegate sub-problems.
+int conv_fwd_general(const ConvGeom& g, const float* x, const float* w, const float* b, float* y,
+                     int act, float alpha, cudaStream_t st);
+int conv_dgrad_general(const ConvGeom& g, const float* dy, const float* w, float* dx, cudaStream_t st);
+size_t conv_wgrad_general_workspace(const ConvGeom& g);
+int conv_wgrad_general(const ConvGeom& g, const float* x, const float* dy, float* dw, float* db,
+                       int accumulate, float* ws, cudaStream_t st);
+
+}  // namespace uocr

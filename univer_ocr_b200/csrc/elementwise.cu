@@ -1,0 +1,602 @@
+// Bandwidth-class kernels of libuocr: array helpers, activations, Upsample2D, MaxPool2D,
+// Conv2DToBatchedFixedWidthed, PredToText hit mask.  All are pure streaming kernels: 128-bit
+// vectorised, grid sized to a few waves over the 148 SMs, no shared memory (no reuse).
+#include "common.cuh"
+
+namespace uocr {
+
+// ---------------------------------------------------------------- generic elementwise driver
+// out[i] = f(a[i], b[i]).  Vector path: 4 x float4 in flight per thread (loads first, then
+// math, then stores) so each CTA keeps 16 KB of loads outstanding.
+template <int NIN, class F>
+__global__ void __launch_bounds__(kThreads) ew_vec4_kernel(float4* out, const float4* a,
+                                                           const float4* b, int64_t n4, F f) {
+    // no __restrict__: `out` may alias an input (in-place `+=`), each element is read then
+    // written by the same thread only
+    constexpr int U = 4;
+    const int64_t tile = (int64_t)kThreads * U;
+    for (int64_t base = (int64_t)blockIdx.x * tile; base < n4; base += (int64_t)gridDim.x * tile) {
+        float4 va[U], vb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
+            if (i < n4) {
+                va[u] = a[i];
+                if (NIN > 1) vb[u] = b[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + (int64_t)u * kThreads + threadIdx.x;
+            if (i < n4) {
+                float4 r;
+                r.x = f(va[u].x, NIN > 1 ? vb[u].x : 0.f);
+                r.y = f(va[u].y, NIN > 1 ? vb[u].y : 0.f);
+                r.z = f(va[u].z, NIN > 1 ? vb[u].z : 0.f);
+                r.w = f(va[u].w, NIN > 1 ? vb[u].w : 0.f);
+                out[i] = r;
+            }
+        }
+    }
+}
+
+template <int NIN, class F>
+__global__ void __launch_bounds__(kThreads) ew_scalar_kernel(float* out, const float* a,
+                                                             const float* b, int64_t n, F f) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kThreads)
+        out[i] = f(a[i], NIN > 1 ? b[i] : 0.f);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int NIN, class F>
+static int launch_ew(const char* name, float* out, const float* a, const float* b, int64_t n, F f,
+                     cudaStream_t st) {
+    if (n <= 0) return UOCR_OK;
+    const bool vec = aligned16(out) && aligned16(a) && (NIN < 2 || aligned16(b));
+    const int64_t n4 = vec ? n / 4 : 0;
+    if (n4 > 0) {
+        ew_vec4_kernel<NIN, F><<<ew_grid(n4, 4), kThreads, 0, st>>>(
+            reinterpret_cast<float4*>(out), reinterpret_cast<const float4*>(a),
+            reinterpret_cast<const float4*>(b), n4, f);
+        UOCR_LAUNCHED(name);
+    }
+    const int64_t done = n4 * 4;
+    if (done < n) {
+        ew_scalar_kernel<NIN, F><<<ew_grid(n - done, 1), kThreads, 0, st>>>(
+            out + done, a + done, NIN > 1 ? b + done : nullptr, n - done, f);
+        UOCR_LAUNCHED(name);
+    }
+    return UOCR_OK;
+}
+
+struct LeakyFwd {
+    float alpha;
+    __device__ float operator()(float x, float) const { return x >= 0.f ? x : alpha * x; }
+};
+struct LeakyBwd {   // a = x (saved input), b = dy
+    float alpha;
+    __device__ float operator()(float x, float dy) const { return x >= 0.f ? dy : (x < 0.f ? alpha * dy : 0.f * dy); }
+};
+struct SigmoidFwd {
+    __device__ float operator()(float x, float) const { return 1.f / (1.f + expf(-x)); }
+};
+struct SigmoidBwd {   // grad * e / (e + 1)^2, e = exp(-x)   (layers.py:413-415)
+    __device__ float operator()(float x, float dy) const {
+        const float e = expf(-x);
+        const float d = e + 1.f;
+        return dy * e / (d * d);
+    }
+};
+struct ActBwdFromOut {   // a = y (activation output), b = dy
+    int act;
+    float alpha;
+    __device__ float operator()(float y, float dy) const {
+        if (act == UOCR_ACT_LEAKY) return y >= 0.f ? dy : alpha * dy;
+        if (act == UOCR_ACT_SIGMOID) return dy * y * (1.f - y);
+        return dy;
+    }
+};
+struct Axpby {   // a = x, b = y(old)
+    float ca, cb;
+    __device__ float operator()(float x, float y) const { return ca * x + cb * y; }
+};
+struct Axpy1 {   // y = y + a*x with cb == 1 (exact `+=`)
+    float ca;
+    __device__ float operator()(float x, float y) const { return fmaf(ca, x, y); }
+};
+struct ScaleOnly {
+    float ca;
+    __device__ float operator()(float x, float) const { return ca * x; }
+};
+struct Mul {
+    __device__ float operator()(float x, float y) const { return x * y; }
+};
+
+// ---------------------------------------------------------------- fill / convert
+__global__ void __launch_bounds__(kThreads) fill_kernel(float* __restrict__ dst, float v, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kThreads)
+        dst[i] = v;
+}
+
+template <typename TO, typename TI>
+__global__ void __launch_bounds__(kThreads) convert_kernel(TO* __restrict__ dst,
+                                                           const TI* __restrict__ src, float scale,
+                                                           int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kThreads)
+        dst[i] = static_cast<TO>(src[i]) * static_cast<TO>(scale);
+}
+
+__global__ void __launch_bounds__(kThreads) nan_flag_kernel(const float* __restrict__ x, int64_t n,
+                                                            int32_t* flag) {
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * kThreads)
+        bad |= isnan(x[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// one CTA, float64 accumulation: deterministic; used for parameter-sized arrays only
+__global__ void __launch_bounds__(1024) sum_kernel(const float* __restrict__ x, int64_t n,
+                                                   float* out, int accumulate) {
+    __shared__ double part[32];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (double)x[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double r = part[threadIdx.x];
+        r = warp_sum(r);
+        if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + (float)r;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) copy2d_kernel(float* __restrict__ dst, int64_t dpitch,
+                                                          const float* __restrict__ src,
+                                                          int64_t spitch, int64_t rows, int64_t cols) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        const int64_t r = i / cols, c = i - r * cols;
+        dst[r * dpitch + c] = src[r * spitch + c];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) pad_hw_kernel(float* __restrict__ dst,
+                                                          const float* __restrict__ src, int64_t n,
+                                                          int64_t h, int64_t w, int64_t c, int64_t top,
+                                                          int64_t left, int64_t ho, int64_t wo,
+                                                          float value) {
+    const int64_t total = n * ho * wo * c;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % c; t /= c;
+        const int64_t x = t % wo; t /= wo;
+        const int64_t y = t % ho; t /= ho;
+        const int64_t sy = y - top, sx = x - left;
+        float v = value;
+        if (sy >= 0 && sy < h && sx >= 0 && sx < w) v = src[((t * h + sy) * w + sx) * c + ch];
+        dst[i] = v;
+    }
+}
+
+// ---------------------------------------------------------------- Upsample2D
+// forward: one thread per OUTPUT element (coalesced writes; each input element is re-read
+// sx times by neighbouring threads and sy times by another row -> L1/L2 hits)
+__global__ void __launch_bounds__(kThreads) upsample_fwd_kernel(const float* __restrict__ x,
+                                                                float* __restrict__ y, int64_t n,
+                                                                int64_t h, int64_t w, int64_t c, int sy,
+                                                                int sx) {
+    const int64_t wo = w * sx, ho = h * sy;
+    const int64_t total = n * ho * wo * c;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % c; t /= c;
+        const int64_t ox = t % wo; t /= wo;
+        const int64_t oy = t % ho; t /= ho;
+        y[i] = x[((t * h + oy / sy) * w + ox / sx) * c + ch];
+    }
+}
+
+// backward: one thread per INPUT-sized element, sums its sy x sx block of dy
+__global__ void __launch_bounds__(kThreads) upsample_bwd_kernel(const float* __restrict__ dy,
+                                                                float* __restrict__ dx, int64_t n,
+                                                                int64_t h, int64_t w, int64_t c, int sy,
+                                                                int sx) {
+    const int64_t wo = w * sx, ho = h * sy;
+    const int64_t total = n * h * w * c;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % c; t /= c;
+        const int64_t ix = t % w; t /= w;
+        const int64_t iy = t % h; t /= h;
+        float acc = 0.f;
+        for (int a = 0; a < sy; ++a)
+            for (int b = 0; b < sx; ++b)
+                acc += dy[((t * ho + iy * sy + a) * wo + ix * sx + b) * c + ch];
+        dx[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- MaxPool2D (CPU semantics)
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(
+    const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ mask, int64_t n,
+    int64_t h, int64_t w, int64_t c, int kh, int kw, int ph, int pw, int sh, int sw, int64_t ho,
+    int64_t wo) {
+    const int64_t hp = h + 2 * ph, wp = w + 2 * pw;
+    const int64_t total = n * ho * wo * c;
+    const int64_t mh = kh * ho, mw = kw * wo;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % c; t /= c;
+        const int64_t ox = t % wo; t /= wo;
+        const int64_t oy = t % ho; t /= ho;
+        const int64_t b = t;
+        float m = -INFINITY;
+        bool any = false;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int64_t py = oy * sh + ky;
+            if (py >= hp) break;                         // overhang beyond the padded array
+            for (int kx = 0; kx < kw; ++kx) {
+                const int64_t px = ox * sw + kx;
+                if (px >= wp) break;
+                const int64_t iy = py - ph, ix = px - pw;
+                const float v = (iy >= 0 && iy < h && ix >= 0 && ix < w)
+                                    ? x[((b * h + iy) * w + ix) * c + ch] : 0.f;   // zero padding tap
+                m = any ? fmaxf(m, v) : v;
+                any = true;
+            }
+        }
+        y[i] = any ? m : 0.f;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int64_t py = oy * sh + ky;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int64_t px = ox * sw + kx;
+                uint8_t hit = 0;
+                if (py < hp && px < wp) {
+                    const int64_t iy = py - ph, ix = px - pw;
+                    const float v = (iy >= 0 && iy < h && ix >= 0 && ix < w)
+                                        ? x[((b * h + iy) * w + ix) * c + ch] : 0.f;
+                    hit = (v == m) ? 1 : 0;
+                }
+                mask[((b * mh + oy * kh + ky) * mw + ox * kw + kx) * c + ch] = hit;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(
+    const float* __restrict__ dy, const uint8_t* __restrict__ mask, float* __restrict__ dx, int64_t n,
+    int64_t h, int64_t w, int64_t c, int kh, int kw, int ph, int pw, int sh, int sw, int64_t ho,
+    int64_t wo) {
+    const int64_t total = n * h * w * c;
+    const int64_t mh = kh * ho, mw = kw * wo;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % c; t /= c;
+        const int64_t ix = t % w; t /= w;
+        const int64_t iy = t % h; t /= h;
+        const int64_t b = t;
+        const int64_t py = iy + ph, px = ix + pw;          // coordinates in the padded array
+        float acc = 0.f;
+        for (int ky = 0; ky < kh; ++ky) {
+            const int64_t ty = py - ky;
+            if (ty < 0 || ty % sh != 0) continue;
+            const int64_t oy = ty / sh;
+            if (oy >= ho) continue;
+            for (int kx = 0; kx < kw; ++kx) {
+                const int64_t tx = px - kx;
+                if (tx < 0 || tx % sw != 0) continue;
+                const int64_t ox = tx / sw;
+                if (ox >= wo) continue;
+                const uint8_t* win = mask + ((b * mh + oy * kh) * mw + ox * kw) * c + ch;
+                if (!win[((int64_t)ky * mw + kx) * c]) continue;
+                int cnt = 0;
+                for (int a = 0; a < kh; ++a)
+                    for (int d = 0; d < kw; ++d) cnt += win[((int64_t)a * mw + d) * c];
+                acc += dy[((b * ho + oy) * wo + ox) * c + ch] / (float)cnt;
+            }
+        }
+        dx[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- Conv2DToBatchedFixedWidthed
+template <typename V>
+__global__ void __launch_bounds__(kThreads) window_fwd_kernel(const V* __restrict__ x,
+                                                              V* __restrict__ y, int64_t n, int64_t h,
+                                                              int64_t w, int64_t cv, int width) {
+    const int hw = width / 2;
+    const int64_t total = n * w * h * width * cv;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % cv; t /= cv;
+        const int64_t k = t % width; t /= width;
+        const int64_t row = t % h; t /= h;
+        const int64_t wi = t % w; t /= w;
+        const int64_t col = wi + k - hw;
+        V v{};
+        if (col >= 0 && col < w) v = x[((t * h + row) * w + col) * cv + ch];
+        y[i] = v;
+    }
+}
+
+__device__ __forceinline__ void vadd(float& a, const float& b) { a += b; }
+__device__ __forceinline__ void vadd(float4& a, const float4& b) {
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(kThreads) window_bwd_kernel(const V* __restrict__ dy,
+                                                              V* __restrict__ dx, int64_t n, int64_t h,
+                                                              int64_t w, int64_t cv, int width) {
+    const int hw = width / 2;
+    const int64_t total = n * h * w * cv;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        int64_t t = i;
+        const int64_t ch = t % cv; t /= cv;
+        const int64_t col = t % w; t /= w;
+        const int64_t row = t % h; t /= h;
+        V acc{};
+        for (int k = 0; k < width; ++k) {
+            const int64_t wi = col - k + hw;
+            if (wi >= 0 && wi < w) vadd(acc, dy[(((t * w + wi) * h + row) * width + k) * cv + ch]);
+        }
+        dx[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- PredToText hit mask
+// one warp per row
+__global__ void __launch_bounds__(kThreads) row_max_hits_kernel(const float* __restrict__ pred,
+                                                                uint8_t* __restrict__ hits,
+                                                                int64_t rows, int64_t cols) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (kThreads / 32);
+    for (int64_t r = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); r < rows; r += warps) {
+        const float* p = pred + r * cols;
+        float m = -INFINITY;
+        for (int64_t j = lane; j < cols; j += 32) m = fmaxf(m, p[j]);
+        m = warp_max(m);
+        for (int64_t j = lane; j < cols; j += 32)
+            hits[r * cols + j] = (p[j] == m && m != 0.f) ? 1 : 0;
+    }
+}
+
+}  // namespace uocr
+
+using namespace uocr;
+
+extern "C" {
+
+int uocr_fill_f32(float* dst, float value, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(dst, "dst is NULL");
+    fill_kernel<<<ew_grid(n, 4), kThreads, 0, as_stream(stream)>>>(dst, value, n);
+    UOCR_LAUNCHED("fill");
+    return UOCR_OK;
+}
+
+int uocr_f64_to_f32(float* dst, const double* src, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    convert_kernel<float, double><<<ew_grid(n, 4), kThreads, 0, as_stream(stream)>>>(dst, src, 1.f, n);
+    UOCR_LAUNCHED("f64_to_f32");
+    return UOCR_OK;
+}
+
+int uocr_f32_to_f64(double* dst, const float* src, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    convert_kernel<double, float><<<ew_grid(n, 4), kThreads, 0, as_stream(stream)>>>(dst, src, 1.f, n);
+    UOCR_LAUNCHED("f32_to_f64");
+    return UOCR_OK;
+}
+
+int uocr_u8_to_f32(float* dst, const uint8_t* src, float scale, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    convert_kernel<float, uint8_t><<<ew_grid(n, 4), kThreads, 0, as_stream(stream)>>>(dst, src, scale, n);
+    UOCR_LAUNCHED("u8_to_f32");
+    return UOCR_OK;
+}
+
+int uocr_axpby_f32(float* y, const float* x, float a, float b, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(y && x, "NULL pointer");
+    if (b == 0.f) return launch_ew<1>("scale", y, x, nullptr, n, ScaleOnly{a}, as_stream(stream));
+    if (b == 1.f) return launch_ew<2>("axpy", y, x, y, n, Axpy1{a}, as_stream(stream));
+    return launch_ew<2>("axpby", y, x, y, n, Axpby{a, b}, as_stream(stream));
+}
+
+int uocr_mul_f32(float* out, const float* a, const float* b, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(out && a && b, "NULL pointer");
+    return launch_ew<2>("mul", out, a, b, n, Mul{}, as_stream(stream));
+}
+
+int uocr_nan_flag_f32(const float* x, int64_t n, int32_t* flag, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(x && flag, "NULL pointer");
+    nan_flag_kernel<<<ew_grid(n, 4), kThreads, 0, as_stream(stream)>>>(x, n, flag);
+    UOCR_LAUNCHED("nan_flag");
+    return UOCR_OK;
+}
+
+int uocr_sum_f32(const float* x, int64_t n, float* out, int accumulate, void* stream) {
+    UOCR_REQUIRE(out && (x || n <= 0), "NULL pointer");
+    sum_kernel<<<1, 1024, 0, as_stream(stream)>>>(x, n < 0 ? 0 : n, out, accumulate);
+    UOCR_LAUNCHED("sum");
+    return UOCR_OK;
+}
+
+int uocr_copy2d_f32(float* dst, int64_t dst_pitch, const float* src, int64_t src_pitch, int64_t rows,
+                    int64_t cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    UOCR_REQUIRE(dst_pitch >= cols && src_pitch >= cols, "pitch smaller than cols");
+    copy2d_kernel<<<ew_grid(rows * cols, 4), kThreads, 0, as_stream(stream)>>>(dst, dst_pitch, src,
+                                                                               src_pitch, rows, cols);
+    UOCR_LAUNCHED("copy2d");
+    return UOCR_OK;
+}
+
+int uocr_pad_hw_f32(float* dst, const float* src, int64_t n, int64_t h, int64_t w, int64_t c,
+                    int64_t top, int64_t bottom, int64_t left, int64_t right, float value,
+                    void* stream) {
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0, "non-positive dimension");
+    UOCR_REQUIRE(top >= 0 && bottom >= 0 && left >= 0 && right >= 0, "negative padding");
+    const int64_t ho = h + top + bottom, wo = w + left + right;
+    pad_hw_kernel<<<ew_grid(n * ho * wo * c, 4), kThreads, 0, as_stream(stream)>>>(
+        dst, src, n, h, w, c, top, left, ho, wo, value);
+    UOCR_LAUNCHED("pad_hw");
+    return UOCR_OK;
+}
+
+int uocr_leaky_relu_fwd(const float* x, float* y, int64_t n, float alpha, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(x && y, "NULL pointer");
+    return launch_ew<1>("leaky_relu_fwd", y, x, nullptr, n, LeakyFwd{alpha}, as_stream(stream));
+}
+
+int uocr_leaky_relu_bwd(const float* x, const float* dy, float* dx, int64_t n, float alpha,
+                        void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(x && dy && dx, "NULL pointer");
+    return launch_ew<2>("leaky_relu_bwd", dx, x, dy, n, LeakyBwd{alpha}, as_stream(stream));
+}
+
+int uocr_sigmoid_fwd(const float* x, float* y, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(x && y, "NULL pointer");
+    return launch_ew<1>("sigmoid_fwd", y, x, nullptr, n, SigmoidFwd{}, as_stream(stream));
+}
+
+int uocr_sigmoid_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(x && dy && dx, "NULL pointer");
+    return launch_ew<2>("sigmoid_bwd", dx, x, dy, n, SigmoidBwd{}, as_stream(stream));
+}
+
+int uocr_act_bwd_from_output(const float* y, const float* dy, float* dx, int64_t n, int act,
+                             float alpha, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(y && dy && dx, "NULL pointer");
+    UOCR_REQUIRE(act != UOCR_ACT_LEAKY || alpha > 0.f,
+                 "leaky backward from the output needs alpha > 0 (sign(y) == sign(x))");
+    return launch_ew<2>("act_bwd_from_output", dx, y, dy, n, ActBwdFromOut{act, alpha},
+                        as_stream(stream));
+}
+
+int uocr_upsample2d_fwd(const float* x, float* y, int64_t n, int64_t h, int64_t w, int64_t c,
+                        int32_t sy, int32_t sx, void* stream) {
+    UOCR_REQUIRE(x && y, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && sy > 0 && sx > 0, "non-positive dimension");
+    upsample_fwd_kernel<<<ew_grid(n * h * w * c * sy * sx, 4), kThreads, 0, as_stream(stream)>>>(
+        x, y, n, h, w, c, sy, sx);
+    UOCR_LAUNCHED("upsample2d_fwd");
+    return UOCR_OK;
+}
+
+int uocr_upsample2d_bwd(const float* dy, float* dx, int64_t n, int64_t h, int64_t w, int64_t c,
+                        int32_t sy, int32_t sx, void* stream) {
+    UOCR_REQUIRE(dy && dx, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && sy > 0 && sx > 0, "non-positive dimension");
+    upsample_bwd_kernel<<<ew_grid(n * h * w * c, 2), kThreads, 0, as_stream(stream)>>>(dy, dx, n, h, w,
+                                                                                       c, sy, sx);
+    UOCR_LAUNCHED("upsample2d_bwd");
+    return UOCR_OK;
+}
+
+int uocr_maxpool2d_out_hw(int64_t h, int64_t w, int32_t kh, int32_t kw, int32_t ph, int32_t pw,
+                          int32_t sh, int32_t sw, int32_t ceil_mode, int64_t* ho, int64_t* wo) {
+    UOCR_REQUIRE(ho && wo, "NULL pointer");
+    UOCR_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0, "bad pooling geometry");
+    const int64_t nh = h + 2 * ph - kh, nw = w + 2 * pw - kw;
+    UOCR_REQUIRE(nh >= 0 && nw >= 0, "kernel larger than padded input");
+    *ho = (ceil_mode ? (nh + sh - 1) / sh : nh / sh) + 1;
+    *wo = (ceil_mode ? (nw + sw - 1) / sw : nw / sw) + 1;
+    return UOCR_OK;
+}
+
+int uocr_maxpool2d_fwd(const float* x, float* y, uint8_t* mask, int64_t n, int64_t h, int64_t w,
+                       int64_t c, int32_t kh, int32_t kw, int32_t ph, int32_t pw, int32_t sh,
+                       int32_t sw, int64_t ho, int64_t wo, void* stream) {
+    UOCR_REQUIRE(x && y && mask, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && ho > 0 && wo > 0, "non-positive dimension");
+    UOCR_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0, "bad pooling geometry");
+    maxpool_fwd_kernel<<<ew_grid(n * ho * wo * c, 1), kThreads, 0, as_stream(stream)>>>(
+        x, y, mask, n, h, w, c, kh, kw, ph, pw, sh, sw, ho, wo);
+    UOCR_LAUNCHED("maxpool2d_fwd");
+    return UOCR_OK;
+}
+
+int uocr_maxpool2d_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t n, int64_t h,
+                       int64_t w, int64_t c, int32_t kh, int32_t kw, int32_t ph, int32_t pw,
+                       int32_t sh, int32_t sw, int64_t ho, int64_t wo, void* stream) {
+    UOCR_REQUIRE(dy && mask && dx, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && ho > 0 && wo > 0, "non-positive dimension");
+    UOCR_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0, "bad pooling geometry");
+    maxpool_bwd_kernel<<<ew_grid(n * h * w * c, 1), kThreads, 0, as_stream(stream)>>>(
+        dy, mask, dx, n, h, w, c, kh, kw, ph, pw, sh, sw, ho, wo);
+    UOCR_LAUNCHED("maxpool2d_bwd");
+    return UOCR_OK;
+}
+
+int uocr_window_batch_fwd(const float* x, float* y, int64_t n, int64_t h, int64_t w, int64_t c,
+                          int32_t width, void* stream) {
+    UOCR_REQUIRE(x && y, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && width > 0, "non-positive dimension");
+    UOCR_REQUIRE(w >= width, "Input width must be >= than output width");
+    const int64_t total = n * w * h * width * c;
+    if (c % 4 == 0 && aligned16(x) && aligned16(y)) {
+        window_fwd_kernel<float4><<<ew_grid(total / 4, 2), kThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), n, h, w, c / 4, width);
+    } else {
+        window_fwd_kernel<float><<<ew_grid(total, 4), kThreads, 0, as_stream(stream)>>>(x, y, n, h, w, c,
+                                                                                     width);
+    }
+    UOCR_LAUNCHED("window_batch_fwd");
+    return UOCR_OK;
+}
+
+int uocr_window_batch_bwd(const float* dy, float* dx, int64_t n, int64_t h, int64_t w, int64_t c,
+                          int32_t width, void* stream) {
+    UOCR_REQUIRE(dy && dx, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && width > 0, "non-positive dimension");
+    UOCR_REQUIRE(w >= width, "Input width must be >= than output width");
+    const int64_t total = n * h * w * c;
+    if (c % 4 == 0 && aligned16(dy) && aligned16(dx)) {
+        window_bwd_kernel<float4><<<ew_grid(total / 4, 1), kThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), n, h, w, c / 4, width);
+    } else {
+        window_bwd_kernel<float><<<ew_grid(total, 2), kThreads, 0, as_stream(stream)>>>(dy, dx, n, h, w,
+                                                                                     c, width);
+    }
+    UOCR_LAUNCHED("window_batch_bwd");
+    return UOCR_OK;
+}
+
+int uocr_row_max_hits(const float* pred, uint8_t* hits, int64_t rows, int64_t cols, void* stream) {
+    if (rows <= 0 || cols <= 0) return UOCR_OK;
+    UOCR_REQUIRE(pred && hits, "NULL pointer");
+    int64_t blocks = ceil_div(rows, kThreads / 32);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    row_max_hits_kernel<<<(int)blocks, kThreads, 0, as_stream(stream)>>>(pred, hits, rows, cols);
+    UOCR_LAUNCHED("row_max_hits");
+    return UOCR_OK;
+}
+
+}  // extern "C"

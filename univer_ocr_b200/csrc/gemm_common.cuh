@@ -1,0 +1,27 @@
+// GEMM argument block + the seam between the FP32 SGEMM (gemm.cu) and the tcgen05 TF32 GEMM
+// (tc_gemm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace uocr {
+
+struct GemmArgs {
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float* C; int64_t ldc;
+    int64_t M, N, K;
+    const float* bias;      // length N, added before the activation (may be NULL)
+    int act; float alpha;
+    int accumulate;         // C += result instead of C = result
+    int64_t a_ones_m;       // row m of op(A) that reads as all ones (-1: none)
+};
+
+int sgemm_fp32(const GemmArgs& p, bool ta, bool tb, int splitk, cudaStream_t st);
+
+// tensor-core paths: UOCR_ERR_UNSUPPORTED when math_mode / shape has no tcgen05 kernel
+int fc_fwd_fast(int math_mode, const float* x, const float* w, float* y, int64_t batch, int64_t n_in,
+                int64_t n_out, int act, float alpha, cudaStream_t st);
+int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                int64_t batch, int64_t n_in, int64_t n_out, int accumulate, cudaStream_t st);
+
+}  // namespace uocr

@@ -1,0 +1,255 @@
+// libuocr runtime plumbing: errors, device info, stream-ordered pooled memory, streams,
+// events, CUDA-graph capture.  Replaces what the reference gets from CuPy / numba.cuda
+// (nn/gpu.py:5-29, cuda.synchronize() in nn/layers/convolutional.py:192).
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace uocr {
+
+static thread_local char tl_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof(tl_error), fmt, ap);
+    va_end(ap);
+}
+
+static std::mutex g_pool_mutex;
+static bool g_pool_ready[64] = {false};
+
+// lift the release threshold once per device so freed blocks stay cached in the pool
+static int ensure_pool(int dev) {
+    if (dev < 0 || dev >= 64) return UOCR_OK;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    if (g_pool_ready[dev]) return UOCR_OK;
+    cudaMemPool_t pool;
+    UOCR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t threshold = UINT64_MAX;
+    UOCR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    g_pool_ready[dev] = true;
+    return UOCR_OK;
+}
+
+}  // namespace uocr
+
+using namespace uocr;
+
+extern "C" {
+
+int uocr_version(void) { return UOCR_VERSION; }
+const char* uocr_last_error(void) { return tl_error; }
+
+int uocr_device_count(int* count) {
+    UOCR_REQUIRE(count, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return UOCR_ERR_CUDA;
+    }
+    return UOCR_OK;
+}
+
+int uocr_set_device(int device) {
+    UOCR_CUDA(cudaSetDevice(device));
+    return ensure_pool(device);
+}
+
+int uocr_get_device(int* device) {
+    UOCR_REQUIRE(device, "device is NULL");
+    UOCR_CUDA(cudaGetDevice(device));
+    return UOCR_OK;
+}
+
+int uocr_device_info(int device, char* name, size_t name_len, int* sm_count, int* cc_major,
+                     int* cc_minor, size_t* total_mem, size_t* free_mem) {
+    cudaDeviceProp prop;
+    UOCR_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (name && name_len) {
+        strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    if (total_mem || free_mem) {
+        int cur;
+        UOCR_CUDA(cudaGetDevice(&cur));
+        if (cur != device) UOCR_CUDA(cudaSetDevice(device));
+        size_t f = 0, t = 0;
+        UOCR_CUDA(cudaMemGetInfo(&f, &t));
+        if (cur != device) UOCR_CUDA(cudaSetDevice(cur));
+        if (total_mem) *total_mem = t;
+        if (free_mem) *free_mem = f;
+    }
+    return UOCR_OK;
+}
+
+int uocr_malloc(void** ptr, size_t bytes, void* stream) {
+    UOCR_REQUIRE(ptr, "ptr is NULL");
+    *ptr = nullptr;
+    if (bytes == 0) return UOCR_OK;
+    int dev;
+    UOCR_CUDA(cudaGetDevice(&dev));
+    int rc = ensure_pool(dev);
+    if (rc != UOCR_OK) return rc;
+    UOCR_CUDA(cudaMallocAsync(ptr, bytes, as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_free(void* ptr, void* stream) {
+    if (!ptr) return UOCR_OK;
+    UOCR_CUDA(cudaFreeAsync(ptr, as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_host_alloc(void** ptr, size_t bytes) {
+    UOCR_REQUIRE(ptr, "ptr is NULL");
+    UOCR_CUDA(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return UOCR_OK;
+}
+
+int uocr_host_free(void* ptr) {
+    if (!ptr) return UOCR_OK;
+    UOCR_CUDA(cudaFreeHost(ptr));
+    return UOCR_OK;
+}
+
+int uocr_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    UOCR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    UOCR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_memcpy_d2d(void* dst, const void* src, size_t bytes, void* stream) {
+    if (bytes == 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    UOCR_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_memset(void* dst, int byte_value, size_t bytes, void* stream) {
+    if (bytes == 0) return UOCR_OK;
+    UOCR_REQUIRE(dst, "NULL pointer");
+    UOCR_CUDA(cudaMemsetAsync(dst, byte_value, bytes, as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_stream_create(void** stream) {
+    UOCR_REQUIRE(stream, "stream is NULL");
+    cudaStream_t s;
+    UOCR_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return UOCR_OK;
+}
+
+int uocr_stream_destroy(void* stream) {
+    if (!stream) return UOCR_OK;
+    UOCR_CUDA(cudaStreamDestroy(as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_stream_sync(void* stream) {
+    UOCR_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_device_sync(void) {
+    UOCR_CUDA(cudaDeviceSynchronize());
+    return UOCR_OK;
+}
+
+int uocr_event_create(void** event) {
+    UOCR_REQUIRE(event, "event is NULL");
+    cudaEvent_t e;
+    UOCR_CUDA(cudaEventCreate(&e));
+    *event = e;
+    return UOCR_OK;
+}
+
+int uocr_event_destroy(void* event) {
+    if (!event) return UOCR_OK;
+    UOCR_CUDA(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event)));
+    return UOCR_OK;
+}
+
+int uocr_event_record(void* event, void* stream) {
+    UOCR_REQUIRE(event, "event is NULL");
+    UOCR_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_event_sync(void* event) {
+    UOCR_REQUIRE(event, "event is NULL");
+    UOCR_CUDA(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event)));
+    return UOCR_OK;
+}
+
+int uocr_event_elapsed_ms(void* start, void* stop, float* ms) {
+    UOCR_REQUIRE(start && stop && ms, "NULL argument");
+    UOCR_CUDA(cudaEventElapsedTime(ms, reinterpret_cast<cudaEvent_t>(start),
+                                   reinterpret_cast<cudaEvent_t>(stop)));
+    return UOCR_OK;
+}
+
+int uocr_stream_wait_event(void* stream, void* event) {
+    UOCR_REQUIRE(event, "event is NULL");
+    UOCR_CUDA(cudaStreamWaitEvent(as_stream(stream), reinterpret_cast<cudaEvent_t>(event), 0));
+    return UOCR_OK;
+}
+
+int uocr_graph_begin(void* stream) {
+    UOCR_REQUIRE(stream, "graph capture needs a non-default stream");
+    UOCR_CUDA(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+    return UOCR_OK;
+}
+
+int uocr_graph_end(void* stream, void** graph_exec) {
+    UOCR_REQUIRE(stream && graph_exec, "NULL argument");
+    cudaGraph_t graph = nullptr;
+    UOCR_CUDA(cudaStreamEndCapture(as_stream(stream), &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        return UOCR_ERR_CUDA;
+    }
+    *graph_exec = exec;
+    return UOCR_OK;
+}
+
+int uocr_graph_launch(void* graph_exec, void* stream) {
+    UOCR_REQUIRE(graph_exec, "graph_exec is NULL");
+    UOCR_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+    return UOCR_OK;
+}
+
+int uocr_graph_destroy(void* graph_exec) {
+    if (!graph_exec) return UOCR_OK;
+    UOCR_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+    return UOCR_OK;
+}
+
+int uocr_launch_count(uint64_t* count) {
+    UOCR_REQUIRE(count, "count is NULL");
+    *count = g_launches.load(std::memory_order_relaxed);
+    return UOCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,613 @@
+"""Layer stack of the B200 path -- same classes, constructor arguments and method protocol as
+the reference's `nn/layers/{layers,convolutional,maxpool,upsample}.py`, with the arithmetic in
+libuocr (include/uocr.h).  Protocol kept from `BaseLayer` (layers.py:24-166):
+
+    initialize(input_shapes)            forward(list-or-array) -> list
+    backward(list-or-array) -> list     params() -> {'w': Param, ...}
+    get_weights() / set_weights(dict)   clear_grads() / update_grads() / regularize()
+    nan_weights() / count_parameters()  get_output_shapes() / get_all_output_shapes()
+    _get_receptive_field() / is_fully_convolutional() / changes_receptive_field()
+    init_progress_tracker() / _set_name()
+
+Differences that are deliberate: arrays are float32 DeviceArrays; the saved
+activations are the *unpadded* inputs (padding is synthesised inside the kernels);
+`regularize()` returns a LazyScalar; nothing synchronises the device per layer.
+"""
+import ctypes
+import math
+
+import numpy as np
+
+from .._lib import ACT_NONE, ConvDesc, lib
+from .gpu import CP, DeviceArray, LazyScalar, as_device, concatenate, slice_axis, stream
+from .help_func import make_list_if_not, tuplize
+from .initializers import kaiming_uniform
+from .optimizers import Adam
+from .progress_tracker import BaseProgressTracker, track_method
+
+_DEFAULT_OPTIMIZER = Adam()     # the reference's default argument is one shared instance (layers.py:31)
+
+
+class Param:
+    """A trainable tensor with its gradient and optimiser hook (layers.py:10-21)."""
+
+    def __init__(self, value, optimizer=None):
+        self._value = None
+        self.value = value
+        self.grad = DeviceArray.zeros(self._value.shape)
+        self.optimizer = optimizer
+        self.optimizer.add_param(self)
+
+    @property
+    def value(self):
+        return self._value
+
+    @value.setter
+    def value(self, new):
+        self._value = new if isinstance(new, DeviceArray) else CP.copy(np.asarray(new, dtype=np.float64))
+
+    def update_grad(self):
+        self.optimizer.update(self)
+
+    def clear_grad(self):
+        if self.grad.shape != self._value.shape:
+            self.grad = DeviceArray.zeros(self._value.shape)
+        else:
+            self.grad.fill(0)
+
+
+class BaseLayer:
+    def __init__(self, name=None, input_shapes=None, trainable=True, initializer=kaiming_uniform,
+                 regularizer=None, optimizer=_DEFAULT_OPTIMIZER):
+        self.name = name
+        self.input_shapes = input_shapes
+        self.inputs_count = len(input_shapes) if input_shapes is not None else None
+        self.trainable = trainable
+        self.initializer = initializer
+        self.regularizer = regularizer
+        self.optimizer = optimizer
+        self.is_initialized = True
+        self._mem = {}
+        self._receptive_fields = {}
+        self.progress_tracker = BaseProgressTracker()
+
+    # ---- lifecycle ----------------------------------------------------------------
+    def initialize_from_X(self, X):
+        self.initialize([x.shape for x in make_list_if_not(X)])
+
+    def initialize(self, input_shapes):
+        self.input_shapes = input_shapes
+        self.inputs_count = len(input_shapes)
+        self.is_initialized = True
+
+    @track_method('forward')
+    def forward(self, inputs):
+        assert self.is_initialized, 'You must initialize() layer before calling forward() method'
+        return [self._forward(as_device(X), mem_id)
+                for mem_id, X in enumerate(make_list_if_not(inputs))]
+
+    @track_method('backward')
+    def backward(self, grads):
+        result = [self._backward(as_device(grad), mem_id)
+                  for mem_id, grad in enumerate(make_list_if_not(grads))]
+        self.clear_memory()
+        return result
+
+    def _forward(self, X, mem_id=0):
+        raise NotImplementedError()
+
+    def _backward(self, grad, mem_id=0):
+        raise NotImplementedError()
+
+    def clear_memory(self):
+        self._mem = {}
+
+    # ---- parameters ---------------------------------------------------------------
+    def params(self):
+        return {}
+
+    def update_grads(self):
+        if not self.trainable:
+            return
+        for param in self.params().values():
+            param.update_grad()
+
+    def clear_grads(self):
+        for param in self.params().values():
+            param.clear_grad()
+
+    def get_weights(self):
+        return {name: param.value.tolist() for name, param in self.params().items()}
+
+    def set_weights(self, weights):
+        """Skips missing keys, NaN tensors and shape mismatches with the reference's messages
+        (layers.py:123-137)."""
+        for name, param in self.params().items():
+            new = weights.get(name, None)
+            if new is None:
+                continue
+            new = np.array(new)
+            error = None
+            if np.any(np.isnan(new)):
+                error = 'NaN found in loaded weights'
+            elif new.shape != param.value.shape:
+                error = f'Shapes don`t match: {new.shape} != {param.value.shape}'
+            if error is not None:
+                print(f'{self.name}/{name}: {error}, skipping')
+                continue
+            param.value = CP.copy(new)
+
+    def nan_weights(self):
+        return any(param.value.isnan_any() for param in self.params().values())
+
+    def count_parameters(self, param=None):
+        if param is not None:
+            return self.params()[param].value.size
+        return sum(p.value.size for p in self.params().values())
+
+    def regularize(self, loss_dev=None):
+        """grad += regulariser gradient for EVERY param of the layer (w and b), returns the
+        regulariser loss (layers.py:147-155).  With `loss_dev` the loss is accumulated into that
+        device scalar (used by Model.regularize) and nothing is returned to the host."""
+        if self.regularizer is None:
+            return 0
+        own = loss_dev is None
+        if own:
+            loss_dev = DeviceArray.zeros((1,))
+        for param in self.params().values():
+            self.regularizer.accumulate(param.value, param.grad, loss_dev)
+        return LazyScalar(loss_dev) if own else 0
+
+    # ---- shapes / receptive fields ------------------------------------------------
+    def get_all_output_shapes(self, input_shapes):
+        return self.get_output_shapes(input_shapes), {}
+
+    def get_output_shapes(self, input_shapes):
+        raise NotImplementedError()
+
+    def get_outputs_count(self):
+        return 1
+
+    def is_fully_convolutional(self):
+        return True
+
+    def changes_receptive_field(self):
+        return False
+
+    def _get_receptive_field(self, axis, position, output_id):
+        assert output_id < self.get_outputs_count(), (
+            f'This layer has only {self.get_outputs_count()} outputs')
+        return {0: {position}}
+
+    def _window_receptive_field(self, axis, position, output_id, kind):
+        """Shared by Convolutional2D / MaxPool2D: taps position*s - p + [0, k)."""
+        assert 0 <= axis < 2, f'{kind} has two axis, found {axis}'
+        assert output_id < self.get_outputs_count(), (
+            f'This layer has only {self.get_outputs_count()} outputs')
+        key = (axis, position, output_id)
+        if key not in self._receptive_fields:
+            start = position * self.stride[axis] - self.padding[axis]
+            self._receptive_fields[key] = {0: set(range(start, start + self.kernel_size[axis]))}
+        return self._receptive_fields[key]
+
+    def _clear_receptive_fields_info(self):
+        self._receptive_fields = {}
+
+    # ---- misc ---------------------------------------------------------------------
+    def _set_name(self, name):
+        self.name = name
+
+    def _init_optimizer(self):
+        for param in self.params().values():
+            self.optimizer.add_param(param)
+
+    def init_progress_tracker(self, progress_tracker, set_names_recursively=False):
+        self.progress_tracker = progress_tracker
+        self.progress_tracker.register_layer(self.name)
+
+
+BaseLayerGPU = BaseLayer     # the reference's CPU/GPU dispatch subclass (layers.py:169-237) collapses
+
+
+# ------------------------------------------------------------------------------------------
+# structural layers
+# ------------------------------------------------------------------------------------------
+
+class Concat(BaseLayer):
+    """layers.py:240-284"""
+
+    def __init__(self, axis=-1, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.axis = axis
+        self.is_initialized = self.inputs_count is not None
+
+    @track_method('forward')
+    def forward(self, inputs):
+        if not isinstance(inputs, list):
+            self._mem = [inputs.shape]
+            return inputs
+        inputs = [as_device(X) for X in inputs]
+        self._mem = [X.shape for X in inputs]
+        return [concatenate(inputs, self.axis)]
+
+    @track_method('backward')
+    def backward(self, grads):
+        grad = as_device(make_list_if_not(grads)[0])
+        result, pos = [], 0
+        for shape in self._mem:
+            width = shape[self.axis]
+            result.append(slice_axis(grad, self.axis, pos, pos + width))
+            pos += width
+        self.clear_memory()
+        return result
+
+    def get_output_shapes(self, input_shapes):
+        input_shapes = make_list_if_not(input_shapes)
+        out = list(input_shapes[0])
+        axis = self.axis % len(out)
+        assert axis != 0 or len(input_shapes) == 1
+        out[axis] = sum(shape[axis] for shape in input_shapes)
+        return [tuple(out)]
+
+    def changes_receptive_field(self):
+        return True
+
+    def _get_receptive_field(self, axis, position, output_id):
+        assert output_id < self.get_outputs_count(), (
+            f'This layer has only {self.get_outputs_count()} outputs')
+        return {in_key: {position} for in_key in range(self.inputs_count)}
+
+
+class Flatten(BaseLayer):
+    """layers.py:287-304"""
+
+    def _forward(self, X, mem_id=0):
+        self._mem[mem_id] = X.shape
+        return X.reshape(self.get_output_shapes(X.shape)[0])
+
+    def _backward(self, grad, mem_id=0):
+        return grad.reshape(self._mem[mem_id])
+
+    def get_output_shapes(self, input_shapes):
+        shape = make_list_if_not(input_shapes)[0]
+        return [(shape[0], int(np.prod(shape[1:])))]
+
+    def is_fully_convolutional(self):
+        return False
+
+    def _get_receptive_field(self, axis, position, output_id):
+        raise NotImplementedError('The method is not supported by Flatten Layer')
+
+
+class Noop(BaseLayer):
+    """layers.py:366-374"""
+
+    def _forward(self, X, mem_id=0):
+        return X
+
+    def _backward(self, grad, mem_id=0):
+        return grad
+
+    def get_output_shapes(self, input_shapes):
+        return make_list_if_not(input_shapes)
+
+
+# ------------------------------------------------------------------------------------------
+# activations
+# ------------------------------------------------------------------------------------------
+
+class LeakyRelu(BaseLayer):
+    """y = X * ((X >= 0) + alpha * (X < 0)) (layers.py:390-404).  The mask is recomputed from
+    the saved input in the backward kernel instead of being stored as a float tensor."""
+
+    def __init__(self, alpha=0.01, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alpha = alpha
+
+    def _forward(self, X, mem_id=0):
+        self._mem[mem_id] = X
+        y = DeviceArray(X.shape)
+        lib.uocr_leaky_relu_fwd(X.ptr, y.ptr, X.size, float(self.alpha), stream())
+        return y
+
+    def _backward(self, grad, mem_id=0):
+        X = self._mem[mem_id]
+        dx = DeviceArray(X.shape)
+        lib.uocr_leaky_relu_bwd(X.ptr, grad.ptr, dx.ptr, X.size, float(self.alpha), stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        return make_list_if_not(input_shapes)
+
+
+class Relu(LeakyRelu):
+    """layers.py:377-387 (mask = X >= 0)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(0.0, *args, **kwargs)
+
+
+class Sigmoid(BaseLayer):
+    """layers.py:407-418"""
+
+    def _forward(self, X, mem_id=0):
+        self._mem[mem_id] = X
+        y = DeviceArray(X.shape)
+        lib.uocr_sigmoid_fwd(X.ptr, y.ptr, X.size, stream())
+        return y
+
+    def _backward(self, grad, mem_id=0):
+        X = self._mem[mem_id]
+        dx = DeviceArray(X.shape)
+        lib.uocr_sigmoid_bwd(X.ptr, grad.ptr, dx.ptr, X.size, stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        return make_list_if_not(input_shapes)
+
+
+# ------------------------------------------------------------------------------------------
+# FullyConnected
+# ------------------------------------------------------------------------------------------
+
+class FullyConnected(BaseLayer):
+    """y = [X, 1] . W with the bias folded in as the last row of W (layers.py:307-363)."""
+
+    def __init__(self, n_input=None, n_output=None, w=None, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.n_input, self.n_output, self.w = n_input, n_output, w
+        if self.input_shapes is None and n_input is not None:
+            self.input_shapes = [(None, self.n_input)]
+        if self.input_shapes is not None:
+            self.initialize(self.input_shapes)
+        else:
+            self.is_initialized = False
+
+    def initialize(self, input_shapes):
+        self.input_shapes = input_shapes
+        self.n_input = self.input_shapes[0][1]
+        if self.n_output is None:
+            self.n_output = self.n_input
+        if self.w is None:
+            self.w = Param(self.initializer(self.n_input + 1, self.n_output), optimizer=self.optimizer)
+        else:
+            assert self.w.shape == (self.n_input + 1, self.n_output)
+            self.w = Param(self.w if not isinstance(self.w, DeviceArray) else self.w.copy(),
+                           optimizer=self.optimizer)
+        self._init_optimizer()
+        self.is_initialized = True
+
+    def _forward(self, X, mem_id=0):
+        assert X.ndim == 2 and X.shape[1] == self.n_input, f'{X.shape} vs n_input={self.n_input}'
+        self._mem[mem_id] = X
+        y = DeviceArray((X.shape[0], self.n_output))
+        lib.uocr_fc_fwd(X.ptr, self.w.value.ptr, y.ptr, X.shape[0], self.n_input, self.n_output,
+                        ACT_NONE, 0.0, CP.math_mode, stream())
+        return y
+
+    def _backward(self, grad, mem_id=0):
+        X = self._mem[mem_id]
+        dx = DeviceArray(X.shape)
+        lib.uocr_fc_bwd(X.ptr, self.w.value.ptr, grad.ptr, dx.ptr, self.w.grad.ptr, X.shape[0],
+                        self.n_input, self.n_output, 1, CP.math_mode, stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        return [(make_list_if_not(input_shapes)[0][0], self.n_output)]
+
+    def is_fully_convolutional(self):
+        return False
+
+    def changes_receptive_field(self):
+        return True
+
+    def _get_receptive_field(self, axis, position, output_id):
+        raise NotImplementedError('The method is not supported by Fully Connected Layer')
+
+    def params(self):
+        return {'w': self.w}
+
+
+# ------------------------------------------------------------------------------------------
+# Convolutional2D + Conv2DToBatchedFixedWidthed
+# ------------------------------------------------------------------------------------------
+
+class Convolutional2D(BaseLayer):
+    """NHWC convolution with padding / padding_value / stride / bias
+    (layers/convolutional.py:12-327).  w: (kh, kw, Cin, Cout), b: (Cout,)."""
+
+    def __init__(self, kernel_size, in_channels=None, out_channels=None, padding=0, padding_value=0,
+                 stride=1, w=None, b=None, bias=True, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.kernel_size = tuplize('kernel_size', kernel_size, 2)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.padding = tuplize('padding', padding, 2)
+        self.padding_value = padding_value
+        self.stride = tuplize('stride', stride, 2)
+        self.w, self.b, self.bias = w, b, bias
+        if self.input_shapes is None and in_channels is not None:
+            self.input_shapes = [(None, None, None, self.in_channels)]
+        if self.input_shapes is not None:
+            self.initialize(self.input_shapes)
+        else:
+            self.is_initialized = False
+
+    def initialize(self, input_shapes):
+        self.input_shapes = input_shapes
+        self.in_channels = self.input_shapes[0][3]
+        if self.out_channels is None:
+            self.out_channels = self.in_channels
+        w_shape = (*self.kernel_size, self.in_channels, self.out_channels)
+        b_shape = (self.out_channels,)
+        # one draw for [w; b] exactly like the reference (convolutional.py:41-45)
+        wb = self.initializer(int(np.prod(w_shape[:3])) + 1, self.out_channels)
+        w = np.reshape(wb[:-1, :], w_shape) if self.w is None else self.w
+        b = np.reshape(wb[-1, :], b_shape) if self.b is None else self.b
+        assert tuple(w.shape) == w_shape, f'{tuple(w.shape)} != {w_shape}'
+        assert tuple(b.shape) == b_shape, f'{tuple(b.shape)} != {b_shape}'
+        self.w = Param(w if not isinstance(w, DeviceArray) else w.copy(), optimizer=self.optimizer)
+        self.b = Param(b if not isinstance(b, DeviceArray) else b.copy(), optimizer=self.optimizer)
+        self._init_optimizer()
+        self.is_initialized = True
+
+    def _desc(self, x_shape):
+        n, h, w, c = x_shape
+        assert c == self.in_channels, f'input has {c} channels, layer expects {self.in_channels}'
+        return ConvDesc(n, h, w, c, self.out_channels, *self.kernel_size, *self.padding, *self.stride,
+                        float(self.padding_value), int(bool(self.bias)), CP.math_mode)
+
+    def _forward(self, X, mem_id=0, act=ACT_NONE, alpha=0.0):
+        assert X.ndim == 4, f'expected NHWC input, got shape {X.shape}'
+        desc = self._desc(X.shape)
+        self._mem[mem_id] = X
+        y = DeviceArray(self.get_output_shapes(X.shape)[0])
+        lib.uocr_conv2d_fwd(ctypes.byref(desc), X.ptr, self.w.value.ptr, self.b.value.ptr, y.ptr,
+                            act, float(alpha), stream())
+        return y
+
+    def _backward(self, grad, mem_id=0, need_dx=True):
+        X = self._mem[mem_id]
+        desc = self._desc(X.shape)
+        assert grad.shape == self.get_output_shapes(X.shape)[0], (
+            f'{grad.shape} != {self.get_output_shapes(X.shape)[0]}')
+        need = ctypes.c_size_t(0)
+        lib.uocr_conv2d_wgrad_workspace(ctypes.byref(desc), ctypes.byref(need))
+        ws = DeviceArray(((need.value + 3) // 4,)) if need.value else None
+        lib.uocr_conv2d_wgrad(ctypes.byref(desc), X.ptr, grad.ptr, self.w.grad.ptr, self.b.grad.ptr,
+                              1, ws.ptr if ws is not None else None, need.value, stream())
+        if not need_dx:
+            return None
+        dx = DeviceArray(X.shape)
+        lib.uocr_conv2d_dgrad(ctypes.byref(desc), grad.ptr, self.w.value.ptr, dx.ptr, stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        batch, height, width, _ = make_list_if_not(input_shapes)[0]
+        (kh, kw), (ph, pw), (sh, sw) = self.kernel_size, self.padding, self.stride
+        return [(batch, math.floor((height + 2 * ph - kh) / sh + 1),
+                 math.floor((width + 2 * pw - kw) / sw + 1), self.out_channels)]
+
+    def changes_receptive_field(self):
+        return True
+
+    def _get_receptive_field(self, axis, position, output_id):
+        return self._window_receptive_field(axis, position, output_id, 'Convolutional2D')
+
+    def params(self):
+        return {'w': self.w, 'b': self.b}
+
+
+class Conv2DToBatchedFixedWidthed(BaseLayer):
+    """Sliding width-`width` windows of the W axis -> batch rows
+    (layers/convolutional.py:330-373): (N, H, W, C) -> (N*W, H, width, C)."""
+
+    def __init__(self, width, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.width = width
+
+    def _forward(self, X, mem_id=0):
+        n, h, w, c = X.shape
+        y = DeviceArray(self.get_output_shapes(X.shape)[0])
+        lib.uocr_window_batch_fwd(X.ptr, y.ptr, n, h, w, c, self.width, stream())
+        self._mem[mem_id] = X.shape
+        return y
+
+    def _backward(self, grad, mem_id=0):
+        n, h, w, c = self._mem[mem_id]
+        dx = DeviceArray((n, h, w, c))
+        lib.uocr_window_batch_bwd(grad.ptr, dx.ptr, n, h, w, c, self.width, stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        out = []
+        for bs, h, w, ch in make_list_if_not(input_shapes):
+            assert w >= self.width, (
+                f'Input width must be >= than output width, found: {w} < {self.width}')
+            out.append((bs * w, h, self.width, ch))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+# MaxPool2D / Upsample2D
+# ------------------------------------------------------------------------------------------
+
+class MaxPool2D(BaseLayer):
+    """Max pooling with zero padding, stride, ceil_mode and tie-aware backward
+    (layers/maxpool.py:10-239; the CPU path :24-90 defines the semantics)."""
+
+    def __init__(self, kernel_size, padding=0, stride=None, ceil_mode=False, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.kernel_size = tuplize('kernel_size', kernel_size, 2)
+        self.padding = tuplize('padding', padding, 2)
+        self.stride = self.kernel_size if stride is None else tuplize('stride', stride, 2)
+        self.ceil_mode = ceil_mode
+
+    def _forward(self, X, mem_id=0):
+        n, h, w, c = X.shape
+        out_shape = self.get_output_shapes(X.shape)[0]
+        _, ho, wo, _ = out_shape
+        (kh, kw) = self.kernel_size
+        y = DeviceArray(out_shape)
+        mask = DeviceArray((n, kh * ho, kw * wo, c), np.uint8)
+        lib.uocr_maxpool2d_fwd(X.ptr, y.ptr, mask.ptr, n, h, w, c, kh, kw, *self.padding,
+                               *self.stride, ho, wo, stream())
+        self._mem[mem_id] = mask, X.shape
+        return y
+
+    def _backward(self, grad, mem_id=0):
+        mask, (n, h, w, c) = self._mem[mem_id]
+        _, ho, wo, _ = grad.shape
+        dx = DeviceArray((n, h, w, c))
+        lib.uocr_maxpool2d_bwd(grad.ptr, mask.ptr, dx.ptr, n, h, w, c, *self.kernel_size,
+                               *self.padding, *self.stride, ho, wo, stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        batch, height, width, channels = make_list_if_not(input_shapes)[0]
+        (kh, kw), (ph, pw), (sh, sw) = self.kernel_size, self.padding, self.stride
+        rnd = math.ceil if self.ceil_mode else math.floor
+        return [(batch, rnd((height + 2 * ph - kh) / sh + 1), rnd((width + 2 * pw - kw) / sw + 1),
+                 channels)]
+
+    def changes_receptive_field(self):
+        return True
+
+    def _get_receptive_field(self, axis, position, output_id):
+        return self._window_receptive_field(axis, position, output_id, 'MaxPool2D')
+
+
+class Upsample2D(BaseLayer):
+    """Nearest-neighbour repeat by (sy, sx); backward = block sum (layers/upsample.py:10-135)."""
+
+    def __init__(self, scale_factor, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.scale_factor = tuplize('scale_factor', scale_factor, 2)
+
+    def _forward(self, X, mem_id=0):
+        n, h, w, c = X.shape
+        self._mem[mem_id] = X.shape
+        y = DeviceArray(self.get_output_shapes(X.shape)[0])
+        lib.uocr_upsample2d_fwd(X.ptr, y.ptr, n, h, w, c, *self.scale_factor, stream())
+        return y
+
+    def _backward(self, grad, mem_id=0):
+        n, h, w, c = self._mem[mem_id]
+        dx = DeviceArray((n, h, w, c))
+        lib.uocr_upsample2d_bwd(grad.ptr, dx.ptr, n, h, w, c, *self.scale_factor, stream())
+        return dx
+
+    def get_output_shapes(self, input_shapes):
+        n, h, w, c = make_list_if_not(input_shapes)[0]
+        return [(n, h * self.scale_factor[0], w * self.scale_factor[1], c)]
+
+    def changes_receptive_field(self):
+        return True
+
+    def _get_receptive_field(self, axis, position, output_id):
+        assert 0 <= axis < 2, f'Upsample2D has two axis, found {axis}'
+        assert output_id < self.get_outputs_count(), (
+            f'This layer has only {self.get_outputs_count()} outputs')
+        key = (axis, position, output_id)
+        if key not in self._receptive_fields:
+            self._receptive_fields[key] = {0: {position // self.scale_factor[axis]}}
+        return self._receptive_fields[key]

@@ -1,0 +1,434 @@
+"""Graph executor: `Model` (a DAG of named layers, possibly nested) and `Sequential`.
+
+Same construction and call protocol as the reference's `nn/models.py` (Model :30-484,
+Sequential :487-502):
+
+    Model(layers: dict, relations: dict, loss=...)      relations: dst -> src | [src, ...]
+        int src  = model input index        int dst = model output index
+        (name, i, j, ...) src = outputs i, j of a nested multi-output model
+    initialize / forward / backward / compute_loss_and_gradients / train / test / predict
+    params / get_weights / set_weights / nan_weights / count_parameters / regularize
+    get_output_shapes / get_all_output_shapes / get_receptive_fields
+
+Nested models are flattened to leaf layers named 'outer/inner' (these names are the keys of
+model_weights.json).  Execution differs from the reference in mechanics only: instead of a
+memoised recursion per call, the evaluation order is resolved once at `initialize()` and
+replayed; no layer call synchronises the device, and loss values stay on the device until read.
+"""
+from .gpu import DeviceArray, LazyScalar
+from .help_func import make_list_if_not
+from .layers import BaseLayer
+from .losses import SoftmaxCrossEntropy
+from .progress_tracker import track_method
+
+
+class BaseModel(BaseLayer):
+    def compute_loss_and_gradients(self, X, y):
+        raise NotImplementedError()
+
+    def train(self, X, y):
+        loss = self.compute_loss_and_gradients(X, y)
+        for param in self.params().values():
+            param.update_grad()
+            param.clear_grad()
+        return loss
+
+    def test(self, X, y):
+        raise NotImplementedError()
+
+    def predict(self, X):
+        raise NotImplementedError()
+
+    def params(self):
+        raise NotImplementedError()
+
+    def count_parameters(self):
+        raise NotImplementedError()
+
+
+class Model(BaseModel):
+    def __init__(self, layers, relations, loss=SoftmaxCrossEntropy(), *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        if not isinstance(layers, dict):
+            raise TypeError(f'layers argument must be dict, found: {type(layers).__name__}')
+        if not isinstance(relations, dict):
+            raise TypeError(f'relations argument must be dict, found: {type(relations).__name__}')
+        self.ravelled_layers = layers
+        self.ravelled_relations = relations
+        self.layers = None
+        self.relations = None
+        self.relations_backward = {}
+        self.inputs_count = max(v for v in relations.values() if isinstance(v, int)) + 1
+        self.outputs_count = max(k for k in relations if isinstance(k, int)) + 1
+        self.layers_outputs = {}
+        self.loss = loss
+        self.input_grads = {}
+        self.is_initialized = False
+        self._receptive_fields = {}
+        self._order = None
+        self.unravel_model()
+
+    # ---- structure ----------------------------------------------------------------
+    def unravel_model(self):
+        """Flattens nested Models: their leaf layers become 'name/leaf', their int inputs are
+        wired to this model's sources and their int outputs replace `name` / `(name, i, ...)`
+        wherever it is consumed (reference :109-158)."""
+        relations = {dst: list(make_list_if_not(src)) for dst, src in self.ravelled_relations.items()}
+        leaves = {}
+        for name, layer in self.ravelled_layers.items():
+            if not isinstance(layer, Model):
+                leaves[name] = layer
+                continue
+            layer.unravel_model()
+            for leaf_name, leaf in layer.layers.items():
+                leaves[f'{name}/{leaf_name}'] = leaf
+            feeds = relations[name]
+            outputs = {}
+            for dst, srcs in layer.relations.items():
+                wired = [feeds[s] if isinstance(s, int) else f'{name}/{s}' for s in srcs]
+                if isinstance(dst, int):
+                    outputs[dst] = wired
+                else:
+                    relations[f'{name}/{dst}'] = wired
+            del relations[name]
+            for dst, srcs in relations.items():
+                rewired = []
+                for src in srcs:
+                    if isinstance(src, str) and src == name:
+                        for out_id in range(layer.get_outputs_count()):
+                            rewired.extend(outputs[out_id])
+                    elif isinstance(src, tuple) and len(src) > 1 and src[0] == name:
+                        for out_id in src[1:]:
+                            rewired.extend(outputs[out_id])
+                    else:
+                        rewired.append(src)
+                relations[dst] = rewired
+        if self.layers is None:
+            self.layers = leaves
+        self.relations = relations
+        for name, layer in self.layers.items():
+            layer._set_name(name)
+
+    def get_leaf_layers(self):
+        return self.layers
+
+    def __getitem__(self, key):
+        return self.layers[key]
+
+    def _output_keys(self):
+        return sorted(k for k in self.relations if isinstance(k, int))
+
+    def _resolve_order(self):
+        """Depth-first from the outputs: evaluation order of the layers that feed an output."""
+        order, state = [], {}
+
+        def visit(name):
+            if isinstance(name, int) and name not in self.relations:
+                return
+            if state.get(name) == 'done':
+                return
+            if state.get(name) == 'open':
+                raise RecursionError(f'Looped on {name} layer, check relations')
+            state[name] = 'open'
+            for src in self.relations[name]:
+                if not isinstance(src, int):
+                    visit(src)
+            state[name] = 'done'
+            if not isinstance(name, int):
+                order.append(name)
+
+        for key in self._output_keys():
+            state.pop(key, None)
+            for src in self.relations[key]:
+                if not isinstance(src, int):
+                    visit(src)
+        return order
+
+    def initialize(self, input_shapes):
+        input_shapes = make_list_if_not(input_shapes)
+        self.input_shapes = input_shapes
+        self._order = self._resolve_order()
+        self.relations_backward = {}
+        shapes = {}
+
+        def shape_of(src):
+            if isinstance(src, int):
+                return input_shapes[src]
+            s = shapes[src]
+            return s[0] if isinstance(s, list) else s
+
+        for name in self._order + self._output_keys():
+            srcs = self.relations[name]
+            for i, src in enumerate(srcs):
+                self.relations_backward.setdefault(src, {})[name] = i
+            if isinstance(name, int):
+                continue
+            in_shapes = [shape_of(src) for src in srcs]
+            layer = self.layers[name]
+            if not layer.is_initialized:
+                layer.initialize(in_shapes)
+            shapes[name] = layer.get_output_shapes(in_shapes)
+
+        never = [n for n in self.layers if n not in shapes]
+        if never:
+            print(f'These layers have never been visited: {never}')
+        self.is_initialized = True
+
+    # ---- execution ----------------------------------------------------------------
+    @track_method('forward')
+    def forward(self, inputs):
+        inputs = make_list_if_not(inputs)
+        if not self.is_initialized:
+            self.initialize_from_X(inputs)
+        outputs = {}
+
+        def value_of(src):
+            return inputs[src] if isinstance(src, int) else outputs[src]
+
+        for name in self._order:
+            layer = self.layers[name]
+            layer.clear_grads()                                    # reference :188
+            out = layer.forward([value_of(src) for src in self.relations[name]])
+            outputs[name] = out[0] if isinstance(out, list) else out
+        for key in self._output_keys():
+            outputs[key] = value_of(self.relations[key][0])
+        self.layers_outputs = outputs
+        return [outputs[k] for k in range(self.outputs_count)]
+
+    @track_method('backward')
+    def backward(self, grads):
+        grads = make_list_if_not(grads)
+        produced = {}                                               # layer -> list of input grads
+
+        def incoming(name):
+            parts = []
+            for dst, slot in self.relations_backward[name].items():
+                parts.append(grads[dst] if isinstance(dst, int) else produced[dst][slot])
+            return sum(parts)                                       # 0 + g1 (+ g2 ...), reference :218
+
+        for name in reversed(self._order):
+            produced[name] = make_list_if_not(self.layers[name].backward(incoming(name)))
+        for key in range(self.inputs_count):
+            self.input_grads[key] = incoming(key)
+        return [self.input_grads[k] for k in range(self.inputs_count)]
+
+    def _loss_for(self, key):
+        return self.loss[key] if isinstance(self.loss, list) else self.loss
+
+    def compute_loss_and_gradients(self, X, y):
+        X, y = make_list_if_not(X), make_list_if_not(y)
+        predicted = self.forward(X)
+        losses, gradients = [], []
+        for key in range(self.outputs_count):
+            loss, grad = self._loss_for(key)(predicted[key], y[key])
+            losses.append(loss)
+            gradients.append(grad)
+        self.backward(gradients)
+        return {'output_losses': losses, 'regularization_loss': self.regularize()}
+
+    def train(self, X, y):
+        losses = self.compute_loss_and_gradients(X, y)
+        self.update_grads()
+        self.clear_grads()
+        return losses
+
+    def test(self, X, y):
+        X, y = make_list_if_not(X), make_list_if_not(y)
+        predicted = self.forward(X)
+        losses = []
+        for key in range(self.outputs_count):
+            fn = self._loss_for(key)
+            try:
+                loss, _ = fn(predicted[key], y[key], want_grad=False)
+            except TypeError:                                       # user-supplied loss object
+                loss, _ = fn(predicted[key], y[key])
+            losses.append(loss)
+        return {'output_losses': losses}
+
+    def predict(self, X):
+        return self.forward(X)
+
+    def update_grads(self):
+        if not self.trainable:
+            return
+        for layer in self.layers.values():
+            layer.update_grads()
+
+    def clear_grads(self):
+        for layer in self.layers.values():
+            layer.clear_grads()
+        self.input_grads = {}
+
+    def regularize(self, loss_dev=None):
+        regularised = [l for l in self.layers.values() if getattr(l, 'regularizer', None) is not None]
+        if not regularised:
+            return 0
+        own = loss_dev is None
+        if own:
+            loss_dev = DeviceArray.zeros((1,))
+        for layer in regularised:
+            layer.regularize(loss_dev)
+        return LazyScalar(loss_dev) if own else 0
+
+    # ---- parameters ---------------------------------------------------------------
+    def params(self):
+        return {f'{layer_name}/{name}': param
+                for layer_name, layer in self.layers.items()
+                for name, param in layer.params().items()}
+
+    def get_weights(self):
+        weights = {name: layer.get_weights() for name, layer in self.layers.items()}
+        return {name: w for name, w in weights.items() if w != {}}
+
+    def set_weights(self, weights):
+        for name, layer in self.layers.items():
+            layer_weights = weights.get(name, None)
+            if layer_weights is not None:
+                layer.set_weights(layer_weights)
+
+    def nan_weights(self):
+        return any(layer.nan_weights() for layer in self.layers.values())
+
+    def count_parameters(self):
+        return sum(layer.count_parameters() for layer in self.layers.values())
+
+    def init_progress_tracker(self, progress_tracker, model_name='model'):
+        if self.name is None:
+            self.name = model_name
+        self.progress_tracker = progress_tracker
+        self.progress_tracker.register_layer(self.name)
+        for layer in self.layers.values():
+            layer.init_progress_tracker(progress_tracker, None)
+
+    # ---- shape analysis -----------------------------------------------------------
+    def get_all_output_shapes(self, input_shapes):
+        input_shapes = make_list_if_not(input_shapes)
+
+        def plain(shapes):
+            out = []
+            for shape in make_list_if_not(shapes):
+                assert isinstance(shape, tuple)
+                out.append(tuple(int(x) for x in shape))
+            return out
+
+        per_layer, extra = {}, {}
+
+        def shape_of(src):
+            if isinstance(src, int):
+                return input_shapes[src]
+            s = per_layer[src]
+            return s[0] if isinstance(s, list) else s
+
+        order = self._order if self._order is not None else self._resolve_order()
+        for name in order:
+            ins = [shape_of(src) for src in self.relations[name]]
+            own, nested = self.layers[name].get_all_output_shapes(ins)
+            per_layer[name] = plain(own)
+            extra.update({f'{name}/{k}': plain(v) for k, v in nested.items()})
+        result = [shape_of(self.relations[key][0]) for key in range(self.outputs_count)]
+        extra.update(per_layer)
+        return plain(result), extra
+
+    def get_output_shapes(self, input_shapes):
+        return self.get_all_output_shapes(input_shapes)[0]
+
+    def get_outputs_count(self):
+        return self.outputs_count
+
+    def is_fully_convolutional(self):
+        return all(layer.is_fully_convolutional() for layer in self.layers.values())
+
+    def changes_receptive_field(self):
+        return any(layer.changes_receptive_field() for layer in self.layers.values())
+
+    # ---- receptive fields (reference :340-432) ------------------------------------
+    def _rf_relations(self):
+        """Relations with every layer that does not change the receptive field spliced out."""
+        if 'relations' in self._receptive_fields:
+            return self._receptive_fields['relations']
+        rel = {dst: list(srcs) for dst, srcs in self.relations.items()}
+        for name, layer in self.layers.items():
+            if layer.changes_receptive_field() or name not in rel:
+                continue
+            sources = rel.pop(name)
+            for dst in rel:
+                spliced = []
+                for src in rel[dst]:
+                    spliced.extend(sources if src == name else [src])
+                rel[dst] = spliced
+        self._receptive_fields['relations'] = rel
+        return rel
+
+    def _get_receptive_field(self, axis, position, output_id):
+        key = (axis, position, output_id)
+        if key in self._receptive_fields:
+            return self._receptive_fields[key]
+        rel = self._rf_relations()
+        memo = {}
+
+        def points(name, pos):
+            if (name, pos) in memo:
+                return memo[name, pos]
+            own = {0: {pos}} if isinstance(name, int) else self.layers[name]._get_receptive_field(axis, pos, 0)
+            acc = {k: set() for k in range(self.inputs_count)}
+            for slot, src in enumerate(rel[name]):
+                if isinstance(src, int):
+                    acc[src].update(own[slot])
+                    continue
+                for p in own[slot]:
+                    for in_key, pts in points(src, p).items():
+                        acc[in_key].update(pts)
+            memo[name, pos] = acc
+            return acc
+
+        for name in rel:
+            self._receptive_fields[name, axis] = points(name, 0)
+        return points(rel[output_id][0], position)
+
+    def get_receptive_fields(self):
+        assert self.is_initialized, 'The model must be initialized before calling this method'
+        assert self.is_fully_convolutional(), (
+            'This method is only available for Fully Convolutional Networks (FCN)')
+        for output_id in range(self.get_outputs_count()):
+            for axis in range(2):
+                self._get_receptive_field(axis, 0, output_id)
+        result = {}
+        for name in self._receptive_fields['relations']:
+            if isinstance(name, int):
+                continue
+            rf_y, rf_x = self._receptive_fields[name, 0], self._receptive_fields[name, 1]
+            result[name] = {}
+            for in_id in rf_y:
+                ys, xs = rf_y[in_id], rf_x[in_id]
+                if not ys or not xs:
+                    continue
+                result[name][f'input {in_id}'] = {
+                    'cnt': (len(ys), len(xs)),
+                    'y': (min(ys), max(ys)),
+                    'x': (min(xs), max(xs)),
+                    'is_solid_y': len(ys) == max(ys) - min(ys) + 1,
+                    'is_solid_x': len(xs) == max(xs) - min(xs) + 1,
+                }
+        self._clear_receptive_fields_info()
+        return result
+
+    def _clear_receptive_fields_info(self):
+        for layer in self.layers.values():
+            layer._clear_receptive_fields_info()
+        self._receptive_fields = {}
+
+
+class Sequential(Model):
+    """Chain of layers named '{i}_{ClassName}' (reference :487-502)."""
+
+    def __init__(self, layers, *args, **kwargs):
+        if not isinstance(layers, list):
+            raise TypeError(f'layers argument must be list, found: {type(layers).__name__}')
+        named, relations, prev = {}, {}, 0
+        for i, layer in enumerate(layers):
+            name = f'{i}_{type(layer).__name__}'
+            named[name] = layer
+            relations[name] = prev
+            prev = name
+        relations[0] = prev
+        super().__init__(layers=named, relations=relations, *args, **kwargs)
