@@ -93,6 +93,20 @@ def init_weights(spec, rng):
     return weights
 
 
+def golden_weights(name, seed):
+    """The float32-representable start weights of the `models` golden cases.  The reference's
+    kaiming_uniform is all-positive, which saturates Char's softmax (loss = NaN from 0 * log 0,
+    losses.py:71); and makes every layer a sum of ~10^3 same-sign terms.  The Char conv / FC
+    weights are therefore centred and scaled by 2.5 (activations stay O(1)), so the golden Char
+    case exercises finite, well-conditioned losses (the NaN case is covered by `sce_nan`)."""
+    spec = net_spec(name)
+    w = init_weights(spec, np.random.default_rng(int(seed)))
+    if name == 'char':
+        for key in w:
+            w[key]['w'] = (w[key]['w'] - w[key]['w'].mean()) * 2.5
+    return {k: {n: v.astype(np.float32).astype(np.float64) for n, v in p.items()} for k, p in w.items()}
+
+
 def forward(spec, weights, X, keep=False, loop=False):
     """Model.predict (nn/models.py:270-271).  With keep=True also returns the per-step inputs
     needed by `backward`."""

@@ -167,8 +167,7 @@ def main():
     for idx, (name, shape) in enumerate(shapes.items()):
         seed = 7000 + idx
         spec = np_models.net_spec(name)
-        w0 = np_models.init_weights(spec, np.random.default_rng(seed))
-        w0 = {k: {n: f32(v) for n, v in p.items()} for k, p in w0.items()}
+        w0 = np_models.golden_weights(name, seed)
         opt = nn.optimizers.Adam(lr=0.0015)
         model = makers[name](shape, optimizer=opt)
         model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})

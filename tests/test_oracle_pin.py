@@ -133,8 +133,7 @@ def test_submodel_train_golden(golden, name):
     """Two Model.train steps of each my_model sub-network + predict before/after."""
     g = golden('models').case(name)
     spec, kind = np_models.net_spec(name), np_models.loss_kind(name)
-    w = np_models.init_weights(spec, np.random.default_rng(int(g['seed'])))
-    w = {k: {n: v.astype(np.float32).astype(np.float64) for n, v in p.items()} for k, p in w.items()}
+    w = np_models.golden_weights(name, g['seed'])
     state = np_models.new_adam_state(w)
     close(np_models.forward(spec, w, g['X']), g['pred0'])
     for step in (1, 2):

@@ -91,6 +91,8 @@ class DeviceArray:
     __array_priority__ = 100.0
 
     def __init__(self, shape, dtype=_F32, buf=None, offset=0):
+        if isinstance(shape, (int, np.integer)):
+            shape = (shape,)
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         self.size = _prod(self.shape)

@@ -123,3 +123,59 @@ def track_function(name, event, progress_tracker):
                 progress_tracker.stop_tracking(name, event)
         return wrapper
     return decorator
+
+
+class CudaEventTracker(BaseProgressTracker):
+    """Device-side per-layer timing through the same hook: a CUDA event pair is recorded on the
+    compute stream around every tracked call; `summary_ms()` synchronises once and returns
+    {(layer, event): [total_ms, calls]}.  Leaf layers only (a Model's own forward/backward
+    contains its layers' time)."""
+
+    def __init__(self, leaf_names=None):
+        self._open = {}
+        self._pairs = []
+        self.leaf_names = set(leaf_names) if leaf_names is not None else None
+
+    @staticmethod
+    def _event():
+        import ctypes
+        from .._lib import lib
+        e = ctypes.c_void_p()
+        lib.uocr_event_create(ctypes.byref(e))
+        return e.value
+
+    def start_tracking(self, name, event):
+        if self.leaf_names is not None and name not in self.leaf_names:
+            return
+        from .._lib import lib
+        from .gpu import stream
+        e = self._event()
+        lib.uocr_event_record(e, stream())
+        self._open[name, event] = e
+
+    def stop_tracking(self, name, event):
+        start = self._open.pop((name, event), None)
+        if start is None:
+            return
+        from .._lib import lib
+        from .gpu import stream
+        e = self._event()
+        lib.uocr_event_record(e, stream())
+        self._pairs.append((name, event, start, e))
+
+    def summary_ms(self):
+        import ctypes
+        from .._lib import lib
+        from .gpu import CP
+        CP.synchronize()
+        out = {}
+        for name, event, e0, e1 in self._pairs:
+            ms = ctypes.c_float(0)
+            lib.uocr_event_elapsed_ms(e0, e1, ctypes.byref(ms))
+            rec = out.setdefault((name, event), [0.0, 0])
+            rec[0] += ms.value
+            rec[1] += 1
+            lib.uocr_event_destroy(e0)
+            lib.uocr_event_destroy(e1)
+        self._pairs = []
+        return out
