@@ -254,10 +254,9 @@ def run_b200(args):
     tracker = CudaEventTracker()
     work = {}
     for mname, model in models.items():
-        shapes = roofline.model_input_shapes(model, in_shapes[mname])
-        for lname, layer in model.layers.items():
+        work.update(roofline.plan_work(model, in_shapes[mname], training=False))
+        for layer in model.layers.values():
             layer.progress_tracker = tracker
-            work[lname] = roofline.layer_work(layer, shapes[lname], 'forward')
     prof_steps = max(2, min(args.steps, 5))
     for i in range(prof_steps):
         step(dev_sets[i % n_sets])
@@ -280,12 +279,12 @@ def run_b200(args):
         achieved = wk['bytes'] / (top_ms / 1e3) / 1e9
         roof = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_note': peaks['source']}
-    roof.update({'kernel': top_name, 'kernel_ms': top_ms, 'share_of_step': top_ms / total_ms,
+    roof.update({'kernel': '+'.join(wk.get('fused', [top_name])), 'kernel_ms': top_ms, 'share_of_step': top_ms / total_ms,
                  'algorithmic_bytes': wk['bytes'], 'algorithmic_flops': wk['flops']})
     layers_out = []
     for name, lms in breakdown[:12]:
         w_ = work[name]
-        layers_out.append({'layer': name, 'ms': round(lms, 4), 'bound': w_['bound'],
+        layers_out.append({'layer': '+'.join(w_.get('fused', [name])), 'ms': round(lms, 4), 'bound': w_['bound'],
                            'GBps': round(w_['bytes'] / (lms / 1e3) / 1e9, 1),
                            'TFLOPs': round(w_['flops'] / (lms / 1e3) / 1e12, 2)})
 

@@ -126,6 +126,9 @@ typedef struct uocr_conv2d_desc {
     float   padding_value;       /* constant the border is filled with              */
     int32_t bias;                /* reference's `bias` flag (b is multiplied by it) */
     int32_t math_mode;           /* UOCR_MATH_*                                     */
+    int32_t in_upsample;         /* 0/1: none.  2: x is (N, H/2, W/2, Cin) and is   */
+                                 /* nearest-upsampled x2 on the fly (Upsample2D(2) + */
+                                 /* Convolutional2D in one pass; forward only)      */
 } uocr_conv2d_desc;
 
 /* Ho = floor((H + 2ph - kh) / sh) + 1 ...   replaces: Convolutional2D.get_output_shapes,
@@ -137,6 +140,15 @@ int uocr_conv2d_out_hw(const uocr_conv2d_desc* d, int64_t* ho, int64_t* wo);
  * layers.py:390-415).  x is the UNPADDED input; the border is synthesised from padding_value. */
 int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, const float* b,
                     float* y, int act, float alpha, void* stream);
+
+/* y = act2(conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2): two chained 3x3 / padding 1 / stride 1
+ * convolutions 1 -> c_mid -> 1 channels with the c_mid-channel intermediate kept in registers
+ * (inference only: nothing is saved for a backward pass).   replaces: the conv_1 -> leaky_relu_1
+ * -> conv_2 -> sigmoid chain of make_monochrome (my_model/model.py:119-122), i.e. four
+ * layer calls of convolutional.py:62-99 / layers.py:390-415.   x, y: (N, H, W, 1). */
+int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
+                          int act1, float alpha1, int act2, float alpha2, void* stream);
 
 /* dx = dgrad(dy, w) (overwrites dx).   replaces: _backward_gpu_kernel_dx + the crop of
  * convolutional.py:141-142 / :203-219,239-250. */

@@ -386,3 +386,78 @@ def test_row_max_hits_bit_exact(nn):
     lib.uocr_row_max_hits(d.ptr, hits.ptr, 300, 162, nn.CP.stream())
     got = np.argwhere(hits.get() != 0)[:, 1]
     assert np.array_equal(got, O.pred_to_ids(pred))
+
+
+# ----------------------------------------------------------------------------- fused paths
+
+@pytest.mark.parametrize('name', list(MODEL_SHAPES))
+def test_fused_plans_match_unfused(nn, name):
+    """Model.fusion (conv+act epilogue, upsample folded into conv, Monochrome conv pair) must give
+    the same predictions, losses and gradients as layer-by-layer execution (rtol 1e-5: same FP32
+    arithmetic, different association only in the pair kernel)."""
+    from univer_ocr_b200 import my_model
+    rng = np.random.default_rng(77)
+    shape = {'monochrome': (3, 40, 52, 1), 'paragraph': (3, 48, 80, 1), 'line': (3, 32, 48, 1),
+             'char': (2, 32, 20, 1)}[name]
+    w0 = np_models.golden_weights(name, 99)
+    results = []
+    for fusion in (False, True):
+        nn.models.Model.fusion = fusion
+        try:
+            model = my_model.MAKERS[name](shape, optimizer=nn.optimizers.Adam(lr=0.002))
+        finally:
+            nn.models.Model.fusion = True
+        model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})
+        X = f32(np.random.default_rng(5).uniform(size=shape))
+        pred = host(model.predict(X)[0])
+        if name == 'char':
+            y = np.zeros(pred.shape)
+            y[np.arange(y.shape[0]), np.random.default_rng(6).integers(0, y.shape[1], size=y.shape[0])] = 1
+        else:
+            y = (np.random.default_rng(6).uniform(size=pred.shape) < 0.2).astype(np.float64)
+        losses = model.compute_loss_and_gradients(X, y)
+        grads = {k: host(p.grad) for k, p in model.params().items()}
+        results.append((pred, float(losses['output_losses'][0]), grads, host(model.input_grads[0]),
+                        [s[0] for s in model._plan_infer]))
+    (p0, l0, g0, dx0, plan0), (p1, l1, g1, dx1, plan1) = results
+    assert all(k == 'layer' for k in plan0) and any(k != 'layer' for k in plan1)
+    if name == 'monochrome':
+        assert plan1 == ['pair']
+    close(p1, p0, 1e-5, 1e-6, 'pred')
+    assert same_scalar(l1, l0, 1e-5)
+    close(dx1, dx0, 1e-4, 1e-6, 'dX')
+    for k in g0:
+        close(g1[k], g0[k], 1e-4, 2e-6, k)
+
+
+def test_conv_pair_and_upsample_fusion_edges(nn):
+    """Ragged sizes for the fused kernels: widths / heights that are not multiples of the
+    per-thread tile (8 columns x 16 rows), 1-pixel images, and odd sizes for upsample+conv."""
+    import ctypes
+    from univer_ocr_b200._lib import ACT_LEAKY, ACT_SIGMOID, ConvDesc, lib
+    rng = np.random.default_rng(31)
+    for (n, h, w), c1 in (((2, 1, 1), 16), ((1, 17, 9), 16), ((2, 33, 70), 16), ((1, 16, 64), 5)):
+        X = f32(rng.standard_normal((n, h, w, 1)))
+        w1 = f32(rng.standard_normal((3, 3, 1, c1)) * 0.4)
+        b1 = f32(rng.standard_normal(c1))
+        w2 = f32(rng.standard_normal((3, 3, c1, 1)) * 0.3)
+        b2 = f32(rng.standard_normal(1))
+        hid = O.leaky_relu_fwd(O.conv2d_fwd(X, w1, b1, 1), 0.01)
+        want = O.sigmoid_fwd(O.conv2d_fwd(hid, w2, b2, 1))
+        d = [nn.CP.copy(a) for a in (X, w1, b1, w2, b2)]
+        y = nn.DeviceArray((n, h, w, 1))
+        lib.uocr_conv3x3_pair_fwd(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, y.ptr, n, h, w, c1,
+                                  ACT_LEAKY, 0.01, ACT_SIGMOID, 0.0, nn.CP.stream())
+        close(y, want, 1e-4, 2e-6, f'pair {(n, h, w, c1)}')
+    for (n, h, w), cin, cout, pad in (((2, 7, 5), 1, 1, 2), ((1, 9, 13), 4, 4, 2), ((2, 6, 11), 4, 2, 2),
+                                      ((1, 5, 4), 3, 5, 1)):
+        X = f32(rng.standard_normal((n, h, w, cin)))
+        wt = f32(rng.standard_normal((5, 5, cin, cout)) * 0.2)
+        b = f32(rng.standard_normal(cout))
+        want = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(X, 2), wt, b, pad), 0.01)
+        desc = ConvDesc(n, 2 * h, 2 * w, cin, cout, 5, 5, pad, pad, 1, 1, 0.0, 1, 0, 2)
+        dx, dw, db = nn.CP.copy(X), nn.CP.copy(wt), nn.CP.copy(b)
+        y = nn.DeviceArray(want.shape)
+        lib.uocr_conv2d_fwd(ctypes.byref(desc), dx.ptr, dw.ptr, db.ptr, y.ptr, ACT_LEAKY, 0.01,
+                            nn.CP.stream())
+        close(y, want, 1e-4, 2e-6, f'ups+conv {(n, h, w, cin, cout)}')

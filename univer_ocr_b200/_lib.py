@@ -35,7 +35,7 @@ class ConvDesc(ctypes.Structure):
                 ('ph', ctypes.c_int32), ('pw', ctypes.c_int32),
                 ('sh', ctypes.c_int32), ('sw', ctypes.c_int32),
                 ('padding_value', ctypes.c_float), ('bias', ctypes.c_int32),
-                ('math_mode', ctypes.c_int32)]
+                ('math_mode', ctypes.c_int32), ('in_upsample', ctypes.c_int32)]
 
 
 _SCALARS = {

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kThreads) conv_fwd_direct_kernel(ConvGeom g, c
             for (int kx = 0; kx < g.kw; ++kx) {
                 const int ix = ix0 + kx;
                 const bool in = yin && ix >= 0 && ix < g.w;
-                const float* xp = x + (((int64_t)n * g.h + iy) * g.w + ix) * g.cin;
+                const float* xp = x + (((int64_t)n * (g.h / g.ups) + iy / g.ups) * (g.w / g.ups) + ix / g.ups) * g.cin;
                 const float* wp = w + ((int64_t)(ky * g.kw + kx) * g.cin) * g.cout + co0;
                 for (int ci = 0; ci < g.cin; ++ci) {
                     const float xv = in ? __ldg(xp + ci) : g.padding_value;
@@ -344,6 +344,9 @@ static int make_geom(const uocr_conv2d_desc* d, ConvGeom* g) {
     g->wo = (g->w + 2 * g->pw - g->kw) / g->sw + 1;
     g->padding_value = d->padding_value;
     g->bias = d->bias ? 1 : 0;
+    g->ups = d->in_upsample >= 2 ? d->in_upsample : 1;
+    UOCR_REQUIRE(g->ups <= 2 && g->h % g->ups == 0 && g->w % g->ups == 0,
+                 "in_upsample must be 0, 1 or 2 and divide H and W");
     return UOCR_OK;
 }
 
@@ -367,9 +370,21 @@ int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, c
     UOCR_REQUIRE(x && w && b && y, "NULL pointer");
     UOCR_REQUIRE(act >= UOCR_ACT_NONE && act <= UOCR_ACT_SIGMOID, "unknown activation %d", act);
     cudaStream_t st = as_stream(stream);
-    rc = conv_fwd_fast(g, d->math_mode, x, w, b, y, act, alpha, st);
+    rc = conv_fwd_fast(g, g.ups, d->math_mode, x, w, b, y, act, alpha, st);
     if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     return conv_fwd_general(g, x, w, b, y, act, alpha, st);
+}
+
+int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
+                          int act1, float alpha1, int act2, float alpha2, void* stream) {
+    UOCR_REQUIRE(x && w1 && b1 && w2 && b2 && y, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c_mid > 0 && c_mid <= 256, "bad dimension");
+    UOCR_REQUIRE(h < (1 << 30) && w < (1 << 30), "dimension too large");
+    UOCR_REQUIRE(act1 >= UOCR_ACT_NONE && act1 <= UOCR_ACT_SIGMOID && act2 >= UOCR_ACT_NONE &&
+                     act2 <= UOCR_ACT_SIGMOID, "unknown activation");
+    return conv3x3_pair_fwd(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,
+                            as_stream(stream));
 }
 
 int uocr_conv2d_dgrad(const uocr_conv2d_desc* d, const float* dy, const float* w, float* dx,
@@ -378,6 +393,7 @@ int uocr_conv2d_dgrad(const uocr_conv2d_desc* d, const float* dy, const float* w
     int rc = make_geom(d, &g);
     if (rc) return rc;
     UOCR_REQUIRE(dy && w && dx, "NULL pointer");
+    UOCR_REQUIRE(g.ups == 1, "in_upsample is a forward-only fusion");
     cudaStream_t st = as_stream(stream);
     rc = conv_dgrad_fast(g, d->math_mode, dy, w, dx, st);
     if (rc != UOCR_ERR_UNSUPPORTED) return rc;
@@ -402,6 +418,7 @@ int uocr_conv2d_wgrad(const uocr_conv2d_desc* d, const float* x, const float* dy
     int rc = make_geom(d, &g);
     if (rc) return rc;
     UOCR_REQUIRE(x && dy && dw && db, "NULL pointer");
+    UOCR_REQUIRE(g.ups == 1, "in_upsample is a forward-only fusion");
     size_t need = 0;
     uocr_conv2d_wgrad_workspace(d, &need);
     if (need > 0 && (!workspace || workspace_bytes < need)) {

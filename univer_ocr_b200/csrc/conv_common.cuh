@@ -11,12 +11,17 @@ struct ConvGeom {
     int ho, wo;
     float padding_value;
     int bias;
+    int ups;            // 1 or 2: nearest upsample folded into the forward input read (h, w are
+                        // the LOGICAL, upsampled sizes; the stored tensor is (h/ups, w/ups))
 };
 
 // Shape-specialised kernels.  Each returns UOCR_ERR_UNSUPPORTED when it has no kernel for the
 // geometry / math mode, in which case the caller runs the general kernel.
-int conv_fwd_fast(const ConvGeom& g, int math_mode, const float* x, const float* w, const float* b,
-                  float* y, int act, float alpha, cudaStream_t st);
+int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
+                  const float* b, float* y, int act, float alpha, cudaStream_t st);
+int conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* y, int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2,
+                     float alpha2, cudaStream_t st);
 int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const float* w, float* dx,
                     cudaStream_t st);
 size_t conv_wgrad_fast_workspace(const ConvGeom& g, int math_mode);

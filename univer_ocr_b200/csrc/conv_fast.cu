@@ -1,13 +1,308 @@
 // Shape-specialised convolution kernels for the my_model geometries.
-// Until a geometry has a tuned kernel the entry points answer UOCR_ERR_UNSUPPORTED and the
-// general FP32 path of conv.cu runs.
+//
+// All of my_model's convolutions except Char conv_2/conv_3 have tiny channel counts
+// (1->16, 16->1, 1->1, 1->4, 4->4, 4->2, 1->64): their arithmetic intensity is far below the
+// tensor-core ridge, so they are CUDA-core stencils bound by HBM / FFMA issue, not GEMMs.
+// Design (forward): one thread = PX consecutive output pixels x COT output channels in
+// registers; the input window row (PX*SW + KW - SW pixels, 128-bit loads over channels) is
+// fetched once per kernel row through L1 and reused for every tap / output channel; weights are
+// staged in shared memory once per CTA and read as warp-broadcast 128-bit loads; bias +
+// activation are applied in the epilogue; an optional x2 nearest-neighbour upsample of the
+// input is folded into the address computation (Upsample2D + Convolutional2D in one pass).
 #include "conv_common.cuh"
 
 namespace uocr {
 
-int conv_fwd_fast(const ConvGeom&, int, const float*, const float*, const float*, float*, int, float,
-                  cudaStream_t) {
+template <int CIV> struct XVec;
+template <> struct XVec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+    __device__ __forceinline__ void fill(float f) { v[0] = f; }
+};
+template <> struct XVec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    __device__ __forceinline__ void fill(float f) { v[0] = v[1] = v[2] = v[3] = f; }
+};
+
+template <int KH, int KW, int SH, int SW, int CIN, int COT, int PX, int UPS>
+__global__ void __launch_bounds__(256) conv_small_fwd_kernel(ConvGeom g, const float* __restrict__ x,
+                                                             const float* __restrict__ w,
+                                                             const float* __restrict__ b,
+                                                             float* __restrict__ y, int act, float alpha) {
+    constexpr int CIV = (CIN % 4 == 0) ? 4 : 1;
+    constexpr int NIN = (PX - 1) * SW + KW;
+    extern __shared__ __align__(16) float s_w[];            // [KH][KW][CIN][cout]
+    const int cout = g.cout;
+    for (int i = threadIdx.x; i < KH * KW * CIN * cout; i += 256) s_w[i] = w[i];
+    __syncthreads();
+
+    const int chunks = cout / COT;
+    const int strips = (g.wo + PX - 1) / PX;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int chunk = (int)(idx % chunks);
+    const int64_t s = idx / chunks;
+    const int xs = (int)(s % strips);
+    const int oy = (int)((s / strips) % g.ho);
+    const int64_t n = s / ((int64_t)strips * g.ho);
+    if (n >= g.n) return;
+    const int co0 = chunk * COT;
+    const int ox0 = xs * PX;
+    const int iy0 = oy * SH - g.ph, ix0 = ox0 * SW - g.pw;
+    const int hp = g.h / UPS, wp = g.w / UPS;               // physical input size
+
+    float acc[PX][COT];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int c = 0; c < COT; ++c) acc[p][c] = 0.f;
+
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+        const int iy = iy0 + ky;
+        const bool yin = iy >= 0 && iy < g.h;
+        const float* xrow = x + ((n * hp + (yin ? iy / UPS : 0)) * (int64_t)wp) * CIN;
+#pragma unroll
+        for (int cg = 0; cg < CIN / CIV; ++cg) {
+            XVec<CIV> xin[NIN];
+#pragma unroll
+            for (int j = 0; j < NIN; ++j) {
+                const int ix = ix0 + j;
+                if (yin && ix >= 0 && ix < g.w) xin[j].load(xrow + (int64_t)(ix / UPS) * CIN + cg * CIV);
+                else xin[j].fill(g.padding_value);
+            }
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+#pragma unroll
+                for (int v = 0; v < CIV; ++v) {
+                    const float* wp_ = s_w + ((ky * KW + kx) * CIN + cg * CIV + v) * cout + co0;
+                    float wr[COT];
+                    if (COT % 4 == 0) {
+#pragma unroll
+                        for (int c = 0; c < COT; c += 4) {
+                            const float4 t = *reinterpret_cast<const float4*>(wp_ + c);
+                            wr[c] = t.x; wr[c + 1] = t.y; wr[c + 2] = t.z; wr[c + 3] = t.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < COT; ++c) wr[c] = wp_[c];
+                    }
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) {
+                        const float xv = xin[p * SW + kx].v[v];
+#pragma unroll
+                        for (int c = 0; c < COT; ++c) acc[p][c] = fmaf(xv, wr[c], acc[p][c]);
+                    }
+                }
+            }
+        }
+    }
+
+    float bias[COT];
+#pragma unroll
+    for (int c = 0; c < COT; ++c) bias[c] = g.bias ? __ldg(b + co0 + c) : 0.f;
+    float* yrow = y + ((n * g.ho + oy) * (int64_t)g.wo + ox0) * cout + co0;
+    if (COT == 1 && cout == 1 && PX % 4 == 0 && (g.wo & 3) == 0 && ox0 + PX <= g.wo) {
+#pragma unroll
+        for (int p = 0; p < PX; p += 4) {
+            float4 t;
+            t.x = apply_act(acc[p][0] + bias[0], act, alpha);
+            t.y = apply_act(acc[p + 1][0] + bias[0], act, alpha);
+            t.z = apply_act(acc[p + 2][0] + bias[0], act, alpha);
+            t.w = apply_act(acc[p + 3][0] + bias[0], act, alpha);
+            *reinterpret_cast<float4*>(yrow + p) = t;
+        }
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        if (ox0 + p >= g.wo) break;
+        float* yp = yrow + (int64_t)p * cout;
+        if (COT % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < COT; c += 4) {
+                float4 t;
+                t.x = apply_act(acc[p][c] + bias[c], act, alpha);
+                t.y = apply_act(acc[p][c + 1] + bias[c + 1], act, alpha);
+                t.z = apply_act(acc[p][c + 2] + bias[c + 2], act, alpha);
+                t.w = apply_act(acc[p][c + 3] + bias[c + 3], act, alpha);
+                *reinterpret_cast<float4*>(yp + c) = t;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < COT; ++c) yp[c] = apply_act(acc[p][c] + bias[c], act, alpha);
+        }
+    }
+}
+
+template <int KH, int KW, int SH, int SW, int CIN, int COT, int PX>
+static int launch_small_fwd(const ConvGeom& g, int ups, const float* x, const float* w, const float* b,
+                            float* y, int act, float alpha, cudaStream_t st) {
+    const int chunks = g.cout / COT;
+    const int strips = (g.wo + PX - 1) / PX;
+    const int64_t items = (int64_t)g.n * g.ho * strips * chunks;
+    const int64_t blocks = ceil_div(items, 256);
+    const size_t smem = sizeof(float) * KH * KW * CIN * g.cout;
+    if (blocks > 0x7fffffff || smem > 48 * 1024) return UOCR_ERR_UNSUPPORTED;
+    if (ups == 2)
+        conv_small_fwd_kernel<KH, KW, SH, SW, CIN, COT, PX, 2><<<(unsigned)blocks, 256, smem, st>>>(
+            g, x, w, b, y, act, alpha);
+    else
+        conv_small_fwd_kernel<KH, KW, SH, SW, CIN, COT, PX, 1><<<(unsigned)blocks, 256, smem, st>>>(
+            g, x, w, b, y, act, alpha);
+    UOCR_LAUNCHED("conv_small_fwd");
+    return UOCR_OK;
+}
+
+int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
+                  const float* b, float* y, int act, float alpha, cudaStream_t st) {
+    (void)math_mode;
+    if (ups != 1 && ups != 2) return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
+#define UOCR_SMALL(KH_, KW_, SH_, SW_, CIN_, COUTMOD, COT_, PX_)                                    \
+    if (g.kh == KH_ && g.kw == KW_ && g.sh == SH_ && g.sw == SW_ && g.cin == CIN_ &&                 \
+        g.cout % COUTMOD == 0 && g.cout >= COT_ && (COT_ != 1 || g.cout == 1) && (COT_ != 2 || g.cout == 2)) \
+        return launch_small_fwd<KH_, KW_, SH_, SW_, CIN_, COT_, PX_>(g, ups, x, w, b, y, act, alpha, st);
+    UOCR_SMALL(3, 3, 1, 1, 1, 16, 16, 4)     // Monochrome conv_1
+    UOCR_SMALL(3, 3, 1, 1, 16, 1, 1, 8)      // Monochrome conv_2
+    UOCR_SMALL(5, 5, 1, 1, 1, 1, 1, 8)       // Paragraph up_*, end
+    UOCR_SMALL(5, 5, 2, 2, 1, 1, 1, 8)       // Paragraph down_*
+    UOCR_SMALL(5, 5, 2, 2, 1, 4, 4, 4)       // Line down_1
+    UOCR_SMALL(5, 5, 2, 2, 4, 4, 4, 4)       // Line down_2
+    UOCR_SMALL(5, 5, 1, 1, 4, 4, 4, 4)       // Line up_*
+    UOCR_SMALL(5, 5, 1, 1, 4, 2, 2, 4)       // Line end
+    UOCR_SMALL(5, 3, 2, 1, 1, 16, 16, 4)     // Char conv_1 (1 -> 64)
+#undef UOCR_SMALL
     return UOCR_ERR_UNSUPPORTED;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused pair: 3x3 conv (1 -> C1) + act1 + 3x3 conv (C1 -> 1) + act2, padding 1, stride 1
+// (my_model's Monochrome net, model.py:119-122, in inference).  The C1-channel hidden map
+// (23 MB per 496x736 tile at C1 = 16) never leaves registers: a thread owns CW output columns and
+// streams down R rows; for every hidden row and channel it evaluates the CW + 2 hidden pixels it
+// needs (9 FFMA each) and immediately scatters them into the three output rows they touch
+// (9 * CW FFMA).  No shared memory traffic except 5 broadcast 128-bit weight loads per channel, no
+// barriers.  Algorithmic cost 288 FMA / pixel, executed (1 + 2/CW)(1 + 2/R) * 144 + (1 + 2/R) * 144.
+// ------------------------------------------------------------------------------------------
+constexpr int PAIR_CW = 8, PAIR_R = 16;
+
+template <int CW, int R>
+__global__ void __launch_bounds__(128) conv3x3_pair_fwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int n_img, int H,
+    int W, int C1, int act1, float alpha1, int act2, float alpha2) {
+    extern __shared__ __align__(16) float s_p[];            // per channel: w1[9], b1, w2[9], pad -> 20
+    for (int i = threadIdx.x; i < C1 * 20; i += 128) {
+        const int c = i / 20, k = i % 20;
+        float v = 0.f;
+        if (k < 9) v = w1[k * C1 + c];                      // w1 (3,3,1,C1)
+        else if (k == 9) v = b1[c];
+        else if (k < 19) v = w2[(k - 10) * C1 + c];         // w2 (3,3,C1,1)
+        s_p[i] = v;
+    }
+    __syncthreads();
+
+    const int strips = (W + CW - 1) / CW;
+    const int rchunks = (H + R - 1) / R;
+    const int64_t idx = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int strip = (int)(idx % strips);
+    const int rc = (int)((idx / strips) % rchunks);
+    const int64_t n = idx / ((int64_t)strips * rchunks);
+    if (n >= n_img) return;
+    const int c0 = strip * CW, r0 = rc * R;
+    const float* xim = x + n * (int64_t)H * W;
+    float* yim = y + n * (int64_t)H * W;
+    const float bias2 = __ldg(b2);
+
+    float xr[3][CW + 4];                                    // x rows hr-1, hr, hr+1; cols c0-2 ..
+    float accA[CW], accB[CW], accC[CW];                     // output rows hr-1, hr, hr+1
+#pragma unroll
+    for (int j = 0; j < CW; ++j) accA[j] = accB[j] = accC[j] = 0.f;
+
+    auto load_row = [&](int row, float* dst) {
+        const bool rin = row >= 0 && row < H;
+#pragma unroll
+        for (int j = 0; j < CW + 4; ++j) {
+            const int col = c0 - 2 + j;
+            dst[j] = (rin && col >= 0 && col < W) ? __ldg(xim + (int64_t)row * W + col) : 0.f;
+        }
+    };
+    load_row(r0 - 2, xr[0]);
+    load_row(r0 - 1, xr[1]);
+
+    const int r_end = min(r0 + R, H);
+    for (int hr = r0 - 1; hr <= r_end; ++hr) {
+        load_row(hr + 1, xr[2]);
+        if (hr >= 0 && hr < H) {
+            for (int c = 0; c < C1; ++c) {
+                const float4* pw = reinterpret_cast<const float4*>(s_p + c * 20);
+                const float4 q0 = pw[0], q1 = pw[1], q2 = pw[2], q3 = pw[3], q4 = pw[4];
+                const float k1[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+                const float bb = q2.y;
+                const float k2[9] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z};
+                float h[CW + 2];
+#pragma unroll
+                for (int j = 0; j < CW + 2; ++j) {
+                    float v = bb;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) v = fmaf(k1[ky * 3 + kx], xr[ky][j + kx], v);
+                    v = apply_act(v, act1, alpha1);
+                    const int col = c0 - 1 + j;
+                    h[j] = (col >= 0 && col < W) ? v : 0.f;     // conv_2's zero padding
+                }
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        accA[j] = fmaf(k2[6 + kx], h[j + kx], accA[j]);   // ky = 2 -> output row hr - 1
+                        accB[j] = fmaf(k2[3 + kx], h[j + kx], accB[j]);   // ky = 1 -> output row hr
+                        accC[j] = fmaf(k2[kx], h[j + kx], accC[j]);       // ky = 0 -> output row hr + 1
+                    }
+                }
+            }
+        }
+        const int orow = hr - 1;
+        if (orow >= r0 && orow < r_end) {
+            float* yp = yim + (int64_t)orow * W + c0;
+            if (c0 + CW <= W && (W & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < CW; j += 4) {
+                    float4 t;
+                    t.x = apply_act(accA[j] + bias2, act2, alpha2);
+                    t.y = apply_act(accA[j + 1] + bias2, act2, alpha2);
+                    t.z = apply_act(accA[j + 2] + bias2, act2, alpha2);
+                    t.w = apply_act(accA[j + 3] + bias2, act2, alpha2);
+                    *reinterpret_cast<float4*>(yp + j) = t;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CW; ++j)
+                    if (c0 + j < W) yp[j] = apply_act(accA[j] + bias2, act2, alpha2);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) { accA[j] = accB[j]; accB[j] = accC[j]; accC[j] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < CW + 4; ++j) { xr[0][j] = xr[1][j]; xr[1][j] = xr[2][j]; }
+    }
+}
+
+int conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* y, int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2,
+                     float alpha2, cudaStream_t st) {
+    const int64_t strips = ceil_div(w, PAIR_CW), rchunks = ceil_div(h, PAIR_R);
+    const int64_t blocks = ceil_div(n * strips * rchunks, 128);
+    if (blocks > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    conv3x3_pair_fwd_kernel<PAIR_CW, PAIR_R><<<(unsigned)blocks, 128, sizeof(float) * 20 * c1, st>>>(
+        x, w1, b1, w2, b2, y, (int)n, (int)h, (int)w, c1, act1, alpha1, act2, alpha2);
+    UOCR_LAUNCHED("conv3x3_pair_fwd");
+    return UOCR_OK;
 }
 
 int conv_dgrad_fast(const ConvGeom&, int, const float*, const float*, float*, cudaStream_t) {

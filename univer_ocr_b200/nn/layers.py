@@ -18,12 +18,21 @@ import math
 
 import numpy as np
 
-from .._lib import ACT_NONE, ConvDesc, lib
+from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, ConvDesc, lib
 from .gpu import CP, DeviceArray, LazyScalar, as_device, concatenate, slice_axis, stream
 from .help_func import make_list_if_not, tuplize
 from .initializers import kaiming_uniform
 from .optimizers import Adam
 from .progress_tracker import BaseProgressTracker, track_method
+
+class FromOutput:
+    """Marker stored in an activation layer's memory when the activation ran as the epilogue
+    of the producing kernel: only its OUTPUT exists, and the backward is evaluated from it."""
+    __slots__ = ('y',)
+
+    def __init__(self, y):
+        self.y = y
+
 
 _DEFAULT_OPTIMIZER = Adam()     # the reference's default argument is one shared instance (layers.py:31)
 
@@ -312,6 +321,11 @@ class LeakyRelu(BaseLayer):
 
     def _backward(self, grad, mem_id=0):
         X = self._mem[mem_id]
+        if isinstance(X, FromOutput):
+            dx = DeviceArray(X.y.shape)
+            lib.uocr_act_bwd_from_output(X.y.ptr, grad.ptr, dx.ptr, dx.size, ACT_LEAKY,
+                                         float(self.alpha), stream())
+            return dx
         dx = DeviceArray(X.shape)
         lib.uocr_leaky_relu_bwd(X.ptr, grad.ptr, dx.ptr, X.size, float(self.alpha), stream())
         return dx
@@ -338,6 +352,10 @@ class Sigmoid(BaseLayer):
 
     def _backward(self, grad, mem_id=0):
         X = self._mem[mem_id]
+        if isinstance(X, FromOutput):
+            dx = DeviceArray(X.y.shape)
+            lib.uocr_act_bwd_from_output(X.y.ptr, grad.ptr, dx.ptr, dx.size, ACT_SIGMOID, 0.0, stream())
+            return dx
         dx = DeviceArray(X.shape)
         lib.uocr_sigmoid_bwd(X.ptr, grad.ptr, dx.ptr, X.size, stream())
         return dx
@@ -450,17 +468,21 @@ class Convolutional2D(BaseLayer):
         self._init_optimizer()
         self.is_initialized = True
 
-    def _desc(self, x_shape):
+    def _desc(self, x_shape, in_upsample=1):
         n, h, w, c = x_shape
         assert c == self.in_channels, f'input has {c} channels, layer expects {self.in_channels}'
-        return ConvDesc(n, h, w, c, self.out_channels, *self.kernel_size, *self.padding, *self.stride,
-                        float(self.padding_value), int(bool(self.bias)), CP.math_mode)
+        return ConvDesc(n, h * in_upsample, w * in_upsample, c, self.out_channels, *self.kernel_size,
+                        *self.padding, *self.stride, float(self.padding_value), int(bool(self.bias)),
+                        CP.math_mode, in_upsample)
 
-    def _forward(self, X, mem_id=0, act=ACT_NONE, alpha=0.0):
+    def _forward(self, X, mem_id=0, act=ACT_NONE, alpha=0.0, in_upsample=1, save=True):
         assert X.ndim == 4, f'expected NHWC input, got shape {X.shape}'
-        desc = self._desc(X.shape)
-        self._mem[mem_id] = X
-        y = DeviceArray(self.get_output_shapes(X.shape)[0])
+        desc = self._desc(X.shape, in_upsample)
+        if save:
+            assert in_upsample == 1
+            self._mem[mem_id] = X
+        n, h, w, c = X.shape
+        y = DeviceArray(self.get_output_shapes((n, h * in_upsample, w * in_upsample, c))[0])
         lib.uocr_conv2d_fwd(ctypes.byref(desc), X.ptr, self.w.value.ptr, self.b.value.ptr, y.ptr,
                             act, float(alpha), stream())
         return y

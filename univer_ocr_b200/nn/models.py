@@ -15,9 +15,12 @@ model_weights.json).  Execution differs from the reference in mechanics only: in
 memoised recursion per call, the evaluation order is resolved once at `initialize()` and
 replayed; no layer call synchronises the device, and loss values stay on the device until read.
 """
-from .gpu import DeviceArray, LazyScalar
+import ctypes
+
+from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
+from .gpu import DeviceArray, LazyScalar, as_device, stream
 from .help_func import make_list_if_not
-from .layers import BaseLayer
+from .layers import (BaseLayer, Convolutional2D, FromOutput, LeakyRelu, Sigmoid, Upsample2D)
 from .losses import SoftmaxCrossEntropy
 from .progress_tracker import track_method
 
@@ -46,7 +49,27 @@ class BaseModel(BaseLayer):
         raise NotImplementedError()
 
 
+def _act_code(layer):
+    """(activation enum, alpha) if `layer` can run as a fused epilogue, else None."""
+    if type(layer) is Sigmoid:
+        return ACT_SIGMOID, 0.0
+    if isinstance(layer, LeakyRelu) and layer.alpha > 0:       # Relu (alpha 0) keeps its own kernel
+        return ACT_LEAKY, float(layer.alpha)
+    return None
+
+
 class Model(BaseModel):
+    # Kernel fusion across layer boundaries (results identical up to FP32 rounding):
+    #   training + inference : Convolutional2D -> LeakyRelu as one kernel (the activation's
+    #                          backward is then evaluated from its OUTPUT, exact for alpha > 0)
+    #   inference only       : Convolutional2D -> Sigmoid as one kernel
+    #   inference only       : Upsample2D(2) -> Convolutional2D folded into the conv's addressing;
+    #                          3x3 conv (1->C) -> act -> 3x3 conv (C->1) [-> act] as one kernel with
+    #                          the C-channel map kept in registers (Monochrome)
+    # Fused-away tensors are absent (None) from `layers_outputs`; set `fusion = False` (class or
+    # instance) before initialize() to get every per-layer output like the reference.
+    fusion = True
+
     def __init__(self, layers, relations, loss=SoftmaxCrossEntropy(), *args, **kwargs):
         super().__init__(*args, **kwargs)
         if not isinstance(layers, dict):
@@ -172,11 +195,78 @@ class Model(BaseModel):
         never = [n for n in self.layers if n not in shapes]
         if never:
             print(f'These layers have never been visited: {never}')
+        self._plan_train = self._make_plan(training=True)
+        self._plan_infer = self._make_plan(training=False)
         self.is_initialized = True
+
+    # ---- fusion planning ----------------------------------------------------------
+    def _sole_consumer(self, name):
+        """The single layer consuming `name`'s output (as its only input), else None."""
+        users = self.relations_backward.get(name, {})
+        if len(users) != 1:
+            return None
+        (dst, _), = users.items()
+        if isinstance(dst, int) or len(self.relations[dst]) != 1 or dst not in self.layers:
+            return None
+        return dst
+
+    def _make_plan(self, training):
+        plan, taken = [], set()
+        for name in self._order:
+            if name in taken:
+                continue
+            layer = self.layers[name]
+            step = None
+            if self.fusion and len(self.relations[name]) == 1:
+                ups = None
+                conv_name = name
+                if (not training and type(layer) is Upsample2D and layer.scale_factor == (2, 2)):
+                    nxt = self._sole_consumer(name)
+                    if nxt is not None and type(self.layers[nxt]) is Convolutional2D:
+                        ups, conv_name = name, nxt
+                conv = self.layers[conv_name]
+                if type(conv) is Convolutional2D:
+                    act_name = self._sole_consumer(conv_name)
+                    act = _act_code(self.layers[act_name]) if act_name is not None else None
+                    # training: a fused Sigmoid would have to be differentiated from its output
+                    # y * (1 - y), which flushes saturated gradients (|x| > 17) to zero in FP32
+                    # while the reference's exp(-x) / (1 + exp(-x))^2 keeps them; LeakyRelu's
+                    # derivative from the output is exact (sign(y) == sign(x))
+                    if act is None or (training and act[0] != ACT_LEAKY):
+                        act_name = None
+                    pair = None
+                    if (not training and ups is None and act_name is not None
+                            and self._pair_head(conv)):
+                        c2_name = self._sole_consumer(act_name)
+                        if c2_name is not None and self._pair_tail(conv, self.layers[c2_name]):
+                            a2_name = self._sole_consumer(c2_name)
+                            a2 = _act_code(self.layers[a2_name]) if a2_name is not None else None
+                            pair = (c2_name, a2_name if a2 is not None else None)
+                    if pair is not None:
+                        step = ('pair', conv_name, act_name, pair[0], pair[1])
+                    elif ups is not None or act_name is not None:
+                        step = ('conv', ups, conv_name, act_name)
+            if step is None:
+                step = ('layer', name)
+            plan.append(step)
+            taken.update(n for n in step[1:] if n is not None)
+        return plan
+
+    @staticmethod
+    def _pair_head(conv):
+        return (conv.kernel_size == (3, 3) and conv.padding == (1, 1) and conv.stride == (1, 1)
+                and conv.in_channels == 1 and conv.padding_value == 0 and conv.bias
+                and conv.out_channels <= 256)
+
+    @staticmethod
+    def _pair_tail(head, conv):
+        return (type(conv) is Convolutional2D and conv.kernel_size == (3, 3)
+                and conv.padding == (1, 1) and conv.stride == (1, 1) and conv.out_channels == 1
+                and conv.in_channels == head.out_channels and conv.padding_value == 0 and conv.bias)
 
     # ---- execution ----------------------------------------------------------------
     @track_method('forward')
-    def forward(self, inputs):
+    def forward(self, inputs, training=True):
         inputs = make_list_if_not(inputs)
         if not self.is_initialized:
             self.initialize_from_X(inputs)
@@ -185,15 +275,63 @@ class Model(BaseModel):
         def value_of(src):
             return inputs[src] if isinstance(src, int) else outputs[src]
 
-        for name in self._order:
-            layer = self.layers[name]
-            layer.clear_grads()                                    # reference :188
-            out = layer.forward([value_of(src) for src in self.relations[name]])
-            outputs[name] = out[0] if isinstance(out, list) else out
+        for step in (self._plan_train if training else self._plan_infer):
+            kind = step[0]
+            if kind == 'layer':
+                name = step[1]
+                layer = self.layers[name]
+                layer.clear_grads()                                # reference :188
+                out = layer.forward([value_of(src) for src in self.relations[name]])
+                outputs[name] = out[0] if isinstance(out, list) else out
+            elif kind == 'conv':
+                self._run_fused_conv(step, value_of, outputs, training)
+            else:
+                self._run_pair(step, value_of, outputs)
         for key in self._output_keys():
             outputs[key] = value_of(self.relations[key][0])
         self.layers_outputs = outputs
         return [outputs[k] for k in range(self.outputs_count)]
+
+    def _run_fused_conv(self, step, value_of, outputs, training):
+        _, ups_name, conv_name, act_name = step
+        first = ups_name if ups_name is not None else conv_name
+        X = as_device(value_of(self.relations[first][0]))
+        conv = self.layers[conv_name]
+        act_layer = self.layers[act_name] if act_name is not None else None
+        act, alpha = _act_code(act_layer) if act_layer is not None else (ACT_NONE, 0.0)
+        tracked = [self.layers[n] for n in (ups_name, conv_name, act_name) if n is not None]
+        for layer in tracked:
+            layer.clear_grads()
+        last = tracked[-1]
+        last.progress_tracker.start_tracking(last.name, 'forward')
+        y = conv._forward(X, 0, act=act, alpha=alpha, in_upsample=2 if ups_name is not None else 1,
+                          save=training)
+        last.progress_tracker.stop_tracking(last.name, 'forward')
+        if training and act_layer is not None:
+            act_layer._mem[0] = FromOutput(y)
+        for n in (ups_name, conv_name, act_name):
+            if n is not None:
+                outputs[n] = None
+        outputs[act_name if act_name is not None else conv_name] = y
+
+    def _run_pair(self, step, value_of, outputs):
+        _, c1_name, a1_name, c2_name, a2_name = step
+        X = as_device(value_of(self.relations[c1_name][0]))
+        c1, c2 = self.layers[c1_name], self.layers[c2_name]
+        act1, alpha1 = _act_code(self.layers[a1_name])
+        act2, alpha2 = _act_code(self.layers[a2_name]) if a2_name is not None else (ACT_NONE, 0.0)
+        n, h, w, cin = X.shape
+        assert cin == 1, f'input has {cin} channels, layer expects 1'
+        last = self.layers[a2_name if a2_name is not None else c2_name]
+        last.progress_tracker.start_tracking(last.name, 'forward')
+        y = DeviceArray((n, h, w, 1))
+        lib.uocr_conv3x3_pair_fwd(X.ptr, c1.w.value.ptr, c1.b.value.ptr, c2.w.value.ptr, c2.b.value.ptr,
+                                  y.ptr, n, h, w, c1.out_channels, act1, alpha1, act2, alpha2, stream())
+        last.progress_tracker.stop_tracking(last.name, 'forward')
+        for nme in (c1_name, a1_name, c2_name, a2_name):
+            if nme is not None:
+                outputs[nme] = None
+        outputs[a2_name if a2_name is not None else c2_name] = y
 
     @track_method('backward')
     def backward(self, grads):
@@ -234,7 +372,7 @@ class Model(BaseModel):
 
     def test(self, X, y):
         X, y = make_list_if_not(X), make_list_if_not(y)
-        predicted = self.forward(X)
+        predicted = self.forward(X, training=False)
         losses = []
         for key in range(self.outputs_count):
             fn = self._loss_for(key)
@@ -246,7 +384,7 @@ class Model(BaseModel):
         return {'output_losses': losses}
 
     def predict(self, X):
-        return self.forward(X)
+        return self.forward(X, training=False)
 
     def update_grads(self):
         if not self.trainable:

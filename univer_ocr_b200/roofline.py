@@ -58,3 +58,29 @@ def model_input_shapes(model, input_shape):
         src = model.relations[name][0]
         shapes[name] = tuple(input_shape) if isinstance(src, int) else tuple(all_shapes[src][0])
     return shapes
+
+
+def plan_work(model, input_shape, training=False):
+    """{tracked layer name: work} for the model's execution plan: a fused step is one kernel and
+    is tracked under its LAST layer's name; its algorithmic bytes are the step's external input
+    + output + weights (the fused-away intermediates cost nothing), its flops the sum."""
+    shapes = model_input_shapes(model, input_shape)
+    _, all_shapes = model.get_all_output_shapes([input_shape])
+    out = {}
+    for step in (model._plan_train if training else model._plan_infer):
+        names = [n for n in step[1:] if n is not None]
+        if step[0] == 'layer':
+            out[names[0]] = layer_work(model.layers[names[0]], shapes[names[0]], 'forward')
+            continue
+        flops, wbytes, bound = 0, 0, 'hbm'
+        for n in names:
+            layer = model.layers[n]
+            wk = layer_work(layer, shapes[n], 'forward')
+            if isinstance(layer, L.Convolutional2D):
+                flops += wk['flops']
+                wbytes += 4 * layer.count_parameters()
+                if wk['bound'] == 'tensor':
+                    bound = 'tensor'
+        nbytes = 4 * (_numel(shapes[names[0]]) + _numel(all_shapes[names[-1]][0])) + wbytes
+        out[names[-1]] = {'bound': bound, 'bytes': nbytes, 'flops': flops, 'fused': names}
+    return out
