@@ -1,0 +1,108 @@
+"""TF32 tensor-core mode (CP.set_math_mode('tf32')): tcgen05 kernels for FullyConnected and the
+Cin % 32 == 0 convolutions against the float64 oracle.
+
+Tolerance (north_star: 1e-3 relative with TF32): |got - want| <= 1e-3 * max|want| elementwise,
+and the mean signed relative error on an all-positive problem must be << 1e-3 (TF32 operands are
+ROUNDED to nearest by TMA, not truncated by the tensor core, so the error is unbiased).
+"""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def nn():
+    import univer_ocr_b200.nn as nn_
+    nn_.CP.use_gpu()
+    nn_.CP.set_math_mode('tf32')
+    yield nn_
+    nn_.CP.set_math_mode('fp32')
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def close_tf32(got, want, what, tol=1e-3):
+    got = np.asarray(got.get() if hasattr(got, 'get') else got, dtype=np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-30)
+    assert err <= tol, f'{what}: max err / max|want| = {err:.3e}'
+    return err
+
+
+@pytest.mark.parametrize('batch,n_in,n_out', [(16384, 512, 1024), (1000, 1024, 128), (300, 128, 162),
+                                              (129, 36, 20)])
+def test_fc_tf32(nn, batch, n_in, n_out):
+    rng = np.random.default_rng(batch + n_in)
+    X = f32(rng.standard_normal((batch, n_in)))
+    W = f32(rng.standard_normal((n_in + 1, n_out)) / np.sqrt(n_in))
+    dy = f32(rng.standard_normal((batch, n_out)))
+    fc = nn.layers.FullyConnected(n_in, n_out, w=W)
+    y = fc.forward(X)[0]
+    close_tf32(y, O.fc_fwd(X, W), 'y')
+    dX = fc.backward(dy)[0]
+    odX, odW = O.fc_bwd(X, W, dy)
+    close_tf32(dX, odX, 'dX')
+    close_tf32(fc.w.grad, odW, 'dW')
+
+
+def test_fc_tf32_rounding_is_unbiased(nn):
+    """All-positive operands: truncation to TF32 would bias every product by ~ -2^-10 and the
+    sums by ~ -1e-3 relative; round-to-nearest leaves |mean relative error| below 1e-4."""
+    rng = np.random.default_rng(0)
+    X = f32(rng.uniform(0.5, 1.5, size=(512, 512)))
+    W = f32(rng.uniform(0.5, 1.5, size=(513, 256)))
+    fc = nn.layers.FullyConnected(512, 256, w=W)
+    y = np.asarray(fc.forward(X)[0].get(), dtype=np.float64)
+    want = O.fc_fwd(X, W)
+    rel = (y - want) / want
+    print('mean signed rel err', rel.mean(), 'max abs rel err', np.abs(rel).max())
+    assert abs(rel.mean()) < 1e-4, rel.mean()
+    assert np.abs(rel).max() < 1e-3
+
+
+@pytest.mark.parametrize('shape,cin,cout,ks,pad,st', [
+    ((3, 14, 256), 64, 64, (5, 3), (0, 1), (2, 1)),      # Char conv_2
+    ((3, 5, 256), 64, 64, (5, 3), (0, 1), (2, 1)),       # Char conv_3
+    ((2, 14, 70), 64, 64, (5, 3), (0, 1), (2, 1)),       # ragged width (partial 128-pixel tile)
+    ((2, 9, 131), 32, 48, (3, 3), (1, 1), (1, 1)),       # other channel counts / square kernel
+], ids=['char2', 'char3', 'ragged', 'c32_48'])
+def test_conv_tf32(nn, shape, cin, cout, ks, pad, st):
+    rng = np.random.default_rng(sum(shape) + cin)
+    n, h, w = shape
+    X = f32(rng.standard_normal((n, h, w, cin)))
+    wt = f32(rng.standard_normal((*ks, cin, cout)) / np.sqrt(ks[0] * ks[1] * cin))
+    b = f32(rng.standard_normal(cout))
+    layer = nn.layers.Convolutional2D(ks, cin, cout, padding=pad, stride=st, w=wt, b=b)
+    y = layer.forward(X)[0]
+    want = O.conv2d_fwd(X, wt, b, pad, 0.0, st)
+    close_tf32(y, want, 'y')
+    dy = f32(rng.standard_normal(want.shape))
+    dX = layer.backward(dy)[0]
+    odX, odW, odb = O.conv2d_bwd(X, wt, dy, pad, 0.0, st)
+    close_tf32(dX, odX, 'dX')
+    close_tf32(layer.w.grad, odW, 'dW')
+    close_tf32(layer.b.grad, odb, 'db')
+
+
+def test_char_model_tf32_matches_fp32(nn):
+    """Whole Char sub-network (inference plan: conv + LeakyRelu epilogues on the tensor-core
+    kernels) in TF32 mode vs FP32 check mode: predictions within 2e-3 of max|logit|."""
+    from oracle import np_models
+    from univer_ocr_b200 import my_model
+    shape = (3, 32, 256, 1)
+    w0 = np_models.golden_weights('char', 5)
+    X = f32(np.random.default_rng(1).uniform(size=shape))
+    preds = {}
+    for mode in ('fp32', 'tf32'):
+        nn.CP.set_math_mode(mode)
+        model = my_model.make_char(shape)
+        model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})
+        preds[mode] = np.asarray(model.predict(X)[0].get(), dtype=np.float64)
+    err = np.max(np.abs(preds['tf32'] - preds['fp32'])) / np.max(np.abs(preds['fp32']))
+    print('char tf32 vs fp32 max err / max', err)
+    assert err < 2e-3

@@ -28,6 +28,10 @@ size_t conv_wgrad_fast_workspace(const ConvGeom& g, int math_mode);
 int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const float* dy, float* dw,
                     float* db, int accumulate, float* ws, cudaStream_t st);
 
+// tcgen05 implicit-GEMM forward (tc_gemm.cu): Cin % 32 == 0, stride_w == 1, zero padding
+int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
+                cudaStream_t st);
+
 // General kernels (conv.cu), exposed so the fast paths can delegate sub-problems.
 int conv_fwd_general(const ConvGeom& g, const float* x, const float* w, const float* b, float* y,
                      int act, float alpha, cudaStream_t st);

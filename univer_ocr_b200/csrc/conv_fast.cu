@@ -159,7 +159,10 @@ static int launch_small_fwd(const ConvGeom& g, int ups, const float* x, const fl
 
 int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
                   const float* b, float* y, int act, float alpha, cudaStream_t st) {
-    (void)math_mode;
+    if (math_mode == UOCR_MATH_TF32) {
+        const int rc = conv_fwd_tc(g, x, w, b, y, act, alpha, st);
+        if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    }
     if (ups != 1 && ups != 2) return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
 #define UOCR_SMALL(KH_, KW_, SH_, SW_, CIN_, COUTMOD, COT_, PX_)                                    \

@@ -1,17 +1,478 @@
-// tcgen05 (5th-gen tensor core) TF32 GEMM paths.  Until the kernels land the seams answer
-// UOCR_ERR_UNSUPPORTED and the FP32 SGEMM of gemm.cu runs.
+// tcgen05 (5th-generation tensor core) TF32 kernels: the dense contractions of the path
+// (Char conv_2 / conv_3 and the three FullyConnected GEMMs).
+//
+//   D[M, N] (+)= A[M, K] . B[N, K]^T        TF32 inputs, FP32 accumulation in TMEM
+//
+// One CTA = one 128 x NT output tile (cta_group::1, UMMA M = 128, N = NT <= 256, K = 8 per
+// instruction).  Warp roles (192 threads):
+//   warp 0    TMA producer: one elected lane streams 128B-swizzled K-major tiles
+//             (A: 128 rows x 32 floats, B: NT rows x 32 floats per stage) into a ring of shared
+//             memory stages, signalling `full[s]` through mbarrier complete_tx
+//   warp 1    allocates TMEM, then one elected lane issues tcgen05.mma (4 per stage) and releases
+//             the stage with tcgen05.commit -> `empty[s]`; the last commit raises `tmem_full`
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (lane = row, column = n), add the bias row,
+//             apply the activation, store to global memory
+// A tiles come either from a plain row-major matrix (2-D tensor map) or -- implicit GEMM for
+// Convolutional2D with Cin % 32 == 0 and stride_w == 1 -- straight from the NHWC activation
+// tensor through a 4-D tensor map: the tile for kernel tap (ky, kx) is the box
+// [32 channels x 128 consecutive pixels] at (x0 + kx - pw, oy * sh + ky - ph); TMA's
+// out-of-bounds zero fill IS the zero padding, so no im2col buffer ever exists.
+//
+// Operands must be K-major; weight matrices that are stored N-major ((kh,kw,Cin,Cout) conv
+// weights, (n_in+1, n_out) FC weights) are transposed into a stream-ordered scratch buffer first
+// (<= 2 MB, microseconds).  FP32 bit patterns would be TRUNCATED to TF32 by the tensor core
+// (biased); the tensor maps therefore use the TFLOAT32 data type, which makes TMA round to
+// nearest while copying.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "conv_common.cuh"
 #include "gemm_common.cuh"
 
 namespace uocr {
 
-int fc_fwd_fast(int, const float*, const float*, float*, int64_t, int64_t, int64_t, int, float,
-                cudaStream_t) {
-    return UOCR_ERR_UNSUPPORTED;
+// ------------------------------------------------------------------ driver entry point (no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
 }
 
-int fc_bwd_fast(int, const float*, const float*, const float*, float*, float*, int64_t, int64_t,
-                int64_t, int, cudaStream_t) {
-    return UOCR_ERR_UNSUPPORTED;
+static CUtensorMapDataType tmap_dtype() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("UOCR_TMA_DTYPE");          // "f32" = raw bits (tensor core truncates)
+        mode = (e && e[0] == 'f') ? 0 : 1;
+    }
+    return mode ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
+// rank-`rank` fp32 tensor, dims innermost first, 128-byte swizzled boxes
+static int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable"); return UOCR_ERR_UNSUPPORTED; }
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    CUresult r = fn(map, tmap_dtype(), (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UOCR_ERR_UNSUPPORTED; }
+    return UOCR_OK;
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives row (lane base + t)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start >> 4 | LBO(=1) << 16 | SBO (1024 B = 8 rows x 128 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+constexpr int TC_BM = 128;           // UMMA M
+constexpr int TC_BK = 32;            // floats per stage along K = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+struct TcParams {
+    float* C; int64_t ldc;
+    int64_t M, N;
+    int num_kb;                       // K blocks of 32
+    int nt;                           // N tile (multiple of 16, <= 256)
+    int stages;
+    const float* bias;                // length N or NULL
+    int act; float alpha;
+    int accumulate;
+    // implicit-GEMM convolution (MODE 1)
+    int ho, wo, sh, ph, pw, kw, cblocks;   // cblocks = Cin / 32
+    int xtiles;                             // ceil(wo / 128)
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                const TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: stages x (A 16 KB + B nt*128 B), then barriers
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = TC_BM * TC_BK * 4;
+    const uint32_t b_bytes = (uint32_t)p.nt * TC_BK * 4;
+    const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- tile coordinates
+    int64_t m0;                       // first output row of this tile (row index into C)
+    int64_t m_rows;                   // valid rows in this tile
+    int cn = 0, coy = 0, cx0 = 0;     // conv: image, output row, first output column
+    const int n0 = blockIdx.y * p.nt;
+    if (MODE == 0) {
+        m0 = (int64_t)blockIdx.x * TC_BM;
+        m_rows = min((int64_t)TC_BM, p.M - m0);
+    } else {
+        const int xt = blockIdx.x % p.xtiles;
+        const int row = blockIdx.x / p.xtiles;          // n * ho + oy
+        coy = row % p.ho;
+        cn = row / p.ho;
+        cx0 = xt * TC_BM;
+        m0 = (int64_t)row * p.wo + cx0;
+        m_rows = min(TC_BM, p.wo - cx0);
+    }
+
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.nt) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t phase = (kb / p.stages) & 1;
+                mbar_wait(smem_u32(&empty[s]), phase ^ 1);
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + a_bytes;
+                const uint32_t bar = smem_u32(&full[s]);
+                mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
+                if (MODE == 0) {
+                    tma_load_2d(sa, &map_a, bar, kb * TC_BK, (int)m0);
+                } else {
+                    const int tap = kb / p.cblocks, cb = kb % p.cblocks;
+                    const int ky = tap / p.kw, kx = tap % p.kw;
+                    tma_load_4d(sa, &map_a, bar, cb * TC_BK, cx0 + kx - p.pw, coy * p.sh + ky - p.ph, cn);
+                }
+                tma_load_2d(sb, &map_b, bar, kb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t phase = (kb / p.stages) & 1;
+                mbar_wait(smem_u32(&full[s]), phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t da = make_kmajor_sw128_desc(sa);
+                const uint64_t db = make_kmajor_sw128_desc(sa + a_bytes);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    // advance 8 TF32 = 32 bytes inside the swizzled 128-byte row: +2 in the >>4 address field
+                    tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&empty[s]));             // frees the stage when these MMAs retire
+            }
+            tc_commit(smem_u32(tmem_full));                  // accumulator complete
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                              // TMEM lane quarter this warp may read
+        mbar_wait(smem_u32(tmem_full), 0);
+        tc_fence_after();
+        const int r = q * 32 + lane;                         // row within the tile
+        const bool row_ok = r < m_rows;
+        float* crow = p.C + (m0 + r) * p.ldc + n0;
+        for (int c0 = 0; c0 < p.nt; c0 += 32) {
+            float v[32];
+            tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (!row_ok) continue;
+            const int ncols = (int)min((int64_t)32, p.N - n0 - c0);
+            if (ncols <= 0) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < ncols) {
+                    float t = v[j] + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+                    v[j] = apply_act(t, p.act, p.alpha);
+                }
+            }
+            float* dst = crow + c0;
+            if (ncols == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+                for (int j = 0; j < ncols; ++j) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+static int pick_stages(int nt, size_t* smem_bytes) {
+    const size_t a_bytes = TC_BM * TC_BK * 4;
+    const size_t b_bytes = (((size_t)nt * TC_BK * 4) + 1023) & ~(size_t)1023;
+    const size_t budget = 200 * 1024;
+    int stages = (int)((budget - 2048) / (a_bytes + b_bytes));
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    *smem_bytes = (size_t)stages * (a_bytes + b_bytes) + 1024 /* align slack */ + (2 * stages + 2) * 8 + 64;
+    return stages;
+}
+
+template <int MODE>
+static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, dim3 grid, cudaStream_t st) {
+    size_t smem = 0;
+    p.stages = pick_stages(p.nt, &smem);
+    static bool configured[2] = {false, false};
+    if (!configured[MODE]) {
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             220 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        configured[MODE] = true;
+    }
+    tc_gemm_kernel<MODE><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+    UOCR_LAUNCHED("tc_gemm_tf32");
+    return UOCR_OK;
+}
+
+static int pick_nt(int64_t n) {
+    if (n >= 256) return 256;                 // full-rate N; wider tiles amortise the A reads
+    return (int)(((n + 15) / 16) * 16);
+}
+
+// D[M,N] = act(A[M,K] . Bt[N,K]^T + bias); A, Bt K-major (rows contiguous in K)
+int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
+               int64_t N, int64_t K, const float* bias, int act, float alpha, int accumulate, cudaStream_t st) {
+    if ((lda % 4) || (ldb % 4) || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt)) & 15))
+        return UOCR_ERR_UNSUPPORTED;            // TMA: 16-byte aligned base and row pitch
+    if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffff || K > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    TcParams p{};
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.num_kb = (int)ceil_div(K, TC_BK);
+    p.nt = pick_nt(N);
+    p.bias = bias; p.act = act; p.alpha = alpha; p.accumulate = accumulate;
+    CUtensorMap ma, mb;
+    const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 4};
+    const uint32_t ba[2] = {TC_BK, TC_BM};
+    int rc = make_tmap(&ma, A, 2, da, sa, ba);
+    if (rc) return rc;
+    const uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldb * 4};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)p.nt};
+    rc = make_tmap(&mb, Bt, 2, db, sb, bb);
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(N, p.nt));
+    return launch_tc<0>(ma, mb, p, grid, st);
+}
+
+// ------------------------------------------------------------------ small transposes into scratch
+// dst[c][r] = src[r][c]   (rows x cols -> cols x rows), 32x32 smem tiles
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                        int rows, int cols, int64_t src_pitch, int64_t dst_pitch) {
+    __shared__ float t[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        t[i][tx] = (r < rows && c < cols) ? src[(int64_t)r * src_pitch + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < cols && r < rows) dst[(int64_t)c * dst_pitch + r] = t[tx][i];
+    }
+}
+
+static int transpose_async(const float* src, float* dst, int rows, int cols, int64_t src_pitch, int64_t dst_pitch,
+                           cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    transpose_kernel<<<grid, 256, 0, st>>>(src, dst, rows, cols, src_pitch, dst_pitch);
+    UOCR_LAUNCHED("transpose");
+    return UOCR_OK;
+}
+
+struct Scratch {                     // stream-ordered scratch from the device pool
+    void* ptr = nullptr;
+    cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(&ptr, bytes, st);
+        if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); ptr = nullptr; return UOCR_ERR_CUDA; }
+        return UOCR_OK;
+    }
+    ~Scratch() { if (ptr) cudaFreeAsync(ptr, st); }
+};
+
+// ------------------------------------------------------------------ FullyConnected
+int fc_fwd_fast(int math_mode, const float* x, const float* w, float* y, int64_t batch, int64_t n_in,
+                int64_t n_out, int act, float alpha, cudaStream_t st) {
+    if (math_mode != UOCR_MATH_TF32) return UOCR_ERR_UNSUPPORTED;
+    if (n_in % 4 || batch < 128 || n_in < 32 || n_out < 16) return UOCR_ERR_UNSUPPORTED;
+    if (!encode_tiled()) return UOCR_ERR_UNSUPPORTED;
+    // W (n_in + 1, n_out) is N-major: transpose the weight rows to Wt (n_out, n_in); the bias row stays
+    Scratch wt(st);
+    int rc = wt.alloc(sizeof(float) * n_out * n_in);
+    if (rc) return rc;
+    rc = transpose_async(w, (float*)wt.ptr, (int)n_in, (int)n_out, n_out, n_in, st);
+    if (rc) return rc;
+    return tc_gemm_tn(x, n_in, (const float*)wt.ptr, n_in, y, n_out, batch, n_out, n_in, w + n_in * n_out, act,
+                      alpha, 0, st);
+}
+
+int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, float* dx, float* dw,
+                int64_t batch, int64_t n_in, int64_t n_out, int accumulate, cudaStream_t st) {
+    if (math_mode != UOCR_MATH_TF32) return UOCR_ERR_UNSUPPORTED;
+    if (n_out % 4 || batch < 128 || n_out < 32 || n_in < 16 || !encode_tiled()) return UOCR_ERR_UNSUPPORTED;
+    // dx = dy . W[:-1]^T : A = dy (batch, n_out) K-major; B^T = W[:-1] (n_in, n_out) is already K-major
+    if (dx) {
+        int rc = tc_gemm_tn(dy, n_out, w, n_out, dx, n_in, batch, n_in, n_out, nullptr, UOCR_ACT_NONE, 0.f, 0, st);
+        if (rc) return rc;
+    }
+    // dW = [x, 1]^T . dy reduces over the batch (both operands batch-major): FP32 split-K SGEMM
+    GemmArgs q{};
+    q.A = x; q.lda = n_in; q.B = dy; q.ldb = n_out; q.C = dw; q.ldc = n_out;
+    q.M = n_in + 1; q.N = n_out; q.K = batch; q.accumulate = accumulate; q.a_ones_m = n_in;
+    const int64_t tiles = ceil_div(q.M, 64) * ceil_div(q.N, 64);
+    int64_t splitk = (148 * 2 + tiles - 1) / tiles;
+    const int64_t max_split = ceil_div(batch, 128);
+    if (splitk > max_split) splitk = max_split;
+    if (splitk < 1) splitk = 1;
+    return sgemm_fp32(q, true, false, (int)splitk, st);
+}
+
+// ------------------------------------------------------------------ Convolutional2D forward
+// implicit GEMM: M = N*Ho*Wo pixels (tiles of 128 consecutive ox), N = Cout, K = kh*kw*Cin
+int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
+                cudaStream_t st) {
+    if (g.cin % TC_BK || g.sw != 1 || g.padding_value != 0.f || g.ups != 1) return UOCR_ERR_UNSUPPORTED;
+    if (g.cout % 16 || g.cout > 256 || g.cout < 16) return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || !encode_tiled()) return UOCR_ERR_UNSUPPORTED;
+    const int K = g.kh * g.kw * g.cin;
+    Scratch wt(st);
+    int rc = wt.alloc(sizeof(float) * (size_t)K * g.cout);
+    if (rc) return rc;
+    rc = transpose_async(w, (float*)wt.ptr, K, g.cout, g.cout, K, st);       // (K, Cout) -> (Cout, K)
+    if (rc) return rc;
+    TcParams p{};
+    p.C = y; p.ldc = g.cout; p.M = (int64_t)g.n * g.ho * g.wo; p.N = g.cout;
+    p.cblocks = g.cin / TC_BK;
+    p.num_kb = g.kh * g.kw * p.cblocks;
+    p.nt = g.cout;
+    p.bias = g.bias ? b : nullptr; p.act = act; p.alpha = alpha; p.accumulate = 0;
+    p.ho = g.ho; p.wo = g.wo; p.sh = g.sh; p.ph = g.ph; p.pw = g.pw; p.kw = g.kw;
+    p.xtiles = (g.wo + TC_BM - 1) / TC_BM;
+    CUtensorMap ma, mb;
+    const uint64_t da[4] = {(uint64_t)g.cin, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.n};
+    const uint64_t sa[3] = {(uint64_t)g.cin * 4, (uint64_t)g.w * g.cin * 4, (uint64_t)g.h * g.w * g.cin * 4};
+    const uint32_t ba[4] = {TC_BK, TC_BM, 1, 1};
+    rc = make_tmap(&ma, x, 4, da, sa, ba);
+    if (rc) return rc;
+    const uint64_t db[2] = {(uint64_t)K, (uint64_t)g.cout}, sb[1] = {(uint64_t)K * 4};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)g.cout};
+    rc = make_tmap(&mb, wt.ptr, 2, db, sb, bb);
+    if (rc) return rc;
+    const int64_t tiles = (int64_t)g.n * g.ho * p.xtiles;
+    if (tiles > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)tiles, 1);
+    return launch_tc<1>(ma, mb, p, grid, st);
 }
 
 }  // namespace uocr
