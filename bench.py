@@ -400,7 +400,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='tiles per GPU per step')
-    ap.add_argument('--math', default=os.environ.get('UOCR_MATH', 'fp32'), choices=['fp32', 'tf32'])
+    ap.add_argument('--math', default=os.environ.get('UOCR_MATH', 'tf32'), choices=['fp32', 'tf32'],
+                    help='tf32: tcgen05 TF32 kernels for the dense contractions (default); fp32: FFMA check mode')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -62,11 +62,14 @@ int uocr_get_device(int* device);
 int uocr_device_info(int device, char* name, size_t name_len, int* sm_count,
                      int* cc_major, int* cc_minor, size_t* total_mem, size_t* free_mem);
 
-/* stream-ordered pooled allocation (cudaMallocAsync on the device's default mempool with the
- * release threshold lifted): replaces CuPy's memory pool behind cupy.asarray / cp.zeros
- * (gpu.py:18-22, layers.py:12-13). */
+/* caching device allocator: uocr_free parks the block in a per-(device, stream) free list and
+ * uocr_malloc reuses a parked block of the same size class for work queued later on the SAME
+ * stream (stream order = reuse order), so steady-state steps never call the driver.  Replaces
+ * CuPy's memory pool behind cupy.asarray / cp.zeros (gpu.py:18-22, layers.py:12-13). */
 int uocr_malloc(void** ptr, size_t bytes, void* stream);
 int uocr_free(void* ptr, void* stream);
+int uocr_mempool_trim(void);                        /* cudaFree every parked block (synchronises) */
+int uocr_mempool_reserved(size_t* bytes);           /* bytes obtained from cudaMalloc so far */
 int uocr_host_alloc(void** ptr, size_t bytes);      /* pinned host memory */
 int uocr_host_free(void* ptr);
 int uocr_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream);   /* CP.copy     gpu.py:18-22 */

@@ -15,6 +15,11 @@ extern std::atomic<uint64_t> g_launches;
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// caching device allocator (runtime.cu); also used for library-internal scratch
+int pool_alloc(void** ptr, size_t bytes, cudaStream_t st);
+int pool_free(void* ptr, cudaStream_t st);
+int pool_trim();
+
 constexpr int kThreads = 256;
 
 // grid size for a grid-stride elementwise kernel: enough CTAs to fill 148 SMs a few times over,

@@ -4,7 +4,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <map>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -20,19 +22,88 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---------------------------------------------------------------- caching device allocator
+// The layer stack allocates the same few dozen tensor sizes every step.  cudaMallocAsync's pool
+// showed multi-millisecond slow paths in steady state (fresh physical mappings), so libuocr keeps
+// its own size-keyed free lists per (device, stream): uocr_free() parks the block, uocr_malloc()
+// returns a parked block of the same rounded size (or up to 1/8 larger) without touching the
+// driver.  Reuse is safe because a parked block is only handed out to work queued LATER on the
+// SAME stream it was freed on (stream order = reuse order).  Misses fall through to cudaMalloc.
+struct PoolKey {
+    int dev;
+    cudaStream_t st;
+    bool operator<(const PoolKey& o) const { return dev != o.dev ? dev < o.dev : st < o.st; }
+};
 static std::mutex g_pool_mutex;
-static bool g_pool_ready[64] = {false};
+static std::map<PoolKey, std::multimap<size_t, void*>> g_free;      // parked blocks by size
+static std::unordered_map<void*, std::pair<size_t, int>> g_live;    // ptr -> (rounded size, device)
+static size_t g_reserved = 0;
 
-// lift the release threshold once per device so freed blocks stay cached in the pool
-static int ensure_pool(int dev) {
-    if (dev < 0 || dev >= 64) return UOCR_OK;
+static size_t round_size(size_t bytes) {
+    if (bytes < 512) return 512;
+    if (bytes < (1u << 20)) return (bytes + 511) & ~(size_t)511;
+    return (bytes + ((1u << 16) - 1)) & ~(size_t)((1u << 16) - 1);       // 64 KiB granules above 1 MiB
+}
+
+int pool_alloc(void** ptr, size_t bytes, cudaStream_t st) {
+    *ptr = nullptr;
+    if (bytes == 0) return UOCR_OK;
+    int dev;
+    UOCR_CUDA(cudaGetDevice(&dev));
+    const size_t want = round_size(bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        auto& lst = g_free[PoolKey{dev, st}];
+        auto it = lst.lower_bound(want);
+        if (it != lst.end() && it->first <= want + want / 8) {
+            *ptr = it->second;
+            g_live[*ptr] = {it->first, dev};
+            lst.erase(it);
+            return UOCR_OK;
+        }
+    }
+    cudaError_t e = cudaMalloc(ptr, want);
+    if (e != cudaSuccess) {
+        // out of memory: drop every parked block and retry once
+        cudaGetLastError();
+        pool_trim();
+        e = cudaMalloc(ptr, want);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            *ptr = nullptr;
+            return UOCR_ERR_CUDA;
+        }
+    }
     std::lock_guard<std::mutex> lock(g_pool_mutex);
-    if (g_pool_ready[dev]) return UOCR_OK;
-    cudaMemPool_t pool;
-    UOCR_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t threshold = UINT64_MAX;
-    UOCR_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
-    g_pool_ready[dev] = true;
+    g_live[*ptr] = {want, dev};
+    g_reserved += want;
+    return UOCR_OK;
+}
+
+int pool_free(void* ptr, cudaStream_t st) {
+    if (!ptr) return UOCR_OK;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    auto it = g_live.find(ptr);
+    if (it == g_live.end()) {
+        set_error("uocr_free: pointer %p was not allocated by uocr_malloc", ptr);
+        return UOCR_ERR_INVALID;
+    }
+    g_free[PoolKey{it->second.second, st}].emplace(it->second.first, ptr);
+    g_live.erase(it);
+    return UOCR_OK;
+}
+
+int pool_trim() {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    cudaDeviceSynchronize();
+    for (auto& kv : g_free) {
+        for (auto& blk : kv.second) {
+            cudaFree(blk.second);
+            g_reserved -= blk.first;
+        }
+        kv.second.clear();
+    }
     return UOCR_OK;
 }
 
@@ -59,7 +130,7 @@ int uocr_device_count(int* count) {
 
 int uocr_set_device(int device) {
     UOCR_CUDA(cudaSetDevice(device));
-    return ensure_pool(device);
+    return UOCR_OK;
 }
 
 int uocr_get_device(int* device) {
@@ -94,19 +165,16 @@ int uocr_device_info(int device, char* name, size_t name_len, int* sm_count, int
 
 int uocr_malloc(void** ptr, size_t bytes, void* stream) {
     UOCR_REQUIRE(ptr, "ptr is NULL");
-    *ptr = nullptr;
-    if (bytes == 0) return UOCR_OK;
-    int dev;
-    UOCR_CUDA(cudaGetDevice(&dev));
-    int rc = ensure_pool(dev);
-    if (rc != UOCR_OK) return rc;
-    UOCR_CUDA(cudaMallocAsync(ptr, bytes, as_stream(stream)));
-    return UOCR_OK;
+    return pool_alloc(ptr, bytes, as_stream(stream));
 }
 
-int uocr_free(void* ptr, void* stream) {
-    if (!ptr) return UOCR_OK;
-    UOCR_CUDA(cudaFreeAsync(ptr, as_stream(stream)));
+int uocr_free(void* ptr, void* stream) { return pool_free(ptr, as_stream(stream)); }
+
+int uocr_mempool_trim(void) { return pool_trim(); }
+
+int uocr_mempool_reserved(size_t* bytes) {
+    UOCR_REQUIRE(bytes, "bytes is NULL");
+    *bytes = g_reserved;
     return UOCR_OK;
 }
 

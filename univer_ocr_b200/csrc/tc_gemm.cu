@@ -389,16 +389,12 @@ static int transpose_async(const float* src, float* dst, int rows, int cols, int
     return UOCR_OK;
 }
 
-struct Scratch {                     // stream-ordered scratch from the device pool
+struct Scratch {                     // stream-ordered scratch from libuocr's caching allocator
     void* ptr = nullptr;
     cudaStream_t st;
     explicit Scratch(cudaStream_t s) : st(s) {}
-    int alloc(size_t bytes) {
-        cudaError_t e = cudaMallocAsync(&ptr, bytes, st);
-        if (e != cudaSuccess) { set_error("cudaMallocAsync: %s", cudaGetErrorString(e)); ptr = nullptr; return UOCR_ERR_CUDA; }
-        return UOCR_OK;
-    }
-    ~Scratch() { if (ptr) cudaFreeAsync(ptr, st); }
+    int alloc(size_t bytes) { return pool_alloc(&ptr, bytes, st); }
+    ~Scratch() { if (ptr) pool_free(ptr, st); }
 };
 
 // ------------------------------------------------------------------ FullyConnected
