@@ -288,6 +288,8 @@ def run_b200(args):
                            'GBps': round(w_['bytes'] / (lms / 1e3) / 1e9, 1),
                            'TFLOPs': round(w_['flops'] / (lms / 1e3) / 1e12, 2)})
 
+    train = None if args.no_train else measure_train(args, dist, nn, my_model, models, dev_sets, rng, B, event)
+
     result = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': dist.world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -306,11 +308,65 @@ def run_b200(args):
         'roofline': roof,
         'layers': layers_out,
     }
+    if train is not None:
+        result['train'] = train
     if dist.rank == 0 and dist.world == 1 and not args.no_cpu_baseline:
         result['cpu_baseline'] = cpu_baseline(budget_s=args.cpu_budget, cores=1)
     if dist.rank == 0:
         print(json.dumps(result), flush=True)
     dist.close()
+
+
+def measure_train(args, dist, nn, my_model, models, dev_sets, rng, B, event):
+    """BASELINE configs[2]: one data-parallel training step of the four sub-networks (forward +
+    loss + backward + NCCL gradient allreduce + fused L2/Adam), batch B per GPU (weak scaling)."""
+    import ctypes as ct
+    from univer_ocr_b200._lib import launch_count, lib
+    from univer_ocr_b200.parallel import DataParallel
+    opt = nn.optimizers.Adam(lr=0.0015)
+    dps = {name: DataParallel(model, optimizer=opt) for name, model in models.items()}
+    inp = dev_sets[0]
+    targets = {
+        'monochrome': nn.CP.copy((rng.random((B, *PAGE_HW, 1), dtype=np.float32) < 0.2).astype(np.float32)),
+        'paragraph': nn.CP.copy((rng.random((B, *PAGE_HW, 1), dtype=np.float32) < 0.2).astype(np.float32)),
+        'line': nn.CP.copy((rng.random((B, *LINE_HW, 2), dtype=np.float32) < 0.2).astype(np.float32)),
+    }
+    onehot = np.zeros((B * CHAR_HW[1], my_model.N_CHARS), dtype=np.float32)
+    onehot[np.arange(onehot.shape[0]), rng.integers(0, my_model.N_CHARS, size=onehot.shape[0])] = 1
+    targets['char'] = nn.CP.copy(onehot)
+    feeds = {'monochrome': inp['page'], 'paragraph': inp['page'], 'line': inp['line'], 'char': inp['char']}
+    stream = nn.CP.stream()
+
+    def step():
+        out = {}
+        for name, dp in dps.items():
+            out[name] = dp.train(feeds[name], targets[name])
+        return out
+
+    for _ in range(3):
+        losses = step()
+    nn.CP.synchronize()
+    dist.barrier()
+    e0, e1 = event(), event()
+    launches0 = launch_count()
+    steps = max(2, min(args.steps, 5))
+    lib.uocr_event_record(e0, stream)
+    for _ in range(steps):
+        losses = step()
+    lib.uocr_event_record(e1, stream)
+    lib.uocr_event_sync(e1)
+    nn.CP.synchronize()
+    launches = launch_count() - launches0
+    dist.barrier()
+    ms = ct.c_float(0)
+    lib.uocr_event_elapsed_ms(e0, e1, ct.byref(ms))
+    ms_per_step = dist.max(ms.value / steps)
+    n_params = sum(dp.flat.total for dp in dps.values())
+    return {'metric': 'my_model train-step images/sec (fwd + loss + bwd + grad allreduce + L2 + Adam of all four sub-networks)',
+            'value': B * dist.world / (ms_per_step / 1e3), 'unit': UNIT, 'ms_per_step': ms_per_step,
+            'steps': steps, 'batch_per_gpu': B, 'global_batch': B * dist.world,
+            'allreduce_bytes_per_step': 4 * n_params if dist.world > 1 else 0, 'gpu_launches': int(launches),
+            'losses': {k: float(v['output_losses'][0]) for k, v in losses.items()}}
 
 
 # ------------------------------------------------------------------------------ CPU arms
@@ -404,6 +460,7 @@ def main():
                     help='tf32: tcgen05 TF32 kernels for the dense contractions (default); fp32: FFMA check mode')
     ap.add_argument('--cpu-budget', type=float, default=15.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':

@@ -461,3 +461,26 @@ def test_conv_pair_and_upsample_fusion_edges(nn):
         lib.uocr_conv2d_fwd(ctypes.byref(desc), dx.ptr, dw.ptr, db.ptr, y.ptr, ACT_LEAKY, 0.01,
                             nn.CP.stream())
         close(y, want, 1e-4, 2e-6, f'ups+conv {(n, h, w, cin, cout)}')
+
+
+@pytest.mark.parametrize('name', list(MODEL_SHAPES))
+def test_fused_data_parallel_step_matches_model_train(nn, golden, name):
+    """parallel.DataParallel (flat parameter buffers, one fused L2+Adam kernel per group, one
+    gradient memset) must reproduce Model.train: same golden losses and updated weights."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.parallel import DataParallel
+    g = golden('models').case(name)
+    w0 = np_models.golden_weights(name, g['seed'])
+    opt = nn.optimizers.Adam(lr=0.0015)
+    model = my_model.MAKERS[name](MODEL_SHAPES[name], optimizer=opt)
+    model.set_weights({k: {n: f32(v).tolist() for n, v in p.items()} for k, p in w0.items()})
+    dp = DataParallel(model, optimizer=opt)
+    for step in (1, 2):
+        losses = dp.train(g['X'], g['y'])
+        assert same_scalar(losses['output_losses'][0], g[f'loss{step}'], 2e-5)
+        assert same_scalar(losses['regularization_loss'], g[f'reg{step}'], 2e-5)
+    for key, param in model.params().items():
+        tag = f'after__{key.replace("/", ".")}'
+        v = host(param.value).ravel()
+        np.testing.assert_allclose(v[g[f'{tag}__idx']], g[f'{tag}__val'], rtol=1e-3, atol=1e-5, err_msg=key)
+    close(model.predict(g['X'])[0], g['pred2'], 1e-3, 1e-5, 'pred2')

@@ -20,6 +20,16 @@ int pool_alloc(void** ptr, size_t bytes, cudaStream_t st);
 int pool_free(void* ptr, cudaStream_t st);
 int pool_trim();
 
+struct Scratch {                     // stream-ordered scratch from libuocr's caching allocator
+    void* ptr = nullptr;
+    cudaStream_t st;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    int alloc(size_t bytes) { return pool_alloc(&ptr, bytes, st); }
+    ~Scratch() { if (ptr) pool_free(ptr, st); }
+};
+
 constexpr int kThreads = 256;
 
 // grid size for a grid-stride elementwise kernel: enough CTAs to fill 148 SMs a few times over,

@@ -177,6 +177,7 @@ int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, con
     UOCR_SMALL(5, 5, 2, 2, 4, 4, 4, 4)       // Line down_2
     UOCR_SMALL(5, 5, 1, 1, 4, 4, 4, 4)       // Line up_*
     UOCR_SMALL(5, 5, 1, 1, 4, 2, 2, 4)       // Line end
+    UOCR_SMALL(5, 5, 1, 1, 2, 4, 4, 4)       // dgrad of Line end (2 -> 4 on flipped weights)
     UOCR_SMALL(5, 3, 2, 1, 1, 16, 16, 4)     // Char conv_1 (1 -> 64)
 #undef UOCR_SMALL
     return UOCR_ERR_UNSUPPORTED;
@@ -306,17 +307,6 @@ int conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const flo
         x, w1, b1, w2, b2, y, (int)n, (int)h, (int)w, c1, act1, alpha1, act2, alpha2);
     UOCR_LAUNCHED("conv3x3_pair_fwd");
     return UOCR_OK;
-}
-
-int conv_dgrad_fast(const ConvGeom&, int, const float*, const float*, float*, cudaStream_t) {
-    return UOCR_ERR_UNSUPPORTED;
-}
-
-size_t conv_wgrad_fast_workspace(const ConvGeom&, int) { return 0; }
-
-int conv_wgrad_fast(const ConvGeom&, int, const float*, const float*, float*, float*, int, float*,
-                    cudaStream_t) {
-    return UOCR_ERR_UNSUPPORTED;
 }
 
 }  // namespace uocr

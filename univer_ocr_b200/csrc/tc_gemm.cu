@@ -389,14 +389,6 @@ static int transpose_async(const float* src, float* dst, int rows, int cols, int
     return UOCR_OK;
 }
 
-struct Scratch {                     // stream-ordered scratch from libuocr's caching allocator
-    void* ptr = nullptr;
-    cudaStream_t st;
-    explicit Scratch(cudaStream_t s) : st(s) {}
-    int alloc(size_t bytes) { return pool_alloc(&ptr, bytes, st); }
-    ~Scratch() { if (ptr) pool_free(ptr, st); }
-};
-
 // ------------------------------------------------------------------ FullyConnected
 int fc_fwd_fast(int math_mode, const float* x, const float* w, float* y, int64_t batch, int64_t n_in,
                 int64_t n_out, int act, float alpha, cudaStream_t st) {

@@ -266,7 +266,9 @@ class Model(BaseModel):
 
     # ---- execution ----------------------------------------------------------------
     @track_method('forward')
-    def forward(self, inputs, training=True):
+    def forward(self, inputs, training=True, clear_grads=True):
+        """`clear_grads=False` skips the reference's per-layer `clear_grads()` before each layer's
+        forward (models.py:188) -- for callers that zero one flat gradient buffer themselves."""
         inputs = make_list_if_not(inputs)
         if not self.is_initialized:
             self.initialize_from_X(inputs)
@@ -280,11 +282,12 @@ class Model(BaseModel):
             if kind == 'layer':
                 name = step[1]
                 layer = self.layers[name]
-                layer.clear_grads()                                # reference :188
+                if clear_grads:
+                    layer.clear_grads()                            # reference :188
                 out = layer.forward([value_of(src) for src in self.relations[name]])
                 outputs[name] = out[0] if isinstance(out, list) else out
             elif kind == 'conv':
-                self._run_fused_conv(step, value_of, outputs, training)
+                self._run_fused_conv(step, value_of, outputs, training, clear_grads)
             else:
                 self._run_pair(step, value_of, outputs)
         for key in self._output_keys():
@@ -292,7 +295,7 @@ class Model(BaseModel):
         self.layers_outputs = outputs
         return [outputs[k] for k in range(self.outputs_count)]
 
-    def _run_fused_conv(self, step, value_of, outputs, training):
+    def _run_fused_conv(self, step, value_of, outputs, training, clear_grads=True):
         _, ups_name, conv_name, act_name = step
         first = ups_name if ups_name is not None else conv_name
         X = as_device(value_of(self.relations[first][0]))
@@ -300,8 +303,9 @@ class Model(BaseModel):
         act_layer = self.layers[act_name] if act_name is not None else None
         act, alpha = _act_code(act_layer) if act_layer is not None else (ACT_NONE, 0.0)
         tracked = [self.layers[n] for n in (ups_name, conv_name, act_name) if n is not None]
-        for layer in tracked:
-            layer.clear_grads()
+        if clear_grads:
+            for layer in tracked:
+                layer.clear_grads()
         last = tracked[-1]
         last.progress_tracker.start_tracking(last.name, 'forward')
         y = conv._forward(X, 0, act=act, alpha=alpha, in_upsample=2 if ups_name is not None else 1,
