@@ -221,6 +221,7 @@ def run_b200(args):
     value = B * dist.world / (ms_per_step / 1e3)
 
     # ---------------- end to end through the public API with host buffers (`e2e`) ----------------
+    # (a) synchronous call: H2D -> forward -> D2H -> sync, one batch at a time
     outs_host = None
 
     def e2e_step(hs):
@@ -234,13 +235,32 @@ def run_b200(args):
         nn.CP.synchronize()                                       # results are on the host
         return outs
 
-    for i in range(max(1, min(args.warmup, 3))):
+    for i in range(3):
         e2e_step(host_sets[i % n_sets])
     dist.barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         e2e_step(host_sets[i % n_sets])
+    sync_s = dist.max((time.perf_counter() - t0) / args.steps)
+    # (b) the pipelined public API (univer_ocr_b200.pipeline.InferencePipeline): H2D of batch i+1,
+    # forward of batch i and D2H of batch i-1 overlap on three streams; every batch is still
+    # uploaded from and downloaded to host memory inside the timed region, fill and drain included
+    from univer_ocr_b200.pipeline import InferencePipeline
+    pipe = InferencePipeline(step, depth=3)
+    for i in range(6):
+        pipe.submit(host_sets[i % n_sets], i)
+    for _ in pipe.drain():
+        pass
+    dist.barrier()
+    t0 = time.perf_counter()
+    delivered = 0
+    for i in range(args.steps):
+        if pipe.submit(host_sets[i % n_sets], i) is not None:
+            delivered += 1
+    for _ in pipe.drain():
+        delivered += 1
     e2e_s = dist.max((time.perf_counter() - t0) / args.steps)
+    assert delivered == args.steps
     dist.barrier()
     clocks = sampler.stop()
     h2d = sum(v.nbytes for v in host_sets[0].values())
@@ -302,7 +322,10 @@ def run_b200(args):
                    'l2_policy': 'inputs rotate over 2 resident sets (206 MB) and each step streams '
                                 '~3.3 GB of intermediates: working set >> 126 MB L2'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': e2e_s * 1e3, 'timing': 'host wall clock around H2D + forward + D2H + sync, max over ranks'},
+                'ms_per_step': e2e_s * 1e3,
+                'api': 'univer_ocr_b200.pipeline.InferencePipeline(depth=3): pinned host in -> H2D -> forward -> D2H -> pinned host out',
+                'timing': 'host wall clock over K submitted batches incl. pipeline fill and drain, max over ranks',
+                'sync_value': B * dist.world / sync_s, 'sync_ms_per_step': sync_s * 1e3},
         'gpu_launches': int(launches),
         'clocks': clocks,
         'roofline': roof,

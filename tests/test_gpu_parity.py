@@ -484,3 +484,26 @@ def test_fused_data_parallel_step_matches_model_train(nn, golden, name):
         v = host(param.value).ravel()
         np.testing.assert_allclose(v[g[f'{tag}__idx']], g[f'{tag}__val'], rtol=1e-3, atol=1e-5, err_msg=key)
     close(model.predict(g['X'])[0], g['pred2'], 1e-3, 1e-5, 'pred2')
+
+
+def test_inference_pipeline_matches_direct_predict(nn):
+    """pipeline.InferencePipeline (three streams, slots, events) returns, in order, exactly what a
+    synchronous predict returns for every submitted batch."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.pipeline import InferencePipeline
+    np.random.seed(3)
+    model = my_model.make_line((4, 32, 64, 1))
+    rng = np.random.default_rng(12)
+    batches = []
+    for _ in range(7):
+        buf = nn.CP.pinned_empty((4, 32, 64, 1), np.float32)
+        buf[...] = rng.uniform(size=buf.shape)
+        batches.append({'x': buf})
+    want = [model.predict(np.asarray(b['x']))[0].get() for b in batches]
+    pipe = InferencePipeline(lambda inp: model.predict(inp['x']), depth=3)
+    got = {}
+    for tag, outs in pipe.run(batches):
+        got[tag] = outs[0].copy()
+    assert sorted(got) == list(range(7))
+    for i in range(7):
+        assert np.array_equal(got[i], want[i]), i

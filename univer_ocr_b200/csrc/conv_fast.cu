@@ -157,6 +157,139 @@ static int launch_small_fwd(const ConvGeom& g, int ups, const float* x, const fl
     return UOCR_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Cin == 1 forward stencil with a shared-memory input tile (Paragraph's five 5x5 1->1 layers,
+// Monochrome conv_1, Line down_1, Char conv_1).  These layers move 4-8 bytes per 25-50 FMA and are
+// HBM-bound; the register-strip kernel above reaches them through strided per-thread L1 loads
+// (8 cache lines per warp load).  Here the CTA stages the (TH*SH + KH - SH) x (TW*SW + KW - SW)
+// input tile with fully coalesced loads (border = padding_value, optional x2 upsample folded into
+// the tile fill), then every thread reads its window as aligned 128-bit shared loads:
+// warp = one output row of the tile, lane = PX consecutive outputs.
+// ------------------------------------------------------------------------------------------
+template <int KH, int KW, int SH, int SW, int COT, int PX, int UPS>
+__global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const float* __restrict__ x,
+                                                          const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ y,
+                                                          int act, float alpha) {
+    constexpr int TH = 8, TW = 32 * PX;
+    constexpr int IH = (TH - 1) * SH + KH;
+    constexpr int NIN = (PX - 1) * SW + KW;
+    constexpr int NV = (NIN + 3) / 4;                        // float4 loads per window row
+    constexpr int IWP = (((TW - 1) * SW + KW) + 3 + 4) / 4 * 4;   // pitch: whole float4s past the last window
+    extern __shared__ __align__(16) float s_mem[];
+    float* s_in = s_mem;                                     // [IH][IWP]
+    float* s_w = s_mem + IH * IWP;                           // [KH*KW][cout]
+    const int cout = g.cout;
+    const int chunks = cout / COT;
+    const int n = blockIdx.z / chunks, chunk = blockIdx.z % chunks;
+    const int co0 = chunk * COT;
+    const int oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
+    const int iy0 = oy0 * SH - g.ph, ix0 = ox0 * SW - g.pw;
+    const int hp = g.h / UPS, wp = g.w / UPS;
+    const float* xim = x + (int64_t)n * hp * wp;
+
+    for (int i = threadIdx.x; i < KH * KW * cout; i += 256) s_w[i] = w[i];
+    for (int i = threadIdx.x; i < IH * IWP; i += 256) {
+        const int r = i / IWP, c = i - r * IWP;
+        const int iy = iy0 + r, ix = ix0 + c;
+        float v = g.padding_value;
+        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = __ldg(xim + (int64_t)(iy / UPS) * wp + ix / UPS);
+        s_in[i] = v;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int oy = oy0 + ty, oxl = ox0 + lane * PX;
+    if (oy >= g.ho || oxl >= g.wo) return;
+
+    float acc[PX][COT];
+#pragma unroll
+    for (int p = 0; p < PX; ++p)
+#pragma unroll
+        for (int c = 0; c < COT; ++c) acc[p][c] = 0.f;
+
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+        const float4* row = reinterpret_cast<const float4*>(s_in + (ty * SH + ky) * IWP + lane * PX * SW);
+        float xin[NV * 4];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 t = row[v];
+            xin[4 * v] = t.x; xin[4 * v + 1] = t.y; xin[4 * v + 2] = t.z; xin[4 * v + 3] = t.w;
+        }
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx) {
+            const float* wp_ = s_w + (ky * KW + kx) * cout + co0;
+            float wr[COT];
+            if (COT % 4 == 0) {
+#pragma unroll
+                for (int c = 0; c < COT; c += 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(wp_ + c);
+                    wr[c] = t.x; wr[c + 1] = t.y; wr[c + 2] = t.z; wr[c + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < COT; ++c) wr[c] = wp_[c];
+            }
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                for (int c = 0; c < COT; ++c) acc[p][c] = fmaf(xin[p * SW + kx], wr[c], acc[p][c]);
+        }
+    }
+
+    float bias[COT];
+#pragma unroll
+    for (int c = 0; c < COT; ++c) bias[c] = g.bias ? __ldg(b + co0 + c) : 0.f;
+    float* yrow = y + (((int64_t)n * g.ho + oy) * g.wo + oxl) * cout + co0;
+    if (COT == 1 && cout == 1 && PX == 4 && (g.wo & 3) == 0) {
+        float4 t;
+        t.x = apply_act(acc[0][0] + bias[0], act, alpha);
+        t.y = apply_act(acc[1][0] + bias[0], act, alpha);
+        t.z = apply_act(acc[2][0] + bias[0], act, alpha);
+        t.w = apply_act(acc[3][0] + bias[0], act, alpha);
+        *reinterpret_cast<float4*>(yrow) = t;
+        return;
+    }
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+        if (oxl + p >= g.wo) break;
+        float* yp = yrow + (int64_t)p * cout;
+        if (COT % 4 == 0) {
+#pragma unroll
+            for (int c = 0; c < COT; c += 4) {
+                float4 t;
+                t.x = apply_act(acc[p][c] + bias[c], act, alpha);
+                t.y = apply_act(acc[p][c + 1] + bias[c + 1], act, alpha);
+                t.z = apply_act(acc[p][c + 2] + bias[c + 2], act, alpha);
+                t.w = apply_act(acc[p][c + 3] + bias[c + 3], act, alpha);
+                *reinterpret_cast<float4*>(yp + c) = t;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < COT; ++c) yp[c] = apply_act(acc[p][c] + bias[c], act, alpha);
+        }
+    }
+}
+
+template <int KH, int KW, int SH, int SW, int COT, int PX>
+static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float* w, const float* b, float* y,
+                         int act, float alpha, cudaStream_t st) {
+    constexpr int TH = 8, TW = 32 * PX;
+    constexpr int IH = (TH - 1) * SH + KH;
+    constexpr int IWP = (((TW - 1) * SW + KW) + 3 + 4) / 4 * 4;
+    const size_t smem = sizeof(float) * (IH * IWP + KH * KW * g.cout);
+    const int64_t gz = (int64_t)g.n * (g.cout / COT);
+    if (smem > 48 * 1024 || gz > 65535 || ceil_div(g.ho, TH) > 65535) return UOCR_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)ceil_div(g.wo, TW), (unsigned)ceil_div(g.ho, TH), (unsigned)gz);
+    if (ups == 2)
+        conv_c1_fwd_kernel<KH, KW, SH, SW, COT, PX, 2><<<grid, 256, smem, st>>>(g, x, w, b, y, act, alpha);
+    else
+        conv_c1_fwd_kernel<KH, KW, SH, SW, COT, PX, 1><<<grid, 256, smem, st>>>(g, x, w, b, y, act, alpha);
+    UOCR_LAUNCHED("conv_c1_fwd");
+    return UOCR_OK;
+}
+
 int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
                   const float* b, float* y, int act, float alpha, cudaStream_t st) {
     if (math_mode == UOCR_MATH_TF32) {
@@ -169,6 +302,18 @@ int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, con
     if (g.kh == KH_ && g.kw == KW_ && g.sh == SH_ && g.sw == SW_ && g.cin == CIN_ &&                 \
         g.cout % COUTMOD == 0 && g.cout >= COT_ && (COT_ != 1 || g.cout == 1) && (COT_ != 2 || g.cout == 2)) \
         return launch_small_fwd<KH_, KW_, SH_, SW_, CIN_, COT_, PX_>(g, ups, x, w, b, y, act, alpha, st);
+#define UOCR_C1(KH_, KW_, SH_, SW_, COUTMOD, COT_, PX_)                                              \
+    if (g.cin == 1 && g.kh == KH_ && g.kw == KW_ && g.sh == SH_ && g.sw == SW_ && g.cout % COUTMOD == 0 && \
+        (COT_ != 1 || g.cout == 1)) {                                                                   \
+        const int rc = launch_c1_fwd<KH_, KW_, SH_, SW_, COT_, PX_>(g, ups, x, w, b, y, act, alpha, st); \
+        if (rc != UOCR_ERR_UNSUPPORTED) return rc;                                                      \
+    }
+    UOCR_C1(5, 5, 1, 1, 1, 1, 4)             // Paragraph up_*, end
+    UOCR_C1(5, 5, 2, 2, 1, 1, 4)             // Paragraph down_*
+    UOCR_C1(5, 5, 2, 2, 4, 4, 4)             // Line down_1
+    UOCR_C1(3, 3, 1, 1, 16, 16, 4)           // Monochrome conv_1
+    UOCR_C1(5, 3, 2, 1, 16, 16, 4)           // Char conv_1
+#undef UOCR_C1
     UOCR_SMALL(3, 3, 1, 1, 1, 16, 16, 4)     // Monochrome conv_1
     UOCR_SMALL(3, 3, 1, 1, 16, 1, 1, 8)      // Monochrome conv_2
     UOCR_SMALL(5, 5, 1, 1, 1, 1, 1, 8)       // Paragraph up_*, end

@@ -1,0 +1,114 @@
+"""Host <-> device pipelining for page-sharded inference.
+
+The reference's PREDICT pipeline moves every batch host -> device -> host synchronously around
+each sub-model (`my_model/model.py:688-717`: `to_gpu`, model, `from_gpu`).  On a B200 the four
+forward passes of a 64-tile batch take ~1.6 ms while the PCIe copies of the same batch (104 MB
+in, 121 MB out) take longer than that, so the copies are overlapped with compute:
+
+    copy-in stream :  H2D(i+1)
+    compute stream :            forward(i)
+    copy-out stream:                        D2H(i-1)
+
+Each in-flight batch owns a *slot* (device input buffers + pinned host output buffers); CUDA
+events order the three streams per slot, the host only ever blocks on the D2H event of the slot
+it is about to reuse.  Results are delivered in submission order.
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib
+from .nn.gpu import CP, DeviceArray, stream as compute_stream
+
+
+def _new_stream():
+    s = ctypes.c_void_p()
+    lib.uocr_stream_create(ctypes.byref(s))
+    return s.value
+
+
+def _new_event():
+    e = ctypes.c_void_p()
+    lib.uocr_event_create(ctypes.byref(e))
+    return e.value
+
+
+class _Slot:
+    def __init__(self):
+        self.dev_in = None          # {name: DeviceArray}
+        self.host_out = None        # [pinned ndarray]
+        self.dev_out = None         # keeps the step's outputs alive until their D2H finished
+        self.ev_h2d, self.ev_comp, self.ev_d2h = _new_event(), _new_event(), _new_event()
+        self.busy = False
+        self.tag = None
+
+
+class InferencePipeline:
+    """`fn(dict of DeviceArray) -> sequence of DeviceArray`, fed with dicts of (preferably pinned)
+    host arrays of fixed shapes.
+
+        pipe = InferencePipeline(step_fn, depth=3)
+        for tag, outs in pipe.run(batches):      # outs: list of pinned host arrays (valid until
+            consume(outs)                         # `depth` further batches have been submitted)
+    """
+
+    def __init__(self, fn, depth=3):
+        self.fn = fn
+        self.depth = max(2, int(depth))
+        CP.use_gpu()
+        self.s_in, self.s_out = _new_stream(), _new_stream()
+        self.slots = [_Slot() for _ in range(self.depth)]
+        self.next = 0
+
+    def _retire(self, slot):
+        """Blocks until the slot's results are on the host and returns (tag, outputs)."""
+        lib.uocr_event_sync(slot.ev_d2h)
+        slot.busy = False
+        slot.dev_out = None
+        return slot.tag, slot.host_out
+
+    def submit(self, host_inputs, tag=None):
+        """Queues one batch; returns the (tag, outputs) of the batch that previously owned the
+        slot, or None while the pipeline is filling."""
+        slot = self.slots[self.next % self.depth]
+        self.next += 1
+        done = self._retire(slot) if slot.busy else None
+        if slot.dev_in is None:
+            slot.dev_in = {k: DeviceArray(v.shape, np.float32) for k, v in host_inputs.items()}
+        comp = compute_stream()
+        # copy-in: the previous forward that read these device buffers must have finished
+        lib.uocr_stream_wait_event(self.s_in, slot.ev_comp)
+        for k, v in host_inputs.items():
+            src = np.ascontiguousarray(v, dtype=np.float32)
+            assert src.shape == slot.dev_in[k].shape, f'{k}: {src.shape} != {slot.dev_in[k].shape}'
+            lib.uocr_memcpy_h2d(slot.dev_in[k].ptr, src.ctypes.data, src.nbytes, self.s_in)
+        lib.uocr_event_record(slot.ev_h2d, self.s_in)
+        # compute
+        lib.uocr_stream_wait_event(comp, slot.ev_h2d)
+        outs = list(self.fn(slot.dev_in))
+        lib.uocr_event_record(slot.ev_comp, comp)
+        # copy-out
+        if slot.host_out is None:
+            slot.host_out = [CP.pinned_empty(o.shape, np.float32) for o in outs]
+        lib.uocr_stream_wait_event(self.s_out, slot.ev_comp)
+        for o, h in zip(outs, slot.host_out):
+            lib.uocr_memcpy_d2h(h.ctypes.data, o.ptr, o.nbytes, self.s_out)
+        lib.uocr_event_record(slot.ev_d2h, self.s_out)
+        slot.dev_out, slot.busy, slot.tag = outs, True, tag
+        return done
+
+    def drain(self):
+        """Yields the results still in flight, in submission order."""
+        for i in range(self.next - self.depth, self.next):
+            if i < 0:
+                continue
+            slot = self.slots[i % self.depth]
+            if slot.busy:
+                yield self._retire(slot)
+
+    def run(self, batches):
+        for i, batch in enumerate(batches):
+            done = self.submit(batch, tag=i)
+            if done is not None:
+                yield done
+        yield from self.drain()
