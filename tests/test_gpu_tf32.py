@@ -70,7 +70,9 @@ def test_fc_tf32_rounding_is_unbiased(nn):
     ((3, 5, 256), 64, 64, (5, 3), (0, 1), (2, 1)),       # Char conv_3
     ((2, 14, 70), 64, 64, (5, 3), (0, 1), (2, 1)),       # ragged width (partial 128-pixel tile)
     ((2, 9, 131), 32, 48, (3, 3), (1, 1), (1, 1)),       # other channel counts / square kernel
-], ids=['char2', 'char3', 'ragged', 'c32_48'])
+    ((2, 11, 67), 32, 64, (3, 3), (1, 1), (1, 1)),       # Cin 32: four taps per wgrad CTA
+    ((1, 9, 40), 128, 32, (2, 3), (1, 1), (2, 1)),       # Cin 128: one tap per wgrad CTA, even kernel height
+], ids=['char2', 'char3', 'ragged', 'c32_48', 'c32_64', 'c128_32'])
 def test_conv_tf32(nn, shape, cin, cout, ks, pad, st):
     rng = np.random.default_rng(sum(shape) + cin)
     n, h, w = shape

@@ -131,6 +131,10 @@ static int launch_small_dgrad(const ConvGeom& g, const float* dy, const float* w
 
 int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const float* w, float* dx,
                     cudaStream_t st) {
+    if (math_mode == UOCR_MATH_TF32) {
+        const int rc = conv_dgrad_tc(g, dy, w, dx, st);
+        if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    }
     if (g.sh == 1 && g.sw == 1 && g.kh - 1 - g.ph >= 0 && g.kw - 1 - g.pw >= 0 &&
         (int64_t)g.kh * g.kw * g.cin * g.cout <= 4096) {
         // stride 1: forward stencil on the flipped / transposed weights
@@ -148,7 +152,6 @@ int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const flo
             rc = conv_fwd_general(t, dy, (const float*)wt.ptr, nullptr, dx, UOCR_ACT_NONE, 0.f, st);
         return rc;
     }
-    (void)math_mode;
 #define UOCR_DG(KH_, KW_, SH_, SW_, PW_, CIN_, COUT_, PX_)                                             \
     if (g.kh == KH_ && g.kw == KW_ && g.sh == SH_ && g.sw == SW_ && g.pw == PW_ && g.cin == CIN_ &&     \
         g.cout == COUT_)                                                                                \
@@ -344,7 +347,10 @@ static int launch_small_wgrad(const ConvGeom& g, const float* x, const float* dy
 
 int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const float* dy, float* dw, float* db,
                     int accumulate, float* ws, cudaStream_t st) {
-    (void)math_mode;
+    if (math_mode == UOCR_MATH_TF32) {
+        const int rc = conv_wgrad_tc(g, x, dy, dw, db, accumulate, st);
+        if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    }
     const SmallWgradPlan p = plan_small_wgrad(g);
     if (!p.ok || !ws) return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) return UOCR_ERR_UNSUPPORTED;

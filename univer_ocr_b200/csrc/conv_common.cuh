@@ -32,6 +32,10 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
 int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
                 cudaStream_t st);
 
+int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, float* dx, cudaStream_t st);
+int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* dy, float* dw, float* db, int accumulate,
+                  cudaStream_t st);
+
 // General kernels (conv.cu), exposed so the fast paths can delegate sub-problems.
 int conv_fwd_general(const ConvGeom& g, const float* x, const float* w, const float* b, float* y,
                      int act, float alpha, cudaStream_t st);

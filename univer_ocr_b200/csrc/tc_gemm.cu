@@ -62,14 +62,17 @@ static CUtensorMapDataType tmap_dtype() {
 
 // rank-`rank` fp32 tensor, dims innermost first, 128-byte swizzled boxes
 static int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+                     const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, bool mn_major = false) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable"); return UOCR_ERR_UNSUPPORTED; }
     cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = fn(map, tmap_dtype(), (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    // MN-major 32-bit operands must use the 32-byte-atom flavour of the 128B swizzle
+                    // (UMMA layout SWIZZLE_128B_BASE32B); K-major operands the plain 16-byte one
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UOCR_ERR_UNSUPPORTED; }
     return UOCR_OK;
@@ -148,30 +151,54 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// MN-major (the contraction index is the OUTER, strided index in memory).  For 32-bit operands the
+// only legal swizzle is SWIZZLE_128B_BASE32B: 128-byte rows of 32 contiguous MN elements whose
+// 32-byte chunks are XOR-ed with (row % 4); atom = 32 MN x 4 K-rows (512 B).  Canonical layout
+// ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in floats: MN blocks of 32 at LBO, 4-row K groups at SBO.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
+    return d;
+}
+
 constexpr int TC_BM = 128;           // UMMA M
-constexpr int TC_BK = 32;            // floats per stage along K = one 128-byte swizzle row
+constexpr int TC_BK = 32;            // contraction elements per stage
 constexpr int TC_THREADS = 192;
+constexpr int TC_BLK = 32 * 32 * 4;  // one MN-major 32 x 32 float block (4 KB)
+
+enum { TC_GEMM = 0, TC_CONV_FWD = 1, TC_CONV_DGRAD = 2, TC_GEMM_MN = 3, TC_CONV_WGRAD = 4 };
 
 struct TcParams {
     float* C; int64_t ldc;
     int64_t M, N;
-    int num_kb;                       // K blocks of 32
-    int nt;                           // N tile (multiple of 16, <= 256)
+    int num_kb;                       // K blocks of 32 (modes 0, 1; total for mode 3)
+    int nt;                           // N tile (multiple of 16 / 32 for MN-major, <= 256)
     int stages;
     const float* bias;                // length N or NULL
     int act; float alpha;
-    int accumulate;
-    // implicit-GEMM convolution (MODE 1)
-    int ho, wo, sh, ph, pw, kw, cblocks;   // cblocks = Cin / 32
-    int xtiles;                             // ceil(wo / 128)
+    int accumulate;                   // C += (plain read-modify-write)
+    int atomic;                       // C += through atomicAdd (split-K CTAs share the tile)
+    // implicit-GEMM convolution
+    int ho, wo, sh, ph, pw, kh, kw;
+    int cblocks;                      // channel blocks of 32 along the contraction (fwd: Cin, dgrad: Cout)
+    int xtiles;                       // ceil(row width / 128)
+    int h_in, w_in, cin;              // dgrad / wgrad: input tensor geometry
+    // split-K
+    int kb_per_split;
+    // conv wgrad
+    int ntaps, taps_per_cta, kbx, rows_total, rows_per_split;
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const TcParams p) {
+    constexpr bool MN = (MODE == TC_GEMM_MN || MODE == TC_CONV_WGRAD);
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: stages x (A 16 KB + B nt*128 B), then barriers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = TC_BM * TC_BK * 4;
     const uint32_t b_bytes = (uint32_t)p.nt * TC_BK * 4;
@@ -184,22 +211,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    // ---- tile coordinates
-    int64_t m0;                       // first output row of this tile (row index into C)
-    int64_t m_rows;                   // valid rows in this tile
-    int cn = 0, coy = 0, cx0 = 0;     // conv: image, output row, first output column
+    // ---- tile coordinates and this CTA's K-block list
+    int64_t m0 = 0;                   // first output row of this tile (row index into C)
+    int64_t m_rows = 0;               // valid rows in this tile
+    int cn = 0, crow = 0, cx0 = 0;    // conv: image, row (oy for fwd, iy for dgrad), first column
+    int num_kb = 0, kb0 = 0;
+    uint32_t ky_mask = 0;             // dgrad: kernel rows that hit this input row
+    int tap0 = 0, r0 = 0;             // wgrad
+    float* cbase = p.C;
     const int n0 = blockIdx.y * p.nt;
-    if (MODE == 0) {
+    if (MODE == TC_GEMM) {
         m0 = (int64_t)blockIdx.x * TC_BM;
         m_rows = min((int64_t)TC_BM, p.M - m0);
-    } else {
-        const int xt = blockIdx.x % p.xtiles;
-        const int row = blockIdx.x / p.xtiles;          // n * ho + oy
-        coy = row % p.ho;
-        cn = row / p.ho;
-        cx0 = xt * TC_BM;
+        num_kb = p.num_kb;
+    } else if (MODE == TC_CONV_FWD) {
+        const int xt = blockIdx.x % p.xtiles, row = blockIdx.x / p.xtiles;     // row = n * ho + oy
+        crow = row % p.ho; cn = row / p.ho; cx0 = xt * TC_BM;
         m0 = (int64_t)row * p.wo + cx0;
         m_rows = min(TC_BM, p.wo - cx0);
+        num_kb = p.num_kb;
+    } else if (MODE == TC_CONV_DGRAD) {
+        const int xt = blockIdx.x % p.xtiles, row = blockIdx.x / p.xtiles;     // row = n * h_in + iy
+        crow = row % p.h_in; cn = row / p.h_in; cx0 = xt * TC_BM;
+        m0 = (int64_t)row * p.w_in + cx0;
+        m_rows = min(TC_BM, p.w_in - cx0);
+        int nky = 0;
+        for (int ky = 0; ky < p.kh; ++ky) {
+            const int ty = crow + p.ph - ky;
+            if (ty >= 0 && ty % p.sh == 0 && ty / p.sh < p.ho) { ky_mask |= 1u << ky; ++nky; }
+        }
+        num_kb = nky * p.kw * p.cblocks;
+    } else if (MODE == TC_GEMM_MN) {
+        m0 = (int64_t)blockIdx.x * TC_BM;
+        m_rows = min((int64_t)TC_BM, p.M - m0);
+        kb0 = blockIdx.z * p.kb_per_split;
+        num_kb = min(p.kb_per_split, p.num_kb - kb0);
+    } else {
+        tap0 = blockIdx.x * p.taps_per_cta;
+        m_rows = min(TC_BM, (p.ntaps - tap0) * p.cin);
+        cbase = p.C + (int64_t)tap0 * p.cin * p.ldc;
+        r0 = blockIdx.z * p.rows_per_split;
+        num_kb = min(p.rows_per_split, p.rows_total - r0) * p.kbx;
     }
 
     uint32_t tmem_cols = 32;
@@ -226,59 +278,114 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            int d_ky = -1, d_left = 0;                       // dgrad: walk the set bits of ky_mask
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t phase = (kb / p.stages) & 1;
                 mbar_wait(smem_u32(&empty[s]), phase ^ 1);
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t sb = sa + a_bytes;
                 const uint32_t bar = smem_u32(&full[s]);
-                mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
-                if (MODE == 0) {
+                if (MODE == TC_GEMM) {
+                    mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
                     tma_load_2d(sa, &map_a, bar, kb * TC_BK, (int)m0);
-                } else {
+                    tma_load_2d(sb, &map_b, bar, kb * TC_BK, n0);
+                } else if (MODE == TC_CONV_FWD) {
+                    mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
                     const int tap = kb / p.cblocks, cb = kb % p.cblocks;
                     const int ky = tap / p.kw, kx = tap % p.kw;
-                    tma_load_4d(sa, &map_a, bar, cb * TC_BK, cx0 + kx - p.pw, coy * p.sh + ky - p.ph, cn);
+                    tma_load_4d(sa, &map_a, bar, cb * TC_BK, cx0 + kx - p.pw, crow * p.sh + ky - p.ph, cn);
+                    tma_load_2d(sb, &map_b, bar, kb * TC_BK, n0);
+                } else if (MODE == TC_CONV_DGRAD) {
+                    mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
+                    if (d_left == 0) {                       // next kernel row with the right parity
+                        do { ++d_ky; } while (!((ky_mask >> d_ky) & 1u));
+                        d_left = p.kw * p.cblocks;
+                    }
+                    const int within = p.kw * p.cblocks - d_left;
+                    --d_left;
+                    const int kx = within / p.cblocks, cb = within % p.cblocks;
+                    const int oy = (crow + p.ph - d_ky) / p.sh;
+                    // A: dy[n, oy, ix + pw - kx, co-block];  B: w[ky, kx, :, co-block] as (Cin rows, 32 cols)
+                    tma_load_4d(sa, &map_a, bar, cb * TC_BK, cx0 + p.pw - kx, oy, cn);
+                    tma_load_2d(sb, &map_b, bar, cb * TC_BK, (d_ky * p.kw + kx) * p.cin);
+                } else if (MODE == TC_GEMM_MN) {
+                    const int k = (kb0 + kb) * TC_BK;
+                    int nblk = 0;
+                    for (int i = 0; i < TC_BM / 32; ++i) nblk += (m0 + 32 * i < p.M);
+                    for (int j = 0; j < p.nt / 32; ++j) nblk += (n0 + 32 * j < p.N);
+                    mbar_arrive_expect_tx(bar, (uint32_t)nblk * TC_BLK);
+                    for (int i = 0; i < TC_BM / 32; ++i)
+                        if (m0 + 32 * i < p.M) tma_load_2d(sa + i * TC_BLK, &map_a, bar, (int)m0 + 32 * i, k);
+                    for (int j = 0; j < p.nt / 32; ++j)
+                        if (n0 + 32 * j < p.N) tma_load_2d(sb + j * TC_BLK, &map_b, bar, n0 + 32 * j, k);
+                } else {
+                    const int row = r0 + kb / p.kbx, ox0 = (kb % p.kbx) * TC_BK;      // row = n * ho + oy
+                    const int oy = row % p.ho, n = row / p.ho;
+                    const int cbl = p.cin / 32;
+                    int nblk = p.nt / 32;
+                    for (int i = 0; i < TC_BM / 32; ++i) nblk += (tap0 + i / cbl < p.ntaps);
+                    mbar_arrive_expect_tx(bar, (uint32_t)nblk * TC_BLK);
+                    for (int i = 0; i < TC_BM / 32; ++i) {
+                        const int tap = tap0 + i / cbl;
+                        if (tap >= p.ntaps) continue;
+                        const int ky = tap / p.kw, kx = tap % p.kw;
+                        tma_load_4d(sa + i * TC_BLK, &map_a, bar, (i % cbl) * 32, ox0 + kx - p.pw,
+                                    oy * p.sh + ky - p.ph, n);
+                    }
+                    for (int j = 0; j < p.nt / 32; ++j) tma_load_4d(sb + j * TC_BLK, &map_b, bar, j * 32, ox0, oy, n);
                 }
-                tma_load_2d(sb, &map_b, bar, kb * TC_BK, n0);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3, M >> 4
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) |
-                                   ((uint32_t)(TC_BM >> 4) << 24);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
+            // instruction descriptor: D = F32, A = B = TF32, N >> 3, M >> 4, major bits for MN-major operands
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (MN ? (1u << 15) | (1u << 16) : 0u) |
+                                   ((uint32_t)(p.nt >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % p.stages;
                 const uint32_t phase = (kb / p.stages) & 1;
                 mbar_wait(smem_u32(&full[s]), phase);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t da = make_kmajor_sw128_desc(sa);
-                const uint64_t db = make_kmajor_sw128_desc(sa + a_bytes);
+                if (!MN) {
+                    const uint64_t da = make_kmajor_sw128_desc(sa);
+                    const uint64_t db = make_kmajor_sw128_desc(sa + a_bytes);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k) {
-                    // advance 8 TF32 = 32 bytes inside the swizzled 128-byte row: +2 in the >>4 address field
-                    tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < TC_BK / 8; ++k)      // +32 bytes inside the swizzled 128-byte row
+                        tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                    (kb > 0 || k > 0) ? 1u : 0u);
+                } else {
+                    const uint64_t da = make_mnmajor_sw128_desc(sa, TC_BLK);
+                    const uint64_t db = make_mnmajor_sw128_desc(sa + a_bytes, TC_BLK);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)      // next 8 K-rows = next 1024-byte atom
+                        tc_mma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc,
+                                    (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 tc_commit(smem_u32(&empty[s]));             // frees the stage when these MMAs retire
             }
-            tc_commit(smem_u32(tmem_full));                  // accumulator complete
+            if (num_kb > 0) tc_commit(smem_u32(tmem_full)); // accumulator complete
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                              // TMEM lane quarter this warp may read
-        mbar_wait(smem_u32(tmem_full), 0);
-        tc_fence_after();
+        if (num_kb > 0) {
+            mbar_wait(smem_u32(tmem_full), 0);
+            tc_fence_after();
+        }
         const int r = q * 32 + lane;                         // row within the tile
         const bool row_ok = r < m_rows;
-        float* crow = p.C + (m0 + r) * p.ldc + n0;
+        float* crow_ptr = cbase + (m0 + r) * p.ldc + n0;
         for (int c0 = 0; c0 < p.nt; c0 += 32) {
             float v[32];
-            tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (num_kb > 0) {
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;     // no tap reaches this row (dgrad)
+            }
             if (!row_ok) continue;
             const int ncols = (int)min((int64_t)32, p.N - n0 - c0);
             if (ncols <= 0) continue;
@@ -289,8 +396,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
                     v[j] = apply_act(t, p.act, p.alpha);
                 }
             }
-            float* dst = crow + c0;
-            if (ncols == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            float* dst = crow_ptr + c0;
+            if (p.atomic) {
+                for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
+            } else if (ncols == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -323,12 +432,12 @@ template <int MODE>
 static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, dim3 grid, cudaStream_t st) {
     size_t smem = 0;
     p.stages = pick_stages(p.nt, &smem);
-    static bool configured[2] = {false, false};
-    if (!configured[MODE]) {
+    static bool configured = false;
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              220 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
-        configured[MODE] = true;
+        configured = true;
     }
     tc_gemm_kernel<MODE><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
     UOCR_LAUNCHED("tc_gemm_tf32");
@@ -360,7 +469,37 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
     rc = make_tmap(&mb, Bt, 2, db, sb, bb);
     if (rc) return rc;
     dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(N, p.nt));
-    return launch_tc<0>(ma, mb, p, grid, st);
+    return launch_tc<TC_GEMM>(ma, mb, p, grid, st);
+}
+
+// C[M,N] += At[K,M]^T . B[K,N]   (both operands stored with the contraction index K as the ROW index:
+// "MN-major"), split over K, partial tiles added with atomicAdd.  C must hold the value to add to.
+int tc_gemm_mn_atomic(const float* At, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                      int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+    if ((lda % 4) || (ldb % 4) || ((reinterpret_cast<uintptr_t>(At) | reinterpret_cast<uintptr_t>(B)) & 15))
+        return UOCR_ERR_UNSUPPORTED;
+    if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffff || K > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    TcParams p{};
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.num_kb = (int)ceil_div(K, TC_BK);
+    p.nt = N >= 256 ? 256 : (int)(((N + 31) / 32) * 32);
+    p.act = UOCR_ACT_NONE; p.atomic = 1;
+    const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, p.nt);
+    int64_t splits = (148 * 2 + tiles - 1) / tiles;
+    if (splits > p.num_kb / 4) splits = p.num_kb / 4;          // >= 4 K blocks per CTA
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    p.kb_per_split = (int)ceil_div(p.num_kb, splits);
+    splits = ceil_div(p.num_kb, p.kb_per_split);
+    CUtensorMap ma, mb;
+    const uint64_t da[2] = {(uint64_t)M, (uint64_t)K}, sa[1] = {(uint64_t)lda * 4};
+    const uint32_t box[2] = {32, TC_BK};
+    int rc = make_tmap(&ma, At, 2, da, sa, box, true);
+    if (rc) return rc;
+    const uint64_t db[2] = {(uint64_t)N, (uint64_t)K}, sb[1] = {(uint64_t)ldb * 4};
+    rc = make_tmap(&mb, B, 2, db, sb, box, true);
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(N, p.nt), (unsigned)splits);
+    return launch_tc<TC_GEMM_MN>(ma, mb, p, grid, st);
 }
 
 // ------------------------------------------------------------------ small transposes into scratch
@@ -405,25 +544,50 @@ int fc_fwd_fast(int math_mode, const float* x, const float* w, float* y, int64_t
                       alpha, 0, st);
 }
 
+// out[c] (+)= sum_r src[r][c] : bias gradients (the "ones" column of [x, 1]^T . dy)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, int64_t rows, int cols,
+                                                     float* __restrict__ out, int accumulate) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ty = threadIdx.x >> 5;
+    float s = 0.f;
+    if (c < cols)
+        for (int64_t r = ty; r < rows; r += 8) s += src[r * cols + c];
+    red[ty][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        out[c] = accumulate ? out[c] + t : t;
+    }
+}
+
+static int colsum_async(const float* src, int64_t rows, int cols, float* out, int accumulate, cudaStream_t st) {
+    colsum_kernel<<<(cols + 31) / 32, 256, 0, st>>>(src, rows, cols, out, accumulate);
+    UOCR_LAUNCHED("colsum");
+    return UOCR_OK;
+}
+
 int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, float* dx, float* dw,
                 int64_t batch, int64_t n_in, int64_t n_out, int accumulate, cudaStream_t st) {
     if (math_mode != UOCR_MATH_TF32) return UOCR_ERR_UNSUPPORTED;
-    if (n_out % 4 || batch < 128 || n_out < 32 || n_in < 16 || !encode_tiled()) return UOCR_ERR_UNSUPPORTED;
+    if (n_out % 4 || n_in % 4 || batch < 128 || n_out < 32 || n_in < 32 || !encode_tiled())
+        return UOCR_ERR_UNSUPPORTED;
     // dx = dy . W[:-1]^T : A = dy (batch, n_out) K-major; B^T = W[:-1] (n_in, n_out) is already K-major
     if (dx) {
         int rc = tc_gemm_tn(dy, n_out, w, n_out, dx, n_in, batch, n_in, n_out, nullptr, UOCR_ACT_NONE, 0.f, 0, st);
         if (rc) return rc;
     }
-    // dW = [x, 1]^T . dy reduces over the batch (both operands batch-major): FP32 split-K SGEMM
-    GemmArgs q{};
-    q.A = x; q.lda = n_in; q.B = dy; q.ldb = n_out; q.C = dw; q.ldc = n_out;
-    q.M = n_in + 1; q.N = n_out; q.K = batch; q.accumulate = accumulate; q.a_ones_m = n_in;
-    const int64_t tiles = ceil_div(q.M, 64) * ceil_div(q.N, 64);
-    int64_t splitk = (148 * 2 + tiles - 1) / tiles;
-    const int64_t max_split = ceil_div(batch, 128);
-    if (splitk > max_split) splitk = max_split;
-    if (splitk < 1) splitk = 1;
-    return sgemm_fp32(q, true, false, (int)splitk, st);
+    // dW[:-1] += x^T . dy : both operands are batch-major -> MN-major tensor-core GEMM, split over the batch
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (n_in + 1) * n_out, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+    }
+    int rc = tc_gemm_mn_atomic(x, n_in, dy, n_out, dw, n_out, n_in, n_out, batch, st);
+    if (rc) return rc;
+    // dW[-1] += column sums of dy (the bias row)
+    return colsum_async(dy, batch, (int)n_out, dw + n_in * n_out, 1, st);
 }
 
 // ------------------------------------------------------------------ Convolutional2D forward
@@ -460,7 +624,88 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
     const int64_t tiles = (int64_t)g.n * g.ho * p.xtiles;
     if (tiles > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)tiles, 1);
-    return launch_tc<1>(ma, mb, p, grid, st);
+    return launch_tc<TC_CONV_FWD>(ma, mb, p, grid, st);
+}
+
+// ------------------------------------------------------------------ Convolutional2D dgrad
+// implicit GEMM over the INPUT pixels: M = 128 consecutive ix of one input row, N = Cin,
+// K = (kernel rows that hit this row's parity) x kw x Cout.  A tiles are boxes of dy, B tiles are
+// the (Cin x 32) slabs of w[ky, kx] -- the weight tensor is already K-major for this product.
+int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, float* dx, cudaStream_t st) {
+    if (g.cout % TC_BK || g.sw != 1 || g.ups != 1 || g.kh > 31) return UOCR_ERR_UNSUPPORTED;
+    if (g.cin % 16 || g.cin > 256 || g.cin < 16) return UOCR_ERR_UNSUPPORTED;
+    if (((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(w)) & 15) || !encode_tiled())
+        return UOCR_ERR_UNSUPPORTED;
+    TcParams p{};
+    p.C = dx; p.ldc = g.cin; p.M = (int64_t)g.n * g.h * g.w; p.N = g.cin;
+    p.nt = g.cin; p.act = UOCR_ACT_NONE;
+    p.ho = g.ho; p.wo = g.wo; p.sh = g.sh; p.ph = g.ph; p.pw = g.pw; p.kh = g.kh; p.kw = g.kw;
+    p.cblocks = g.cout / TC_BK; p.cin = g.cin; p.h_in = g.h; p.w_in = g.w;
+    p.xtiles = (g.w + TC_BM - 1) / TC_BM;
+    CUtensorMap ma, mb;
+    const uint64_t da[4] = {(uint64_t)g.cout, (uint64_t)g.wo, (uint64_t)g.ho, (uint64_t)g.n};
+    const uint64_t sa[3] = {(uint64_t)g.cout * 4, (uint64_t)g.wo * g.cout * 4, (uint64_t)g.ho * g.wo * g.cout * 4};
+    const uint32_t ba[4] = {TC_BK, TC_BM, 1, 1};
+    int rc = make_tmap(&ma, dy, 4, da, sa, ba);
+    if (rc) return rc;
+    const uint64_t db[2] = {(uint64_t)g.cout, (uint64_t)g.kh * g.kw * g.cin}, sb[1] = {(uint64_t)g.cout * 4};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)g.cin};
+    rc = make_tmap(&mb, w, 2, db, sb, bb);
+    if (rc) return rc;
+    const int64_t tiles = (int64_t)g.n * g.h * p.xtiles;
+    if (tiles > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    return launch_tc<TC_CONV_DGRAD>(ma, mb, p, dim3((unsigned)tiles, 1), st);
+}
+
+// ------------------------------------------------------------------ Convolutional2D wgrad
+// dW[(tap, ci), co] += sum over pixels x[n, oy*sh+ky-ph, ox+kx-pw, ci] * dy[n, oy, ox, co]:
+// the contraction runs over pixels, which are the ROWS of both NHWC tensors -> MN-major operands.
+// One CTA owns 128 / Cin kernel taps (M = 128 rows of dW) and a slice of the (n, oy) rows; per
+// 32-pixel K block it fetches the shifted x boxes of its taps and the dy box, partial tiles are
+// added with atomicAdd.  db is a column sum of dy.  Requires zero padding (TMA zero fill).
+int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* dy, float* dw, float* db, int accumulate,
+                  cudaStream_t st) {
+    if (g.sw != 1 || g.ups != 1 || g.padding_value != 0.f) return UOCR_ERR_UNSUPPORTED;
+    if (!(g.cin == 32 || g.cin == 64 || g.cin == 128) || g.cout % 32 || g.cout > 256) return UOCR_ERR_UNSUPPORTED;
+    if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) || !encode_tiled())
+        return UOCR_ERR_UNSUPPORTED;
+    const int64_t kc = (int64_t)g.kh * g.kw * g.cin * g.cout;
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * kc, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+    }
+    TcParams p{};
+    p.C = dw; p.ldc = g.cout; p.N = g.cout; p.M = (int64_t)g.kh * g.kw * g.cin;
+    p.nt = g.cout; p.act = UOCR_ACT_NONE; p.atomic = 1;
+    p.ho = g.ho; p.wo = g.wo; p.sh = g.sh; p.ph = g.ph; p.pw = g.pw; p.kh = g.kh; p.kw = g.kw; p.cin = g.cin;
+    p.ntaps = g.kh * g.kw; p.taps_per_cta = TC_BM / g.cin;
+    p.kbx = (g.wo + TC_BK - 1) / TC_BK;
+    p.rows_total = g.n * g.ho;
+    const int tap_groups = (p.ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
+    int64_t splits = (148 * 2 + tap_groups - 1) / tap_groups;
+    if (splits > p.rows_total) splits = p.rows_total;
+    if (splits < 1) splits = 1;
+    p.rows_per_split = (int)ceil_div(p.rows_total, splits);
+    splits = ceil_div(p.rows_total, p.rows_per_split);
+    if (splits > 65535) return UOCR_ERR_UNSUPPORTED;
+    CUtensorMap ma, mb;
+    const uint32_t box[4] = {32, TC_BK, 1, 1};
+    const uint64_t da[4] = {(uint64_t)g.cin, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.n};
+    const uint64_t sa[3] = {(uint64_t)g.cin * 4, (uint64_t)g.w * g.cin * 4, (uint64_t)g.h * g.w * g.cin * 4};
+    int rc = make_tmap(&ma, x, 4, da, sa, box, true);
+    if (rc) return rc;
+    const uint64_t db_[4] = {(uint64_t)g.cout, (uint64_t)g.wo, (uint64_t)g.ho, (uint64_t)g.n};
+    const uint64_t sb[3] = {(uint64_t)g.cout * 4, (uint64_t)g.wo * g.cout * 4, (uint64_t)g.ho * g.wo * g.cout * 4};
+    rc = make_tmap(&mb, dy, 4, db_, sb, box, true);
+    if (rc) return rc;
+    rc = launch_tc<TC_CONV_WGRAD>(ma, mb, p, dim3((unsigned)tap_groups, 1, (unsigned)splits), st);
+    if (rc) return rc;
+    if (g.bias) return colsum_async(dy, (int64_t)g.n * g.ho * g.wo, g.cout, db, accumulate, st);
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(db, 0, sizeof(float) * g.cout, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+    }
+    return UOCR_OK;
 }
 
 }  // namespace uocr
