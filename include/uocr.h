@@ -148,10 +148,12 @@ int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, c
  * convolutions 1 -> c_mid -> 1 channels with the c_mid-channel intermediate kept in registers
  * (inference only: nothing is saved for a backward pass).   replaces: the conv_1 -> leaky_relu_1
  * -> conv_2 -> sigmoid chain of make_monochrome (my_model/model.py:119-122), i.e. four
- * layer calls of convolutional.py:62-99 / layers.py:390-415.   x, y: (N, H, W, 1). */
+ * layer calls of convolutional.py:62-99 / layers.py:390-415.   x, y: (N, H, W, 1).
+ * math_mode TF32 with c_mid == 16: the first convolution runs on the CUDA cores into a shared-memory
+ * tile laid out as a tcgen05 operand, the 16 -> 1 convolution as 18 tcgen05.mma per 128 pixels. */
 int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2,
                           const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
-                          int act1, float alpha1, int act2, float alpha2, void* stream);
+                          int act1, float alpha1, int act2, float alpha2, int math_mode, void* stream);
 
 /* dx = dgrad(dy, w) (overwrites dx).   replaces: _backward_gpu_kernel_dx + the crop of
  * convolutional.py:141-142 / :203-219,239-250. */

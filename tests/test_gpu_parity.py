@@ -447,7 +447,7 @@ def test_conv_pair_and_upsample_fusion_edges(nn):
         d = [nn.CP.copy(a) for a in (X, w1, b1, w2, b2)]
         y = nn.DeviceArray((n, h, w, 1))
         lib.uocr_conv3x3_pair_fwd(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, y.ptr, n, h, w, c1,
-                                  ACT_LEAKY, 0.01, ACT_SIGMOID, 0.0, nn.CP.stream())
+                                  ACT_LEAKY, 0.01, ACT_SIGMOID, 0.0, 0, nn.CP.stream())
         close(y, want, 1e-4, 2e-6, f'pair {(n, h, w, c1)}')
     for (n, h, w), cin, cout, pad in (((2, 7, 5), 1, 1, 2), ((1, 9, 13), 4, 4, 2), ((2, 6, 11), 4, 2, 2),
                                       ((1, 5, 4), 3, 5, 1)):

@@ -108,3 +108,32 @@ def test_char_model_tf32_matches_fp32(nn):
     err = np.max(np.abs(preds['tf32'] - preds['fp32'])) / np.max(np.abs(preds['fp32']))
     print('char tf32 vs fp32 max err / max', err)
     assert err < 2e-3
+
+
+def test_monochrome_pair_on_tensor_cores(nn):
+    """uocr_conv3x3_pair_fwd in TF32 mode (hidden tile on CUDA cores -> smem operand planes ->
+    tcgen05.mma for the 16 -> 1 convolution) vs the float64 oracle: |err| <= 1e-3 * max (outputs are
+    sigmoid values in (0, 1)) for aligned and ragged sizes, plus agreement with the FP32 pair kernel."""
+    import ctypes
+    from univer_ocr_b200._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
+    rng = np.random.default_rng(17)
+    for (n, h, w), act2 in (((2, 16, 256), ACT_SIGMOID), ((3, 21, 150), ACT_SIGMOID), ((1, 5, 3), ACT_NONE),
+                            ((2, 496, 736), ACT_SIGMOID)):
+        X = f32(rng.uniform(size=(n, h, w, 1)))
+        w1 = f32(rng.standard_normal((3, 3, 1, 16)) * 0.4)
+        b1 = f32(rng.standard_normal(16) * 0.2)
+        w2 = f32(rng.standard_normal((3, 3, 16, 1)) * 0.3)
+        b2 = f32(rng.standard_normal(1))
+        hid = O.leaky_relu_fwd(O.conv2d_fwd(X, w1, b1, 1), 0.01)
+        want = O.conv2d_fwd(hid, w2, b2, 1)
+        if act2 == ACT_SIGMOID:
+            want = O.sigmoid_fwd(want)
+        d = [nn.CP.copy(a) for a in (X, w1, b1, w2, b2)]
+        outs = []
+        for mode in (0, 1):
+            y = nn.DeviceArray((n, h, w, 1))
+            lib.uocr_conv3x3_pair_fwd(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, y.ptr, n, h, w, 16,
+                                      ACT_LEAKY, 0.01, act2, 0.0, mode, nn.CP.stream())
+            outs.append(np.asarray(y.get(), dtype=np.float64))
+        close_tf32(outs[1], want, f'tc pair {(n, h, w)}')
+        close_tf32(outs[1], outs[0], f'tc vs fp32 pair {(n, h, w)}')

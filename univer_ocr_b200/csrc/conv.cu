@@ -377,12 +377,17 @@ int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, c
 
 int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2,
                           const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
-                          int act1, float alpha1, int act2, float alpha2, void* stream) {
+                          int act1, float alpha1, int act2, float alpha2, int math_mode, void* stream) {
     UOCR_REQUIRE(x && w1 && b1 && w2 && b2 && y, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c_mid > 0 && c_mid <= 256, "bad dimension");
     UOCR_REQUIRE(h < (1 << 30) && w < (1 << 30), "dimension too large");
     UOCR_REQUIRE(act1 >= UOCR_ACT_NONE && act1 <= UOCR_ACT_SIGMOID && act2 >= UOCR_ACT_NONE &&
                      act2 <= UOCR_ACT_SIGMOID, "unknown activation");
+    if (math_mode == UOCR_MATH_TF32) {
+        const int rc = conv3x3_pair_tc(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,
+                                       as_stream(stream));
+        if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    }
     return conv3x3_pair_fwd(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,
                             as_stream(stream));
 }

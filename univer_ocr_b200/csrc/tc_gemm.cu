@@ -708,4 +708,198 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* dy, float* dw,
     return UOCR_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Monochrome pair on tensor cores: y = act2(conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2),
+// 1 -> 16 -> 1 channels (my_model/model.py:119-122), inference.
+//
+// The 16 -> 1 convolution holds half of the pair's 288 FMA / pixel.  As an implicit GEMM it is
+// M = 128 pixels of one output row, K = 9 taps x 16 channels, N = 1 (padded to the minimum UMMA
+// N = 16): 18 tcgen05.mma (128x16x8, 8 cycles each) per 128 pixels instead of 128 x 144 FFMA.
+// The CTA first evaluates the hidden tile ((TH+2) x 130 pixels x 16 channels) on the CUDA cores and
+// stores it in shared memory as four channel-quad PLANES of 16-byte pixel entries -- the K-major
+// no-swizzle canonical layout with a pixel stride of 16 B, so that "8 rows" are always 128
+// contiguous bytes (SBO = 128) and the channel quads are LBO = one plane apart.  Because the
+// layout is linear in the pixel index, the A operand of kernel tap (ky, kx) for output row r is the
+// SAME buffer addressed from pixel ((r + ky) * 130 + kx): no im2col copy, just a start address.
+// One accumulator (16 TMEM columns, column 0 meaningful) per output row; the epilogue reads
+// column 0 with tcgen05.ld.32x32b.x1 -- lane = pixel, so the stores are fully coalesced.
+// ------------------------------------------------------------------------------------------
+constexpr int PT_TH = 8;             // output rows per CTA
+constexpr int PT_TW = 128;           // output columns per CTA = UMMA M
+constexpr int PT_HP = PT_TW + 2;     // hidden tile width
+constexpr int PT_XP = 136;           // x tile pitch (>= PT_TW + 4)
+constexpr int PT_C1 = 16;
+constexpr int PT_PLANE = (PT_TH + 2) * PT_HP * 16;    // bytes per channel-quad plane
+
+__device__ __forceinline__ float round_tf32(float v) {        // the tensor core would truncate: round instead
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
+
+__device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo_bytes >> 4) << 16;               // K direction: next 16-byte chunk
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;               // M/N direction: next group of 8 rows
+    d |= (uint64_t)1 << 46;
+    return d;                                            // layout type 0: no swizzle
+}
+
+__global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
+    const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int H, int W, int act1,
+    float alpha1, int act2, float alpha2) {
+    extern __shared__ __align__(128) uint8_t pt_smem[];
+    float* s_h = reinterpret_cast<float*>(pt_smem);                                  // 4 planes
+    float* s_b = reinterpret_cast<float*>(pt_smem + 4 * PT_PLANE);                   // 36 chunks x 256 B
+    float* s_x = s_b + 36 * 64;                                                      // (TH+4) x XP
+    float* s_w1 = s_x + (PT_TH + 4) * PT_XP;                                         // 9*16 + 16
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_w1 + 160);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * PT_TW, y0 = blockIdx.y * PT_TH;
+    const float* xim = x + (int64_t)blockIdx.z * H * W;
+    float* yim = y + (int64_t)blockIdx.z * H * W;
+
+    // ---- phase 0: stage x tile, weights, the B operand; allocate TMEM
+    for (int i = tid; i < (PT_TH + 4) * PT_XP; i += 256) {
+        const int r = i / PT_XP, c = i - r * PT_XP;
+        const int gy = y0 - 2 + r, gx = x0 - 2 + c;
+        s_x[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xim + (int64_t)gy * W + gx) : 0.f;
+    }
+    for (int i = tid; i < 160; i += 256) s_w1[i] = i < 144 ? w1[i] : b1[i - 144];
+    for (int i = tid; i < 36 * 64; i += 256) {
+        // chunk q = tap * 4 + quad; 64 floats per chunk = 16 rows (n) x 4 floats; only n == 0 is real
+        const int q = i >> 6, within = i & 63;
+        s_b[i] = within < 4 ? round_tf32(w2[(q >> 2) * PT_C1 + (q & 3) * 4 + within]) : 0.f;
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    constexpr uint32_t TMEM_COLS = PT_TH * 16;          // 128
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- phase 1: hidden tile on the CUDA cores, strips of 5 pixels, 4 channels at a time
+    constexpr int STRIPS_PER_ROW = PT_HP / 5;           // 26
+    for (int s = tid; s < (PT_TH + 2) * STRIPS_PER_ROW; s += 256) {
+        const int r = s / STRIPS_PER_ROW, c0 = (s - r * STRIPS_PER_ROW) * 5;
+        const int hy = y0 - 1 + r;
+        float xw[3][7];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 7; ++b) xw[a][b] = s_x[(r + a) * PT_XP + c0 + b];
+        const bool row_in = hy >= 0 && hy < H;
+#pragma unroll
+        for (int quad = 0; quad < 4; ++quad) {
+            const float4 bq = *reinterpret_cast<const float4*>(s_w1 + 144 + quad * 4);
+            float acc[5][4];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) { acc[p][0] = bq.x; acc[p][1] = bq.y; acc[p][2] = bq.z; acc[p][3] = bq.w; }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 wq = *reinterpret_cast<const float4*>(s_w1 + t * PT_C1 + quad * 4);
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    const float xv = xw[t / 3][p + t % 3];
+                    acc[p][0] = fmaf(xv, wq.x, acc[p][0]);
+                    acc[p][1] = fmaf(xv, wq.y, acc[p][1]);
+                    acc[p][2] = fmaf(xv, wq.z, acc[p][2]);
+                    acc[p][3] = fmaf(xv, wq.w, acc[p][3]);
+                }
+            }
+            float4* plane = reinterpret_cast<float4*>(pt_smem + quad * PT_PLANE) + r * PT_HP + c0;
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const int hx = x0 - 1 + c0 + p;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);      // conv_2's zero padding outside the image
+                if (row_in && hx >= 0 && hx < W)
+                    o = make_float4(round_tf32(apply_act(acc[p][0], act1, alpha1)),
+                                    round_tf32(apply_act(acc[p][1], act1, alpha1)),
+                                    round_tf32(apply_act(acc[p][2], act1, alpha1)),
+                                    round_tf32(apply_act(acc[p][3], act1, alpha1)));
+                plane[p] = o;
+            }
+        }
+    }
+    // generic-proxy shared-memory writes must be visible to the tensor core's async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    // ---- phase 2: 18 MMAs per output row, issued by one thread
+    if (tid == 0) {
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t sh = smem_u32(s_h), sb = smem_u32(s_b);
+#pragma unroll 1
+        for (int r = 0; r < PT_TH; ++r) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const uint32_t pix = (uint32_t)((r + t / 3) * PT_HP + t % 3) * 16u;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const uint64_t da = make_kmajor_nosw_desc(sh + (uint32_t)(2 * m) * PT_PLANE + pix, PT_PLANE, 128);
+                    const uint64_t db = make_kmajor_nosw_desc(sb + (uint32_t)(t * 4 + 2 * m) * 256u, 256, 128);
+                    tc_mma_tf32(tmem_base + (uint32_t)(r * 16), da, db, idesc, (t > 0 || m > 0) ? 1u : 0u);
+                }
+            }
+        }
+        tc_commit(smem_u32(bar));
+    }
+
+    // ---- phase 3: epilogue, lane = pixel
+    mbar_wait(smem_u32(bar), 0);
+    tc_fence_after();
+    {
+        const int q = warp & 3, half = warp >> 2;
+        const int gx = x0 + q * 32 + lane;
+        const float bias2 = __ldg(b2);
+#pragma unroll
+        for (int rr = 0; rr < PT_TH / 2; ++rr) {
+            const int r = half * (PT_TH / 2) + rr;
+            uint32_t v;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];"
+                         : "=r"(v) : "r"(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(r * 16)) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int gy = y0 + r;
+            if (gy < H && gx < W) yim[(int64_t)gy * W + gx] = apply_act(__uint_as_float(v) + bias2, act2, alpha2);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+int conv3x3_pair_tc(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
+                    int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
+                    cudaStream_t st) {
+    if (c1 != PT_C1 || n > 65535 || ceil_div(h, PT_TH) > 65535) return UOCR_ERR_UNSUPPORTED;
+    const size_t smem = 4 * PT_PLANE + 36 * 256 + sizeof(float) * ((PT_TH + 4) * PT_XP + 160) + 16;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(w, PT_TW), (unsigned)ceil_div(h, PT_TH), (unsigned)n);
+    conv3x3_pair_tc_kernel<<<grid, 256, smem, st>>>(x, w1, b1, w2, b2, y, (int)h, (int)w, act1, alpha1, act2, alpha2);
+    UOCR_LAUNCHED("conv3x3_pair_tc");
+    return UOCR_OK;
+}
 }  // namespace uocr

@@ -18,7 +18,7 @@ replayed; no layer call synchronises the device, and loss values stay on the dev
 import ctypes
 
 from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
-from .gpu import DeviceArray, LazyScalar, as_device, stream
+from .gpu import CP, DeviceArray, LazyScalar, as_device, stream
 from .help_func import make_list_if_not
 from .layers import (BaseLayer, Convolutional2D, FromOutput, LeakyRelu, Sigmoid, Upsample2D)
 from .losses import SoftmaxCrossEntropy
@@ -330,7 +330,8 @@ class Model(BaseModel):
         last.progress_tracker.start_tracking(last.name, 'forward')
         y = DeviceArray((n, h, w, 1))
         lib.uocr_conv3x3_pair_fwd(X.ptr, c1.w.value.ptr, c1.b.value.ptr, c2.w.value.ptr, c2.b.value.ptr,
-                                  y.ptr, n, h, w, c1.out_channels, act1, alpha1, act2, alpha2, stream())
+                                  y.ptr, n, h, w, c1.out_channels, act1, alpha1, act2, alpha2, CP.math_mode,
+                                  stream())
         last.progress_tracker.stop_tracking(last.name, 'forward')
         for nme in (c1_name, a1_name, c2_name, a2_name):
             if nme is not None:
