@@ -5,10 +5,14 @@ Tolerance (north_star: 1e-3 relative with TF32): |got - want| <= 1e-3 * max|want
 and the mean signed relative error on an all-positive problem must be << 1e-3 (TF32 operands are
 ROUNDED to nearest by TMA, not truncated by the tensor core, so the error is unbiased).
 """
+import os
+
 import numpy as np
 import pytest
 
 from oracle import np_oracle as O
+
+os.environ['UOCR_PAIR_TC'] = '1'       # exercise the opt-in tensor-core Monochrome pair kernel too
 
 pytestmark = pytest.mark.gpu
 

@@ -7,6 +7,8 @@
 //                   db += bias * sum(dy)
 // These kernels handle EVERY geometry (any kernel size / padding / stride / channel count);
 // the shape-specialised fast paths (conv_fast.cu, tc_gemm.cu) are validated against them.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "conv_common.cuh"
 
@@ -383,7 +385,13 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
     UOCR_REQUIRE(h < (1 << 30) && w < (1 << 30), "dimension too large");
     UOCR_REQUIRE(act1 >= UOCR_ACT_NONE && act1 <= UOCR_ACT_SIGMOID && act2 >= UOCR_ACT_NONE &&
                      act2 <= UOCR_ACT_SIGMOID, "unknown activation");
-    if (math_mode == UOCR_MATH_TF32) {
+    // The tensor-core variant is correct but SLOWER than the CUDA-core pair kernel (1.32 ms vs 0.45 ms
+    // for 64 tiles of 496x736): with Cout = 1 the UMMA N dimension is 1-in-16 useful and every
+    // 128x16x8 MMA still reads a 4 KB A operand from shared memory (32 cycles), i.e. 32 useful
+    // MAC/cycle/SM against 128 FFMA/cycle/SM.  Kept opt-in (UOCR_PAIR_TC=1) as a measured negative
+    // result; see DESIGN.md.
+    static const bool pair_tc = [] { const char* e = getenv("UOCR_PAIR_TC"); return e && e[0] == '1'; }();
+    if (math_mode == UOCR_MATH_TF32 && pair_tc) {
         const int rc = conv3x3_pair_tc(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,
                                        as_stream(stream));
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;

@@ -746,7 +746,9 @@ __device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, ui
     return d;                                            // layout type 0: no swizzle
 }
 
-__global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
+constexpr int PT_THREADS = 288;      // warps 0-7: hidden tile + epilogue; warp 8: hidden tile + MMA issue
+
+__global__ void __launch_bounds__(PT_THREADS, 2) conv3x3_pair_tc_kernel(
     const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
     const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int H, int W, int act1,
     float alpha1, int act2, float alpha2) {
@@ -764,13 +766,13 @@ __global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
     float* yim = y + (int64_t)blockIdx.z * H * W;
 
     // ---- phase 0: stage x tile, weights, the B operand; allocate TMEM
-    for (int i = tid; i < (PT_TH + 4) * PT_XP; i += 256) {
+    for (int i = tid; i < (PT_TH + 4) * PT_XP; i += PT_THREADS) {
         const int r = i / PT_XP, c = i - r * PT_XP;
         const int gy = y0 - 2 + r, gx = x0 - 2 + c;
         s_x[i] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(xim + (int64_t)gy * W + gx) : 0.f;
     }
-    for (int i = tid; i < 160; i += 256) s_w1[i] = i < 144 ? w1[i] : b1[i - 144];
-    for (int i = tid; i < 36 * 64; i += 256) {
+    for (int i = tid; i < 160; i += PT_THREADS) s_w1[i] = i < 144 ? w1[i] : b1[i - 144];
+    for (int i = tid; i < 36 * 64; i += PT_THREADS) {
         // chunk q = tap * 4 + quad; 64 floats per chunk = 16 rows (n) x 4 floats; only n == 0 is real
         const int q = i >> 6, within = i & 63;
         s_b[i] = within < 4 ? round_tf32(w2[(q >> 2) * PT_C1 + (q & 3) * 4 + within]) : 0.f;
@@ -790,9 +792,10 @@ __global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // ---- phase 1: hidden tile on the CUDA cores, strips of 5 pixels, 4 channels at a time
+    // ---- phase 1: hidden tile on the CUDA cores; work item = (strip of 5 pixels, channel quad)
     constexpr int STRIPS_PER_ROW = PT_HP / 5;           // 26
-    for (int s = tid; s < (PT_TH + 2) * STRIPS_PER_ROW; s += 256) {
+    for (int item = tid; item < (PT_TH + 2) * STRIPS_PER_ROW * 4; item += PT_THREADS) {
+        const int quad = item & 3, s = item >> 2;
         const int r = s / STRIPS_PER_ROW, c0 = (s - r * STRIPS_PER_ROW) * 5;
         const int hy = y0 - 1 + r;
         float xw[3][7];
@@ -801,36 +804,33 @@ __global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
 #pragma unroll
             for (int b = 0; b < 7; ++b) xw[a][b] = s_x[(r + a) * PT_XP + c0 + b];
         const bool row_in = hy >= 0 && hy < H;
+        const float4 bq = *reinterpret_cast<const float4*>(s_w1 + 144 + quad * 4);
+        float acc[5][4];
 #pragma unroll
-        for (int quad = 0; quad < 4; ++quad) {
-            const float4 bq = *reinterpret_cast<const float4*>(s_w1 + 144 + quad * 4);
-            float acc[5][4];
+        for (int p = 0; p < 5; ++p) { acc[p][0] = bq.x; acc[p][1] = bq.y; acc[p][2] = bq.z; acc[p][3] = bq.w; }
 #pragma unroll
-            for (int p = 0; p < 5; ++p) { acc[p][0] = bq.x; acc[p][1] = bq.y; acc[p][2] = bq.z; acc[p][3] = bq.w; }
-#pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const float4 wq = *reinterpret_cast<const float4*>(s_w1 + t * PT_C1 + quad * 4);
-#pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    const float xv = xw[t / 3][p + t % 3];
-                    acc[p][0] = fmaf(xv, wq.x, acc[p][0]);
-                    acc[p][1] = fmaf(xv, wq.y, acc[p][1]);
-                    acc[p][2] = fmaf(xv, wq.z, acc[p][2]);
-                    acc[p][3] = fmaf(xv, wq.w, acc[p][3]);
-                }
-            }
-            float4* plane = reinterpret_cast<float4*>(pt_smem + quad * PT_PLANE) + r * PT_HP + c0;
+        for (int t = 0; t < 9; ++t) {
+            const float4 wq = *reinterpret_cast<const float4*>(s_w1 + t * PT_C1 + quad * 4);
 #pragma unroll
             for (int p = 0; p < 5; ++p) {
-                const int hx = x0 - 1 + c0 + p;
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);      // conv_2's zero padding outside the image
-                if (row_in && hx >= 0 && hx < W)
-                    o = make_float4(round_tf32(apply_act(acc[p][0], act1, alpha1)),
-                                    round_tf32(apply_act(acc[p][1], act1, alpha1)),
-                                    round_tf32(apply_act(acc[p][2], act1, alpha1)),
-                                    round_tf32(apply_act(acc[p][3], act1, alpha1)));
-                plane[p] = o;
+                const float xv = xw[t / 3][p + t % 3];
+                acc[p][0] = fmaf(xv, wq.x, acc[p][0]);
+                acc[p][1] = fmaf(xv, wq.y, acc[p][1]);
+                acc[p][2] = fmaf(xv, wq.z, acc[p][2]);
+                acc[p][3] = fmaf(xv, wq.w, acc[p][3]);
             }
+        }
+        float4* plane = reinterpret_cast<float4*>(pt_smem + quad * PT_PLANE) + r * PT_HP + c0;
+#pragma unroll
+        for (int p = 0; p < 5; ++p) {
+            const int hx = x0 - 1 + c0 + p;
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);          // conv_2's zero padding outside the image
+            if (row_in && hx >= 0 && hx < W)
+                o = make_float4(round_tf32(apply_act(acc[p][0], act1, alpha1)),
+                                round_tf32(apply_act(acc[p][1], act1, alpha1)),
+                                round_tf32(apply_act(acc[p][2], act1, alpha1)),
+                                round_tf32(apply_act(acc[p][3], act1, alpha1)));
+            plane[p] = o;
         }
     }
     // generic-proxy shared-memory writes must be visible to the tensor core's async proxy
@@ -839,8 +839,10 @@ __global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
     __syncthreads();
     tc_fence_after();
 
-    // ---- phase 2: 18 MMAs per output row, issued by one thread
-    if (tid == 0) {
+    // ---- phase 2: 18 MMAs per output row, issued by one lane of the dedicated warp 8 (its other
+    // lanes go straight to the final barrier; a lane spinning on the mbarrier in the SAME warp
+    // would starve the issuing lane)
+    if (warp == 8 && lane == 0) {
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
         const uint32_t sh = smem_u32(s_h), sb = smem_u32(s_b);
 #pragma unroll 1
@@ -859,10 +861,10 @@ __global__ void __launch_bounds__(256, 2) conv3x3_pair_tc_kernel(
         tc_commit(smem_u32(bar));
     }
 
-    // ---- phase 3: epilogue, lane = pixel
-    mbar_wait(smem_u32(bar), 0);
-    tc_fence_after();
-    {
+    // ---- phase 3: epilogue (warps 0-7), lane = pixel
+    if (warp < 8) {
+        mbar_wait(smem_u32(bar), 0);
+        tc_fence_after();
         const int q = warp & 3, half = warp >> 2;
         const int gx = x0 + q * 32 + lane;
         const float bias2 = __ldg(b2);
@@ -898,7 +900,7 @@ int conv3x3_pair_tc(const float* x, const float* w1, const float* b1, const floa
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(w, PT_TW), (unsigned)ceil_div(h, PT_TH), (unsigned)n);
-    conv3x3_pair_tc_kernel<<<grid, 256, smem, st>>>(x, w1, b1, w2, b2, y, (int)h, (int)w, act1, alpha1, act2, alpha2);
+    conv3x3_pair_tc_kernel<<<grid, PT_THREADS, smem, st>>>(x, w1, b1, w2, b2, y, (int)h, (int)w, act1, alpha1, act2, alpha2);
     UOCR_LAUNCHED("conv3x3_pair_tc");
     return UOCR_OK;
 }
