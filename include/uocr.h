@@ -155,6 +155,18 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
                           const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
                           int act1, float alpha1, int act2, float alpha2, int math_mode, void* stream);
 
+/* Backward of the same pair in TRAINING (y = conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2, the final
+ * activation handled by its own layer): dw1/db1/dw2/db2 (+)= parameter gradients, dx = input gradient
+ * (skipped when dx == NULL), from x and dy = dL/dy only -- the c_mid-channel hidden map is recomputed
+ * inside the kernels instead of being stored.   replaces: Convolutional2D._backward of conv_2 and
+ * conv_1 plus LeakyRelu._backward (convolutional.py:101-145, layers.py:399-401) and the saved
+ * (N,H,W,c_mid) activations they need.  act1: UOCR_ACT_LEAKY (alpha > 0) or UOCR_ACT_NONE. */
+int uocr_conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int32_t c_mid, size_t* bytes);
+int uocr_conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
+                          float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
+                          int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* dx = dgrad(dy, w) (overwrites dx).   replaces: _backward_gpu_kernel_dx + the crop of
  * convolutional.py:141-142 / :203-219,239-250. */
 int uocr_conv2d_dgrad(const uocr_conv2d_desc* d, const float* dy, const float* w, float* dx,

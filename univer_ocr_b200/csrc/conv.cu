@@ -400,6 +400,30 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
                             as_stream(stream));
 }
 
+int uocr_conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int32_t c_mid, size_t* bytes) {
+    UOCR_REQUIRE(bytes && n > 0 && h > 0 && w > 0 && c_mid > 0, "bad argument");
+    *bytes = conv3x3_pair_bwd_workspace(n, h, w, c_mid);
+    return UOCR_OK;
+}
+
+int uocr_conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
+                          float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
+                          int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    UOCR_REQUIRE(x && w1 && b1 && w2 && dy && dw1 && db1 && dw2 && db2, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c_mid > 0 && c_mid <= 256, "bad dimension");
+    UOCR_REQUIRE(h < (1 << 30) && w < (1 << 30), "dimension too large");
+    UOCR_REQUIRE(act1 == UOCR_ACT_NONE || (act1 == UOCR_ACT_LEAKY && alpha1 > 0.f),
+                 "the middle activation must be LeakyRelu (alpha > 0) or none");
+    const size_t need = conv3x3_pair_bwd_workspace(n, h, w, c_mid);
+    if (!workspace || workspace_bytes < need) {
+        set_error("pair backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return UOCR_ERR_WORKSPACE;
+    }
+    return conv3x3_pair_bwd(x, w1, b1, w2, dy, dx, dw1, db1, dw2, db2, n, h, w, c_mid, act1, alpha1, accumulate,
+                            (float*)workspace, as_stream(stream));
+}
+
 int uocr_conv2d_dgrad(const uocr_conv2d_desc* d, const float* dy, const float* w, float* dx,
                       void* stream) {
     ConvGeom g;

@@ -375,4 +375,274 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
     return UOCR_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused backward of the 3x3 conv pair  x -(w1,b1)-> act1 -> h -(w2,b2)-> y   (1 -> C1 -> 1 channels,
+// padding 1, stride 1; my_model's Monochrome net in training).  Layer by layer this needs the
+// C1-channel hidden map four times (saved activation, its gradient, the activation mask, the
+// pre-activation gradient: ~12 GB of traffic per 64 tiles at C1 = 16).  Here nothing C1-wide is
+// ever stored: both kernels RECOMPUTE h from x (9 FMA per value) next to the gradient math.
+//
+//   pair_wgrad : thread = 8 hidden columns x 16 rows, channel loop OUTSIDE the row sweep so only
+//                19 accumulators (dw1[9], db1, dw2[9]) are live; per hidden value 9 (h) + 9 (dh)
+//                + 9 (dw2) + 9 (dw1) + 2 FMA; one CTA reduction per channel; partials to
+//                workspace[(c, k)][cta], summed by a finalize kernel (deterministic)
+//   pair_dgrad : dx = conv^T(w1, dpre), same row-streaming scheme as the forward pair kernel
+//                (only launched when the caller wants the input gradient)
+// ------------------------------------------------------------------------------------------
+constexpr int PB_CW = 8, PB_R = 16, PB_THREADS = 128;
+
+template <int CW, int R>
+__global__ void __launch_bounds__(PB_THREADS) conv3x3_pair_wgrad_kernel(
+    const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ dy, float* __restrict__ ws, int n_img, int H, int W,
+    int C1, int act1, float alpha1, int nblk) {
+    extern __shared__ __align__(16) float s_p[];             // per channel: w1[9], b1, w2[9], pad -> 20
+    __shared__ float red[PB_THREADS / 32][20];
+    for (int i = threadIdx.x; i < C1 * 20; i += PB_THREADS) {
+        const int c = i / 20, k = i % 20;
+        float v = 0.f;
+        if (k < 9) v = w1[k * C1 + c];
+        else if (k == 9) v = b1[c];
+        else if (k < 19) v = w2[(k - 10) * C1 + c];
+        s_p[i] = v;
+    }
+    __syncthreads();
+
+    const int strips = (W + CW - 1) / CW, rchunks = (H + R - 1) / R;
+    const int64_t idx = (int64_t)blockIdx.x * PB_THREADS + threadIdx.x;
+    const int strip = (int)(idx % strips);
+    const int rc = (int)((idx / strips) % rchunks);
+    const int64_t n = idx / ((int64_t)strips * rchunks);
+    const bool live = n < n_img;
+    const int c0 = strip * CW, r0 = rc * R;
+    const int r_end = min(r0 + R, H);
+    const float* xim = x + (live ? n : 0) * (int64_t)H * W;
+    const float* gim = dy + (live ? n : 0) * (int64_t)H * W;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    auto load_row = [&](const float* im, int row, float* dst) {
+        const bool rin = live && row >= 0 && row < H;
+#pragma unroll
+        for (int j = 0; j < CW + 2; ++j) {
+            const int col = c0 - 1 + j;
+            dst[j] = (rin && col >= 0 && col < W) ? __ldg(im + (int64_t)row * W + col) : 0.f;
+        }
+    };
+
+    for (int c = 0; c <= C1; ++c) {
+        // c == C1: extra sweep-free slot for db2 (sum of dy over the owned pixels)
+        float gw1[9], gw2[9], gb1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) gw1[t] = gw2[t] = 0.f;
+        if (c < C1) {
+            const float4* pw = reinterpret_cast<const float4*>(s_p + c * 20);
+            const float4 q0 = pw[0], q1 = pw[1], q2 = pw[2], q3 = pw[3], q4 = pw[4];
+            const float k1[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+            const float bb = q2.y;
+            const float k2[9] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z};
+            float xw[3][CW + 2], gw[3][CW + 2];
+            load_row(xim, r0 - 1, xw[0]); load_row(xim, r0, xw[1]);
+            load_row(gim, r0 - 1, gw[0]); load_row(gim, r0, gw[1]);
+            for (int hr = r0; hr < r_end; ++hr) {
+                load_row(xim, hr + 1, xw[2]);
+                load_row(gim, hr + 1, gw[2]);
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    if (c0 + j < W) {
+                        float hp = bb, dh = 0.f;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                hp = fmaf(k1[ky * 3 + kx], xw[ky][j + kx], hp);
+                                dh = fmaf(k2[ky * 3 + kx], gw[2 - ky][j + 2 - kx], dh);
+                            }
+                        float hval = hp, mask = 1.f;
+                        if (act1 == UOCR_ACT_LEAKY && hp < 0.f) { hval = alpha1 * hp; mask = alpha1; }
+                        const float dpre = dh * mask;
+                        gb1 += dpre;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                gw1[ky * 3 + kx] = fmaf(dpre, xw[ky][j + kx], gw1[ky * 3 + kx]);
+                                gw2[ky * 3 + kx] = fmaf(gw[2 - ky][j + 2 - kx], hval, gw2[ky * 3 + kx]);
+                            }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < CW + 2; ++j) {
+                    xw[0][j] = xw[1][j]; xw[1][j] = xw[2][j];
+                    gw[0][j] = gw[1][j]; gw[1][j] = gw[2][j];
+                }
+            }
+        } else {
+            for (int hr = r0; hr < r_end; ++hr) {
+                float row[CW + 2];
+                load_row(gim, hr, row);
+#pragma unroll
+                for (int j = 0; j < CW; ++j) gb1 += row[j + 1];       // col c0 + j (beyond W reads as 0)
+            }
+        }
+        // ---- CTA reduction of the 19 sums of this channel
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const float a = warp_sum(gw1[t]), b = warp_sum(gw2[t]);
+            if (lane == 0) { red[wid][t] = a; red[wid][10 + t] = b; }
+        }
+        {
+            const float a = warp_sum(gb1);
+            if (lane == 0) red[wid][9] = a;
+        }
+        __syncthreads();
+        if (threadIdx.x < 19) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < PB_THREADS / 32; ++k) s += red[k][threadIdx.x];
+            ws[((int64_t)c * 19 + threadIdx.x) * nblk + blockIdx.x] = s;
+        }
+    }
+}
+
+// element e = c * 19 + k: k < 9 -> dw1[k][c]; k == 9 -> db1[c] (c == C1: db2); k >= 10 -> dw2[k-10][c]
+__global__ void __launch_bounds__(256) conv3x3_pair_wgrad_finalize_kernel(const float* __restrict__ ws, int nblk,
+                                                                          int C1, float* dw1, float* db1, float* dw2,
+                                                                          float* db2, int accumulate) {
+    __shared__ float red[8];
+    const int c = blockIdx.x / 19, k = blockIdx.x % 19;
+    const float* src = ws + (int64_t)blockIdx.x * nblk;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < nblk; i += 256) s += src[i];
+    s = block_sum(s, red);
+    if (threadIdx.x != 0) return;
+    float* dst = nullptr;
+    if (c == C1) { if (k == 9) dst = db2; }
+    else if (k < 9) dst = dw1 + k * C1 + c;
+    else if (k == 9) dst = db1 + c;
+    else dst = dw2 + (k - 10) * C1 + c;
+    if (dst) *dst = accumulate ? *dst + s : s;
+}
+
+template <int CW, int R>
+__global__ void __launch_bounds__(PB_THREADS) conv3x3_pair_dgrad_kernel(
+    const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
+    const float* __restrict__ w2, const float* __restrict__ dy, float* __restrict__ dx, int n_img, int H, int W,
+    int C1, int act1, float alpha1) {
+    extern __shared__ __align__(16) float s_p[];
+    for (int i = threadIdx.x; i < C1 * 20; i += PB_THREADS) {
+        const int c = i / 20, k = i % 20;
+        float v = 0.f;
+        if (k < 9) v = w1[k * C1 + c];
+        else if (k == 9) v = b1[c];
+        else if (k < 19) v = w2[(k - 10) * C1 + c];
+        s_p[i] = v;
+    }
+    __syncthreads();
+    const int strips = (W + CW - 1) / CW, rchunks = (H + R - 1) / R;
+    const int64_t idx = (int64_t)blockIdx.x * PB_THREADS + threadIdx.x;
+    const int strip = (int)(idx % strips);
+    const int rc = (int)((idx / strips) % rchunks);
+    const int64_t n = idx / ((int64_t)strips * rchunks);
+    if (n >= n_img) return;
+    const int c0 = strip * CW, r0 = rc * R;
+    const int r_end = min(r0 + R, H);
+    const float* xim = x + n * (int64_t)H * W;
+    const float* gim = dy + n * (int64_t)H * W;
+    float* dim = dx + n * (int64_t)H * W;
+
+    // windows cover hidden columns c0-1 .. c0+CW (CW + 2) and their 3x3 neighbourhoods (CW + 4)
+    float xw[3][CW + 4], gw[3][CW + 4];
+    float accA[CW], accB[CW], accC[CW];                      // dx rows hr-1, hr, hr+1
+#pragma unroll
+    for (int j = 0; j < CW; ++j) accA[j] = accB[j] = accC[j] = 0.f;
+    auto load_row = [&](const float* im, int row, float* dst) {
+        const bool rin = row >= 0 && row < H;
+#pragma unroll
+        for (int j = 0; j < CW + 4; ++j) {
+            const int col = c0 - 2 + j;
+            dst[j] = (rin && col >= 0 && col < W) ? __ldg(im + (int64_t)row * W + col) : 0.f;
+        }
+    };
+    load_row(xim, r0 - 2, xw[0]); load_row(xim, r0 - 1, xw[1]);
+    load_row(gim, r0 - 2, gw[0]); load_row(gim, r0 - 1, gw[1]);
+    for (int hr = r0 - 1; hr <= r_end; ++hr) {
+        load_row(xim, hr + 1, xw[2]);
+        load_row(gim, hr + 1, gw[2]);
+        if (hr >= 0 && hr < H) {
+            for (int c = 0; c < C1; ++c) {
+                const float4* pw = reinterpret_cast<const float4*>(s_p + c * 20);
+                const float4 q0 = pw[0], q1 = pw[1], q2 = pw[2], q3 = pw[3], q4 = pw[4];
+                const float k1[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
+                const float bb = q2.y;
+                const float k2[9] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z};
+                float dp[CW + 2];
+#pragma unroll
+                for (int j = 0; j < CW + 2; ++j) {
+                    float hp = bb, dh = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            hp = fmaf(k1[ky * 3 + kx], xw[ky][j + kx], hp);
+                            dh = fmaf(k2[ky * 3 + kx], gw[2 - ky][j + 2 - kx], dh);
+                        }
+                    const float mask = (act1 == UOCR_ACT_LEAKY && hp < 0.f) ? alpha1 : 1.f;
+                    const int col = c0 - 1 + j;
+                    dp[j] = (col >= 0 && col < W) ? dh * mask : 0.f;      // hidden pixel outside the image
+                }
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        // hidden (hr, col) feeds dx(hr + ky - 1, col + kx - 1)
+                        accA[j] = fmaf(k1[kx], dp[j + 2 - kx], accA[j]);          // ky = 0 -> row hr - 1
+                        accB[j] = fmaf(k1[3 + kx], dp[j + 2 - kx], accB[j]);      // ky = 1 -> row hr
+                        accC[j] = fmaf(k1[6 + kx], dp[j + 2 - kx], accC[j]);      // ky = 2 -> row hr + 1
+                    }
+                }
+            }
+        }
+        const int orow = hr - 1;
+        if (orow >= r0 && orow < r_end) {
+            float* op = dim + (int64_t)orow * W + c0;
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+                if (c0 + j < W) op[j] = accA[j];
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j) { accA[j] = accB[j]; accB[j] = accC[j]; accC[j] = 0.f; }
+#pragma unroll
+        for (int j = 0; j < CW + 4; ++j) {
+            xw[0][j] = xw[1][j]; xw[1][j] = xw[2][j];
+            gw[0][j] = gw[1][j]; gw[1][j] = gw[2][j];
+        }
+    }
+}
+
+size_t conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int c1) {
+    const int64_t nblk = ceil_div(n * ceil_div(w, PB_CW) * ceil_div(h, PB_R), PB_THREADS);
+    return sizeof(float) * (size_t)nblk * (c1 + 1) * 19;
+}
+
+int conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* dx,
+                     float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h, int64_t w, int c1,
+                     int act1, float alpha1, int accumulate, float* ws, cudaStream_t st) {
+    const int64_t items = n * ceil_div(w, PB_CW) * ceil_div(h, PB_R);
+    const int64_t nblk = ceil_div(items, PB_THREADS);
+    if (nblk > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    const size_t smem = sizeof(float) * 20 * c1;
+    conv3x3_pair_wgrad_kernel<PB_CW, PB_R><<<(unsigned)nblk, PB_THREADS, smem, st>>>(
+        x, w1, b1, w2, dy, ws, (int)n, (int)h, (int)w, c1, act1, alpha1, (int)nblk);
+    UOCR_LAUNCHED("conv3x3_pair_wgrad");
+    conv3x3_pair_wgrad_finalize_kernel<<<(c1 + 1) * 19, 256, 0, st>>>(ws, (int)nblk, c1, dw1, db1, dw2, db2, accumulate);
+    UOCR_LAUNCHED("conv3x3_pair_wgrad_finalize");
+    if (dx) {
+        conv3x3_pair_dgrad_kernel<PB_CW, PB_R><<<(unsigned)nblk, PB_THREADS, smem, st>>>(
+            x, w1, b1, w2, dy, dx, (int)n, (int)h, (int)w, c1, act1, alpha1);
+        UOCR_LAUNCHED("conv3x3_pair_dgrad");
+    }
+    return UOCR_OK;
+}
+
 }  // namespace uocr

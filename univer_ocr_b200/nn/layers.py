@@ -503,6 +503,15 @@ class Convolutional2D(BaseLayer):
         lib.uocr_conv2d_dgrad(ctypes.byref(desc), grad.ptr, self.w.value.ptr, dx.ptr, stream())
         return dx
 
+    def backward_params_only(self, grads):
+        """dW / db only (no dX): used for first layers when the caller does not want input gradients."""
+        tracker = self.progress_tracker
+        tracker.start_tracking(self.name, 'backward')
+        for mem_id, grad in enumerate(make_list_if_not(grads)):
+            self._backward(as_device(grad), mem_id, need_dx=False)
+        self.clear_memory()
+        tracker.stop_tracking(self.name, 'backward')
+
     def get_output_shapes(self, input_shapes):
         batch, height, width, _ = make_list_if_not(input_shapes)[0]
         (kh, kw), (ph, pw), (sh, sw) = self.kernel_size, self.padding, self.stride

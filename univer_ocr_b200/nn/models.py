@@ -69,6 +69,9 @@ class Model(BaseModel):
     # Fused-away tensors are absent (None) from `layers_outputs`; set `fusion = False` (class or
     # instance) before initialize() to get every per-layer output like the reference.
     fusion = True
+    # False: skip the gradient w.r.t. the model INPUTS (the reference always computes it,
+    # models.py:207-230, but a training step never uses it); `input_grads` entries are then None
+    compute_input_grads = True
 
     def __init__(self, layers, relations, loss=SoftmaxCrossEntropy(), *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -235,11 +238,11 @@ class Model(BaseModel):
                     if act is None or (training and act[0] != ACT_LEAKY):
                         act_name = None
                     pair = None
-                    if (not training and ups is None and act_name is not None
-                            and self._pair_head(conv)):
+                    if (ups is None and act_name is not None and self._pair_head(conv)
+                            and (not training or act[0] == ACT_LEAKY)):
                         c2_name = self._sole_consumer(act_name)
                         if c2_name is not None and self._pair_tail(conv, self.layers[c2_name]):
-                            a2_name = self._sole_consumer(c2_name)
+                            a2_name = self._sole_consumer(c2_name) if not training else None
                             a2 = _act_code(self.layers[a2_name]) if a2_name is not None else None
                             pair = (c2_name, a2_name if a2 is not None else None)
                     if pair is not None:
@@ -289,7 +292,7 @@ class Model(BaseModel):
             elif kind == 'conv':
                 self._run_fused_conv(step, value_of, outputs, training, clear_grads)
             else:
-                self._run_pair(step, value_of, outputs)
+                self._run_pair(step, value_of, outputs, training)
         for key in self._output_keys():
             outputs[key] = value_of(self.relations[key][0])
         self.layers_outputs = outputs
@@ -318,10 +321,12 @@ class Model(BaseModel):
                 outputs[n] = None
         outputs[act_name if act_name is not None else conv_name] = y
 
-    def _run_pair(self, step, value_of, outputs):
+    def _run_pair(self, step, value_of, outputs, training=False):
         _, c1_name, a1_name, c2_name, a2_name = step
         X = as_device(value_of(self.relations[c1_name][0]))
         c1, c2 = self.layers[c1_name], self.layers[c2_name]
+        if training:
+            c1._mem[0] = X                                      # all the fused backward needs
         act1, alpha1 = _act_code(self.layers[a1_name])
         act2, alpha2 = _act_code(self.layers[a2_name]) if a2_name is not None else (ACT_NONE, 0.0)
         n, h, w, cin = X.shape
@@ -349,11 +354,54 @@ class Model(BaseModel):
                 parts.append(grads[dst] if isinstance(dst, int) else produced[dst][slot])
             return sum(parts)                                       # 0 + g1 (+ g2 ...), reference :218
 
+        pairs = {}                                                  # member layer -> ('pair', c1, a1, c2, None)
+        for step in self._plan_train:
+            if step[0] == 'pair':
+                for member in step[1:4]:
+                    pairs[member] = step
+        stash = {}
         for name in reversed(self._order):
-            produced[name] = make_list_if_not(self.layers[name].backward(incoming(name)))
+            step = pairs.get(name)
+            layer = self.layers[name]
+            if step is None:
+                first = all(isinstance(src, int) for src in self.relations[name])
+                if first and not self.compute_input_grads and hasattr(layer, 'backward_params_only'):
+                    layer.backward_params_only(incoming(name))
+                    produced[name] = [None] * len(self.relations[name])
+                else:
+                    produced[name] = make_list_if_not(layer.backward(incoming(name)))
+            elif name == step[3]:                                   # conv_2: keep its output gradient
+                stash[step[1]] = incoming(name)
+                produced[name] = [None]
+            elif name == step[2]:                                   # the activation in between
+                produced[name] = [None]
+            else:                                                   # conv_1: the fused backward
+                first = all(isinstance(src, int) for src in self.relations[name])
+                produced[name] = [self._pair_backward(step, stash.pop(name),
+                                                      need_dx=self.compute_input_grads or not first)]
         for key in range(self.inputs_count):
-            self.input_grads[key] = incoming(key)
+            self.input_grads[key] = incoming(key) if self.compute_input_grads else None
         return [self.input_grads[k] for k in range(self.inputs_count)]
+
+    def _pair_backward(self, step, grad, need_dx=True):
+        _, c1_name, a1_name, c2_name, _ = step
+        c1, c2 = self.layers[c1_name], self.layers[c2_name]
+        act1, alpha1 = _act_code(self.layers[a1_name])
+        X = c1._mem.pop(0)
+        grad = as_device(grad)
+        n, h, w, _ = X.shape
+        need = ctypes.c_size_t(0)
+        lib.uocr_conv3x3_pair_bwd_workspace(n, h, w, c1.out_channels, ctypes.byref(need))
+        ws = DeviceArray(((need.value + 3) // 4,))
+        dx = DeviceArray(X.shape) if need_dx else None
+        tracker = c1.progress_tracker
+        tracker.start_tracking(c1.name, 'backward')
+        lib.uocr_conv3x3_pair_bwd(X.ptr, c1.w.value.ptr, c1.b.value.ptr, c2.w.value.ptr, grad.ptr,
+                                  dx.ptr if need_dx else None, c1.w.grad.ptr, c1.b.grad.ptr, c2.w.grad.ptr,
+                                  c2.b.grad.ptr, n, h, w, c1.out_channels, act1, alpha1, 1, ws.ptr, need.value,
+                                  stream())
+        tracker.stop_tracking(c1.name, 'backward')
+        return dx
 
     def _loss_for(self, key):
         return self.loss[key] if isinstance(self.loss, list) else self.loss

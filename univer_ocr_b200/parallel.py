@@ -83,6 +83,7 @@ class DataParallel:
 
     def __init__(self, model, optimizer=None, process_group=None):
         self.model = model
+        model.compute_input_grads = False            # a training step never reads dL/dX
         self.flat = FlatParameters(model)
         self.optimizer = optimizer if optimizer is not None else self._find_optimizer(model)
         if not isinstance(self.optimizer, optimizers.Adam):
