@@ -194,7 +194,7 @@ struct TcParams {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 const TcParams p) {
     constexpr bool MN = (MODE == TC_GEMM_MN || MODE == TC_CONV_WGRAD);
@@ -417,10 +417,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const __grid_con
     }
 }
 
+static int env_int(const char* name, int fallback) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : fallback;
+}
+
 static int pick_stages(int nt, size_t* smem_bytes) {
     const size_t a_bytes = TC_BM * TC_BK * 4;
     const size_t b_bytes = (((size_t)nt * TC_BK * 4) + 1023) & ~(size_t)1023;
-    const size_t budget = 200 * 1024;
+    static const int budget_kb = env_int("UOCR_TC_SMEM_KB", 70);     // ~3 CTAs / SM: their prologues and
+                                                                       // epilogues overlap other CTAs' main loops
+    const size_t budget = (size_t)budget_kb * 1024;
     int stages = (int)((budget - 2048) / (a_bytes + b_bytes));
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
@@ -445,7 +452,8 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, 
 }
 
 static int pick_nt(int64_t n) {
-    if (n >= 256) return 256;                 // full-rate N; wider tiles amortise the A reads
+    static const int cap = env_int("UOCR_TC_NT", 64);
+    if (n >= cap) return cap;                 // full-rate N; wider tiles amortise the A reads
     return (int)(((n + 15) / 16) * 16);
 }
 
