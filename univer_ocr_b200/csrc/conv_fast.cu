@@ -166,12 +166,12 @@ static int launch_small_fwd(const ConvGeom& g, int ups, const float* x, const fl
 // the tile fill), then every thread reads its window as aligned 128-bit shared loads:
 // warp = one output row of the tile, lane = PX consecutive outputs.
 // ------------------------------------------------------------------------------------------
-template <int KH, int KW, int SH, int SW, int COT, int PX, int UPS>
+template <int KH, int KW, int SH, int SW, int COT, int PX, int UPS, int TH>
 __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const float* __restrict__ x,
                                                           const float* __restrict__ w,
                                                           const float* __restrict__ b, float* __restrict__ y,
                                                           int act, float alpha) {
-    constexpr int TH = 8, TW = 32 * PX;
+    constexpr int TW = 32 * PX;
     constexpr int IH = (TH - 1) * SH + KH;
     constexpr int NIN = (PX - 1) * SW + KW;
     constexpr int NV = (NIN + 3) / 4;                        // float4 loads per window row
@@ -189,85 +189,98 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
     const float* xim = x + (int64_t)n * hp * wp;
 
     for (int i = threadIdx.x; i < KH * KW * cout; i += 256) s_w[i] = w[i];
+    // asynchronous tile fill (LDGSTS): every in-bounds element is one 4-byte cp.async, so a thread
+    // has all of its ~19 loads in flight at once instead of a load -> store dependency per element
     for (int i = threadIdx.x; i < IH * IWP; i += 256) {
         const int r = i / IWP, c = i - r * IWP;
         const int iy = iy0 + r, ix = ix0 + c;
-        float v = g.padding_value;
-        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) v = __ldg(xim + (int64_t)(iy / UPS) * wp + ix / UPS);
-        s_in[i] = v;
+        if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) {
+            const float* src = xim + (int64_t)(iy / UPS) * wp + ix / UPS;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(s_in + i)), "l"(src) : "memory");
+        } else {
+            s_in[i] = g.padding_value;
+        }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int oy = oy0 + ty, oxl = ox0 + lane * PX;
-    if (oy >= g.ho || oxl >= g.wo) return;
-
-    float acc[PX][COT];
-#pragma unroll
-    for (int p = 0; p < PX; ++p)
-#pragma unroll
-        for (int c = 0; c < COT; ++c) acc[p][c] = 0.f;
-
-#pragma unroll
-    for (int ky = 0; ky < KH; ++ky) {
-        const float4* row = reinterpret_cast<const float4*>(s_in + (ty * SH + ky) * IWP + lane * PX * SW);
-        float xin[NV * 4];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            const float4 t = row[v];
-            xin[4 * v] = t.x; xin[4 * v + 1] = t.y; xin[4 * v + 2] = t.z; xin[4 * v + 3] = t.w;
-        }
-#pragma unroll
-        for (int kx = 0; kx < KW; ++kx) {
-            const float* wp_ = s_w + (ky * KW + kx) * cout + co0;
-            float wr[COT];
-            if (COT % 4 == 0) {
-#pragma unroll
-                for (int c = 0; c < COT; c += 4) {
-                    const float4 t = *reinterpret_cast<const float4*>(wp_ + c);
-                    wr[c] = t.x; wr[c + 1] = t.y; wr[c + 2] = t.z; wr[c + 3] = t.w;
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < COT; ++c) wr[c] = wp_[c];
-            }
-#pragma unroll
-            for (int p = 0; p < PX; ++p)
-#pragma unroll
-                for (int c = 0; c < COT; ++c) acc[p][c] = fmaf(xin[p * SW + kx], wr[c], acc[p][c]);
-        }
-    }
-
+    const int lane = threadIdx.x & 31;
+    const int oxl = ox0 + lane * PX;
+    if (oxl >= g.wo) return;
     float bias[COT];
 #pragma unroll
     for (int c = 0; c < COT; ++c) bias[c] = g.bias ? __ldg(b + co0 + c) : 0.f;
-    float* yrow = y + (((int64_t)n * g.ho + oy) * g.wo + oxl) * cout + co0;
-    if (COT == 1 && cout == 1 && PX == 4 && (g.wo & 3) == 0) {
-        float4 t;
-        t.x = apply_act(acc[0][0] + bias[0], act, alpha);
-        t.y = apply_act(acc[1][0] + bias[0], act, alpha);
-        t.z = apply_act(acc[2][0] + bias[0], act, alpha);
-        t.w = apply_act(acc[3][0] + bias[0], act, alpha);
-        *reinterpret_cast<float4*>(yrow) = t;
-        return;
-    }
+
+    // each warp walks rows ty, ty + 8, ... of the tile (a tall tile keeps ~20 KB of loads in flight
+    // per CTA and cuts the halo re-read to (TH*SH + KH - SH) / (TH*SH))
+    for (int ty = threadIdx.x >> 5; ty < TH; ty += 8) {
+        const int oy = oy0 + ty;
+        if (oy >= g.ho) break;
+        float acc[PX][COT];
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-        if (oxl + p >= g.wo) break;
-        float* yp = yrow + (int64_t)p * cout;
-        if (COT % 4 == 0) {
+        for (int p = 0; p < PX; ++p)
 #pragma unroll
-            for (int c = 0; c < COT; c += 4) {
-                float4 t;
-                t.x = apply_act(acc[p][c] + bias[c], act, alpha);
-                t.y = apply_act(acc[p][c + 1] + bias[c + 1], act, alpha);
-                t.z = apply_act(acc[p][c + 2] + bias[c + 2], act, alpha);
-                t.w = apply_act(acc[p][c + 3] + bias[c + 3], act, alpha);
-                *reinterpret_cast<float4*>(yp + c) = t;
+            for (int c = 0; c < COT; ++c) acc[p][c] = 0.f;
+
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+            const float4* row = reinterpret_cast<const float4*>(s_in + (ty * SH + ky) * IWP + lane * PX * SW);
+            float xin[NV * 4];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const float4 t = row[v];
+                xin[4 * v] = t.x; xin[4 * v + 1] = t.y; xin[4 * v + 2] = t.z; xin[4 * v + 3] = t.w;
             }
-        } else {
 #pragma unroll
-            for (int c = 0; c < COT; ++c) yp[c] = apply_act(acc[p][c] + bias[c], act, alpha);
+            for (int kx = 0; kx < KW; ++kx) {
+                const float* wp_ = s_w + (ky * KW + kx) * cout + co0;
+                float wr[COT];
+                if (COT % 4 == 0) {
+#pragma unroll
+                    for (int c = 0; c < COT; c += 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(wp_ + c);
+                        wr[c] = t.x; wr[c + 1] = t.y; wr[c + 2] = t.z; wr[c + 3] = t.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < COT; ++c) wr[c] = wp_[c];
+                }
+#pragma unroll
+                for (int p = 0; p < PX; ++p)
+#pragma unroll
+                    for (int c = 0; c < COT; ++c) acc[p][c] = fmaf(xin[p * SW + kx], wr[c], acc[p][c]);
+            }
+        }
+
+        float* yrow = y + (((int64_t)n * g.ho + oy) * g.wo + oxl) * cout + co0;
+        if (COT == 1 && cout == 1 && PX == 4 && (g.wo & 3) == 0) {
+            float4 t;
+            t.x = apply_act(acc[0][0] + bias[0], act, alpha);
+            t.y = apply_act(acc[1][0] + bias[0], act, alpha);
+            t.z = apply_act(acc[2][0] + bias[0], act, alpha);
+            t.w = apply_act(acc[3][0] + bias[0], act, alpha);
+            *reinterpret_cast<float4*>(yrow) = t;
+            continue;
+        }
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+            if (oxl + p >= g.wo) break;
+            float* yp = yrow + (int64_t)p * cout;
+            if (COT % 4 == 0) {
+#pragma unroll
+                for (int c = 0; c < COT; c += 4) {
+                    float4 t;
+                    t.x = apply_act(acc[p][c] + bias[c], act, alpha);
+                    t.y = apply_act(acc[p][c + 1] + bias[c + 1], act, alpha);
+                    t.z = apply_act(acc[p][c + 2] + bias[c + 2], act, alpha);
+                    t.w = apply_act(acc[p][c + 3] + bias[c + 3], act, alpha);
+                    *reinterpret_cast<float4*>(yp + c) = t;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < COT; ++c) yp[c] = apply_act(acc[p][c] + bias[c], act, alpha);
+            }
         }
     }
 }
@@ -275,7 +288,9 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
 template <int KH, int KW, int SH, int SW, int COT, int PX>
 static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float* w, const float* b, float* y,
                          int act, float alpha, cudaStream_t st) {
-    constexpr int TH = 8, TW = 32 * PX;
+    // tall tiles for big images (stride-1: 32 rows, 19.6 KB of input per CTA; stride-2: 16 rows, 37 KB)
+    constexpr int TH = (SH == 1) ? 32 : 16;
+    constexpr int TW = 32 * PX;
     constexpr int IH = (TH - 1) * SH + KH;
     constexpr int IWP = (((TW - 1) * SW + KW) + 3 + 4) / 4 * 4;
     const size_t smem = sizeof(float) * (IH * IWP + KH * KW * g.cout);
@@ -283,9 +298,9 @@ static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float
     if (smem > 48 * 1024 || gz > 65535 || ceil_div(g.ho, TH) > 65535) return UOCR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)ceil_div(g.wo, TW), (unsigned)ceil_div(g.ho, TH), (unsigned)gz);
     if (ups == 2)
-        conv_c1_fwd_kernel<KH, KW, SH, SW, COT, PX, 2><<<grid, 256, smem, st>>>(g, x, w, b, y, act, alpha);
+        conv_c1_fwd_kernel<KH, KW, SH, SW, COT, PX, 2, TH><<<grid, 256, smem, st>>>(g, x, w, b, y, act, alpha);
     else
-        conv_c1_fwd_kernel<KH, KW, SH, SW, COT, PX, 1><<<grid, 256, smem, st>>>(g, x, w, b, y, act, alpha);
+        conv_c1_fwd_kernel<KH, KW, SH, SW, COT, PX, 1, TH><<<grid, 256, smem, st>>>(g, x, w, b, y, act, alpha);
     UOCR_LAUNCHED("conv_c1_fwd");
     return UOCR_OK;
 }
