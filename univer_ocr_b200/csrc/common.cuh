@@ -104,6 +104,15 @@ __device__ __forceinline__ T block_sum(T v, T* smem /* >= 8 elements */) {
     return r;
 }
 
+// epilogue flavour for the convolution kernels: ex2.approx + fast reciprocal (|rel err| ~ 1e-6 on
+// the sigmoid, far inside the 1e-4 conv tolerance) -- the IEEE expf + divide sequence costs ~25
+// instructions per output, which made the Cin = 1 stencils issue-bound (ncu: issue slots 80 % busy)
+__device__ __forceinline__ float apply_act_fast(float v, int act, float alpha) {
+    if (act == UOCR_ACT_LEAKY) return v >= 0.f ? v : alpha * v;
+    if (act == UOCR_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-v));
+    return v;
+}
+
 __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
     if (act == UOCR_ACT_LEAKY) return v >= 0.f ? v : alpha * v;
     if (act == UOCR_ACT_SIGMOID) return 1.f / (1.f + expf(-v));

@@ -109,10 +109,10 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(ConvGeom g, const f
 #pragma unroll
         for (int p = 0; p < PX; p += 4) {
             float4 t;
-            t.x = apply_act(acc[p][0] + bias[0], act, alpha);
-            t.y = apply_act(acc[p + 1][0] + bias[0], act, alpha);
-            t.z = apply_act(acc[p + 2][0] + bias[0], act, alpha);
-            t.w = apply_act(acc[p + 3][0] + bias[0], act, alpha);
+            t.x = apply_act_fast(acc[p][0] + bias[0], act, alpha);
+            t.y = apply_act_fast(acc[p + 1][0] + bias[0], act, alpha);
+            t.z = apply_act_fast(acc[p + 2][0] + bias[0], act, alpha);
+            t.w = apply_act_fast(acc[p + 3][0] + bias[0], act, alpha);
             *reinterpret_cast<float4*>(yrow + p) = t;
         }
         return;
@@ -125,15 +125,15 @@ __global__ void __launch_bounds__(256) conv_small_fwd_kernel(ConvGeom g, const f
 #pragma unroll
             for (int c = 0; c < COT; c += 4) {
                 float4 t;
-                t.x = apply_act(acc[p][c] + bias[c], act, alpha);
-                t.y = apply_act(acc[p][c + 1] + bias[c + 1], act, alpha);
-                t.z = apply_act(acc[p][c + 2] + bias[c + 2], act, alpha);
-                t.w = apply_act(acc[p][c + 3] + bias[c + 3], act, alpha);
+                t.x = apply_act_fast(acc[p][c] + bias[c], act, alpha);
+                t.y = apply_act_fast(acc[p][c + 1] + bias[c + 1], act, alpha);
+                t.z = apply_act_fast(acc[p][c + 2] + bias[c + 2], act, alpha);
+                t.w = apply_act_fast(acc[p][c + 3] + bias[c + 3], act, alpha);
                 *reinterpret_cast<float4*>(yp + c) = t;
             }
         } else {
 #pragma unroll
-            for (int c = 0; c < COT; ++c) yp[c] = apply_act(acc[p][c] + bias[c], act, alpha);
+            for (int c = 0; c < COT; ++c) yp[c] = apply_act_fast(acc[p][c] + bias[c], act, alpha);
         }
     }
 }
@@ -191,9 +191,10 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
     for (int i = threadIdx.x; i < KH * KW * cout; i += 256) s_w[i] = w[i];
     // asynchronous tile fill (LDGSTS): every in-bounds element is one 4-byte cp.async, so a thread
     // has all of its ~19 loads in flight at once instead of a load -> store dependency per element
-    for (int i = threadIdx.x; i < IH * IWP; i += 256) {
-        const int r = i / IWP, c = i - r * IWP;
-        const int iy = iy0 + r, ix = ix0 + c;
+    int fr = threadIdx.x / IWP, fc = threadIdx.x - fr * IWP;
+    for (int i = threadIdx.x; i < IH * IWP; i += 256, fr += 256 / IWP, fc += 256 % IWP) {
+        if (fc >= IWP) { fc -= IWP; ++fr; }
+        const int iy = iy0 + fr, ix = ix0 + fc;
         if (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) {
             const float* src = xim + (int64_t)(iy / UPS) * wp + ix / UPS;
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
@@ -212,6 +213,11 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
 #pragma unroll
     for (int c = 0; c < COT; ++c) bias[c] = g.bias ? __ldg(b + co0 + c) : 0.f;
 
+    float wreg[COT == 1 ? KH * KW : 1];                      // single-output-channel weights live in registers
+    if (COT == 1) {
+#pragma unroll
+        for (int t = 0; t < KH * KW; ++t) wreg[t] = s_w[t * cout + co0];
+    }
     // each warp walks rows ty, ty + 8, ... of the tile (a tall tile keeps ~20 KB of loads in flight
     // per CTA and cuts the halo re-read to (TH*SH + KH - SH) / (TH*SH))
     for (int ty = threadIdx.x >> 5; ty < TH; ty += 8) {
@@ -236,7 +242,9 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
             for (int kx = 0; kx < KW; ++kx) {
                 const float* wp_ = s_w + (ky * KW + kx) * cout + co0;
                 float wr[COT];
-                if (COT % 4 == 0) {
+                if (COT == 1) {
+                    wr[0] = wreg[ky * KW + kx];
+                } else if (COT % 4 == 0) {
 #pragma unroll
                     for (int c = 0; c < COT; c += 4) {
                         const float4 t = *reinterpret_cast<const float4*>(wp_ + c);
@@ -256,10 +264,10 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
         float* yrow = y + (((int64_t)n * g.ho + oy) * g.wo + oxl) * cout + co0;
         if (COT == 1 && cout == 1 && PX == 4 && (g.wo & 3) == 0) {
             float4 t;
-            t.x = apply_act(acc[0][0] + bias[0], act, alpha);
-            t.y = apply_act(acc[1][0] + bias[0], act, alpha);
-            t.z = apply_act(acc[2][0] + bias[0], act, alpha);
-            t.w = apply_act(acc[3][0] + bias[0], act, alpha);
+            t.x = apply_act_fast(acc[0][0] + bias[0], act, alpha);
+            t.y = apply_act_fast(acc[1][0] + bias[0], act, alpha);
+            t.z = apply_act_fast(acc[2][0] + bias[0], act, alpha);
+            t.w = apply_act_fast(acc[3][0] + bias[0], act, alpha);
             *reinterpret_cast<float4*>(yrow) = t;
             continue;
         }
@@ -271,15 +279,15 @@ __global__ void __launch_bounds__(256) conv_c1_fwd_kernel(ConvGeom g, const floa
 #pragma unroll
                 for (int c = 0; c < COT; c += 4) {
                     float4 t;
-                    t.x = apply_act(acc[p][c] + bias[c], act, alpha);
-                    t.y = apply_act(acc[p][c + 1] + bias[c + 1], act, alpha);
-                    t.z = apply_act(acc[p][c + 2] + bias[c + 2], act, alpha);
-                    t.w = apply_act(acc[p][c + 3] + bias[c + 3], act, alpha);
+                    t.x = apply_act_fast(acc[p][c] + bias[c], act, alpha);
+                    t.y = apply_act_fast(acc[p][c + 1] + bias[c + 1], act, alpha);
+                    t.z = apply_act_fast(acc[p][c + 2] + bias[c + 2], act, alpha);
+                    t.w = apply_act_fast(acc[p][c + 3] + bias[c + 3], act, alpha);
                     *reinterpret_cast<float4*>(yp + c) = t;
                 }
             } else {
 #pragma unroll
-                for (int c = 0; c < COT; ++c) yp[c] = apply_act(acc[p][c] + bias[c], act, alpha);
+                for (int c = 0; c < COT; ++c) yp[c] = apply_act_fast(acc[p][c] + bias[c], act, alpha);
             }
         }
     }
@@ -354,7 +362,11 @@ int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, con
 // ------------------------------------------------------------------------------------------
 constexpr int PAIR_CW = 8, PAIR_R = 16;
 
-template <int CW, int R>
+// LMAX: act1 is LeakyRelu with 0 < alpha <= 1, evaluated as max(v, alpha * v) (FMUL + FMNMX instead of
+// compare + multiply + select).  ncu showed this kernel issue-bound (issue slots 83 % busy) with a third
+// of the slots spent on ALU work around the hidden values, so the activation and the image-border
+// masking of the hidden pixels (needed by edge strips only) are kept off the common path.
+template <int CW, int R, bool LMAX>
 __global__ void __launch_bounds__(128) conv3x3_pair_fwd_kernel(
     const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
     const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ y, int n_img, int H,
@@ -399,37 +411,42 @@ __global__ void __launch_bounds__(128) conv3x3_pair_fwd_kernel(
     load_row(r0 - 1, xr[1]);
 
     const int r_end = min(r0 + R, H);
+    // does any strip of this warp touch the left / right image border?  (warp-uniform)
+    const bool warp_has_edge = __any_sync(__activemask(), (c0 == 0) || (c0 + CW >= W));
     for (int hr = r0 - 1; hr <= r_end; ++hr) {
         load_row(hr + 1, xr[2]);
         if (hr >= 0 && hr < H) {
-            for (int c = 0; c < C1; ++c) {
-                const float4* pw = reinterpret_cast<const float4*>(s_p + c * 20);
-                const float4 q0 = pw[0], q1 = pw[1], q2 = pw[2], q3 = pw[3], q4 = pw[4];
-                const float k1[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};
-                const float bb = q2.y;
-                const float k2[9] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z};
-                float h[CW + 2];
-#pragma unroll
-                for (int j = 0; j < CW + 2; ++j) {
-                    float v = bb;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) v = fmaf(k1[ky * 3 + kx], xr[ky][j + kx], v);
-                    v = apply_act(v, act1, alpha1);
-                    const int col = c0 - 1 + j;
-                    h[j] = (col >= 0 && col < W) ? v : 0.f;     // conv_2's zero padding
-                }
-#pragma unroll
-                for (int j = 0; j < CW; ++j) {
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        accA[j] = fmaf(k2[6 + kx], h[j + kx], accA[j]);   // ky = 2 -> output row hr - 1
-                        accB[j] = fmaf(k2[3 + kx], h[j + kx], accB[j]);   // ky = 1 -> output row hr
-                        accC[j] = fmaf(k2[kx], h[j + kx], accC[j]);       // ky = 0 -> output row hr + 1
-                    }
-                }
+            // two copies of the channel loop: warps that contain an image-border strip mask the
+            // out-of-image hidden columns (conv_2's zero padding); all other warps skip that work
+#define UOCR_PAIR_CHANNEL_LOOP(MASKED)                                                                  \
+            for (int c = 0; c < C1; ++c) {                                                              \
+                const float4* pw = reinterpret_cast<const float4*>(s_p + c * 20);                      \
+                const float4 q0 = pw[0], q1 = pw[1], q2 = pw[2], q3 = pw[3], q4 = pw[4];               \
+                const float k1[9] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x};            \
+                const float bb = q2.y;                                                                  \
+                const float k2[9] = {q2.z, q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z};            \
+                float h[CW + 2];                                                                        \
+                _Pragma("unroll") for (int j = 0; j < CW + 2; ++j) {                                    \
+                    float v = bb;                                                                       \
+                    _Pragma("unroll") for (int ky = 0; ky < 3; ++ky)                                    \
+                        _Pragma("unroll") for (int kx = 0; kx < 3; ++kx)                                \
+                            v = fmaf(k1[ky * 3 + kx], xr[ky][j + kx], v);                               \
+                    h[j] = LMAX ? fmaxf(v, alpha1 * v) : apply_act_fast(v, act1, alpha1);               \
+                    if (MASKED) {                                                                       \
+                        const int col = c0 - 1 + j;                                                     \
+                        if (col < 0 || col >= W) h[j] = 0.f;                                            \
+                    }                                                                                   \
+                }                                                                                       \
+                _Pragma("unroll") for (int j = 0; j < CW; ++j) {                                        \
+                    _Pragma("unroll") for (int kx = 0; kx < 3; ++kx) {                                  \
+                        accA[j] = fmaf(k2[6 + kx], h[j + kx], accA[j]); /* ky = 2 -> output row hr - 1 */ \
+                        accB[j] = fmaf(k2[3 + kx], h[j + kx], accB[j]); /* ky = 1 -> output row hr     */ \
+                        accC[j] = fmaf(k2[kx], h[j + kx], accC[j]);     /* ky = 0 -> output row hr + 1 */ \
+                    }                                                                                   \
+                }                                                                                       \
             }
+            if (warp_has_edge) { UOCR_PAIR_CHANNEL_LOOP(true) } else { UOCR_PAIR_CHANNEL_LOOP(false) }
+#undef UOCR_PAIR_CHANNEL_LOOP
         }
         const int orow = hr - 1;
         if (orow >= r0 && orow < r_end) {
@@ -438,16 +455,16 @@ __global__ void __launch_bounds__(128) conv3x3_pair_fwd_kernel(
 #pragma unroll
                 for (int j = 0; j < CW; j += 4) {
                     float4 t;
-                    t.x = apply_act(accA[j] + bias2, act2, alpha2);
-                    t.y = apply_act(accA[j + 1] + bias2, act2, alpha2);
-                    t.z = apply_act(accA[j + 2] + bias2, act2, alpha2);
-                    t.w = apply_act(accA[j + 3] + bias2, act2, alpha2);
+                    t.x = apply_act_fast(accA[j] + bias2, act2, alpha2);
+                    t.y = apply_act_fast(accA[j + 1] + bias2, act2, alpha2);
+                    t.z = apply_act_fast(accA[j + 2] + bias2, act2, alpha2);
+                    t.w = apply_act_fast(accA[j + 3] + bias2, act2, alpha2);
                     *reinterpret_cast<float4*>(yp + j) = t;
                 }
             } else {
 #pragma unroll
                 for (int j = 0; j < CW; ++j)
-                    if (c0 + j < W) yp[j] = apply_act(accA[j] + bias2, act2, alpha2);
+                    if (c0 + j < W) yp[j] = apply_act_fast(accA[j] + bias2, act2, alpha2);
             }
         }
 #pragma unroll
@@ -463,8 +480,12 @@ int conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const flo
     const int64_t strips = ceil_div(w, PAIR_CW), rchunks = ceil_div(h, PAIR_R);
     const int64_t blocks = ceil_div(n * strips * rchunks, 128);
     if (blocks > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
-    conv3x3_pair_fwd_kernel<PAIR_CW, PAIR_R><<<(unsigned)blocks, 128, sizeof(float) * 20 * c1, st>>>(
-        x, w1, b1, w2, b2, y, (int)n, (int)h, (int)w, c1, act1, alpha1, act2, alpha2);
+    if (act1 == UOCR_ACT_LEAKY && alpha1 > 0.f && alpha1 <= 1.f)
+        conv3x3_pair_fwd_kernel<PAIR_CW, PAIR_R, true><<<(unsigned)blocks, 128, sizeof(float) * 20 * c1, st>>>(
+            x, w1, b1, w2, b2, y, (int)n, (int)h, (int)w, c1, act1, alpha1, act2, alpha2);
+    else
+        conv3x3_pair_fwd_kernel<PAIR_CW, PAIR_R, false><<<(unsigned)blocks, 128, sizeof(float) * 20 * c1, st>>>(
+            x, w1, b1, w2, b2, y, (int)n, (int)h, (int)w, c1, act1, alpha1, act2, alpha2);
     UOCR_LAUNCHED("conv3x3_pair_fwd");
     return UOCR_OK;
 }
