@@ -385,15 +385,15 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
     UOCR_REQUIRE(h < (1 << 30) && w < (1 << 30), "dimension too large");
     UOCR_REQUIRE(act1 >= UOCR_ACT_NONE && act1 <= UOCR_ACT_SIGMOID && act2 >= UOCR_ACT_NONE &&
                      act2 <= UOCR_ACT_SIGMOID, "unknown activation");
-    // The tensor-core variant is correct but SLOWER than the CUDA-core pair kernel (1.32 ms vs 0.45 ms
-    // for 64 tiles of 496x736): with Cout = 1 the UMMA N dimension is 1-in-16 useful and every
-    // 128x16x8 MMA still reads a 4 KB A operand from shared memory (32 cycles), i.e. 32 useful
-    // MAC/cycle/SM against 128 FFMA/cycle/SM.  Kept opt-in (UOCR_PAIR_TC=1) as a measured negative
-    // result; see DESIGN.md.
-    static const bool pair_tc = [] { const char* e = getenv("UOCR_PAIR_TC"); return e && e[0] == '1'; }();
+    // TF32 mode, c_mid == 16: tensor-core variants.  UOCR_PAIR_TC = 2 (default): both convolutions as
+    // tcgen05.mma with TMEM-resident A operands (conv_pair_tc.cu); 1: the earlier variant whose hidden tile
+    // is evaluated on the CUDA cores and only the 16 -> 1 convolution runs as MMA from shared memory (kept
+    // as a measured negative result, 3x slower than the CUDA-core kernel); 0: CUDA-core pair kernel.
+    static const int pair_tc = [] { const char* e = getenv("UOCR_PAIR_TC"); return e ? atoi(e) : 2; }();
     if (math_mode == UOCR_MATH_TF32 && pair_tc) {
-        const int rc = conv3x3_pair_tc(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,
-                                       as_stream(stream));
+        const int rc = pair_tc == 2
+            ? conv3x3_pair_tmem(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream))
+            : conv3x3_pair_tc(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream));
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     }
     return conv3x3_pair_fwd(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,

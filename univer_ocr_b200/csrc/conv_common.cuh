@@ -35,6 +35,10 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
 int conv3x3_pair_tc(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                     int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
                     cudaStream_t st);
+// both convolutions as tcgen05.mma with TMEM-resident A operands (conv_pair_tc.cu)
+int conv3x3_pair_tmem(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
+                      int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
+                      cudaStream_t st);
 size_t conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int c1);
 int conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* dx,
                      float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h, int64_t w, int c1,

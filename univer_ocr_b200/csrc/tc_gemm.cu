@@ -29,6 +29,7 @@
 
 #include "conv_common.cuh"
 #include "gemm_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace uocr {
 
@@ -76,93 +77,6 @@ static int make_tmap(CUtensorMap* map, const void* base, int rank, const uint64_
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return UOCR_ERR_UNSUPPORTED; }
     return UOCR_OK;
-}
-
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp receives row (lane base + t)
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float* v) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start >> 4 | LBO(=1) << 16 | SBO (1024 B = 8 rows x 128 B) >> 4 << 32 | version 1 << 46 | SWIZZLE_128B (2) << 61
-__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// MN-major (the contraction index is the OUTER, strided index in memory).  For 32-bit operands the
-// only legal swizzle is SWIZZLE_128B_BASE32B: 128-byte rows of 32 contiguous MN elements whose
-// 32-byte chunks are XOR-ed with (row % 4); atom = 32 MN x 4 K-rows (512 B).  Canonical layout
-// ((4,8,m),(4,k)) : ((1,4,LBO),(32,SBO)) in floats: MN blocks of 32 at LBO, 4-row K groups at SBO.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;
-    d |= (uint64_t)(512 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)1 << 61;                                 // SWIZZLE_128B_BASE32B
-    return d;
 }
 
 constexpr int TC_BM = 128;           // UMMA M
@@ -396,15 +310,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) tc_gemm_kernel(const __grid_con
                     v[j] = apply_act(t, p.act, p.alpha);
                 }
             }
+            // (every loop over v[] is fully unrolled with predicates: a runtime index would push the
+            // accumulator fragment into local memory -- that made the epilogue the bottleneck)
             float* dst = crow_ptr + c0;
             if (p.atomic) {
-                for (int j = 0; j < ncols; ++j) atomicAdd(dst + j, v[j]);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) atomicAdd(dst + j, v[j]);
             } else if (ncols == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
-                for (int j = 0; j < ncols; ++j) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j < ncols) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
             }
         }
     }
@@ -457,12 +377,23 @@ static int pick_nt(int64_t n) {
     return (int)(((n + 15) / 16) * 16);
 }
 
+static int tc_gemm_tn_persistent(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
+                                 int64_t M, int64_t N, int64_t K, const float* bias, int act, float alpha,
+                                 int accumulate, cudaStream_t st);
+
 // D[M,N] = act(A[M,K] . Bt[N,K]^T + bias); A, Bt K-major (rows contiguous in K)
 int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc, int64_t M,
                int64_t N, int64_t K, const float* bias, int act, float alpha, int accumulate, cudaStream_t st) {
     if ((lda % 4) || (ldb % 4) || ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Bt)) & 15))
         return UOCR_ERR_UNSUPPORTED;            // TMA: 16-byte aligned base and row pitch
     if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffff || K > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    {
+        // enough 128 x NT tiles to give every SM at least one
+        static const int persist = env_int("UOCR_TC_PERSISTENT", 1);
+        const int64_t nt = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+        if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= 148)
+            return tc_gemm_tn_persistent(A, lda, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
+    }
     TcParams p{};
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.num_kb = (int)ceil_div(K, TC_BK);
     p.nt = pick_nt(N);
@@ -478,6 +409,195 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
     if (rc) return rc;
     dim3 grid((unsigned)ceil_div(M, TC_BM), (unsigned)ceil_div(N, p.nt));
     return launch_tc<TC_GEMM>(ma, mb, p, grid, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent variant for the large K-major GEMMs (FullyConnected forward / dgrad at batch >= ~10k rows).
+// One CTA per SM loops over 128 x NT output tiles (NT up to 256: 43.7 flop per L2 byte instead of 21.8
+// for the 128 x 64 tiles above, which ncu showed L2-bandwidth bound).  The accumulator is DOUBLE
+// BUFFERED in TMEM (2 x NT columns): while the four epilogue warps drain tile i (tcgen05.ld -> bias ->
+// activation -> global), the MMA warp already accumulates tile i + 1 and the TMA warp runs further ahead
+// through the shared-memory ring, so neither the pipeline fill nor the epilogue is exposed per tile.
+//   full[s] / empty[s]          : TMA <-> MMA, per shared-memory stage
+//   tmem_full[b] / tmem_empty[b]: MMA <-> epilogue, per accumulator buffer (empty: 4 arrivals, one per warp)
+// Tiles are walked n-tile-major so the ~148 CTAs working at the same time share one B tile in L2.
+// ------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                           const __grid_constant__ CUtensorMap map_b,
+                                                                           const TcParams p, int m_tiles, int n_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = TC_BM * TC_BK * 4;
+    const uint32_t b_bytes = (uint32_t)p.nt * TC_BK * 4;
+    const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;            // [2]
+    uint64_t* tmem_empty = bars + 2 * p.stages + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = m_tiles * n_tiles;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < 2 * p.nt) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&tmem_full[b]), 1);
+            mbar_init(smem_u32(&tmem_empty[b]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int it = 0;                                    // running K-block counter across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile % m_tiles) * TC_BM, n0 = (tile / m_tiles) * p.nt;
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t phase = (it / p.stages) & 1;
+                    mbar_wait(smem_u32(&empty[s]), phase ^ 1);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t bar = smem_u32(&full[s]);
+                    mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
+                    tma_load_2d(sa, &map_a, bar, kb * TC_BK, m0);
+                    tma_load_2d(sa + a_bytes, &map_b, bar, kb * TC_BK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            int it = 0, local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                const int buf = local & 1;
+                mbar_wait(smem_u32(&tmem_empty[buf]), ((local >> 1) & 1) ^ 1);   // epilogue drained this buffer
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + (uint32_t)(buf * p.nt);
+                for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t phase = (it / p.stages) & 1;
+                    mbar_wait(smem_u32(&full[s]), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint64_t da = make_kmajor_sw128_desc(sa);
+                    const uint64_t db = make_kmajor_sw128_desc(sa + a_bytes);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                    (kb > 0 || k > 0) ? 1u : 0u);
+                    tc_commit(smem_u32(&empty[s]));
+                }
+                tc_commit(smem_u32(&tmem_full[buf]));
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            const int buf = local & 1;
+            const int64_t m0 = (int64_t)(tile % m_tiles) * TC_BM;
+            const int n0 = (tile / m_tiles) * p.nt;
+            mbar_wait(smem_u32(&tmem_full[buf]), (local >> 1) & 1);
+            tc_fence_after();
+            const int r = q * 32 + lane;
+            const bool row_ok = m0 + r < p.M;
+            float* crow_ptr = p.C + (m0 + r) * p.ldc + n0;
+            for (int c0 = 0; c0 < p.nt; c0 += 32) {
+                float v[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt + c0), v);
+                if (c0 + 32 >= p.nt) {                       // last chunk is in registers: release the buffer
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
+                }
+                if (!row_ok) continue;
+                const int ncols = (int)min((int64_t)32, p.N - n0 - c0);
+                if (ncols <= 0) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (j < ncols) {
+                        float t = v[j] + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
+                        v[j] = apply_act(t, p.act, p.alpha);
+                    }
+                }
+                float* dst = crow_ptr + c0;
+                if (ncols == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+static int tc_gemm_tn_persistent(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
+                                 int64_t M, int64_t N, int64_t K, const float* bias, int act, float alpha,
+                                 int accumulate, cudaStream_t st) {
+    TcParams p{};
+    p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.num_kb = (int)ceil_div(K, TC_BK);
+    p.nt = N >= 256 ? 256 : (int)(((N + 15) / 16) * 16);
+    p.bias = bias; p.act = act; p.alpha = alpha; p.accumulate = accumulate;
+    const size_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (((size_t)p.nt * TC_BK * 4) + 1023) & ~(size_t)1023;
+    p.stages = (int)((200 * 1024) / (a_bytes + b_bytes));
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return UOCR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + 1024 + (2 * p.stages + 5) * 8 + 64;
+    CUtensorMap ma, mb;
+    const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 4};
+    const uint32_t ba[2] = {TC_BK, TC_BM};
+    int rc = make_tmap(&ma, A, 2, da, sa, ba);
+    if (rc) return rc;
+    const uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldb * 4};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)p.nt};
+    rc = make_tmap(&mb, Bt, 2, db, sb, bb);
+    if (rc) return rc;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             220 * 1024);
+        if (e != cudaSuccess) { num_sms = 0; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+    }
+    const int m_tiles = (int)ceil_div(M, TC_BM), n_tiles = (int)ceil_div(N, p.nt);
+    const int64_t tiles = (int64_t)m_tiles * n_tiles;
+    const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
+    tc_gemm_persistent_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, m_tiles, n_tiles);
+    UOCR_LAUNCHED("tc_gemm_persistent_tf32");
+    return UOCR_OK;
 }
 
 // C[M,N] += At[K,M]^T . B[K,N]   (both operands stored with the contraction index K as the ROW index:
@@ -739,20 +859,7 @@ constexpr int PT_XP = 136;           // x tile pitch (>= PT_TW + 4)
 constexpr int PT_C1 = 16;
 constexpr int PT_PLANE = (PT_TH + 2) * PT_HP * 16;    // bytes per channel-quad plane
 
-__device__ __forceinline__ float round_tf32(float v) {        // the tensor core would truncate: round instead
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    return __uint_as_float(u);
-}
 
-__device__ __forceinline__ uint64_t make_kmajor_nosw_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(lbo_bytes >> 4) << 16;               // K direction: next 16-byte chunk
-    d |= (uint64_t)(sbo_bytes >> 4) << 32;               // M/N direction: next group of 8 rows
-    d |= (uint64_t)1 << 46;
-    return d;                                            // layout type 0: no swizzle
-}
 
 constexpr int PT_THREADS = 288;      // warps 0-7: hidden tile + epilogue; warp 8: hidden tile + MMA issue
 
