@@ -149,8 +149,9 @@ int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, c
  * (inference only: nothing is saved for a backward pass).   replaces: the conv_1 -> leaky_relu_1
  * -> conv_2 -> sigmoid chain of make_monochrome (my_model/model.py:119-122), i.e. four
  * layer calls of convolutional.py:62-99 / layers.py:390-415.   x, y: (N, H, W, 1).
- * With UOCR_PAIR_TC=1 in the environment, math_mode TF32 and c_mid == 16 select an experimental
- * variant whose 16 -> 1 convolution runs as tcgen05.mma (slower than the CUDA-core kernel: N = 1). */
+ * math_mode TF32 with c_mid == 16 runs BOTH convolutions on the tensor cores (tcgen05.mma with the A operands
+ * resident in tensor memory, csrc/conv_pair_tc.cu); UOCR_PAIR_TC=0 in the environment keeps the CUDA-core
+ * kernel, UOCR_PAIR_TC=1 selects the earlier shared-memory MMA variant (a measured negative result). */
 int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2,
                           const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
                           int act1, float alpha1, int act2, float alpha2, int math_mode, void* stream);

@@ -115,14 +115,16 @@ def test_char_model_tf32_matches_fp32(nn):
 
 
 def test_monochrome_pair_on_tensor_cores(nn):
-    """uocr_conv3x3_pair_fwd in TF32 mode (hidden tile on CUDA cores -> smem operand planes ->
-    tcgen05.mma for the 16 -> 1 convolution) vs the float64 oracle: |err| <= 1e-3 * max (outputs are
-    sigmoid values in (0, 1)) for aligned and ragged sizes, plus agreement with the FP32 pair kernel."""
+    """uocr_conv3x3_pair_fwd in TF32 mode (both convolutions as tcgen05.mma with TMEM-resident A
+    operands, csrc/conv_pair_tc.cu) vs the float64 oracle: |err| <= 1e-3 * max (outputs are sigmoid
+    values in (0, 1)) for aligned and ragged sizes (strip / band / step remainders, single-pixel
+    rows and columns), plus agreement with the FP32 pair kernel."""
     import ctypes
     from univer_ocr_b200._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
     rng = np.random.default_rng(17)
     for (n, h, w), act2 in (((2, 16, 256), ACT_SIGMOID), ((3, 21, 150), ACT_SIGMOID), ((1, 5, 3), ACT_NONE),
-                            ((2, 496, 736), ACT_SIGMOID)):
+                            ((2, 1, 1), ACT_NONE), ((1, 63, 31), ACT_SIGMOID), ((1, 130, 61), ACT_NONE),
+                            ((5, 3, 240), ACT_SIGMOID), ((2, 496, 736), ACT_SIGMOID)):
         X = f32(rng.uniform(size=(n, h, w, 1)))
         w1 = f32(rng.standard_normal((3, 3, 1, 16)) * 0.4)
         b1 = f32(rng.standard_normal(16) * 0.2)

@@ -389,7 +389,7 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
     if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffff || K > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     {
         // enough 128 x NT tiles to give every SM at least one
-        static const int persist = env_int("UOCR_TC_PERSISTENT", 1);
+        static const int persist = env_int("UOCR_TC_PERSISTENT", 0);   // opt-in: measured slower so far
         const int64_t nt = N >= 256 ? 256 : ((N + 15) / 16) * 16;
         if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= 148)
             return tc_gemm_tn_persistent(A, lda, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
