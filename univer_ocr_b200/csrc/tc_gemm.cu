@@ -362,7 +362,7 @@ static int launch_tc(const CUtensorMap& ma, const CUtensorMap& mb, TcParams& p, 
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             220 * 1024);
+                                             227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
         configured = true;
     }
@@ -391,8 +391,10 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
         // enough 128 x NT tiles to give every SM at least one
         static const int persist = env_int("UOCR_TC_PERSISTENT", 0);   // opt-in: measured slower so far
         const int64_t nt = N >= 256 ? 256 : ((N + 15) / 16) * 16;
-        if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= 148)
-            return tc_gemm_tn_persistent(A, lda, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
+        if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= 148) {
+            const int rc = tc_gemm_tn_persistent(A, lda, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
+            if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+        }
     }
     TcParams p{};
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.num_kb = (int)ceil_div(K, TC_BK);
@@ -423,7 +425,9 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
 // Tiles are walked n-tile-major so the ~148 CTAs working at the same time share one B tile in L2.
 // ------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
+constexpr int TCP_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+
+__global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                            const __grid_constant__ CUtensorMap map_b,
                                                                            const TcParams p, int m_tiles, int n_tiles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -437,11 +441,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const
     uint64_t* tmem_full = bars + 2 * p.stages;            // [2]
     uint64_t* tmem_empty = bars + 2 * p.stages + 2;       // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 4);
+    // bias row staged once per CTA (zero padded; all zeros without a bias): the epilogue reads it with
+    // broadcast 128-bit shared loads instead of 32 dependent global loads per chunk (ncu: the epilogue
+    // warps sat on the long scoreboard of those loads and the tensor pipe idled at 15 %)
+    float* s_bias = reinterpret_cast<float*>(bars + 2 * p.stages + 6);
+    float* s_stage = s_bias + n_tiles * p.nt;               // 8 epilogue warps x 2 KB transpose staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < 2 * p.nt) tmem_cols <<= 1;
+    for (int i = threadIdx.x; i < n_tiles * p.nt; i += TCP_THREADS)
+        s_bias[i] = (p.bias && i < p.N) ? __ldg(p.bias + i) : 0.f;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -450,7 +461,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tmem_full[b]), 1);
-            mbar_init(smem_u32(&tmem_empty[b]), 4);
+            mbar_init(smem_u32(&tmem_empty[b]), 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -470,6 +481,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const
             int it = 0;                                    // running K-block counter across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m0 = (tile % m_tiles) * TC_BM, n0 = (tile / m_tiles) * p.nt;
+                // Every CTA walks the K blocks from a different starting block (the sum does not care about
+                // the order): the ~148 CTAs that share one B tile then read different lines of it at any
+                // moment instead of hammering the same L2 slices.
+                const int rot = (int)(blockIdx.x % (unsigned)p.num_kb);
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t phase = (it / p.stages) & 1;
@@ -477,8 +492,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t bar = smem_u32(&full[s]);
                     mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
-                    tma_load_2d(sa, &map_a, bar, kb * TC_BK, m0);
-                    tma_load_2d(sa + a_bytes, &map_b, bar, kb * TC_BK, n0);
+                    const int kk = (kb + rot >= p.num_kb ? kb + rot - p.num_kb : kb + rot) * TC_BK;
+                    tma_load_2d(sa, &map_a, bar, kk, m0);
+                    tma_load_2d(sa + a_bytes, &map_b, bar, kk, n0);
                 }
             }
         }
@@ -511,45 +527,76 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_persistent_kernel(const
             }
         }
     } else {
-        // ===================== epilogue (warps 2..5) =====================
-        const int q = warp & 3;
+        // ===================== epilogue (warps 2..9) =====================
+        // Two warps per TMEM lane quarter (q = warp % 4), alternating 16-column half-chunks.  The tile is
+        // drained at MMA pace only if (a) the next tcgen05.ld is in flight while the current half-chunk is
+        // processed and (b) global stores are row-contiguous: thread = accumulator row after tcgen05.ld, so
+        // a direct 128-bit store touches 32 cache lines; the 32 x 16 block is transposed through a per-warp
+        // 2 KB staging block (16-byte granules XOR-swizzled with the row, conflict-free both ways) and
+        // leaves as 8 rows x 64 contiguous bytes per store instruction.
+        const int e = warp - 2, q = warp & 3, half = e >> 2;
+        float4* stg = reinterpret_cast<float4*>(s_stage) + e * 128;
+        const int nhc = p.nt >> 4;                           // half-chunks per tile
+        const int sub_r = lane >> 2, sub_g = lane & 3;       // store phase: row within a group of 8, granule
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         int local = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
             const int buf = local & 1;
-            const int64_t m0 = (int64_t)(tile % m_tiles) * TC_BM;
+            const int64_t row0 = (int64_t)(tile % m_tiles) * TC_BM + q * 32;   // first row of this warp
             const int n0 = (tile / m_tiles) * p.nt;
             mbar_wait(smem_u32(&tmem_full[buf]), (local >> 1) & 1);
             tc_fence_after();
-            const int r = q * 32 + lane;
-            const bool row_ok = m0 + r < p.M;
-            float* crow_ptr = p.C + (m0 + r) * p.ldc + n0;
-            for (int c0 = 0; c0 < p.nt; c0 += 32) {
-                float v[32];
-                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt + c0), v);
-                if (c0 + 32 >= p.nt) {                       // last chunk is in registers: release the buffer
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
+            uint32_t va[16], vb[16];
+            auto handle = [&](uint32_t* cur, uint32_t* nxt, int hc) {
+                tc_wait_ld();                                // cur[] is in registers
+                if (hc + 2 < nhc) {
+                    tc_ld16_nowait(tq + (uint32_t)((hc + 2) * 16), nxt);
+                } else {                                     // this warp has read all its columns of the buffer
                     tc_fence_before();
                     if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
                 }
-                if (!row_ok) continue;
-                const int ncols = (int)min((int64_t)32, p.N - n0 - c0);
-                if (ncols <= 0) continue;
+                const int c = n0 + hc * 16;
+                const int ncols = (int)min((int64_t)16, p.N - c);
+                if (ncols <= 0) return;                      // warp-uniform
+                const float4* bs = reinterpret_cast<const float4*>(s_bias + c);
+                __syncwarp();                                // earlier reads of the staging block are done
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    if (j < ncols) {
-                        float t = v[j] + (p.bias ? __ldg(p.bias + n0 + c0 + j) : 0.f);
-                        v[j] = apply_act(t, p.act, p.alpha);
+                for (int g = 0; g < 4; ++g) {
+                    const float4 b4 = bs[g];
+                    stg[lane * 4 + (g ^ ((lane >> 1) & 3))] =
+                        make_float4(apply_act_fast(__uint_as_float(cur[4 * g]) + b4.x, p.act, p.alpha),
+                                    apply_act_fast(__uint_as_float(cur[4 * g + 1]) + b4.y, p.act, p.alpha),
+                                    apply_act_fast(__uint_as_float(cur[4 * g + 2]) + b4.z, p.act, p.alpha),
+                                    apply_act_fast(__uint_as_float(cur[4 * g + 3]) + b4.w, p.act, p.alpha));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rr = 8 * i + sub_r;
+                    const float4 o = stg[rr * 4 + (sub_g ^ ((rr >> 1) & 3))];
+                    if (row0 + rr >= p.M) continue;
+                    float* dst = p.C + (row0 + rr) * p.ldc + c + 4 * sub_g;
+                    if (vec_ok && ncols == 16) {
+                        if (p.accumulate) {
+                            const float4 c4 = *reinterpret_cast<const float4*>(dst);
+                            *reinterpret_cast<float4*>(dst) = make_float4(c4.x + o.x, c4.y + o.y, c4.z + o.z, c4.w + o.w);
+                        } else {
+                            *reinterpret_cast<float4*>(dst) = o;
+                        }
+                    } else {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (4 * sub_g + k < ncols) dst[k] = p.accumulate ? dst[k] + ov[k] : ov[k];
                     }
                 }
-                float* dst = crow_ptr + c0;
-                if (ncols == 32 && !p.accumulate && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (j < ncols) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
-                }
+            };
+            if (half < nhc) tc_ld16_nowait(tq + (uint32_t)(half * 16), va);
+            else { tc_fence_before(); if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf])); }
+            for (int hc = half; hc < nhc; hc += 4) {
+                handle(va, vb, hc);
+                if (hc + 2 < nhc) handle(vb, va, hc + 2);
             }
         }
     }
@@ -570,10 +617,12 @@ static int tc_gemm_tn_persistent(const float* A, int64_t lda, const float* Bt, i
     p.nt = N >= 256 ? 256 : (int)(((N + 15) / 16) * 16);
     p.bias = bias; p.act = act; p.alpha = alpha; p.accumulate = accumulate;
     const size_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (((size_t)p.nt * TC_BK * 4) + 1023) & ~(size_t)1023;
-    p.stages = (int)((200 * 1024) / (a_bytes + b_bytes));
+    p.stages = (int)((196 * 1024) / (a_bytes + b_bytes));
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return UOCR_ERR_UNSUPPORTED;
-    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + 1024 + (2 * p.stages + 5) * 8 + 64;
+    const size_t bias_floats = (size_t)ceil_div(N, p.nt) * p.nt;
+    if (bias_floats > 2048) return UOCR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + 1024 + (2 * p.stages + 6) * 8 + bias_floats * 4 + 8 * 2048 + 64;
     CUtensorMap ma, mb;
     const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 4};
     const uint32_t ba[2] = {TC_BK, TC_BM};
@@ -589,13 +638,13 @@ static int tc_gemm_tn_persistent(const float* A, int64_t lda, const float* Bt, i
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             220 * 1024);
+                                             227 * 1024);
         if (e != cudaSuccess) { num_sms = 0; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
     }
     const int m_tiles = (int)ceil_div(M, TC_BM), n_tiles = (int)ceil_div(N, p.nt);
     const int64_t tiles = (int64_t)m_tiles * n_tiles;
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    tc_gemm_persistent_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p, m_tiles, n_tiles);
+    tc_gemm_persistent_kernel<<<grid, TCP_THREADS, smem, st>>>(ma, mb, p, m_tiles, n_tiles);
     UOCR_LAUNCHED("tc_gemm_persistent_tf32");
     return UOCR_OK;
 }
