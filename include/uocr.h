@@ -156,6 +156,18 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
                           const float* b2, float* y, int64_t n, int64_t h, int64_t w, int32_t c_mid,
                           int act1, float alpha1, int act2, float alpha2, int math_mode, void* stream);
 
+/* y = the whole single-channel "hourglass" network in ONE kernel (inference only):
+ *   conv5x5 s2 + LeakyRelu -> conv5x5 s2 + LeakyRelu -> Upsample2D(2), conv5x5 + LeakyRelu ->
+ *   Upsample2D(2), conv5x5 + LeakyRelu -> conv5x5 + act_end           (all 1 -> 1 channels, padding 2, zero padding)
+ * replaces: make_paragraph's down_1, down_2, up_2, up_1, end blocks (my_model/model.py:137-190), i.e. five
+ * Convolutional2D._forward (convolutional.py:62-99), two Upsample2D._forward (upsample.py:21-39) and five
+ * activation layers (layers.py:390-415); every intermediate map stays in shared memory.
+ * weights / biases: HOST arrays of 5 device pointers in the order down_1, down_2, up_2, up_1, end ((5,5,1,1) and (1)).
+ * x, y: (N, H, W, 1) with H % 4 == 0 and W % 4 == 0 (the geometry for which the network's own output shape equals
+ * its input shape); UOCR_ERR_UNSUPPORTED otherwise.  FP32 FFMA in every math mode. */
+int uocr_hourglass1_fwd(const float* x, const float* const* weights, const float* const* biases, float* y,
+                        int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end, void* stream);
+
 /* Backward of the same pair in TRAINING (y = conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2, the final
  * activation handled by its own layer): dw1/db1/dw2/db2 (+)= parameter gradients, dx = input gradient
  * (skipped when dx == NULL), from x and dy = dL/dy only -- the c_mid-channel hidden map is recomputed

@@ -506,4 +506,56 @@ def test_inference_pipeline_matches_direct_predict(nn):
         got[tag] = outs[0].copy()
     assert sorted(got) == list(range(7))
     for i in range(7):
-        assert np.array_equal(got[i], want[i]), i
+        assert np.array_equal(got[i], want[i]), i@pytest.mark.gpu
+def test_hourglass_fused_kernel_vs_oracle(nn):
+    """uocr_hourglass1_fwd (the whole Paragraph network in one kernel, parity-folded upsample convs)
+    vs the float64 oracle chain of five conv layers, for block-aligned, ragged (H, W not multiples of
+    the 32 x 128 block), tiny and full-tile sizes; FP32 tolerance (rtol 1e-4 + 2e-6 max)."""
+    import ctypes
+    from univer_ocr_b200._lib import ACT_NONE, ACT_SIGMOID, lib
+    rng = np.random.default_rng(123)
+    for (n, h, w), act_end in (((2, 32, 128), ACT_SIGMOID), ((1, 36, 140), ACT_NONE), ((3, 4, 4), ACT_SIGMOID),
+                               ((2, 8, 300), ACT_NONE), ((1, 132, 12), ACT_SIGMOID), ((1, 496, 736), ACT_SIGMOID)):
+        X = f32(rng.uniform(size=(n, h, w, 1)))
+        ws = [f32(rng.standard_normal((5, 5, 1, 1)) * 0.25) for _ in range(5)]
+        bs = [f32(rng.standard_normal(1) * 0.3) for _ in range(5)]
+        t = O.leaky_relu_fwd(O.conv2d_fwd(X, ws[0], bs[0], 2, stride=2), 0.01)
+        t = O.leaky_relu_fwd(O.conv2d_fwd(t, ws[1], bs[1], 2, stride=2), 0.01)
+        t = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(t, 2), ws[2], bs[2], 2), 0.01)
+        t = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(t, 2), ws[3], bs[3], 2), 0.01)
+        want = O.conv2d_fwd(t, ws[4], bs[4], 2)
+        if act_end == ACT_SIGMOID:
+            want = O.sigmoid_fwd(want)
+        dX = nn.CP.copy(X)
+        dw = [nn.CP.copy(a) for a in ws]
+        db = [nn.CP.copy(a) for a in bs]
+        ptrs = ctypes.c_void_p * 5
+        y = nn.DeviceArray((n, h, w, 1))
+        lib.uocr_hourglass1_fwd(dX.ptr, ptrs(*[a.ptr for a in dw]), ptrs(*[a.ptr for a in db]), y.ptr, n, h, w,
+                                0.01, act_end, 0.0, nn.CP.stream())
+        close(host(y), want, 1e-4, 2e-6, f'hourglass {(n, h, w)}')
+
+
+@pytest.mark.gpu
+def test_paragraph_predict_uses_hourglass_kernel(nn):
+    """Model.predict of make_paragraph takes the fused whole-network kernel (one launch) when H and W
+    are multiples of 4, the layer plan otherwise, with the same result either way."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200._lib import launch_count
+    w0 = np_models.golden_weights('paragraph', 99)
+    for shape, fused in (((2, 48, 80, 1), True), ((2, 496, 736, 1), True)):
+        X = f32(np.random.default_rng(8).uniform(size=shape))
+        model = my_model.make_paragraph(shape)
+        model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})
+        dX = nn.CP.copy(X)
+        before = launch_count()
+        got = host(model.predict(dX)[0])
+        launches = launch_count() - before
+        assert (launches == 1) == fused, launches
+        hook, model.infer_fusion = model.infer_fusion, None
+        ref = host(model.predict(dX)[0])
+        model.infer_fusion = hook
+        close(got, ref, 1e-4, 2e-6, f'paragraph fused vs layers {shape}')
+
+
+

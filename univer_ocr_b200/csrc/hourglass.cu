@@ -1,0 +1,280 @@
+// Fused single-channel "hourglass" forward (inference): the whole Paragraph network in one kernel.
+//
+//   x -> conv5x5 s2 + act -> conv5x5 s2 + act -> up x2, conv5x5 + act -> up x2, conv5x5 + act -> conv5x5 + act_end -> y
+//        (down_1)            (down_2)            (up_2)                  (up_1)                  (end)
+//   replaces, for make_paragraph (my_model/model.py:137-190, channels = 1): five Convolutional2D._forward calls
+//   (convolutional.py:62-99), two Upsample2D._forward (upsample.py:21-39) and five LeakyRelu / Sigmoid._forward
+//   (layers.py:390-415), i.e. 12 layer calls that move 18.6 MB per 496 x 736 tile between them; fused, a tile is
+//   read once and written once (2.92 MB).
+//
+// One CTA produces a TH x TW block of the output.  Working backwards through the five 5 x 5 convolutions gives
+// the region of every intermediate map the block depends on (receptive field 29 + the stride-2 alignment):
+//   X  (TH + 25) x (TW + 25)   full resolution, origin (oy0 - 14, ox0 - 14)
+//   D1 (TH/2 + 11) x (TW/2 + 11)   half,    origin (oy0/2 - 6, ..)       D2 (TH/4 + 4) x (TW/4 + 4)  quarter, origin (oy0/4 - 2, ..)
+//   U2 (TH/2 + 4) x (TW/2 + 4)     half,    origin (oy0/2 - 2, ..)       U1 (TH + 4) x (TW + 4)      full,    origin (oy0 - 2, ..)
+// all of which live in shared memory (70 KB for 32 x 128 blocks, 3 CTAs per SM); halo recomputation costs 22 % extra
+// FMAs.  Values outside an intermediate map's image are stored as 0 -- they are the next convolution's zero padding.
+// With these origins every level reads its source at (2 r + ky, 2 c + kx) or (r + ky, c + kx): no index arithmetic.
+//
+// A 5 x 5 convolution over a x2 nearest-upsampled map only ever sees 3 x 3 distinct source pixels: for output row
+// parity 0 the kernel rows {0,1}, {2,3}, {4} hit source rows m-1, m, m+1, for parity 1 the rows {0}, {1,2}, {3,4};
+// same for columns.  The two "up" levels therefore run as four parity-specific 3 x 3 convolutions on the low-resolution
+// map with pre-summed weights (9 FMA per output instead of 25; the upsampled map is never materialised).
+// Register tiling: a thread computes 4 (stride-2 levels) or 8 (stride-1 / up levels) outputs of a row from 64-bit
+// shared loads, weights in registers.
+#include "conv_common.cuh"
+
+namespace uocr {
+
+struct HourglassParams {
+    const float* x; float* y;
+    const float* w[5]; const float* b[5];       // down_1, down_2, up_2, up_1, end : (5,5,1,1) + (1)
+    int H, W;
+    float alpha;                                 // LeakyReLU slope of the four inner activations
+    int act_end; float alpha_end;
+};
+
+template <int TH, int TW>
+struct HG {
+    // X block: origin column ox0 - 16 (16-byte aligned for cp.async; the convolution reads from column 2 on),
+    // two spare rows for the last 4-row strip of D1
+    static constexpr int XH = TH + 25, XW = TW + 27, XP = (XW + 3 + 3) & ~3, XROWS = XH + 2;
+    static constexpr int D1H = TH / 2 + 11, D1W = TW / 2 + 11, D1P = (D1W + 3 + 3) & ~3;
+    static constexpr int D2H = TH / 4 + 4, D2W = TW / 4 + 4, D2P = (D2W + 2 + 3 + 3) & ~3;
+    static constexpr int U2H = TH / 2 + 4, U2W = TW / 2 + 4, U2P = (U2W + 3 + 3) & ~3;
+    static constexpr int U1H = TH + 4, U1W = TW + 4, U1P = (U1W + 3 + 3) & ~3;
+    static constexpr int FLOATS = XROWS * XP + D1H * D1P + D2H * D2P + U2H * U2P + U1H * U1P + 5 * 26 + 2 * 36 + 6;
+};
+
+constexpr int HG_THREADS = 256;
+
+// dst (DH x DW, origin (gy0, gx0) at its resolution, image hl x wl) = act(conv5x5 stride 2 (src) + b); src(2r+ky, 2c+kx).
+// Thread = one output column x 4 rows: neighbouring lanes read neighbouring 8-byte words (no bank conflicts).
+template <int DH, int DW, int DP, int SP>
+__device__ __forceinline__ void hg_down(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ wb,
+                                        int gy0, int gx0, int hl, int wl, float alpha) {
+    float w[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) w[i] = wb[i];
+    const float bias = wb[25];
+    constexpr int STRIPS = (DH + 3) / 4;
+    for (int item = threadIdx.x; item < STRIPS * DW; item += HG_THREADS) {
+        const int s = item / DW, c = item - s * DW, r0 = 4 * s;
+        float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+        for (int rr = 0; rr < 11; ++rr) {
+            const float2* row = reinterpret_cast<const float2*>(src + (2 * r0 + rr) * SP + 2 * c);
+            const float2 a = row[0], b = row[1], e = row[2];
+            const float in[5] = {a.x, a.y, b.x, b.y, e.x};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ky = rr - 2 * j;
+                if (ky >= 0 && ky < 5) {
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) acc[j] = fmaf(w[ky * 5 + kx], in[kx], acc[j]);
+                }
+            }
+        }
+        const bool colin = (unsigned)(gx0 + c) < (unsigned)wl;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float v = fmaxf(acc[j], acc[j] * alpha);
+            if (r0 + j < DH) dst[(r0 + j) * DP + c] = (colin && (unsigned)(gy0 + r0 + j) < (unsigned)hl) ? v : 0.f;
+        }
+    }
+}
+
+// dst (DH x DW at 2x the source resolution, origin (gy0, gx0) even) = act(conv5x5(upsample2(src)) + b) through the four
+// parity-folded 3 x 3 kernels wf[py][px][a][b]; output rows (2j, 2j+1) x columns (2n, 2n+1) read src(j + a, n + b).
+// Thread = 2 source cells = a 2 x 4 output block (8-byte loads, 16-byte stores at lane stride: conflict-free).
+template <int DH, int DW, int DP, int SP>
+__device__ __forceinline__ void hg_up(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ wf,
+                                      float bias, int gy0, int gx0, int hl, int wl, float alpha) {
+    float w[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) w[i] = wf[i];
+    constexpr int GROUPS = (DW + 3) / 4;
+    for (int item = threadIdx.x; item < (DH / 2) * GROUPS; item += HG_THREADS) {
+        const int j = item / GROUPS, n0 = (item - j * GROUPS) * 2;
+        float s[3][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float2* row = reinterpret_cast<const float2*>(src + (j + a) * SP + n0);
+            const float2 u = row[0], v = row[1];
+            s[a][0] = u.x; s[a][1] = u.y; s[a][2] = v.x; s[a][3] = v.y;
+        }
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    float acc = bias;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int b = 0; b < 3; ++b) acc = fmaf(w[((py * 2 + px) * 3 + a) * 3 + b], s[a][i + b], acc);
+                    o[2 * i + px] = fmaxf(acc, acc * alpha);
+                }
+            const bool rowin = (unsigned)(gy0 + 2 * j + py) < (unsigned)hl;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (!(rowin && (unsigned)(gx0 + 2 * n0 + k) < (unsigned)wl)) o[k] = 0.f;
+            *reinterpret_cast<float4*>(dst + (2 * j + py) * DP + 2 * n0) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// wf[py][px][a][b] = sum of the 5 x 5 weights whose row / column lands on source offset a / b for that parity
+__device__ __forceinline__ void hg_fold(const float* __restrict__ w25, float* __restrict__ wf) {
+    for (int i = threadIdx.x; i < 36; i += HG_THREADS) {
+        const int b = i % 3, a = (i / 3) % 3, px = (i / 9) % 2, py = i / 18;
+        // parity 0: kernel indices {0,1} {2,3} {4};  parity 1: {0} {1,2} {3,4}
+        const int ylo = py == 0 ? 2 * a : (a == 0 ? 0 : 2 * a - 1), yhi = py == 0 ? min(2 * a + 1, 4) : (a == 0 ? 0 : 2 * a);
+        const int xlo = px == 0 ? 2 * b : (b == 0 ? 0 : 2 * b - 1), xhi = px == 0 ? min(2 * b + 1, 4) : (b == 0 ? 0 : 2 * b);
+        float s = 0.f;
+        for (int ky = ylo; ky <= yhi; ++ky)
+            for (int kx = xlo; kx <= xhi; ++kx) s += w25[ky * 5 + kx];
+        wf[i] = s;
+    }
+}
+
+template <int TH, int TW>
+__global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const HourglassParams p) {
+    using G = HG<TH, TW>;
+    extern __shared__ __align__(16) float hg_smem[];
+    float* sX = hg_smem;
+    float* sD1 = sX + G::XROWS * G::XP;
+    float* sD2 = sD1 + G::D1H * G::D1P;
+    float* sU2 = sD2 + G::D2H * G::D2P;
+    float* sU1 = sU2 + G::U2H * G::U2P;
+    float* sW = sU1 + G::U1H * G::U1P;               // 5 x (25 weights + bias)
+    float* sF = sW + 5 * 26;                         // folded kernels of up_2, up_1
+
+    const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
+    const float* xim = p.x + (int64_t)blockIdx.z * p.H * p.W;
+    float* yim = p.y + (int64_t)blockIdx.z * p.H * p.W;
+    const int tid = threadIdx.x;
+
+    // ---- level 0: x block -> shared memory with 16-byte cp.async (zero fill outside the image through src-size 0;
+    // gx and W are multiples of 4, so a 16-byte word is entirely inside or outside).  Nothing is staged in registers
+    // and all of a thread's copies are in flight at once (the first version's LDG -> STS loop was the bottleneck).
+    {
+        constexpr int QUADS = G::XP / 4;
+        const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sX));
+        for (int i = tid; i < G::XH * QUADS; i += HG_THREADS) {
+            const int r = i / QUADS, c = (i - r * QUADS) * 4;
+            const int gy = oy0 - 14 + r, gx = ox0 - 16 + c;
+            const bool in = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
+            const float* gsrc = in ? xim + (int64_t)gy * p.W + gx : xim;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                         ::"r"(sbase + (uint32_t)(r * G::XP + c) * 4u), "l"(gsrc), "r"(in ? 16 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int i = tid; i < 5 * 26; i += HG_THREADS) {
+        const int l = i / 26, k = i - l * 26;
+        sW[i] = k < 25 ? __ldg(p.w[l] + k) : __ldg(p.b[l]);
+    }
+    // spare rows / pad columns the strip loops may read must be finite
+    for (int i = tid; i < 2 * G::XP; i += HG_THREADS) sX[G::XH * G::XP + i] = 0.f;
+    for (int i = tid; i < G::D2H * G::D2P; i += HG_THREADS) sD2[i] = 0.f;
+    for (int i = tid; i < G::U2H * G::U2P; i += HG_THREADS) sU2[i] = 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    hg_fold(sW + 2 * 26, sF);
+    hg_fold(sW + 3 * 26, sF + 36);
+    const int hy0 = oy0 / 2, hx0 = ox0 / 2, qy0 = oy0 / 4, qx0 = ox0 / 4;
+    hg_down<G::D1H, G::D1W, G::D1P, G::XP>(sX + 2, sD1, sW, hy0 - 6, hx0 - 6, p.H / 2, p.W / 2, p.alpha);
+    __syncthreads();
+    hg_down<G::D2H, G::D2W, G::D2P, G::D1P>(sD1, sD2, sW + 26, qy0 - 2, qx0 - 2, p.H / 4, p.W / 4, p.alpha);
+    __syncthreads();
+    hg_up<G::U2H, G::U2W, G::U2P, G::D2P>(sD2, sU2, sF, sW[2 * 26 + 25], hy0 - 2, hx0 - 2, p.H / 2, p.W / 2, p.alpha);
+    __syncthreads();
+    hg_up<G::U1H, G::U1W, G::U1P, G::U2P>(sU2, sU1, sF + 36, sW[3 * 26 + 25], oy0 - 2, ox0 - 2, p.H, p.W, p.alpha);
+    __syncthreads();
+    // ---- end: y(r, c) = act_end(conv5x5(U1)(r + ky, c + kx) + b); thread = 2 rows x 4 columns (16-byte loads at
+    // lane stride: conflict-free)
+    {
+        float w[25];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) w[i] = sW[4 * 26 + i];
+        const float bias = sW[4 * 26 + 25];
+        constexpr int GROUPS = TW / 4;
+        for (int item = tid; item < (TH / 2) * GROUPS; item += HG_THREADS) {
+            const int r = (item / GROUPS) * 2, c0 = (item - (item / GROUPS) * GROUPS) * 4;
+            float acc[2][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = bias;
+#pragma unroll
+            for (int rr = 0; rr < 6; ++rr) {
+                const float4* row = reinterpret_cast<const float4*>(sU1 + (r + rr) * G::U1P + c0);
+                const float4 u = row[0], v = row[1];
+                const float in[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int ky = rr - k;
+                    if (ky >= 0 && ky < 5) {
+#pragma unroll
+                        for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(w[ky * 5 + kx], in[j + kx], acc[k][j]);
+                    }
+                }
+            }
+            const int gx = ox0 + c0;
+            if (gx < p.W) {                                              // W % 4 == 0: float4 granularity
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int gy = oy0 + r + k;
+                    if (gy < p.H)
+                        *reinterpret_cast<float4*>(yim + (int64_t)gy * p.W + gx) =
+                            make_float4(apply_act_fast(acc[k][0], p.act_end, p.alpha_end),
+                                        apply_act_fast(acc[k][1], p.act_end, p.alpha_end),
+                                        apply_act_fast(acc[k][2], p.act_end, p.alpha_end),
+                                        apply_act_fast(acc[k][3], p.act_end, p.alpha_end));
+                }
+            }
+        }
+    }
+}
+
+int hourglass1_fwd(const float* x, const float* const* w, const float* const* b, float* y, int64_t n, int64_t h,
+                   int64_t wd, float alpha, int act_end, float alpha_end, cudaStream_t st) {
+    constexpr int TH = 32, TW = 128;
+    if (h % 4 || wd % 4 || n > 65535 || alpha < 0.f || alpha > 1.f) return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
+    HourglassParams p{};
+    p.x = x; p.y = y;
+    for (int l = 0; l < 5; ++l) { p.w[l] = w[l]; p.b[l] = b[l]; }
+    p.H = (int)h; p.W = (int)wd; p.alpha = alpha; p.act_end = act_end; p.alpha_end = alpha_end;
+    const size_t smem = sizeof(float) * HG<TH, TW>::FLOATS;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(hourglass1_fwd_kernel<TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(wd, TW), (unsigned)ceil_div(h, TH), (unsigned)n);
+    if (grid.y > 65535) return UOCR_ERR_UNSUPPORTED;
+    hourglass1_fwd_kernel<TH, TW><<<grid, HG_THREADS, smem, st>>>(p);
+    UOCR_LAUNCHED("hourglass1_fwd");
+    return UOCR_OK;
+}
+
+}  // namespace uocr
+
+extern "C" int uocr_hourglass1_fwd(const float* x, const float* const* weights, const float* const* biases, float* y,
+                                   int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end,
+                                   void* stream) {
+    using namespace uocr;
+    UOCR_REQUIRE(x && y && weights && biases, "NULL pointer");
+    for (int l = 0; l < 5; ++l) UOCR_REQUIRE(weights[l] && biases[l], "NULL weight pointer (level %d)", l);
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && h < (1 << 30) && w < (1 << 30), "bad dimension");
+    UOCR_REQUIRE(act_end >= UOCR_ACT_NONE && act_end <= UOCR_ACT_SIGMOID, "unknown activation %d", act_end);
+    const int rc = hourglass1_fwd(x, weights, biases, y, n, h, w, alpha, act_end, alpha_end, as_stream(stream));
+    if (rc == UOCR_ERR_UNSUPPORTED) set_error("hourglass1_fwd: unsupported geometry (H, W must be multiples of 4)");
+    return rc;
+}

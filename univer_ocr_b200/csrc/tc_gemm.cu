@@ -389,7 +389,7 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
     if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffff || K > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     {
         // enough 128 x NT tiles to give every SM at least one
-        static const int persist = env_int("UOCR_TC_PERSISTENT", 0);   // opt-in: measured slower so far
+        static const int persist = env_int("UOCR_TC_PERSISTENT", 1);
         const int64_t nt = N >= 256 ? 256 : ((N + 15) / 16) * 16;
         if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= 148) {
             const int rc = tc_gemm_tn_persistent(A, lda, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
@@ -721,27 +721,51 @@ int fc_fwd_fast(int math_mode, const float* x, const float* w, float* y, int64_t
                       alpha, 0, st);
 }
 
-// out[c] (+)= sum_r src[r][c] : bias gradients (the "ones" column of [x, 1]^T . dy)
+// out[c] += sum_r src[r][c] : bias gradients (the "ones" column of [x, 1]^T . dy).  Rows are split over
+// gridDim.y blocks (enough CTAs to pull the matrix at HBM speed -- one block per 32 columns took 1.2 ms
+// for Char conv_2's 21 MB); each block adds its partial column sums with atomicAdd, like the split-K
+// weight gradients they accompany.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ src, int64_t rows, int cols,
-                                                     float* __restrict__ out, int accumulate) {
+                                                     int64_t rows_per_block, float* __restrict__ out) {
     __shared__ float red[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const int ty = threadIdx.x >> 5;
-    float s = 0.f;
-    if (c < cols)
-        for (int64_t r = ty; r < rows; r += 8) s += src[r * cols + c];
-    red[ty][threadIdx.x & 31] = s;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+    const int64_t r1 = min(rows, r0 + rows_per_block);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < cols) {
+        int64_t r = r0 + ty;
+        for (; r + 24 < r1; r += 32) {                       // 4 independent loads in flight per thread
+            s0 += __ldg(src + r * cols + c);
+            s1 += __ldg(src + (r + 8) * cols + c);
+            s2 += __ldg(src + (r + 16) * cols + c);
+            s3 += __ldg(src + (r + 24) * cols + c);
+        }
+        for (; r < r1; r += 8) s0 += __ldg(src + r * cols + c);
+    }
+    red[ty][threadIdx.x & 31] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (ty == 0 && c < cols) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-        out[c] = accumulate ? out[c] + t : t;
+        atomicAdd(out + c, t);
     }
 }
 
 static int colsum_async(const float* src, int64_t rows, int cols, float* out, int accumulate, cudaStream_t st) {
-    colsum_kernel<<<(cols + 31) / 32, 256, 0, st>>>(src, rows, cols, out, accumulate);
+    if (!accumulate) {
+        cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * cols, st);
+        if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+    }
+    const int gx = (cols + 31) / 32;
+    int64_t gy = ceil_div(148 * 8, gx);                      // ~8 CTAs per SM in total
+    const int64_t max_gy = ceil_div(rows, 64);               // at least 64 rows per block
+    if (gy > max_gy) gy = max_gy;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    const int64_t rpb = ceil_div(rows, gy);
+    colsum_kernel<<<dim3((unsigned)gx, (unsigned)ceil_div(rows, rpb)), 256, 0, st>>>(src, rows, cols, rpb, out);
     UOCR_LAUNCHED("colsum");
     return UOCR_OK;
 }

@@ -15,7 +15,7 @@ from .nn.help_func import make_list_if_not
 from .nn.layers import (Concat, Conv2DToBatchedFixedWidthed, Convolutional2D, Flatten,
                         FullyConnected, LeakyRelu, Sigmoid, Upsample2D)
 from .nn.losses import SegmentationDice2D, SoftmaxCrossEntropy
-from .nn.models import Model
+from .nn.models import HourglassFusion, Model
 from .nn.optimizers import Adam
 from .nn.regularizations import L2
 
@@ -109,6 +109,8 @@ def _make_hourglass(name, input_shape, channels, out_channels, optimizer):
         0: 'end',
     }
     model = wrap(name, Model(layers=layers, relations=relations), loss=SegmentationDice2D())
+    if channels == 1 and out_channels == 1:
+        model.infer_fusion = HourglassFusion(name)      # whole-network inference kernel (Paragraph)
     model.initialize(input_shape)
     return model
 

@@ -69,6 +69,11 @@ class Model(BaseModel):
     # Fused-away tensors are absent (None) from `layers_outputs`; set `fusion = False` (class or
     # instance) before initialize() to get every per-layer output like the reference.
     fusion = True
+    # Optional whole-network inference kernel: a callable (model, inputs) -> list of outputs or None
+    # (None = geometry not supported, run the layer plan).  Set by builders that know the topology
+    # (my_model._make_hourglass -> HourglassFusion); only consulted when `fusion` is on and training
+    # is off, so training, gradient checks and `fusion = False` see the plain layer graph.
+    infer_fusion = None
     # False: skip the gradient w.r.t. the model INPUTS (the reference always computes it,
     # models.py:207-230, but a training step never uses it); `input_grads` entries are then None
     compute_input_grads = True
@@ -200,6 +205,7 @@ class Model(BaseModel):
             print(f'These layers have never been visited: {never}')
         self._plan_train = self._make_plan(training=True)
         self._plan_infer = self._make_plan(training=False)
+        self._fusion_planned = bool(self.fusion)                    # like the plans: fixed at initialize
         self.is_initialized = True
 
     # ---- fusion planning ----------------------------------------------------------
@@ -276,6 +282,12 @@ class Model(BaseModel):
         if not self.is_initialized:
             self.initialize_from_X(inputs)
         outputs = {}
+        if not training and self._fusion_planned and self.infer_fusion is not None:
+            fused = self.infer_fusion(self, inputs)
+            if fused is not None:
+                self.layers_outputs = {**{name: None for name in self.layers},
+                                       **{k: fused[k] for k in range(self.outputs_count)}}
+                return fused
 
         def value_of(src):
             return inputs[src] if isinstance(src, int) else outputs[src]
@@ -623,3 +635,72 @@ class Sequential(Model):
             prev = name
         relations[0] = prev
         super().__init__(layers=named, relations=relations, *args, **kwargs)
+
+
+class HourglassFusion:
+    """Whole-network inference kernel for the single-channel hourglass of make_paragraph
+    (my_model/model.py:137-190): down_1, down_2 (conv 5x5 stride 2 + LeakyRelu), up_2, up_1
+    (Upsample2D(2) + conv 5x5 + LeakyRelu), end (conv 5x5 + Sigmoid) as ONE launch of
+    uocr_hourglass1_fwd; the intermediate maps never leave shared memory.
+
+    Attached to the (flattened) top-level Model as `infer_fusion`; returns None (-> layer-by-layer
+    plan) whenever the topology, the hyper-parameters or the input geometry are not the ones the
+    kernel implements."""
+
+    def __init__(self, prefix):
+        p = prefix
+        self.chain = [f'{p}/down_1/conv_1', f'{p}/down_1/leaky_relu_1',
+                      f'{p}/down_2/conv_1', f'{p}/down_2/leaky_relu_1',
+                      f'{p}/up_2/upsample', f'{p}/up_2/conv_block/conv_1', f'{p}/up_2/conv_block/leaky_relu_1',
+                      f'{p}/up_1/upsample', f'{p}/up_1/conv_block/conv_1', f'{p}/up_1/conv_block/leaky_relu_1',
+                      f'{p}/end/conv_1', f'{p}/end/sigmoid']
+
+    def _blocks(self, model):
+        """[(conv, act)] in kernel order, or None if the network is not the expected hourglass."""
+        if set(model.layers) != set(self.chain) or model.outputs_count != 1 or model.inputs_count != 1:
+            return None
+        prev = 0
+        for name in self.chain:                              # a plain chain input -> ... -> output
+            if list(model.relations[name]) != [prev]:
+                return None
+            prev = name
+        if list(model.relations[0]) != [prev]:
+            return None
+        L = model.layers
+        out = []
+        for conv_i, act_i, ups_i, stride in ((0, 1, None, (2, 2)), (2, 3, None, (2, 2)), (5, 6, 4, (1, 1)),
+                                             (8, 9, 7, (1, 1)), (10, 11, None, (1, 1))):
+            conv, act = L[self.chain[conv_i]], L[self.chain[act_i]]
+            if ups_i is not None:
+                ups = L[self.chain[ups_i]]
+                if type(ups) is not Upsample2D or ups.scale_factor != (2, 2):
+                    return None
+            if (type(conv) is not Convolutional2D or conv.kernel_size != (5, 5) or conv.padding != (2, 2)
+                    or conv.stride != stride or conv.in_channels != 1 or conv.out_channels != 1
+                    or conv.padding_value != 0 or not conv.bias):
+                return None
+            out.append((conv, act))
+        return out
+
+    def __call__(self, model, inputs):
+        blocks = self._blocks(model)
+        if blocks is None:
+            return None
+        X = as_device(inputs[0])
+        if len(X.shape) != 4 or X.shape[3] != 1 or X.shape[1] % 4 or X.shape[2] % 4 or X.shape[0] > 65535:
+            return None
+        inner = [_act_code(act) for _, act in blocks[:4]]
+        end = _act_code(blocks[4][1])
+        if (end is None or any(a is None or a[0] != ACT_LEAKY or a[1] > 1 for a in inner)
+                or len({a[1] for a in inner}) != 1):
+            return None
+        n, h, w, _ = X.shape
+        ptrs = ctypes.c_void_p * 5
+        wp = ptrs(*[conv.w.value.ptr for conv, _ in blocks])
+        bp = ptrs(*[conv.b.value.ptr for conv, _ in blocks])
+        last = blocks[4][1]
+        last.progress_tracker.start_tracking(last.name, 'forward')
+        y = DeviceArray((n, h, w, 1))
+        lib.uocr_hourglass1_fwd(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], stream())
+        last.progress_tracker.stop_tracking(last.name, 'forward')
+        return [y]
