@@ -304,11 +304,10 @@ def run_b200(args):
         if tr and tr['batch'] == B:
             roof['traffic'] = tr['bytes']
             roof['traffic_source'] = tr['profile']
+            if tr.get('note'):
+                roof['note'] = tr['note']
     except (OSError, ValueError):
         pass
-    if wk.get('fused') and len(wk['fused']) == 4:
-        roof['note'] = ('graded against HBM per SURVEY 8d, but the fused pair is FFMA-issue bound (AI 72 flop/B >> '
-                        'FP32-core ridge ~11 flop/B): ncu shows the FMA pipe 62% busy, DRAM 4%')
     roof.update({'kernel': '+'.join(wk.get('fused', [top_name])), 'kernel_ms': top_ms, 'share_of_step': top_ms / total_ms,
                  'algorithmic_bytes': wk['bytes'], 'algorithmic_flops': wk['flops']})
     layers_out = []

@@ -163,13 +163,17 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     {
         constexpr int QUADS = G::XP / 4;
         const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sX));
-        for (int i = tid; i < G::XH * QUADS; i += HG_THREADS) {
-            const int r = i / QUADS, c = (i - r * QUADS) * 4;
-            const int gy = oy0 - 14 + r, gx = ox0 - 16 + c;
+        // (r, q) advance by HG_THREADS quads per iteration without a division
+        constexpr int DR = HG_THREADS / QUADS, DQ = HG_THREADS % QUADS;
+        int r = tid / QUADS, q = tid - r * QUADS;
+        for (; r < G::XH; ) {
+            const int gy = oy0 - 14 + r, gx = ox0 - 16 + 4 * q;
             const bool in = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
             const float* gsrc = in ? xim + (int64_t)gy * p.W + gx : xim;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                         ::"r"(sbase + (uint32_t)(r * G::XP + c) * 4u), "l"(gsrc), "r"(in ? 16 : 0) : "memory");
+                         ::"r"(sbase + (uint32_t)(r * G::XP + 4 * q) * 4u), "l"(gsrc), "r"(in ? 16 : 0) : "memory");
+            r += DR; q += DQ;
+            if (q >= QUADS) { q -= QUADS; ++r; }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
@@ -177,10 +181,8 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
         const int l = i / 26, k = i - l * 26;
         sW[i] = k < 25 ? __ldg(p.w[l] + k) : __ldg(p.b[l]);
     }
-    // spare rows / pad columns the strip loops may read must be finite
+    // the two spare rows the last strip of D1 reads must be finite
     for (int i = tid; i < 2 * G::XP; i += HG_THREADS) sX[G::XH * G::XP + i] = 0.f;
-    for (int i = tid; i < G::D2H * G::D2P; i += HG_THREADS) sD2[i] = 0.f;
-    for (int i = tid; i < G::U2H * G::U2P; i += HG_THREADS) sU2[i] = 0.f;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     hg_fold(sW + 2 * 26, sF);

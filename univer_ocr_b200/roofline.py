@@ -67,6 +67,17 @@ def plan_work(model, input_shape, training=False):
     shapes = model_input_shapes(model, input_shape)
     _, all_shapes = model.get_all_output_shapes([input_shape])
     out = {}
+    hook = getattr(model, 'infer_fusion', None)
+    if (not training and hook is not None and getattr(model, '_fusion_planned', False)
+            and hook._blocks(model) is not None and input_shape[1] % 4 == 0 and input_shape[2] % 4 == 0):
+        # whole-network kernel (HourglassFusion): one launch, tracked under the last layer's name
+        names = list(hook.chain)
+        flops = sum(layer_work(model.layers[n], shapes[n], 'forward')['flops'] for n in names
+                    if isinstance(model.layers[n], L.Convolutional2D))
+        wbytes = sum(4 * model.layers[n].count_parameters() for n in names
+                     if isinstance(model.layers[n], L.Convolutional2D))
+        nbytes = 4 * (_numel(input_shape) + _numel(all_shapes[names[-1]][0])) + wbytes
+        return {names[-1]: {'bound': 'hbm', 'bytes': nbytes, 'flops': flops, 'fused': names}}
     for step in (model._plan_train if training else model._plan_infer):
         names = [n for n in step[1:] if n is not None]
         if step[0] == 'layer':
