@@ -131,7 +131,8 @@ typedef struct uocr_conv2d_desc {
     int32_t math_mode;           /* UOCR_MATH_*                                     */
     int32_t in_upsample;         /* 0/1: none.  2: x is (N, H/2, W/2, Cin) and is   */
                                  /* nearest-upsampled x2 on the fly (Upsample2D(2) + */
-                                 /* Convolutional2D in one pass; forward only)      */
+                                 /* Convolutional2D in one pass): forward, and the   */
+                                 /* weight gradient of 5x5 / 1 -> 1 / stride 1 convs */
 } uocr_conv2d_desc;
 
 /* Ho = floor((H + 2ph - kh) / sh) + 1 ...   replaces: Convolutional2D.get_output_shapes,

@@ -160,8 +160,11 @@ def test_nested_model_flattening_order_and_fusion_plan():
     assert infer[2] == ('conv', 'Paragraph/up_2/upsample', 'Paragraph/up_2/conv_block/conv_1',
                         'Paragraph/up_2/conv_block/leaky_relu_1')
     assert infer[4] == ('conv', None, 'Paragraph/end/conv_1', 'Paragraph/end/sigmoid')
-    # training: conv+LeakyRelu fuse, upsample and the final Sigmoid stay separate layers
-    assert ('layer', 'Paragraph/up_1/upsample') in train and ('layer', 'Paragraph/end/sigmoid') in train
+    # training: conv+LeakyRelu fuse; the upsample folds into the 5x5 1->1 conv (its wgrad kernel reads
+    # through the upsampling); the final Sigmoid stays a separate layer
+    assert ('conv', 'Paragraph/up_1/upsample', 'Paragraph/up_1/conv_block/conv_1',
+            'Paragraph/up_1/conv_block/leaky_relu_1') in train
+    assert ('layer', 'Paragraph/end/sigmoid') in train
     assert ('conv', None, 'Paragraph/end/conv_1', None) not in train
     assert ('conv', None, 'Paragraph/down_1/conv_1', 'Paragraph/down_1/leaky_relu_1') in train
 

@@ -455,7 +455,6 @@ int uocr_conv2d_wgrad(const uocr_conv2d_desc* d, const float* x, const float* dy
     int rc = make_geom(d, &g);
     if (rc) return rc;
     UOCR_REQUIRE(x && dy && dw && db, "NULL pointer");
-    UOCR_REQUIRE(g.ups == 1, "in_upsample is a forward-only fusion");
     size_t need = 0;
     uocr_conv2d_wgrad_workspace(d, &need);
     if (need > 0 && (!workspace || workspace_bytes < need)) {
@@ -465,6 +464,8 @@ int uocr_conv2d_wgrad(const uocr_conv2d_desc* d, const float* x, const float* dy
     cudaStream_t st = as_stream(stream);
     rc = conv_wgrad_fast(g, d->math_mode, x, dy, dw, db, accumulate, (float*)workspace, st);
     if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    // x stored at half resolution (in_upsample == 2) is only understood by the 5x5 / 1 -> 1 / stride 1 kernel
+    UOCR_REQUIRE(g.ups == 1, "in_upsample == 2: no weight-gradient kernel for this geometry");
     return conv_wgrad_general(g, x, dy, dw, db, accumulate, (float*)workspace, st);
 }
 

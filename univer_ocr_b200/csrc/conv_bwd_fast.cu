@@ -272,6 +272,101 @@ __global__ void __launch_bounds__(256) conv_small_wgrad_kernel(ConvGeom g, const
     }
 }
 
+// 5 x 5 / stride 1 / 1 -> 1 channel weight gradient (Paragraph up_*, end): same decomposition and workspace layout
+// as conv_small_wgrad_kernel<5,5,1,1,1,1,1,8,R>, but the five input rows an output row needs stay in a register
+// ring while the thread walks down its R rows -- one new input row (6 x 64-bit loads) and one dy row (2 x 128-bit
+// loads) per 200 FMA instead of 68 scalar loads (the generic kernel was L1-wavefront bound: 157 us for 187 MB).
+// UPS: x is stored at half resolution (N, H/2, W/2) and the convolution reads its x2 nearest upsampling (the
+// Upsample2D layer in front folded into the addressing, as in the forward kernels): input pixel (iy, ix) = x(iy/2, ix/2).
+template <int R, bool UPS>
+__global__ void __launch_bounds__(256) conv55_c1_wgrad_roll_kernel(ConvGeom g, const float* __restrict__ x,
+                                                                   const float* __restrict__ dy,
+                                                                   float* __restrict__ ws, int nblk) {
+    constexpr int PX = 8, NIN = 12, NOUT = 26;
+    __shared__ float red[8][NOUT];
+    const int strips = (g.wo + PX - 1) / PX;
+    const int rgroups = (g.ho + R - 1) / R;
+    const int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int xs = (int)(idx % strips);
+    const int rg = (int)((idx / strips) % rgroups);
+    const int64_t n = idx / ((int64_t)strips * rgroups);
+    float acc[5][5];
+    float dbacc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) acc[a][b] = 0.f;
+    if (n < g.n) {
+        const int ox0 = xs * PX, ix0 = ox0 - 2;
+        const int oy0 = rg * R, oy_end = min(g.ho, oy0 + R);
+        const int sw_ = UPS ? g.w / 2 : g.w;                 // stored row pitch
+        const float* xim = x + n * (int64_t)(UPS ? g.h / 2 : g.h) * sw_;
+        const float* dyim = dy + n * g.ho * (int64_t)g.wo;
+        float xr[5][NIN];                                    // ring slot = (input row - (oy0 - 2)) % 5
+        auto load_row = [&](int iy, float* dst) {
+            const bool yin = iy >= 0 && iy < g.h;
+            const float* row = xim + (int64_t)(yin ? (UPS ? iy >> 1 : iy) : 0) * sw_;
+#pragma unroll
+            for (int q = 0; q < NIN / 2; ++q) {
+                const int ix = ix0 + 2 * q;                  // even; W even: the pair is inside or outside together
+                float2 v = make_float2(g.padding_value, g.padding_value);
+                if (yin && ix >= 0 && ix < g.w) {
+                    if (UPS) { const float t = __ldg(row + (ix >> 1)); v = make_float2(t, t); }
+                    else v = __ldg(reinterpret_cast<const float2*>(row + ix));
+                }
+                dst[2 * q] = v.x; dst[2 * q + 1] = v.y;
+            }
+        };
+#pragma unroll
+        for (int a = 0; a < 4; ++a) load_row(oy0 - 2 + a, xr[a]);
+        for (int ob = 0; ob < R; ob += 5) {
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                const int oy = oy0 + ob + u;
+                if (oy < oy_end) {                           // thread-uniform
+                    load_row(oy + 2, xr[(u + 4) % 5]);
+                    float dyv[PX];
+                    const float* drow = dyim + (int64_t)oy * g.wo + ox0;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ox0 + 4 * q < g.wo) v = __ldg(reinterpret_cast<const float4*>(drow + 4 * q));   // wo % 4 == 0
+                        dyv[4 * q] = v.x; dyv[4 * q + 1] = v.y; dyv[4 * q + 2] = v.z; dyv[4 * q + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) dbacc += dyv[p];
+#pragma unroll
+                    for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+                            for (int p = 0; p < PX; ++p)
+                                acc[ky][kx] = fmaf(xr[(u + ky) % 5][p + kx], dyv[p], acc[ky][kx]);
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            const float t = warp_sum(acc[a][b]);
+            if (lane == 0) red[wid][a * 5 + b] = t;
+        }
+    {
+        const float t = warp_sum(dbacc);
+        if (lane == 0) red[wid][25] = t;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < NOUT; e += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][e];
+        ws[((int64_t)blockIdx.y * NOUT + e) * nblk + blockIdx.x] = t;
+    }
+}
+
 // one CTA per output element: sums its nblk partials and scatters into dw / db
 __global__ void __launch_bounds__(256) conv_small_wgrad_finalize_kernel(
     const float* __restrict__ ws, int nblk, int kh, int kw, int cin, int civ, int cot, int cout, int bias,
@@ -347,7 +442,7 @@ static int launch_small_wgrad(const ConvGeom& g, const float* x, const float* dy
 
 int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const float* dy, float* dw, float* db,
                     int accumulate, float* ws, cudaStream_t st) {
-    if (math_mode == UOCR_MATH_TF32) {
+    if (math_mode == UOCR_MATH_TF32 && g.ups == 1) {
         const int rc = conv_wgrad_tc(g, x, dy, dw, db, accumulate, st);
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     }
@@ -362,6 +457,14 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
     if (k33 && g.cin == 1) rc = launch_small_wgrad<3, 3, 1, 1, 1, 1, 4, 4, 16>(g, x, dy, ws, nblk, chunks, st);
     else if (k33 && g.cin == 16) rc = launch_small_wgrad<3, 3, 1, 1, 16, 4, 1, 4, 16>(g, x, dy, ws, nblk, chunks, st);
     else if (k33 && g.cin == 4) rc = launch_small_wgrad<3, 3, 1, 1, 4, 4, 1, 4, 16>(g, x, dy, ws, nblk, chunks, st);
+    else if (g.kw == 5 && g.sh == 1 && g.cin == 1 && g.cout == 1 && g.w % 2 == 0 && g.wo % 4 == 0 && g.ph == 2 &&
+             g.pw == 2) {
+        if (g.ups == 2) conv55_c1_wgrad_roll_kernel<16, true><<<dim3(nblk, chunks), 256, 0, st>>>(g, x, dy, ws, nblk);
+        else conv55_c1_wgrad_roll_kernel<16, false><<<dim3(nblk, chunks), 256, 0, st>>>(g, x, dy, ws, nblk);   // plan: px 8, r 16
+        UOCR_LAUNCHED("conv55_c1_wgrad_roll");
+        rc = UOCR_OK;
+    }
+    else if (g.ups != 1) return UOCR_ERR_UNSUPPORTED;      // only the kernel above reads an upsampled input
     else if (g.kw == 5 && g.sh == 1 && g.cin == 1) rc = launch_small_wgrad<5, 5, 1, 1, 1, 1, 1, 8, 16>(g, x, dy, ws, nblk, chunks, st);
     else if (g.kw == 5 && g.sh == 2 && g.cin == 1 && p.cot == 1) rc = launch_small_wgrad<5, 5, 2, 2, 1, 1, 1, 4, 16>(g, x, dy, ws, nblk, chunks, st);
     else if (g.kw == 5 && g.sh == 2 && g.cin == 1 && p.cot == 2) rc = launch_small_wgrad<5, 5, 2, 2, 1, 1, 2, 4, 8>(g, x, dy, ws, nblk, chunks, st);

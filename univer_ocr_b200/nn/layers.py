@@ -25,6 +25,14 @@ from .initializers import kaiming_uniform
 from .optimizers import Adam
 from .progress_tracker import BaseProgressTracker, track_method
 
+class UpsampledInput:
+    """Saved-for-backward input of a Convolutional2D that ran with a folded Upsample2D(2) in front:
+    the LOW-resolution tensor (what is kept in memory) and the upsampling factor."""
+
+    def __init__(self, array, factor):
+        self.array, self.factor = array, factor
+
+
 class FromOutput:
     """Marker stored in an activation layer's memory when the activation ran as the epilogue
     of the producing kernel: only its OUTPUT exists, and the backward is evaluated from it."""
@@ -479,19 +487,30 @@ class Convolutional2D(BaseLayer):
         assert X.ndim == 4, f'expected NHWC input, got shape {X.shape}'
         desc = self._desc(X.shape, in_upsample)
         if save:
-            assert in_upsample == 1
-            self._mem[mem_id] = X
+            assert in_upsample == 1 or self.supports_upsampled_input_grad()
+            self._mem[mem_id] = X if in_upsample == 1 else UpsampledInput(X, in_upsample)
         n, h, w, c = X.shape
         y = DeviceArray(self.get_output_shapes((n, h * in_upsample, w * in_upsample, c))[0])
         lib.uocr_conv2d_fwd(ctypes.byref(desc), X.ptr, self.w.value.ptr, self.b.value.ptr, y.ptr,
                             act, float(alpha), stream())
         return y
 
+    def supports_upsampled_input_grad(self):
+        """True if the weight gradient can read its input through a folded Upsample2D(2)
+        (conv55_c1_wgrad_roll_kernel<UPS>): 5x5, stride 1, padding 2, 1 -> 1 channels."""
+        return (self.kernel_size == (5, 5) and self.stride == (1, 1) and self.padding == (2, 2)
+                and self.in_channels == 1 and self.out_channels == 1)
+
     def _backward(self, grad, mem_id=0, need_dx=True):
         X = self._mem[mem_id]
-        desc = self._desc(X.shape)
-        assert grad.shape == self.get_output_shapes(X.shape)[0], (
-            f'{grad.shape} != {self.get_output_shapes(X.shape)[0]}')
+        ups = 1
+        if isinstance(X, UpsampledInput):        # saved at low resolution; the conv saw its x2 upsampling
+            X, ups = X.array, X.factor
+        n, h, w, c = X.shape
+        in_shape = (n, h * ups, w * ups, c)
+        desc = self._desc(X.shape, ups)
+        assert grad.shape == self.get_output_shapes(in_shape)[0], (
+            f'{grad.shape} != {self.get_output_shapes(in_shape)[0]}')
         need = ctypes.c_size_t(0)
         lib.uocr_conv2d_wgrad_workspace(ctypes.byref(desc), ctypes.byref(need))
         ws = DeviceArray(((need.value + 3) // 4,)) if need.value else None
@@ -499,8 +518,8 @@ class Convolutional2D(BaseLayer):
                               1, ws.ptr if ws is not None else None, need.value, stream())
         if not need_dx:
             return None
-        dx = DeviceArray(X.shape)
-        lib.uocr_conv2d_dgrad(ctypes.byref(desc), grad.ptr, self.w.value.ptr, dx.ptr, stream())
+        dx = DeviceArray(in_shape)               # gradient w.r.t. the (upsampled) tensor the conv read
+        lib.uocr_conv2d_dgrad(ctypes.byref(self._desc(in_shape)), grad.ptr, self.w.value.ptr, dx.ptr, stream())
         return dx
 
     def backward_params_only(self, grads):

@@ -229,9 +229,11 @@ class Model(BaseModel):
             if self.fusion and len(self.relations[name]) == 1:
                 ups = None
                 conv_name = name
-                if (not training and type(layer) is Upsample2D and layer.scale_factor == (2, 2)):
+                if type(layer) is Upsample2D and layer.scale_factor == (2, 2):
                     nxt = self._sole_consumer(name)
-                    if nxt is not None and type(self.layers[nxt]) is Convolutional2D:
+                    # training: only where the conv's weight gradient can read through the upsampling
+                    if (nxt is not None and type(self.layers[nxt]) is Convolutional2D
+                            and (not training or self.layers[nxt].supports_upsampled_input_grad())):
                         ups, conv_name = name, nxt
                 conv = self.layers[conv_name]
                 if type(conv) is Convolutional2D:
@@ -322,6 +324,12 @@ class Model(BaseModel):
             for layer in tracked:
                 layer.clear_grads()
         last = tracked[-1]
+        if training and ups_name is not None:
+            if X.shape[2] % 2:                   # the upsampled-input wgrad kernel needs Wo % 4 == 0
+                X = as_device(self.layers[ups_name].forward([X])[0])
+                outputs[ups_name], ups_name = X, None
+            else:
+                self.layers[ups_name]._mem[0] = X.shape         # all Upsample2D._backward needs
         last.progress_tracker.start_tracking(last.name, 'forward')
         y = conv._forward(X, 0, act=act, alpha=alpha, in_upsample=2 if ups_name is not None else 1,
                           save=training)
