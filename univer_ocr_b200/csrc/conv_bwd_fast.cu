@@ -494,8 +494,8 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
 // ------------------------------------------------------------------------------------------
 constexpr int PB_CW = 8, PB_R = 16, PB_THREADS = 128;
 
-template <int CW, int R>
-__global__ void __launch_bounds__(PB_THREADS) conv3x3_pair_wgrad_kernel(
+template <int CW, int R, int MINB>
+__global__ void __launch_bounds__(PB_THREADS, MINB) conv3x3_pair_wgrad_kernel(
     const float* __restrict__ x, const float* __restrict__ w1, const float* __restrict__ b1,
     const float* __restrict__ w2, const float* __restrict__ dy, float* __restrict__ ws, int n_img, int H, int W,
     int C1, int act1, float alpha1, int nblk) {
@@ -546,37 +546,40 @@ __global__ void __launch_bounds__(PB_THREADS) conv3x3_pair_wgrad_kernel(
             float xw[3][CW + 2], gw[3][CW + 2];
             load_row(xim, r0 - 1, xw[0]); load_row(xim, r0, xw[1]);
             load_row(gim, r0 - 1, gw[0]); load_row(gim, r0, gw[1]);
-            for (int hr = r0; hr < r_end; ++hr) {
-                load_row(xim, hr + 1, xw[2]);
-                load_row(gim, hr + 1, gw[2]);
+            // rows in groups of 3 so that the 3-row windows are register RINGS with static slots
+            // (slot = (row - (r0 - 1)) % 3) instead of being shifted after every row (40 MOV per row)
+            for (int hb = r0; hb < r_end; hb += 3) {
 #pragma unroll
-                for (int j = 0; j < CW; ++j) {
-                    if (c0 + j < W) {
-                        float hp = bb, dh = 0.f;
+                for (int u = 0; u < 3; ++u) {
+                    const int hr = hb + u;
+                    if (hr < r_end) {                                   // thread-uniform
+                        load_row(xim, hr + 1, xw[(u + 2) % 3]);
+                        load_row(gim, hr + 1, gw[(u + 2) % 3]);
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
+                        for (int j = 0; j < CW; ++j) {
+                            if (c0 + j < W) {
+                                float hp = bb, dh = 0.f;
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                hp = fmaf(k1[ky * 3 + kx], xw[ky][j + kx], hp);
-                                dh = fmaf(k2[ky * 3 + kx], gw[2 - ky][j + 2 - kx], dh);
+                                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) {
+                                        hp = fmaf(k1[ky * 3 + kx], xw[(u + ky) % 3][j + kx], hp);
+                                        dh = fmaf(k2[ky * 3 + kx], gw[(u + 2 - ky) % 3][j + 2 - kx], dh);
+                                    }
+                                float hval = hp, mask = 1.f;
+                                if (act1 == UOCR_ACT_LEAKY && hp < 0.f) { hval = alpha1 * hp; mask = alpha1; }
+                                const float dpre = dh * mask;
+                                gb1 += dpre;
+#pragma unroll
+                                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) {
+                                        gw1[ky * 3 + kx] = fmaf(dpre, xw[(u + ky) % 3][j + kx], gw1[ky * 3 + kx]);
+                                        gw2[ky * 3 + kx] = fmaf(gw[(u + 2 - ky) % 3][j + 2 - kx], hval, gw2[ky * 3 + kx]);
+                                    }
                             }
-                        float hval = hp, mask = 1.f;
-                        if (act1 == UOCR_ACT_LEAKY && hp < 0.f) { hval = alpha1 * hp; mask = alpha1; }
-                        const float dpre = dh * mask;
-                        gb1 += dpre;
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                gw1[ky * 3 + kx] = fmaf(dpre, xw[ky][j + kx], gw1[ky * 3 + kx]);
-                                gw2[ky * 3 + kx] = fmaf(gw[2 - ky][j + 2 - kx], hval, gw2[ky * 3 + kx]);
-                            }
+                        }
                     }
-                }
-#pragma unroll
-                for (int j = 0; j < CW + 2; ++j) {
-                    xw[0][j] = xw[1][j]; xw[1][j] = xw[2][j];
-                    gw[0][j] = gw[1][j]; gw[1][j] = gw[2][j];
                 }
             }
         } else {
@@ -735,8 +738,11 @@ int conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const flo
     const int64_t nblk = ceil_div(items, PB_THREADS);
     if (nblk > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     const size_t smem = sizeof(float) * 20 * c1;
-    conv3x3_pair_wgrad_kernel<PB_CW, PB_R><<<(unsigned)nblk, PB_THREADS, smem, st>>>(
-        x, w1, b1, w2, dy, ws, (int)n, (int)h, (int)w, c1, act1, alpha1, (int)nblk);
+    static const int minb = [] { const char* e = getenv("UOCR_PAIRBWD_MINB"); return e ? atoi(e) : 4; }();
+#define PB_LAUNCH(MB) conv3x3_pair_wgrad_kernel<PB_CW, PB_R, MB><<<(unsigned)nblk, PB_THREADS, smem, st>>>( \
+        x, w1, b1, w2, dy, ws, (int)n, (int)h, (int)w, c1, act1, alpha1, (int)nblk)
+    if (minb >= 5) PB_LAUNCH(5); else if (minb == 4) PB_LAUNCH(4); else PB_LAUNCH(3);
+#undef PB_LAUNCH
     UOCR_LAUNCHED("conv3x3_pair_wgrad");
     conv3x3_pair_wgrad_finalize_kernel<<<(c1 + 1) * 19, 256, 0, st>>>(ws, (int)nblk, c1, dw1, db1, dw2, db2, accumulate);
     UOCR_LAUNCHED("conv3x3_pair_wgrad_finalize");
