@@ -403,12 +403,16 @@ class FullyConnected(BaseLayer):
         self._init_optimizer()
         self.is_initialized = True
 
-    def _forward(self, X, mem_id=0):
+    def _forward(self, X, mem_id=0, act=ACT_NONE, alpha=0.0, in_upsample=1, save=True):
+        """`act` / `alpha`: activation applied in the GEMM epilogue (Model fuses a following
+        LeakyRelu / Sigmoid layer into this call)."""
         assert X.ndim == 2 and X.shape[1] == self.n_input, f'{X.shape} vs n_input={self.n_input}'
-        self._mem[mem_id] = X
+        assert in_upsample == 1
+        if save:
+            self._mem[mem_id] = X
         y = DeviceArray((X.shape[0], self.n_output))
         lib.uocr_fc_fwd(X.ptr, self.w.value.ptr, y.ptr, X.shape[0], self.n_input, self.n_output,
-                        ACT_NONE, 0.0, CP.math_mode, stream())
+                        act, float(alpha), CP.math_mode, stream())
         return y
 
     def _backward(self, grad, mem_id=0):

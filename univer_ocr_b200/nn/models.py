@@ -20,7 +20,8 @@ import ctypes
 from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
 from .gpu import CP, DeviceArray, LazyScalar, as_device, stream
 from .help_func import make_list_if_not
-from .layers import (BaseLayer, Convolutional2D, FromOutput, LeakyRelu, Sigmoid, Upsample2D)
+from .layers import (BaseLayer, Convolutional2D, FromOutput, FullyConnected, LeakyRelu, Sigmoid,
+                     Upsample2D)
 from .losses import SoftmaxCrossEntropy
 from .progress_tracker import track_method
 
@@ -236,7 +237,7 @@ class Model(BaseModel):
                             and (not training or self.layers[nxt].supports_upsampled_input_grad())):
                         ups, conv_name = name, nxt
                 conv = self.layers[conv_name]
-                if type(conv) is Convolutional2D:
+                if type(conv) is Convolutional2D or (type(conv) is FullyConnected and ups is None):
                     act_name = self._sole_consumer(conv_name)
                     act = _act_code(self.layers[act_name]) if act_name is not None else None
                     # training: a fused Sigmoid would have to be differentiated from its output
@@ -246,7 +247,8 @@ class Model(BaseModel):
                     if act is None or (training and act[0] != ACT_LEAKY):
                         act_name = None
                     pair = None
-                    if (ups is None and act_name is not None and self._pair_head(conv)
+                    if (ups is None and act_name is not None and type(conv) is Convolutional2D
+                            and self._pair_head(conv)
                             and (not training or act[0] == ACT_LEAKY)):
                         c2_name = self._sole_consumer(act_name)
                         if c2_name is not None and self._pair_tail(conv, self.layers[c2_name]):

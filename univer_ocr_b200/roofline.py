@@ -87,7 +87,7 @@ def plan_work(model, input_shape, training=False):
         for n in names:
             layer = model.layers[n]
             wk = layer_work(layer, shapes[n], 'forward')
-            if isinstance(layer, L.Convolutional2D):
+            if isinstance(layer, (L.Convolutional2D, L.FullyConnected)):
                 flops += wk['flops']
                 wbytes += 4 * layer.count_parameters()
                 if wk['bound'] == 'tensor':
