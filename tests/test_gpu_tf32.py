@@ -12,8 +12,6 @@ import pytest
 
 from oracle import np_oracle as O
 
-os.environ['UOCR_PAIR_TC'] = '1'       # exercise the opt-in tensor-core Monochrome pair kernel too
-
 pytestmark = pytest.mark.gpu
 
 
@@ -135,11 +133,46 @@ def test_monochrome_pair_on_tensor_cores(nn):
         if act2 == ACT_SIGMOID:
             want = O.sigmoid_fwd(want)
         d = [nn.CP.copy(a) for a in (X, w1, b1, w2, b2)]
-        outs = []
-        for mode in (0, 1):
-            y = nn.DeviceArray((n, h, w, 1))
-            lib.uocr_conv3x3_pair_fwd(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, y.ptr, n, h, w, 16,
-                                      ACT_LEAKY, 0.01, act2, 0.0, mode, nn.CP.stream())
-            outs.append(np.asarray(y.get(), dtype=np.float64))
-        close_tf32(outs[1], want, f'tc pair {(n, h, w)}')
-        close_tf32(outs[1], outs[0], f'tc vs fp32 pair {(n, h, w)}')
+        outs = {}
+        # math mode 0 = FP32 pair kernel; mode 1 with UOCR_PAIR_TC = 2 (default): both convs as tcgen05.mma with
+        # TMEM-resident operands; = 1: the earlier shared-memory MMA variant (kept as a measured negative result)
+        for key, mode, variant in (('fp32', 0, None), ('tmem', 1, '2'), ('smem', 1, '1')):
+            if variant is not None:
+                os.environ['UOCR_PAIR_TC'] = variant
+            try:
+                y = nn.DeviceArray((n, h, w, 1))
+                lib.uocr_conv3x3_pair_fwd(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, y.ptr, n, h, w, 16,
+                                          ACT_LEAKY, 0.01, act2, 0.0, mode, nn.CP.stream())
+                outs[key] = np.asarray(y.get(), dtype=np.float64)
+            finally:
+                os.environ.pop('UOCR_PAIR_TC', None)
+        for key in ('tmem', 'smem'):
+            close_tf32(outs[key], want, f'{key} pair {(n, h, w)}')
+            close_tf32(outs[key], outs['fp32'], f'{key} vs fp32 pair {(n, h, w)}')
+
+
+@pytest.mark.parametrize('shape,cout,ups', [
+    ((2, 128, 256), 4, 1), ((2, 128, 256), 2, 1),          # Line up_1 (after its upsample) / end
+    ((2, 64, 128), 4, 2), ((3, 32, 64), 4, 2),             # Line up_1 / up_2 reading through the folded upsample
+    ((1, 37, 45), 4, 1), ((2, 5, 3), 2, 1), ((1, 30, 70), 2, 2), ((1, 1, 1), 4, 1),   # ragged strips / bands
+], ids=['up1', 'end', 'up1_ups', 'up2_ups', 'ragged4', 'tiny2', 'ragged_ups', 'one_px'])
+def test_conv55_row_gemm_tf32(nn, shape, cout, ups):
+    """5x5 / stride 1 / Cin = 4 convolutions as a tcgen05 row GEMM with TMEM-resident windows
+    (csrc/conv_row_tc.cu), plain and through a folded Upsample2D(2), + LeakyRelu / Sigmoid epilogue,
+    vs the float64 oracle at the TF32 tolerance."""
+    import ctypes
+    from univer_ocr_b200._lib import ACT_LEAKY, ACT_SIGMOID, ConvDesc, MATH_TF32, lib
+    rng = np.random.default_rng(sum(shape) + cout + ups)
+    n, h, w = shape                                          # stored input size
+    X = f32(rng.standard_normal((n, h, w, 4)))
+    wt = f32(rng.standard_normal((5, 5, 4, cout)) / 10.0)
+    b = f32(rng.standard_normal(cout) * 0.3)
+    Xin = O.upsample2d_fwd(X, 2) if ups == 2 else X
+    want = O.conv2d_fwd(Xin, wt, b, 2, 0.0, 1)
+    for act, fn in ((ACT_LEAKY, lambda t: O.leaky_relu_fwd(t, 0.01)), (ACT_SIGMOID, O.sigmoid_fwd)):
+        desc = ConvDesc(n, h * ups, w * ups, 4, cout, 5, 5, 2, 2, 1, 1, 0.0, 1, MATH_TF32, ups)
+        dX, dw, db = nn.CP.copy(X), nn.CP.copy(wt), nn.CP.copy(b)
+        y = nn.DeviceArray((n, h * ups, w * ups, cout))
+        before = ctypes.c_uint64(0)
+        lib.uocr_conv2d_fwd(ctypes.byref(desc), dX.ptr, dw.ptr, db.ptr, y.ptr, act, 0.01, nn.CP.stream())
+        close_tf32(y, fn(want), f'row gemm {shape} cout {cout} ups {ups} act {act}')

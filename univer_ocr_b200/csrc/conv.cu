@@ -389,7 +389,8 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
     // tcgen05.mma with TMEM-resident A operands (conv_pair_tc.cu); 1: the earlier variant whose hidden tile
     // is evaluated on the CUDA cores and only the 16 -> 1 convolution runs as MMA from shared memory (kept
     // as a measured negative result, 3x slower than the CUDA-core kernel); 0: CUDA-core pair kernel.
-    static const int pair_tc = [] { const char* e = getenv("UOCR_PAIR_TC"); return e ? atoi(e) : 2; }();
+    const char* pair_env = getenv("UOCR_PAIR_TC");       // read per call: tests switch between the variants
+    const int pair_tc = pair_env ? atoi(pair_env) : 2;
     if (math_mode == UOCR_MATH_TF32 && pair_tc) {
         const int rc = pair_tc == 2
             ? conv3x3_pair_tmem(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream))

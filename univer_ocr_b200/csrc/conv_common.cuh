@@ -35,6 +35,9 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
 int conv3x3_pair_tc(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                     int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
                     cudaStream_t st);
+// 5x5 / stride 1 / Cin = 4 forward as a row GEMM on tcgen05 with TMEM-resident windows (conv_row_tc.cu)
+int conv55_row_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
+                  cudaStream_t st);
 // both convolutions as tcgen05.mma with TMEM-resident A operands (conv_pair_tc.cu)
 int conv3x3_pair_tmem(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                       int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,

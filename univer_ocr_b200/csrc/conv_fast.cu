@@ -316,8 +316,14 @@ static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float
 int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
                   const float* b, float* y, int act, float alpha, cudaStream_t st) {
     if (math_mode == UOCR_MATH_TF32) {
-        const int rc = conv_fwd_tc(g, x, w, b, y, act, alpha, st);
+        int rc = conv_fwd_tc(g, x, w, b, y, act, alpha, st);
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+        // 5x5 / stride 1 / Cin = 4 (Line up_*, end): row GEMM with TMEM-resident windows (conv_row_tc.cu)
+        static const bool row_tc = [] { const char* e = getenv("UOCR_ROW_TC"); return !e || e[0] != '0'; }();
+        if (row_tc && g.ups == ups) {
+            rc = conv55_row_tc(g, x, w, b, y, act, alpha, st);
+            if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+        }
     }
     if (ups != 1 && ups != 2) return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
