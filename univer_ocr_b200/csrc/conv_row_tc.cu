@@ -27,7 +27,7 @@
 namespace uocr {
 
 constexpr int RT_THREADS = 128;
-constexpr int RT_R = 4;                       // input rows per pipeline step
+constexpr int RT_R = 2;                       // input rows per pipeline step (128 TMEM columns: 4 CTAs per SM)
 constexpr int RT_SLOT = 64;                   // TMEM columns per row in flight: A at +0 (24), Z at +32 (32)
 
 struct RowTcParams {
@@ -67,7 +67,7 @@ __device__ __forceinline__ void rt_wait(uint32_t bar, uint32_t parity) {
 }
 
 template <int COUT, bool UPS>
-__global__ void __launch_bounds__(RT_THREADS, 2) conv55_row_tc_kernel(const RowTcParams p) {
+__global__ void __launch_bounds__(RT_THREADS, 4) conv55_row_tc_kernel(const RowTcParams p) {
     constexpr int NPAD = COUT == 4 ? 32 : 16;
     constexpr int NZ = 5 * COUT;                          // useful Z columns
     __shared__ __align__(128) float s_b[6 * NPAD * 4];    // chunk kq (= kx, 5 = bias): NPAD rows (n) x 4 floats (ci)
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(RT_THREADS, 2) conv55_row_tc_kernel(const RowT
         coff[kx] = UPS ? (cc >> 1) : cc;
     }
 
-    uint32_t xq[RT_R][5][4];                               // windows of the step's 4 input rows (prefetched)
+    uint32_t xq[RT_R][5][4];                               // windows of the step's input rows (prefetched)
     auto load_rows = [&](int k) {
 #pragma unroll
         for (int r = 0; r < RT_R; ++r) {
@@ -230,12 +230,21 @@ int conv55_row_tc(const ConvGeom& g, const float* x, const float* w, const float
     if ((g.cout != 4 && g.cout != 2) || g.padding_value != 0.f || !g.bias || (g.ups != 1 && g.ups != 2))
         return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
-    static const int rb_env = [] { const char* e = getenv("UOCR_ROWTC_RB"); return e ? atoi(e) : 28; }();
+    // output rows per band: tall bands amortise the 4 halo rows, short ones give enough CTAs for a few waves
+    // (4 resident per SM); measured on the Line shapes: 12 rows beat 28 and 60 there
+    static const int rb_env = [] { const char* e = getenv("UOCR_ROWTC_RB"); return e ? atoi(e) : 0; }();
     RowTcParams p{};
     p.x = x; p.w = w; p.b = b; p.y = y;
     p.H = g.h; p.W = g.w;
-    p.rb = g.h < rb_env ? g.h : rb_env;
     p.strips = (int)ceil_div(g.w, 32);
+    int rb = rb_env;
+    if (rb <= 0) {
+        rb = 12;
+        for (int cand : {60, 28}) {
+            if ((int64_t)g.n * ceil_div(g.h, cand) * p.strips / 4 >= 3 * 4 * 148) { rb = cand; break; }
+        }
+    }
+    p.rb = g.h < rb ? g.h : rb;
     p.bands = (int)ceil_div(g.h, p.rb);
     p.items = (int64_t)g.n * p.bands * p.strips;
     p.steps = (p.rb + 4 + RT_R - 1) / RT_R;

@@ -388,10 +388,11 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
         return UOCR_ERR_UNSUPPORTED;            // TMA: 16-byte aligned base and row pitch
     if (M <= 0 || N <= 0 || K <= 0 || M > 0x7fffffff || K > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     {
-        // enough 128 x NT tiles to give every SM at least one
+        // enough 128 x NT tiles to keep most SMs busy (dense_2: 128 tiles, 46 -> 34 us)
         static const int persist = env_int("UOCR_TC_PERSISTENT", 1);
         const int64_t nt = N >= 256 ? 256 : ((N + 15) / 16) * 16;
-        if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= 148) {
+        static const int min_tiles = env_int("UOCR_TC_PERSISTENT_MIN_TILES", 96);   // >= ~2/3 of the SMs busy
+        if (persist && N >= 128 && ceil_div(M, TC_BM) * ceil_div(N, nt) >= min_tiles) {
             const int rc = tc_gemm_tn_persistent(A, lda, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
             if (rc != UOCR_ERR_UNSUPPORTED) return rc;
         }
