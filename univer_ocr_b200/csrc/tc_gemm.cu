@@ -794,6 +794,9 @@ int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, 
 
 // ------------------------------------------------------------------ Convolutional2D forward
 // implicit GEMM: M = N*Ho*Wo pixels (tiles of 128 consecutive ox), N = Cout, K = kh*kw*Cin
+static int conv_fwd_tc_slab(const ConvGeom& g, const float* x, const float* wt, const float* b, float* y, int act,
+                            float alpha, cudaStream_t st);
+
 int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
                 cudaStream_t st) {
     if (g.cin % TC_BK || g.sw != 1 || g.padding_value != 0.f || g.ups != 1) return UOCR_ERR_UNSUPPORTED;
@@ -805,6 +808,8 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
     if (rc) return rc;
     rc = transpose_async(w, (float*)wt.ptr, K, g.cout, g.cout, K, st);       // (K, Cout) -> (Cout, K)
     if (rc) return rc;
+    rc = conv_fwd_tc_slab(g, x, (const float*)wt.ptr, b, y, act, alpha, st);
+    if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     TcParams p{};
     p.C = y; p.ldc = g.cout; p.M = (int64_t)g.n * g.ho * g.wo; p.N = g.cout;
     p.cblocks = g.cin / TC_BK;
@@ -827,6 +832,203 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
     if (tiles > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     dim3 grid((unsigned)tiles, 1);
     return launch_tc<TC_CONV_FWD>(ma, mb, p, grid, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Convolutional2D forward, slab variant (Char conv_2 / conv_3: 5x3, 64 -> 64, stride (2, 1)).
+// ncu on the one-tile-per-CTA kernel above: every (ky, kx, channel block) step re-fetches a 16 KB A tile and an
+// 8 KB B tile from L2 -- 720 KB per 128-pixel tile, 460 MB through L2 for a 59 MB input, i.e. L2 -> SM bandwidth
+// bound at 20 % of the tensor peak.  Here a pipeline stage holds, for one (ky, channel block),
+//   * XB input-row SLABS of 128 + kw - 1 pixels x 32 channels (one per 128-pixel x-block of the output row): the
+//     kw horizontal taps are the SAME slab read from a start address shifted by kx pixel rows (128 B each; the
+//     128-byte swizzle is a function of the absolute shared-memory address, so a start address that is not
+//     1024-byte aligned needs nothing else -- setting the descriptor's base-offset field to the row phase gives
+//     wrong results, tested), so A is fetched once per kernel ROW instead of once per tap, and
+//   * the kw weight chunks of that kernel row, shared by the XB x-blocks (two accumulators in TMEM).
+// Per 128-pixel tile that is 286 KB instead of 720 KB through L2.
+// ------------------------------------------------------------------------------------------
+struct SlabParams {
+    float* y; const float* bias;
+    int n_img, ho, wo, cout, nt;
+    int kh, kw, sh, ph, pw, cblocks;
+    int xb;                           // x-blocks per CTA (1 or 2)
+    int stages;
+    uint32_t slab_bytes, slab_box_bytes, b_bytes;
+    int act; float alpha;
+    int base_offset_mode;             // 1: descriptor base offset = row phase of the start address
+};
+
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_addr, int with_base_offset) {
+    uint64_t d = make_kmajor_sw128_desc(smem_addr);
+    if (with_base_offset == 1) d |= (uint64_t)((smem_addr >> 7) & 7u) << 49;
+    return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                     const __grid_constant__ CUtensorMap map_b,
+                                                                     const SlabParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t stage_bytes = (uint32_t)p.xb * p.slab_bytes + (uint32_t)p.kw * p.b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + p.stages;
+    uint64_t* tmem_full = bars + 2 * p.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+    float* s_bias = reinterpret_cast<float*>(bars + 2 * p.stages + 2);      // nt floats (zeros without a bias)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < p.nt; i += TC_THREADS) s_bias[i] = (p.bias && i < p.cout) ? __ldg(p.bias + i) : 0.f;
+    const int cx_base = blockIdx.x * p.xb * TC_BM, oy = blockIdx.y, cn = blockIdx.z;
+    const int xb_live = min(p.xb, (p.wo - cx_base + TC_BM - 1) / TC_BM);       // x-blocks inside the row
+    const int num_it = p.kh * p.cblocks;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.xb * p.nt) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < num_it; ++it) {
+                const int s = it % p.stages;
+                mbar_wait(smem_u32(&empty[s]), ((it / p.stages) & 1) ^ 1);
+                const int ky = it / p.cblocks, cb = it - ky * p.cblocks;
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)p.xb * p.slab_bytes;
+                const uint32_t bar = smem_u32(&full[s]);
+                mbar_arrive_expect_tx(bar, (uint32_t)xb_live * p.slab_box_bytes + (uint32_t)p.kw * p.b_bytes);
+                for (int xb = 0; xb < xb_live; ++xb)
+                    tma_load_4d(sa + (uint32_t)xb * p.slab_bytes, &map_a, bar, cb * TC_BK, cx_base + xb * TC_BM - p.pw,
+                                oy * p.sh + ky - p.ph, cn);
+                for (int kx = 0; kx < p.kw; ++kx)
+                    tma_load_2d(sb + (uint32_t)kx * p.b_bytes, &map_b, bar, ((ky * p.kw + kx) * p.cblocks + cb) * TC_BK, 0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            for (int it = 0; it < num_it; ++it) {
+                const int s = it % p.stages;
+                mbar_wait(smem_u32(&full[s]), (it / p.stages) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t sb = sa + (uint32_t)p.xb * p.slab_bytes;
+                for (int xb = 0; xb < xb_live; ++xb)
+                    for (int kx = 0; kx < p.kw; ++kx) {
+                        // the tap's A operand = the slab from pixel row kx on
+                        const uint64_t da = make_kmajor_sw128_desc_off(sa + (uint32_t)xb * p.slab_bytes + (uint32_t)kx * (p.base_offset_mode == 3 ? 0u : 128u),
+                                                                       p.base_offset_mode);
+                        const uint64_t db = make_kmajor_sw128_desc(sb + (uint32_t)kx * p.b_bytes);
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 8; ++k)
+                            tc_mma_tf32(tmem_base + (uint32_t)(xb * p.nt), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                        (it > 0 || kx > 0 || k > 0) ? 1u : 0u);
+                    }
+                tc_commit(smem_u32(&empty[s]));
+            }
+            tc_commit(smem_u32(tmem_full));
+        }
+    } else {
+        const int q = warp & 3;
+        mbar_wait(smem_u32(tmem_full), 0);
+        tc_fence_after();
+        for (int xb = 0; xb < xb_live; ++xb) {
+            const int ox = cx_base + xb * TC_BM + q * 32 + lane;
+            float* dst = p.y + (((int64_t)cn * p.ho + oy) * p.wo + ox) * p.cout;
+            for (int c0 = 0; c0 < p.nt; c0 += 32) {
+                float v[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(xb * p.nt + c0), v);
+                if (ox >= p.wo) continue;
+                const float4* bs = reinterpret_cast<const float4*>(s_bias + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (c0 + j < p.cout) {                                   // cout % 16 == 0
+                        const float4 b4 = bs[j >> 2];
+                        float4 o;
+                        o.x = apply_act_fast(v[j] + b4.x, p.act, p.alpha);
+                        o.y = apply_act_fast(v[j + 1] + b4.y, p.act, p.alpha);
+                        o.z = apply_act_fast(v[j + 2] + b4.z, p.act, p.alpha);
+                        o.w = apply_act_fast(v[j + 3] + b4.w, p.act, p.alpha);
+                        *reinterpret_cast<float4*>(dst + c0 + j) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+static int conv_fwd_tc_slab(const ConvGeom& g, const float* x, const float* wt /* (Cout, K) */, const float* b, float* y,
+                            int act, float alpha, cudaStream_t st) {
+    static const int mode = env_int("UOCR_CONV_SLAB", 2);          // 0: off; 2: plain descriptors (correct: the swizzle is a
+                                                                   // function of the absolute smem address); 1: with the row phase in
+                                                                   // the base-offset field -- measured WRONG results, kept for the record
+    if (!mode || g.kw > 8 || g.cout > 128 || (reinterpret_cast<uintptr_t>(y) & 15)) return UOCR_ERR_UNSUPPORTED;
+    if (g.n > 65535 || g.ho > 65535) return UOCR_ERR_UNSUPPORTED;
+    SlabParams p{};
+    p.y = y; p.bias = g.bias ? b : nullptr;
+    p.n_img = g.n; p.ho = g.ho; p.wo = g.wo; p.cout = g.cout; p.nt = g.cout;
+    p.kh = g.kh; p.kw = g.kw; p.sh = g.sh; p.ph = g.ph; p.pw = g.pw; p.cblocks = g.cin / TC_BK;
+    p.act = act; p.alpha = alpha; p.base_offset_mode = mode == 1 ? 1 : (mode == 3 ? 3 : 0);
+    const int xtiles = (g.wo + TC_BM - 1) / TC_BM;
+    // Measured on Char conv_2 (64 tiles of 5 x 256 pixels): 1 x-block + 2 stages (84 KB: two CTAs per SM, so one
+    // CTA's prologue / epilogue overlaps the other's main loop) 0.050 ms; 2 x-blocks sharing B with 3 stages (one CTA
+    // per SM) 0.067 ms; the one-tile-per-CTA kernel 0.065 ms.  UOCR_CONV_SLAB_XB / _STAGES override.
+    static const int xb_env = env_int("UOCR_CONV_SLAB_XB", 1);
+    p.xb = xb_env == 2 && xtiles >= 2 ? 2 : 1;
+    static const int max_stages = env_int("UOCR_CONV_SLAB_STAGES", 2);
+    static const int box_round = env_int("UOCR_CONV_SLAB_BOXROUND", 1);
+    const uint32_t box_rows = box_round > 1 ? ((TC_BM + g.kw - 1 + box_round - 1) / box_round) * box_round : TC_BM + g.kw - 1;
+    p.slab_box_bytes = box_rows * 128u;
+    p.slab_bytes = (p.slab_box_bytes + 1023u) & ~1023u;
+    p.b_bytes = (uint32_t)g.cout * 128u;                            // cout % 16 == 0 -> multiple of 2048: 1024-aligned
+    const uint32_t stage_bytes = (uint32_t)p.xb * p.slab_bytes + (uint32_t)g.kw * p.b_bytes;
+    p.stages = (int)((200u * 1024u) / stage_bytes);
+    if (p.stages > max_stages) p.stages = max_stages;
+    if (p.stages < 2 || (p.b_bytes & 1023u)) return UOCR_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * p.stages + 2) * 8 + 4 * 128 + 64;
+    const int K = g.kh * g.kw * g.cin;
+    CUtensorMap ma, mb;
+    const uint64_t da[4] = {(uint64_t)g.cin, (uint64_t)g.w, (uint64_t)g.h, (uint64_t)g.n};
+    const uint64_t sa[3] = {(uint64_t)g.cin * 4, (uint64_t)g.w * g.cin * 4, (uint64_t)g.h * g.w * g.cin * 4};
+    const uint32_t ba[4] = {TC_BK, box_rows, 1, 1};
+    int rc = make_tmap(&ma, x, 4, da, sa, ba);
+    if (rc) return rc;
+    const uint64_t db[2] = {(uint64_t)K, (uint64_t)g.cout}, sb[1] = {(uint64_t)K * 4};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)g.cout};
+    rc = make_tmap(&mb, wt, 2, db, sb, bb);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(xtiles, p.xb), (unsigned)g.ho, (unsigned)g.n);
+    tc_conv_slab_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+    UOCR_LAUNCHED("tc_conv_slab_tf32");
+    return UOCR_OK;
 }
 
 // ------------------------------------------------------------------ Convolutional2D dgrad
