@@ -144,6 +144,15 @@ int uocr_conv2d_out_hw(const uocr_conv2d_desc* d, int64_t* ho, int64_t* wo);
  * layers.py:390-415).  x is the UNPADDED input; the border is synthesised from padding_value. */
 int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, const float* b,
                     float* y, int act, float alpha, void* stream);
+/* Same, with a caller-cached K-major copy of the weights: w_kmajor (Cout, kh*kw*Cin) = uocr_weights_to_kmajor(w,
+ * kh*kw*Cin, Cout).  The tensor-core kernels read their B operand K-major; without the copy they transpose w into
+ * scratch on every call (a few microseconds per layer -- 4 % of a my_model inference step).  The copy is only read by
+ * the tcgen05 paths; every other geometry / math mode uses w as usual.  The caller keeps it in sync with w. */
+int uocr_conv2d_fwd_kmajor(const uocr_conv2d_desc* d, const float* x, const float* w, const float* w_kmajor,
+                           const float* b, float* y, int act, float alpha, void* stream);
+/* wt (n_cols, k_rows) = transpose of w (k_rows, n_cols): conv weights (kh*kw*Cin, Cout), FC weights WITHOUT the bias
+ * row (n_in, n_out). */
+int uocr_weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_cols, void* stream);
 
 /* y = act2(conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2): two chained 3x3 / padding 1 / stride 1
  * convolutions 1 -> c_mid -> 1 channels with the c_mid-channel intermediate kept in registers
@@ -245,6 +254,10 @@ int uocr_act_bwd_from_output(const float* y, const float* dy, float* dx, int64_t
  * y = act([x, 1] . W), W (n_in + 1, n_out).   replaces: layers.py:335-339 */
 int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t n_in,
                 int64_t n_out, int act, float alpha, int math_mode, void* stream);
+/* Same, with a caller-cached K-major copy w_kmajor (n_out, n_in) of the weight rows (see uocr_conv2d_fwd_kmajor);
+ * the bias row is still read from w. */
+int uocr_fc_fwd_kmajor(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
+                       int64_t n_out, int act, float alpha, int math_mode, void* stream);
 /* dx = dy . W[:-1]^T (skipped when dx == NULL); dw (+)= [x, 1]^T . dy.  replaces: layers.py:341-347 */
 int uocr_fc_bwd(const float* x, const float* w, const float* dy, float* dx, float* dw,
                 int64_t batch, int64_t n_in, int64_t n_out, int accumulate, int math_mode,

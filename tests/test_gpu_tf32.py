@@ -176,3 +176,42 @@ def test_conv55_row_gemm_tf32(nn, shape, cout, ups):
         before = ctypes.c_uint64(0)
         lib.uocr_conv2d_fwd(ctypes.byref(desc), dX.ptr, dw.ptr, db.ptr, y.ptr, act, 0.01, nn.CP.stream())
         close_tf32(y, fn(want), f'row gemm {shape} cout {cout} ups {ups} act {act}')
+
+
+def test_kmajor_weight_cache_follows_updates(nn):
+    """Inference in TF32 mode caches K-major weight copies per layer (uocr_*_fwd_kmajor).  The cache must be
+    dropped by every way parameters change: Model.train (optimizer update), DataParallel's flat-buffer update and
+    set_weights -- checked against the FP32 mode (which has no cache) of the same model after each change."""
+    from oracle import np_models
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.parallel import DataParallel
+    rng = np.random.default_rng(3)
+    shape = (2, 32, 256, 1)
+    w0 = np_models.golden_weights('char', 5)
+    opt = nn.optimizers.Adam(lr=0.05)                      # large steps: a stale cache is unmistakable
+    model = my_model.make_char(shape, optimizer=opt)
+    model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})
+    X = f32(rng.uniform(size=shape))
+    y = np.zeros((shape[0] * shape[2], 162))
+    y[np.arange(y.shape[0]), rng.integers(0, 162, size=y.shape[0])] = 1
+
+    def check(what, prev=None):
+        nn.CP.set_math_mode('tf32')
+        got = np.asarray(model.predict(X)[0].get(), dtype=np.float64)
+        nn.CP.set_math_mode('fp32')
+        want = np.asarray(model.predict(X)[0].get(), dtype=np.float64)
+        nn.CP.set_math_mode('tf32')
+        close_tf32(got, want, what, tol=3e-3)
+        if prev is not None:
+            assert np.max(np.abs(got - prev)) > 1e-2 * np.max(np.abs(prev)), f'{what}: predictions did not move'
+        return got
+
+    p0 = check('initial')
+    model.train(X, y)
+    p1 = check('after Model.train', p0)
+    dp = DataParallel(model, optimizer=opt)
+    dp.train(nn.CP.copy(X), nn.CP.copy(y))
+    p2 = check('after DataParallel.train', p1)
+    w1 = np_models.golden_weights('char', 6)
+    model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w1.items()})
+    check('after set_weights', p2)

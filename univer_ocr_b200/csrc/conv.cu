@@ -364,17 +364,27 @@ int uocr_conv2d_out_hw(const uocr_conv2d_desc* d, int64_t* ho, int64_t* wo) {
     return UOCR_OK;
 }
 
-int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, const float* b,
-                    float* y, int act, float alpha, void* stream) {
+static int conv2d_fwd_impl(const uocr_conv2d_desc* d, const float* x, const float* w, const float* w_kmajor,
+                           const float* b, float* y, int act, float alpha, void* stream) {
     ConvGeom g;
     int rc = make_geom(d, &g);
     if (rc) return rc;
     UOCR_REQUIRE(x && w && b && y, "NULL pointer");
     UOCR_REQUIRE(act >= UOCR_ACT_NONE && act <= UOCR_ACT_SIGMOID, "unknown activation %d", act);
     cudaStream_t st = as_stream(stream);
-    rc = conv_fwd_fast(g, g.ups, d->math_mode, x, w, b, y, act, alpha, st);
+    rc = conv_fwd_fast(g, g.ups, d->math_mode, x, w, b, y, act, alpha, st, w_kmajor);
     if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     return conv_fwd_general(g, x, w, b, y, act, alpha, st);
+}
+
+int uocr_conv2d_fwd(const uocr_conv2d_desc* d, const float* x, const float* w, const float* b,
+                    float* y, int act, float alpha, void* stream) {
+    return conv2d_fwd_impl(d, x, w, nullptr, b, y, act, alpha, stream);
+}
+
+int uocr_conv2d_fwd_kmajor(const uocr_conv2d_desc* d, const float* x, const float* w, const float* w_kmajor,
+                           const float* b, float* y, int act, float alpha, void* stream) {
+    return conv2d_fwd_impl(d, x, w, w_kmajor, b, y, act, alpha, stream);
 }
 
 int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2,

@@ -18,7 +18,7 @@ struct ConvGeom {
 // Shape-specialised kernels.  Each returns UOCR_ERR_UNSUPPORTED when it has no kernel for the
 // geometry / math mode, in which case the caller runs the general kernel.
 int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
-                  const float* b, float* y, int act, float alpha, cudaStream_t st);
+                  const float* b, float* y, int act, float alpha, cudaStream_t st, const float* w_kmajor = nullptr);
 int conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                      float* y, int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2,
                      float alpha2, cudaStream_t st);
@@ -29,8 +29,8 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
                     float* db, int accumulate, float* ws, cudaStream_t st);
 
 // tcgen05 implicit-GEMM forward (tc_gemm.cu): Cin % 32 == 0, stride_w == 1, zero padding
-int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
-                cudaStream_t st);
+int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* w_kmajor /* (Cout, K) or NULL */,
+                const float* b, float* y, int act, float alpha, cudaStream_t st);
 
 int conv3x3_pair_tc(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                     int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,

@@ -314,9 +314,9 @@ static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float
 }
 
 int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
-                  const float* b, float* y, int act, float alpha, cudaStream_t st) {
+                  const float* b, float* y, int act, float alpha, cudaStream_t st, const float* w_kmajor) {
     if (math_mode == UOCR_MATH_TF32) {
-        int rc = conv_fwd_tc(g, x, w, b, y, act, alpha, st);
+        int rc = conv_fwd_tc(g, x, w, w_kmajor, b, y, act, alpha, st);
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;
         // 5x5 / stride 1 / Cin = 4 (Line up_*, end): row GEMM with TMEM-resident windows (conv_row_tc.cu)
         static const bool row_tc = [] { const char* e = getenv("UOCR_ROW_TC"); return !e || e[0] != '0'; }();

@@ -112,13 +112,32 @@ using namespace uocr;
 
 extern "C" {
 
+int uocr_weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_cols, void* stream) {
+    UOCR_REQUIRE(w && wt, "NULL pointer");
+    UOCR_REQUIRE(k_rows > 0 && n_cols > 0, "non-positive dimension");
+    return weights_to_kmajor(w, wt, k_rows, n_cols, as_stream(stream));
+}
+
+static int fc_fwd_impl(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
+                       int64_t n_out, int act, float alpha, int math_mode, void* stream);
+
 int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t n_in, int64_t n_out,
                 int act, float alpha, int math_mode, void* stream) {
+    return fc_fwd_impl(x, w, nullptr, y, batch, n_in, n_out, act, alpha, math_mode, stream);
+}
+
+int uocr_fc_fwd_kmajor(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
+                       int64_t n_out, int act, float alpha, int math_mode, void* stream) {
+    return fc_fwd_impl(x, w, w_kmajor, y, batch, n_in, n_out, act, alpha, math_mode, stream);
+}
+
+static int fc_fwd_impl(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
+                       int64_t n_out, int act, float alpha, int math_mode, void* stream) {
     UOCR_REQUIRE(x && w && y, "NULL pointer");
     UOCR_REQUIRE(batch > 0 && n_in > 0 && n_out > 0, "non-positive dimension");
     UOCR_REQUIRE(act >= UOCR_ACT_NONE && act <= UOCR_ACT_SIGMOID, "unknown activation %d", act);
     cudaStream_t st = as_stream(stream);
-    int rc = fc_fwd_fast(math_mode, x, w, y, batch, n_in, n_out, act, alpha, st);
+    int rc = fc_fwd_fast(math_mode, x, w, w_kmajor, y, batch, n_in, n_out, act, alpha, st);
     if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     GemmArgs p{};
     p.A = x; p.lda = n_in; p.B = w; p.ldb = n_out; p.C = y; p.ldc = n_out;

@@ -707,19 +707,27 @@ static int transpose_async(const float* src, float* dst, int rows, int cols, int
 }
 
 // ------------------------------------------------------------------ FullyConnected
-int fc_fwd_fast(int math_mode, const float* x, const float* w, float* y, int64_t batch, int64_t n_in,
-                int64_t n_out, int act, float alpha, cudaStream_t st) {
+int fc_fwd_fast(int math_mode, const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch,
+                int64_t n_in, int64_t n_out, int act, float alpha, cudaStream_t st) {
     if (math_mode != UOCR_MATH_TF32) return UOCR_ERR_UNSUPPORTED;
     if (n_in % 4 || batch < 128 || n_in < 32 || n_out < 16) return UOCR_ERR_UNSUPPORTED;
     if (!encode_tiled()) return UOCR_ERR_UNSUPPORTED;
-    // W (n_in + 1, n_out) is N-major: transpose the weight rows to Wt (n_out, n_in); the bias row stays
+    // W (n_in + 1, n_out) is N-major: the tensor cores want the weight rows K-major, Wt (n_out, n_in) -- either the
+    // caller's cached copy (uocr_weights_to_kmajor) or a transpose into stream-ordered scratch; the bias row stays
     Scratch wt(st);
-    int rc = wt.alloc(sizeof(float) * n_out * n_in);
-    if (rc) return rc;
-    rc = transpose_async(w, (float*)wt.ptr, (int)n_in, (int)n_out, n_out, n_in, st);
-    if (rc) return rc;
-    return tc_gemm_tn(x, n_in, (const float*)wt.ptr, n_in, y, n_out, batch, n_out, n_in, w + n_in * n_out, act,
-                      alpha, 0, st);
+    if (!w_kmajor) {
+        int rc = wt.alloc(sizeof(float) * n_out * n_in);
+        if (rc) return rc;
+        rc = transpose_async(w, (float*)wt.ptr, (int)n_in, (int)n_out, n_out, n_in, st);
+        if (rc) return rc;
+        w_kmajor = (const float*)wt.ptr;
+    }
+    return tc_gemm_tn(x, n_in, w_kmajor, n_in, y, n_out, batch, n_out, n_in, w + n_in * n_out, act, alpha, 0, st);
+}
+
+int weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_cols, cudaStream_t st) {
+    if (k_rows > 0x7fffffff || n_cols > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    return transpose_async(w, wt, (int)k_rows, (int)n_cols, n_cols, k_rows, st);
 }
 
 // out[c] += sum_r src[r][c] : bias gradients (the "ones" column of [x, 1]^T . dy).  Rows are split over
@@ -797,18 +805,22 @@ int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, 
 static int conv_fwd_tc_slab(const ConvGeom& g, const float* x, const float* wt, const float* b, float* y, int act,
                             float alpha, cudaStream_t st);
 
-int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
-                cudaStream_t st) {
+int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* w_kmajor, const float* b, float* y,
+                int act, float alpha, cudaStream_t st) {
     if (g.cin % TC_BK || g.sw != 1 || g.padding_value != 0.f || g.ups != 1) return UOCR_ERR_UNSUPPORTED;
     if (g.cout % 16 || g.cout > 256 || g.cout < 16) return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) & 15) || !encode_tiled()) return UOCR_ERR_UNSUPPORTED;
     const int K = g.kh * g.kw * g.cin;
     Scratch wt(st);
-    int rc = wt.alloc(sizeof(float) * (size_t)K * g.cout);
-    if (rc) return rc;
-    rc = transpose_async(w, (float*)wt.ptr, K, g.cout, g.cout, K, st);       // (K, Cout) -> (Cout, K)
-    if (rc) return rc;
-    rc = conv_fwd_tc_slab(g, x, (const float*)wt.ptr, b, y, act, alpha, st);
+    int rc;
+    if (!w_kmajor) {
+        rc = wt.alloc(sizeof(float) * (size_t)K * g.cout);
+        if (rc) return rc;
+        rc = transpose_async(w, (float*)wt.ptr, K, g.cout, g.cout, K, st);       // (K, Cout) -> (Cout, K)
+        if (rc) return rc;
+        w_kmajor = (const float*)wt.ptr;
+    }
+    rc = conv_fwd_tc_slab(g, x, w_kmajor, b, y, act, alpha, st);
     if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     TcParams p{};
     p.C = y; p.ldc = g.cout; p.M = (int64_t)g.n * g.ho * g.wo; p.N = g.cout;
@@ -826,7 +838,7 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
     if (rc) return rc;
     const uint64_t db[2] = {(uint64_t)K, (uint64_t)g.cout}, sb[1] = {(uint64_t)K * 4};
     const uint32_t bb[2] = {TC_BK, (uint32_t)g.cout};
-    rc = make_tmap(&mb, wt.ptr, 2, db, sb, bb);
+    rc = make_tmap(&mb, w_kmajor, 2, db, sb, bb);
     if (rc) return rc;
     const int64_t tiles = (int64_t)g.n * g.ho * p.xtiles;
     if (tiles > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;

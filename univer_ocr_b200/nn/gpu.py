@@ -432,6 +432,9 @@ class CP:
     cp = _DeviceNamespace
     is_gpu_used = True
     math_mode = MATH_FP32
+    # bumped by everything that changes parameter values (Param.value = ..., optimizer updates, the flat-buffer
+    # DataParallel update): layers key their cached K-major weight copies on it
+    weights_generation = 0
 
     @staticmethod
     def use_gpu():

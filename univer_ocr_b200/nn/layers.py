@@ -18,7 +18,7 @@ import math
 
 import numpy as np
 
-from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, ConvDesc, lib
+from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, MATH_TF32, ConvDesc, lib
 from .gpu import CP, DeviceArray, LazyScalar, as_device, concatenate, slice_axis, stream
 from .help_func import make_list_if_not, tuplize
 from .initializers import kaiming_uniform
@@ -42,6 +42,18 @@ class FromOutput:
         self.y = y
 
 
+def _kmajor_copy(layer, w, k_rows, n_cols):
+    """K-major (n_cols, k_rows) copy of the layer's weight matrix `w` (k_rows [+ bias row], n_cols) for the
+    tensor-core kernels, cached on the layer until any parameter changes (CP.weights_generation)."""
+    cached = getattr(layer, '_kmajor_cache', None)
+    if cached is not None and cached[0] == CP.weights_generation and cached[1] == w.ptr:
+        return cached[2]
+    wt = DeviceArray((n_cols, k_rows))
+    lib.uocr_weights_to_kmajor(w.ptr, wt.ptr, k_rows, n_cols, stream())
+    layer._kmajor_cache = (CP.weights_generation, w.ptr, wt)
+    return wt
+
+
 _DEFAULT_OPTIMIZER = Adam()     # the reference's default argument is one shared instance (layers.py:31)
 
 
@@ -62,9 +74,11 @@ class Param:
     @value.setter
     def value(self, new):
         self._value = new if isinstance(new, DeviceArray) else CP.copy(np.asarray(new, dtype=np.float64))
+        CP.weights_generation += 1
 
     def update_grad(self):
         self.optimizer.update(self)
+        CP.weights_generation += 1
 
     def clear_grad(self):
         if self.grad.shape != self._value.shape:
@@ -411,8 +425,13 @@ class FullyConnected(BaseLayer):
         if save:
             self._mem[mem_id] = X
         y = DeviceArray((X.shape[0], self.n_output))
-        lib.uocr_fc_fwd(X.ptr, self.w.value.ptr, y.ptr, X.shape[0], self.n_input, self.n_output,
-                        act, float(alpha), CP.math_mode, stream())
+        if not save and CP.math_mode == MATH_TF32:       # inference: weights are static, cache their K-major copy
+            wt = _kmajor_copy(self, self.w.value, self.n_input, self.n_output)
+            lib.uocr_fc_fwd_kmajor(X.ptr, self.w.value.ptr, wt.ptr, y.ptr, X.shape[0], self.n_input, self.n_output,
+                                   act, float(alpha), CP.math_mode, stream())
+        else:
+            lib.uocr_fc_fwd(X.ptr, self.w.value.ptr, y.ptr, X.shape[0], self.n_input, self.n_output,
+                            act, float(alpha), CP.math_mode, stream())
         return y
 
     def _backward(self, grad, mem_id=0):
@@ -495,8 +514,15 @@ class Convolutional2D(BaseLayer):
             self._mem[mem_id] = X if in_upsample == 1 else UpsampledInput(X, in_upsample)
         n, h, w, c = X.shape
         y = DeviceArray(self.get_output_shapes((n, h * in_upsample, w * in_upsample, c))[0])
-        lib.uocr_conv2d_fwd(ctypes.byref(desc), X.ptr, self.w.value.ptr, self.b.value.ptr, y.ptr,
-                            act, float(alpha), stream())
+        if (not save and CP.math_mode == MATH_TF32 and in_upsample == 1 and self.in_channels % 32 == 0
+                and self.out_channels % 16 == 0):        # a tcgen05 implicit-GEMM layer in inference
+            kh, kw = self.kernel_size
+            wt = _kmajor_copy(self, self.w.value, kh * kw * self.in_channels, self.out_channels)
+            lib.uocr_conv2d_fwd_kmajor(ctypes.byref(desc), X.ptr, self.w.value.ptr, wt.ptr, self.b.value.ptr, y.ptr,
+                                       act, float(alpha), stream())
+        else:
+            lib.uocr_conv2d_fwd(ctypes.byref(desc), X.ptr, self.w.value.ptr, self.b.value.ptr, y.ptr,
+                                act, float(alpha), stream())
         return y
 
     def supports_upsampled_input_grad(self):

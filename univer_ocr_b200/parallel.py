@@ -20,7 +20,7 @@ The L2 gradient depends on the weights only, so it is added once, after the allr
 import numpy as np
 
 from .nn import optimizers
-from .nn.gpu import DeviceArray, LazyScalar, stream
+from .nn.gpu import CP, DeviceArray, LazyScalar, stream
 from .nn.losses import SegmentationDice2D, SegmentationJaccard2D
 from .nn.regularizations import L2
 from ._lib import lib
@@ -143,6 +143,7 @@ class DataParallel:
                                  float(opt.lr), float(opt.beta1), float(opt.beta2), optimizers.EPS,
                                  float(self.grad_scale), l2, reg_loss.ptr if l2 else None, stream())
         lib.uocr_memset(flat.grads.ptr, 0, flat.grads.nbytes, stream())
+        CP.weights_generation += 1                      # the parameter views changed under the layers
         return LazyScalar(reg_loss)
 
     def train(self, X, y):
