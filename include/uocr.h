@@ -256,6 +256,13 @@ int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t
                 int64_t n_out, int act, float alpha, int math_mode, void* stream);
 /* Same, with a caller-cached K-major copy w_kmajor (n_out, n_in) of the weight rows (see uocr_conv2d_fwd_kmajor);
  * the bias row is still read from w. */
+/* y (n*w, n_out) = act([windows(x), 1] . W) for x (n, 1, w, c): Conv2DToBatchedFixedWidthed(width) + Flatten + FullyConnected
+ * in one call.   replaces: convolutional.py:330-360 + layers.py:287-294 + layers.py:335-339 (the head of make_char,
+ * my_model/model.py:250-304).  In TF32 mode with w % 128 == 0 and c % 32 == 0 the GEMM's A tiles are gathered from x by
+ * TMA (implicit 1-D convolution; the (n*w, width*c) window matrix is never materialised); otherwise the windows go
+ * through library scratch.  w_kmajor: optional cached K-major copy (n_out, width*c) of W's weight rows, may be NULL. */
+int uocr_window_fc_fwd(const float* x, const float* w, const float* w_kmajor, float* y, int64_t n, int64_t wd,
+                       int64_t c, int32_t width, int64_t n_out, int act, float alpha, int math_mode, void* stream);
 int uocr_fc_fwd_kmajor(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
                        int64_t n_out, int act, float alpha, int math_mode, void* stream);
 /* dx = dy . W[:-1]^T (skipped when dx == NULL); dw (+)= [x, 1]^T . dy.  replaces: layers.py:341-347 */

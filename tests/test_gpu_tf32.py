@@ -215,3 +215,28 @@ def test_kmajor_weight_cache_follows_updates(nn):
     w1 = np_models.golden_weights('char', 6)
     model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w1.items()})
     check('after set_weights', p2)
+
+
+@pytest.mark.parametrize('n,w,c,width,n_out', [(64, 256, 64, 8, 1024), (48, 128, 32, 8, 256), (3, 200, 64, 8, 1024),
+                                              (2, 256, 48, 6, 200)],
+                         ids=['char_head', 'small', 'w_not_128', 'c_not_32'])
+def test_window_fc_fused(nn, n, w, c, width, n_out):
+    """uocr_window_fc_fwd: Conv2DToBatchedFixedWidthed + Flatten + FullyConnected (+ LeakyRelu) in one call -- with the
+    window matrix gathered by TMA inside the persistent tcgen05 GEMM (first two cases), or through scratch (other
+    geometries) -- vs the float64 oracle of the three layers."""
+    from univer_ocr_b200._lib import ACT_LEAKY, MATH_TF32, lib
+    rng = np.random.default_rng(n + w + c)
+    X = f32(rng.standard_normal((n, 1, w, c)))
+    W = f32(rng.standard_normal((width * c + 1, n_out)) / np.sqrt(width * c))
+    win = O.window_batch_fwd(X, width)
+    want = O.leaky_relu_fwd(O.fc_fwd(win.reshape(n * w, -1), W), 0.01)
+    dX, dW = nn.CP.copy(X), nn.CP.copy(W)
+    for cached in (False, True):
+        wt = None
+        if cached:
+            wt = nn.DeviceArray((n_out, width * c))
+            lib.uocr_weights_to_kmajor(dW.ptr, wt.ptr, width * c, n_out, nn.CP.stream())
+        y = nn.DeviceArray((n * w, n_out))
+        lib.uocr_window_fc_fwd(dX.ptr, dW.ptr, wt.ptr if wt is not None else None, y.ptr, n, w, c, width, n_out,
+                               ACT_LEAKY, 0.01, MATH_TF32, nn.CP.stream())
+        close_tf32(y, want, f'window fc {(n, w, c, width, n_out)} cached={cached}')

@@ -121,6 +121,24 @@ int uocr_weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_
 static int fc_fwd_impl(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
                        int64_t n_out, int act, float alpha, int math_mode, void* stream);
 
+int uocr_window_fc_fwd(const float* x, const float* w, const float* w_kmajor, float* y, int64_t n, int64_t wd,
+                       int64_t c, int32_t width, int64_t n_out, int act, float alpha, int math_mode, void* stream) {
+    UOCR_REQUIRE(x && w && y, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && wd > 0 && c > 0 && width > 0 && n_out > 0, "non-positive dimension");
+    UOCR_REQUIRE(wd >= width, "Input width must be >= than output width");
+    UOCR_REQUIRE(act >= UOCR_ACT_NONE && act <= UOCR_ACT_SIGMOID, "unknown activation %d", act);
+    cudaStream_t st = as_stream(stream);
+    int rc = fc_window_fwd_fast(math_mode, x, w, w_kmajor, y, n, wd, c, width, n_out, act, alpha, st);
+    if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    // any other geometry / math mode: materialise the windows in scratch, then the ordinary FullyConnected
+    Scratch win(st);
+    rc = win.alloc(sizeof(float) * (size_t)n * wd * width * c);
+    if (rc) return rc;
+    rc = uocr_window_batch_fwd(x, (float*)win.ptr, n, 1, wd, c, width, stream);
+    if (rc) return rc;
+    return fc_fwd_impl((const float*)win.ptr, w, w_kmajor, y, n * wd, (int64_t)width * c, n_out, act, alpha, math_mode, stream);
+}
+
 int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t n_in, int64_t n_out,
                 int act, float alpha, int math_mode, void* stream) {
     return fc_fwd_impl(x, w, nullptr, y, batch, n_in, n_out, act, alpha, math_mode, stream);

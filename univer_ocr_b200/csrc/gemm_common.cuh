@@ -21,6 +21,8 @@ int sgemm_fp32(const GemmArgs& p, bool ta, bool tb, int splitk, cudaStream_t st)
 // tensor-core paths: UOCR_ERR_UNSUPPORTED when math_mode / shape has no tcgen05 kernel
 int fc_fwd_fast(int math_mode, const float* x, const float* w, const float* w_kmajor /* may be NULL */, float* y,
                 int64_t batch, int64_t n_in, int64_t n_out, int act, float alpha, cudaStream_t st);
+int fc_window_fwd_fast(int math_mode, const float* x, const float* w, const float* w_kmajor, float* y, int64_t n,
+                       int64_t wd, int64_t c, int width, int64_t n_out, int act, float alpha, cudaStream_t st);
 int weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_cols, cudaStream_t st);
 int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, float* dx, float* dw,
                 int64_t batch, int64_t n_in, int64_t n_out, int accumulate, cudaStream_t st);

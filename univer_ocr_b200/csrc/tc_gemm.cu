@@ -105,6 +105,9 @@ struct TcParams {
     int kb_per_split;
     // conv wgrad
     int ntaps, taps_per_cta, kbx, rows_total, rows_per_split;
+    // persistent GEMM with the A operand gathered as sliding windows (Conv2DToBatchedFixedWidthed + Flatten folded
+    // into the FullyConnected that follows): row (n, wi) of A, K index (k, ch) = x[n, wi + k - win_half, ch]
+    int win_w, win_cblocks, win_half, win_tiles_per_img;
 };
 
 template <int MODE>
@@ -493,8 +496,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t bar = smem_u32(&full[s]);
                     mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
-                    const int kk = (kb + rot >= p.num_kb ? kb + rot - p.num_kb : kb + rot) * TC_BK;
-                    tma_load_2d(sa, &map_a, bar, kk, m0);
+                    const int kbr = kb + rot >= p.num_kb ? kb + rot - p.num_kb : kb + rot;
+                    const int kk = kbr * TC_BK;
+                    if (p.win_w) {                         // 128 consecutive window positions of one image: a 3-D box
+                        const int mt = tile % m_tiles;
+                        const int k = kbr / p.win_cblocks, cb = kbr - k * p.win_cblocks;
+                        tma_load_3d(sa, &map_a, bar, cb * TC_BK, (mt % p.win_tiles_per_img) * TC_BM + k - p.win_half,
+                                    mt / p.win_tiles_per_img);
+                    } else {
+                        tma_load_2d(sa, &map_a, bar, kk, m0);
+                    }
                     tma_load_2d(sa + a_bytes, &map_b, bar, kk, n0);
                 }
             }
@@ -610,11 +621,27 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     }
 }
 
+struct WindowGeom { int64_t n, w, c; int width; };      // A = sliding windows over x (n, w, c): see TcParams::win_*
+
+static int tc_gemm_tn_persistent_impl(const float* A, int64_t lda, const WindowGeom* win, const float* Bt, int64_t ldb,
+                                      float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int act,
+                                      float alpha, int accumulate, cudaStream_t st);
+
 static int tc_gemm_tn_persistent(const float* A, int64_t lda, const float* Bt, int64_t ldb, float* C, int64_t ldc,
                                  int64_t M, int64_t N, int64_t K, const float* bias, int act, float alpha,
                                  int accumulate, cudaStream_t st) {
+    return tc_gemm_tn_persistent_impl(A, lda, nullptr, Bt, ldb, C, ldc, M, N, K, bias, act, alpha, accumulate, st);
+}
+
+static int tc_gemm_tn_persistent_impl(const float* A, int64_t lda, const WindowGeom* win, const float* Bt, int64_t ldb,
+                                      float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias, int act,
+                                      float alpha, int accumulate, cudaStream_t st) {
     TcParams p{};
     p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.num_kb = (int)ceil_div(K, TC_BK);
+    if (win) {
+        p.win_w = (int)win->w; p.win_cblocks = (int)(win->c / TC_BK); p.win_half = win->width / 2;
+        p.win_tiles_per_img = (int)(win->w / TC_BM);
+    }
     p.nt = N >= 256 ? 256 : (int)(((N + 15) / 16) * 16);
     p.bias = bias; p.act = act; p.alpha = alpha; p.accumulate = accumulate;
     const size_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (((size_t)p.nt * TC_BK * 4) + 1023) & ~(size_t)1023;
@@ -625,9 +652,17 @@ static int tc_gemm_tn_persistent(const float* A, int64_t lda, const float* Bt, i
     if (bias_floats > 2048) return UOCR_ERR_UNSUPPORTED;
     const size_t smem = (size_t)p.stages * (a_bytes + b_bytes) + 1024 + (2 * p.stages + 6) * 8 + bias_floats * 4 + 8 * 2048 + 64;
     CUtensorMap ma, mb;
-    const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 4};
-    const uint32_t ba[2] = {TC_BK, TC_BM};
-    int rc = make_tmap(&ma, A, 2, da, sa, ba);
+    int rc;
+    if (win) {                                            // x (n, w, c): out-of-range window columns read as zeros
+        const uint64_t da[3] = {(uint64_t)win->c, (uint64_t)win->w, (uint64_t)win->n};
+        const uint64_t sa[2] = {(uint64_t)win->c * 4, (uint64_t)win->w * win->c * 4};
+        const uint32_t ba[3] = {TC_BK, TC_BM, 1};
+        rc = make_tmap(&ma, A, 3, da, sa, ba);
+    } else {
+        const uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 4};
+        const uint32_t ba[2] = {TC_BK, TC_BM};
+        rc = make_tmap(&ma, A, 2, da, sa, ba);
+    }
     if (rc) return rc;
     const uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldb * 4};
     const uint32_t bb[2] = {TC_BK, (uint32_t)p.nt};
@@ -723,6 +758,29 @@ int fc_fwd_fast(int math_mode, const float* x, const float* w, const float* w_km
         w_kmajor = (const float*)wt.ptr;
     }
     return tc_gemm_tn(x, n_in, w_kmajor, n_in, y, n_out, batch, n_out, n_in, w + n_in * n_out, act, alpha, 0, st);
+}
+
+// y (n*w, n_out) = act([windows(x), 1] . W): Conv2DToBatchedFixedWidthed(width) + Flatten + FullyConnected in one GEMM whose
+// A tiles are gathered from x (n, 1, w, c) by TMA (an implicit 1-D convolution over the width): the (n*w, width*c)
+// window matrix (33 MB for Char at batch 64) is never written or read.
+int fc_window_fwd_fast(int math_mode, const float* x, const float* w, const float* w_kmajor, float* y, int64_t n,
+                       int64_t wd, int64_t c, int width, int64_t n_out, int act, float alpha, cudaStream_t st) {
+    const int64_t n_in = (int64_t)width * c, batch = n * wd;
+    if (math_mode != UOCR_MATH_TF32 || !encode_tiled()) return UOCR_ERR_UNSUPPORTED;
+    if (wd % TC_BM || c % TC_BK || n_out < 128 || n_out % 4 || (reinterpret_cast<uintptr_t>(x) & 15)) return UOCR_ERR_UNSUPPORTED;
+    const int64_t nt = n_out >= 256 ? 256 : ((n_out + 15) / 16) * 16;
+    if (ceil_div(batch, TC_BM) * ceil_div(n_out, nt) < 96) return UOCR_ERR_UNSUPPORTED;
+    Scratch wt(st);
+    if (!w_kmajor) {
+        int rc = wt.alloc(sizeof(float) * n_out * n_in);
+        if (rc) return rc;
+        rc = transpose_async(w, (float*)wt.ptr, (int)n_in, (int)n_out, n_out, n_in, st);
+        if (rc) return rc;
+        w_kmajor = (const float*)wt.ptr;
+    }
+    const WindowGeom win{n, wd, c, width};
+    return tc_gemm_tn_persistent_impl(x, 0, &win, w_kmajor, n_in, y, n_out, batch, n_out, n_in, w + n_in * n_out, act,
+                                      alpha, 0, st);
 }
 
 int weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_cols, cudaStream_t st) {

@@ -17,11 +17,11 @@ replayed; no layer call synchronises the device, and loss values stay on the dev
 """
 import ctypes
 
-from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
+from .._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, MATH_TF32, lib
 from .gpu import CP, DeviceArray, LazyScalar, as_device, stream
 from .help_func import make_list_if_not
-from .layers import (BaseLayer, Convolutional2D, FromOutput, FullyConnected, LeakyRelu, Sigmoid,
-                     Upsample2D)
+from .layers import (BaseLayer, Conv2DToBatchedFixedWidthed, Convolutional2D, Flatten, FromOutput, FullyConnected,
+                     LeakyRelu, Sigmoid, Upsample2D, _kmajor_copy)
 from .losses import SoftmaxCrossEntropy
 from .progress_tracker import track_method
 
@@ -259,6 +259,17 @@ class Model(BaseModel):
                         step = ('pair', conv_name, act_name, pair[0], pair[1])
                     elif ups is not None or act_name is not None:
                         step = ('conv', ups, conv_name, act_name)
+            if (step is None and self.fusion and not training and type(layer) is Conv2DToBatchedFixedWidthed
+                    and len(self.relations[name]) == 1):
+                # inference: window batching + Flatten + FullyConnected (+ activation) as one GEMM whose A operand
+                # is gathered from the un-windowed tensor (uocr_window_fc_fwd)
+                flat = self._sole_consumer(name)
+                fc = self._sole_consumer(flat) if flat is not None and type(self.layers[flat]) is Flatten else None
+                if fc is not None and type(self.layers[fc]) is FullyConnected:
+                    act_name = self._sole_consumer(fc)
+                    if act_name is not None and _act_code(self.layers[act_name]) is None:
+                        act_name = None
+                    step = ('winfc', name, flat, fc, act_name)
             if step is None:
                 step = ('layer', name)
             plan.append(step)
@@ -307,6 +318,8 @@ class Model(BaseModel):
                 outputs[name] = out[0] if isinstance(out, list) else out
             elif kind == 'conv':
                 self._run_fused_conv(step, value_of, outputs, training, clear_grads)
+            elif kind == 'winfc':
+                self._run_winfc(step, value_of, outputs)
             else:
                 self._run_pair(step, value_of, outputs, training)
         for key in self._output_keys():
@@ -342,6 +355,33 @@ class Model(BaseModel):
             if n is not None:
                 outputs[n] = None
         outputs[act_name if act_name is not None else conv_name] = y
+
+    def _run_winfc(self, step, value_of, outputs):
+        """Inference only: Conv2DToBatchedFixedWidthed -> Flatten -> FullyConnected (-> activation)."""
+        _, win_name, flat_name, fc_name, act_name = step
+        X = as_device(value_of(self.relations[win_name][0]))
+        win, fc = self.layers[win_name], self.layers[fc_name]
+        n, h, w, c = X.shape
+        names = [nm for nm in (win_name, flat_name, fc_name, act_name) if nm is not None]
+        if h != 1 or win.width * c != fc.n_input:          # not the Char head's geometry: layer by layer
+            cur = X
+            for nm in names:
+                out = self.layers[nm].forward([cur])
+                cur = out[0] if isinstance(out, list) else out
+                outputs[nm] = cur
+            return
+        assert w >= win.width, f'Input width must be >= than output width, found: {w} < {win.width}'
+        act, alpha = _act_code(self.layers[act_name]) if act_name is not None else (ACT_NONE, 0.0)
+        last = self.layers[names[-1]]
+        last.progress_tracker.start_tracking(last.name, 'forward')
+        y = DeviceArray((n * w, fc.n_output))
+        wt = _kmajor_copy(fc, fc.w.value, fc.n_input, fc.n_output) if CP.math_mode == MATH_TF32 else None
+        lib.uocr_window_fc_fwd(X.ptr, fc.w.value.ptr, wt.ptr if wt is not None else None, y.ptr, n, w, c, win.width,
+                               fc.n_output, act, float(alpha), CP.math_mode, stream())
+        last.progress_tracker.stop_tracking(last.name, 'forward')
+        for nm in names:
+            outputs[nm] = None
+        outputs[names[-1]] = y
 
     def _run_pair(self, step, value_of, outputs, training=False):
         _, c1_name, a1_name, c2_name, a2_name = step
