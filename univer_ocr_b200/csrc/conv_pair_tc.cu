@@ -41,7 +41,7 @@
 namespace uocr {
 
 constexpr int PM_OUT = 30;            // output columns per warp strip
-constexpr int PM_THREADS = 128;       // 4 warps = the 128 rows of one UMMA
+constexpr int PM_THREADS = 160;       // 4 compute warps = the 128 rows of one UMMA, + 1 MMA-issuing warp
 constexpr int PM_R = 4;               // hidden rows per pipeline step
 constexpr int PM_NS = PM_R + 2;       // x rows live during a step = ring slots
 constexpr int PM_TMEM_COLS = 32 * PM_R;   // per hidden row in flight: 16 columns X9 / Z + 16 columns H / A2
@@ -108,30 +108,40 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity) 
     } while (!done);
 }
 
-// One pipeline step = hidden rows i0 = PM_R k .. i0 + PM_R - 1 of the band.  PX = i0 % PM_NS (x ring phase) and
-// PH = i0 % 3 (partial-sum ring phase) are compile-time so that every register array index is static.
+// Barriers, per half h of a step (rows 2h, 2h + 1): [0] windows stored (128 arrivals), [1] MMA1 committed,
+// [2] A2 stored (128 arrivals), [3] MMA2 committed.  Every barrier completes once per step: parity = k & 1.
+__device__ __forceinline__ uint32_t pm_bar(uint32_t bars, int half, int which) { return bars + (uint32_t)(half * 4 + which) * 8u; }
+
+// One pipeline step = hidden rows i0 = PM_R k .. i0 + PM_R - 1 of the band, as TWO half-steps (rows 0-1, rows 2-3)
+// whose phases are interleaved so that a warp computes on one half while the other half's MMAs are in flight:
+//   A(0) A(1) | B(0) B(1) | C(0) C(1)        (A: windows -> TMEM, B: H -> act -> A2, C: Z -> shift-add -> output)
+// The MMAs are issued by a dedicated fifth warp (pm_issuer), so no compute warp ever waits for the other three.
+// PX = i0 % PM_NS (x ring phase) and PH = i0 % 3 (partial-sum ring phase) are compile-time: static register indices.
 template <int PX, int PH, bool LEAKY, bool SIGMOID>
 __device__ __forceinline__ void pm_step(const PairTcParams& p, PairTcState& s, int k, const float* __restrict__& xnext,
                                         float* __restrict__& ynext, int hr0, int nrows, bool c0, bool c1, bool c2,
-                                        bool store_lane, bool warp0, uint32_t tlane, uint32_t bars, uint32_t sb1,
-                                        uint32_t sb2, uint32_t stm, float bias2) {
+                                        bool store_lane, uint32_t tlane, uint32_t bars, float bias2) {
     const uint32_t par = (uint32_t)(k & 1);
     const int i0 = PM_R * k;
-    // ---------------- phase A: 3 x 3 windows of PM_R hidden rows -> TMEM (GEMM 1's A operand)
+    // ---------------- phase A: 3 x 3 windows -> TMEM (GEMM 1's A operand)
 #pragma unroll
-    for (int r = 0; r < PM_R; ++r) {
-        const int hr = hr0 + i0 + r;
-        const uint32_t tx = tlane + (uint32_t)(32 * r);
-        if (hr >= 0 && hr < p.H) {                        // warp-uniform
+    for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int a = 0; a < 3; ++a) tc_st4_nowait(tx + 4 * a, s.xw[(PX + r + a) % PM_NS]);
-        } else {                                          // hidden rows outside the image are conv_2's zero padding
-            tc_st16_zero(tx);
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * half + rr;
+            const int hr = hr0 + i0 + r;
+            const uint32_t tx = tlane + (uint32_t)(32 * r);
+            if (hr >= 0 && hr < p.H) {                    // warp-uniform
+#pragma unroll
+                for (int a = 0; a < 3; ++a) tc_st4_nowait(tx + 4 * a, s.xw[(PX + r + a) % PM_NS]);
+            } else {                                      // hidden rows outside the image are conv_2's zero padding
+                tc_st16_zero(tx);
+            }
         }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(pm_bar(bars, half, 0));
     }
-    tc_wait_st();
-    tc_fence_before();
-    mbar_arrive(bars + 0);
     // Prefetch the PM_R x rows the NEXT step adds to the window, straight into the ring slots that died with this
     // step's stores; their latency hides behind this step's waits; they are rounded to TF32 at the end of phase C.
 #pragma unroll
@@ -140,80 +150,48 @@ __device__ __forceinline__ void pm_step(const PairTcParams& p, PairTcState& s, i
         pm_load_row(xnext, xr >= 0 && xr < p.H, c0, c1, c2, s.xw[(PX + j) % PM_NS]);
         xnext += p.W;
     }
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-    if (warp0) {                                          // warp 0 issues the MMAs of the whole CTA
-        mbar_wait_sleepy(bars + 0, par);
+    // ---------------- phase B: H -> act1 -> A2 (in place)
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        mbar_wait_sleepy(pm_bar(bars, half, 1), par);
         tc_fence_after();
-        if (elect_one()) {
-            const uint32_t tb = pm_tmem_base(stm);        // re-read: keeps the MMA operand addresses out of the
-#pragma unroll                                            // loop-carried register set
-            for (int r = 0; r < PM_R; ++r)
 #pragma unroll
-                for (int m = 0; m < 2; ++m)
-                    tc_mma_tf32_ts(tb + (uint32_t)(32 * r + 16), tb + (uint32_t)(32 * r + 8 * m),
-                                   make_kmajor_nosw_desc(sb1 + (uint32_t)(2 * m) * 256u, 256, 128), idesc, m);
-            tc_commit(bars + 8);
-        }
-        __syncwarp();
-    }
-    // ---------------- phase B: H -> act1 -> A2 (in place); the load of row r + 1 is in flight while row r computes
-    mbar_wait_sleepy(bars + 8, par);
-    tc_fence_after();
-    {
-        uint32_t h[2][16];
-        tc_ld16_nowait(tlane + 16u, h[0]);
-#pragma unroll
-        for (int r = 0; r < PM_R; ++r) {
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * half + rr;
+            uint32_t h[16];
+            tc_ld16_nowait(tlane + (uint32_t)(32 * r + 16), h);
             tc_wait_ld();
-            if (r + 1 < PM_R) tc_ld16_nowait(tlane + (uint32_t)(32 * (r + 1) + 16), h[(r + 1) & 1]);
             if (LEAKY) {
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
-                    const float v = __uint_as_float(h[r & 1][c]);
-                    h[r & 1][c] = __float_as_uint(fmaxf(v, v * p.alpha1));
+                    const float v = __uint_as_float(h[c]);
+                    h[c] = __float_as_uint(fmaxf(v, v * p.alpha1));
                 }
             }
-            tc_st16_nowait(tlane + (uint32_t)(32 * r + 16), h[r & 1]);
+            tc_st16_nowait(tlane + (uint32_t)(32 * r + 16), h);
         }
-    }
-    tc_wait_st();
-    tc_fence_before();
-    mbar_arrive(bars + 16);
-    if (warp0) {
-        mbar_wait_sleepy(bars + 16, par);
-        tc_fence_after();
-        if (elect_one()) {
-            const uint32_t tb = pm_tmem_base(stm);
-#pragma unroll
-            for (int r = 0; r < PM_R; ++r)
-#pragma unroll
-                for (int m = 0; m < 2; ++m)
-                    tc_mma_tf32_ts(tb + (uint32_t)(32 * r), tb + (uint32_t)(32 * r + 16 + 8 * m),
-                                   make_kmajor_nosw_desc(sb2 + (uint32_t)(2 * m) * 256u, 256, 128), idesc, m);
-            tc_commit(bars + 24);
-        }
-        __syncwarp();
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(pm_bar(bars, half, 2));
     }
     // ---------------- phase C: Z -> rolling shift-and-add -> output rows
-    mbar_wait_sleepy(bars + 24, par);
-    tc_fence_after();
-    {
-        uint32_t z[2][9];
-        tc_ld8_nowait(tlane, z[0]);
-        tc_ld1_nowait(tlane + 8u, z[0] + 8);
 #pragma unroll
-        for (int r = 0; r < PM_R; ++r) {
+    for (int half = 0; half < 2; ++half) {
+        mbar_wait_sleepy(pm_bar(bars, half, 3), par);
+        tc_fence_after();
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = 2 * half + rr;
             const int ph = (PH + r) % 3;
+            uint32_t z[9];
+            tc_ld8_nowait(tlane + (uint32_t)(32 * r), z);
+            tc_ld1_nowait(tlane + (uint32_t)(32 * r + 8), z + 8);
             tc_wait_ld();
-            if (r + 1 < PM_R) {
-                tc_ld8_nowait(tlane + (uint32_t)(32 * (r + 1)), z[(r + 1) & 1]);
-                tc_ld1_nowait(tlane + (uint32_t)(32 * (r + 1) + 8), z[(r + 1) & 1] + 8);
-            }
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                s.acc[(ph + 2) % 3][kx] = __uint_as_float(z[r & 1][kx]);          // ky = 0: opens output row i + 2
-                s.acc[(ph + 1) % 3][kx] += __uint_as_float(z[r & 1][3 + kx]);     // ky = 1: output row i + 1
-                s.acc[ph][kx] += __uint_as_float(z[r & 1][6 + kx]);               // ky = 2: completes output row i
+                s.acc[(ph + 2) % 3][kx] = __uint_as_float(z[kx]);             // ky = 0: opens output row i + 2
+                s.acc[(ph + 1) % 3][kx] += __uint_as_float(z[3 + kx]);        // ky = 1: output row i + 1
+                s.acc[ph][kx] += __uint_as_float(z[6 + kx]);                  // ky = 2: completes output row i
             }
             // y[oy, ox] = b2 + Z-sum of hidden columns ox - 1 (kx = 0), ox (kx = 1), ox + 1 (kx = 2)
             const float left = __shfl_up_sync(0xffffffffu, s.acc[ph][0], 1);
@@ -230,11 +208,45 @@ __device__ __forceinline__ void pm_step(const PairTcParams& p, PairTcState& s, i
     for (int j = 0; j < PM_R; ++j) pm_round_row(s.xw[(PX + j) % PM_NS]);
 }
 
+// The fifth warp: waits for each half's operands and issues its MMAs (one elected lane).
+__device__ __forceinline__ void pm_issuer(int steps, uint32_t tmem_base, uint32_t bars, uint32_t sb1, uint32_t sb2) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+#pragma unroll 1
+    for (int k = 0; k < steps; ++k) {
+        const uint32_t par = (uint32_t)(k & 1);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {                     // g = 0: GEMM 1 (windows -> H), g = 1: GEMM 2 (A2 -> Z)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait_sleepy(pm_bar(bars, half, g == 0 ? 0 : 2), par);
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int rr = 0; rr < 2; ++rr) {
+                        const uint32_t t = tmem_base + (uint32_t)(32 * (2 * half + rr));
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            if (g == 0)
+                                tc_mma_tf32_ts(t + 16, t + (uint32_t)(8 * m),
+                                               make_kmajor_nosw_desc(sb1 + (uint32_t)(2 * m) * 256u, 256, 128), idesc, m);
+                            else
+                                tc_mma_tf32_ts(t, t + (uint32_t)(16 + 8 * m),
+                                               make_kmajor_nosw_desc(sb2 + (uint32_t)(2 * m) * 256u, 256, 128), idesc, m);
+                        }
+                    }
+                    tc_commit(pm_bar(bars, half, g == 0 ? 1 : 3));
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
 template <bool LEAKY, bool SIGMOID>
 __global__ void __launch_bounds__(PM_THREADS, 4) conv3x3_pair_tmem_kernel(const PairTcParams p) {
     __shared__ __align__(128) float s_b1[256];          // chunk kq: 16 rows (n = channel) x 4 floats (k = 4 kq + kk)
     __shared__ __align__(128) float s_b2[256];          // chunk kq: 16 rows (n = tap) x 4 floats (k = channel)
-    __shared__ __align__(8) uint64_t s_bar[4];
+    __shared__ __align__(8) uint64_t s_bar[8];
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform for the compiler
@@ -250,14 +262,17 @@ __global__ void __launch_bounds__(PM_THREADS, 4) conv3x3_pair_tmem_kernel(const 
         s_b2[i] = n < 9 ? round_tf32(__ldg(p.w2 + n * 16 + kq * 4 + kk)) : 0.f;
     }
     if (tid == 0) {
-        mbar_init(smem_u32(&s_bar[0]), PM_THREADS);       // X9 stored by every thread
-        mbar_init(smem_u32(&s_bar[1]), 1);                // MMA1 committed
-        mbar_init(smem_u32(&s_bar[2]), PM_THREADS);       // A2 stored
-        mbar_init(smem_u32(&s_bar[3]), 1);                // MMA2 committed
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            mbar_init(smem_u32(&s_bar[half * 4 + 0]), 128);      // windows stored by every compute thread
+            mbar_init(smem_u32(&s_bar[half * 4 + 1]), 1);        // MMA1 committed
+            mbar_init(smem_u32(&s_bar[half * 4 + 2]), 128);      // A2 stored
+            mbar_init(smem_u32(&s_bar[half * 4 + 3]), 1);        // MMA2 committed
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // s_b1 / s_b2 are read by the async proxy
-    if (warp == 0) {
+    if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(&s_tmem)), "r"((uint32_t)PM_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -265,67 +280,69 @@ __global__ void __launch_bounds__(PM_THREADS, 4) conv3x3_pair_tmem_kernel(const 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tlane = s_tmem + ((uint32_t)(warp * 32) << 16);
-    // columns 12 .. 15 of every X block are never stored by phase A (zero weights) but must hold finite numbers
-#pragma unroll
-    for (int r = 0; r < PM_R; ++r) tc_st16_zero(tlane + (uint32_t)(32 * r));
-    tc_wait_st();
-
-    // work item of this warp: (image, band, strip); warps past the end run on zeros and store nothing
-    int64_t item = (int64_t)blockIdx.x * 4 + warp;
-    const bool active = item < p.items;
-    if (!active) item = p.items - 1;
-    const int strip = (int)(item % p.strips);
-    const int64_t rest = item / p.strips;
-    const int band = (int)(rest % p.bands);
-    const int64_t img = rest / p.bands;
-    const int hc = strip * PM_OUT - 1 + lane;           // hidden column of this lane
-    const bool c1 = active && hc >= 0 && hc < p.W;      // hidden pixels outside the image are zero padding
-    const bool c0 = c1 && hc - 1 >= 0, c2 = c1 && hc + 1 < p.W;
-    const bool store_lane = c1 && lane >= 1 && lane <= PM_OUT;
-    const int hr0 = band * p.rb - 1;                    // first hidden row of the band
-    const int nrows = min(p.H - band * p.rb, p.rb);     // output rows of the band
-    const float bias2 = __ldg(p.b2);
-    // &x[first x row of the band = hr0 - 1, hc] (never dereferenced outside the image), &y[band's first row, hc]
-    const float* xnext = p.x + (img * p.H + (hr0 - 1)) * p.W + hc;
-    // ynext = &y[output row completed by the step's first hidden row = band row - 2, hc] (stores are predicated)
-    float* ynext = p.y + (img * p.H + (hr0 - 1)) * p.W + hc;
-
-    PairTcState s;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) s.acc[a][b] = 0.f;
-#pragma unroll
-    for (int a = 0; a < PM_NS; ++a) {
-        const int xr = hr0 - 1 + a;
-        pm_load_row(xnext, xr >= 0 && xr < p.H, c0, c1, c2, s.xw[a]);
-        // (blockIdx.y is 0, which the compiler cannot know: one physical register per slot instead of one shared
-        // register, so that every quad is contiguous for tcgen05.st.x4 without moves)
-        s.xw[a][3] = (c1 ? __float_as_uint(1.f) : 0u) ^ (blockIdx.y * (uint32_t)(a + 1));
-        xnext += p.W;
-    }
-#pragma unroll
-    for (int a = 0; a < PM_NS; ++a) pm_round_row(s.xw[a]);
     const uint32_t bars = smem_u32(&s_bar[0]);
-    const uint32_t sb1 = smem_u32(s_b1), sb2 = smem_u32(s_b2);
-    const bool warp0 = warp == 0;
+
+    if (warp == 4) {
+        pm_issuer(p.steps, s_tmem, bars, smem_u32(s_b1), smem_u32(s_b2));
+    } else {
+        const uint32_t tlane = s_tmem + ((uint32_t)(warp * 32) << 16);
+        // columns 12 .. 15 of every X block are never stored by phase A (zero weights) but must hold finite numbers
+#pragma unroll
+        for (int r = 0; r < PM_R; ++r) tc_st16_zero(tlane + (uint32_t)(32 * r));
+        tc_wait_st();
+
+        // work item of this warp: (image, band, strip); warps past the end run on zeros and store nothing
+        int64_t item = (int64_t)blockIdx.x * 4 + warp;
+        const bool active = item < p.items;
+        if (!active) item = p.items - 1;
+        const int strip = (int)(item % p.strips);
+        const int64_t rest = item / p.strips;
+        const int band = (int)(rest % p.bands);
+        const int64_t img = rest / p.bands;
+        const int hc = strip * PM_OUT - 1 + lane;       // hidden column of this lane
+        const bool c1 = active && hc >= 0 && hc < p.W;  // hidden pixels outside the image are zero padding
+        const bool c0 = c1 && hc - 1 >= 0, c2 = c1 && hc + 1 < p.W;
+        const bool store_lane = c1 && lane >= 1 && lane <= PM_OUT;
+        const int hr0 = band * p.rb - 1;                // first hidden row of the band
+        const int nrows = min(p.H - band * p.rb, p.rb); // output rows of the band
+        const float bias2 = __ldg(p.b2);
+        // &x[first x row of the band = hr0 - 1, hc] (never dereferenced outside the image)
+        const float* xnext = p.x + (img * p.H + (hr0 - 1)) * p.W + hc;
+        // ynext = &y[output row completed by the step's first hidden row = band row - 2, hc] (stores are predicated)
+        float* ynext = p.y + (img * p.H + (hr0 - 1)) * p.W + hc;
+
+        PairTcState s;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) s.acc[a][b] = 0.f;
+#pragma unroll
+        for (int a = 0; a < PM_NS; ++a) {
+            const int xr = hr0 - 1 + a;
+            pm_load_row(xnext, xr >= 0 && xr < p.H, c0, c1, c2, s.xw[a]);
+            // (blockIdx.y is 0, which the compiler cannot know: one physical register per slot instead of one shared
+            // register, so that every quad is contiguous for tcgen05.st.x4 without moves)
+            s.xw[a][3] = (c1 ? __float_as_uint(1.f) : 0u) ^ (blockIdx.y * (uint32_t)(a + 1));
+            xnext += p.W;
+        }
+#pragma unroll
+        for (int a = 0; a < PM_NS; ++a) pm_round_row(s.xw[a]);
 
 #define PM_STEP(PX, PH, K) \
-    pm_step<PX, PH, LEAKY, SIGMOID>(p, s, K, xnext, ynext, hr0, nrows, c0, c1, c2, store_lane, warp0, tlane, bars, sb1, \
-                                    sb2, smem_u32(&s_tmem), bias2)
-    static_assert(PM_R == 4 && PM_NS == 6, "the unrolled phases below are (4k) % 6 and (4k) % 3");
+        pm_step<PX, PH, LEAKY, SIGMOID>(p, s, K, xnext, ynext, hr0, nrows, c0, c1, c2, store_lane, tlane, bars, bias2)
+        static_assert(PM_R == 4 && PM_NS == 6, "the unrolled phases below are (4k) % 6 and (4k) % 3");
 #pragma unroll 1
-    for (int k = 0; k < p.steps; k += 3) {
-        PM_STEP(0, 0, k);
-        if (k + 1 < p.steps) PM_STEP(4, 1, k + 1);
-        if (k + 2 < p.steps) PM_STEP(2, 2, k + 2);
-    }
+        for (int k = 0; k < p.steps; k += 3) {
+            PM_STEP(0, 0, k);
+            if (k + 1 < p.steps) PM_STEP(4, 1, k + 1);
+            if (k + 2 < p.steps) PM_STEP(2, 2, k + 2);
+        }
 #undef PM_STEP
+    }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
                      ::"r"(s_tmem), "r"((uint32_t)PM_TMEM_COLS) : "memory");
