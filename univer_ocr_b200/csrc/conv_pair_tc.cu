@@ -161,11 +161,16 @@ __device__ __forceinline__ void pm_step(const PairTcParams& p, PairTcState& s, i
             uint32_t h[16];
             tc_ld16_nowait(tlane + (uint32_t)(32 * r + 16), h);
             tc_wait_ld();
-            if (LEAKY) {
+            if (LEAKY) {                                   // max(h, alpha h): packed multiply (FMUL2) + FMNMX
+                const uint32_t ab = __float_as_uint(p.alpha1);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const float v = __uint_as_float(h[c]);
-                    h[c] = __float_as_uint(fmaxf(v, v * p.alpha1));
+                for (int c = 0; c < 16; c += 2) {
+                    uint32_t t0, t1;
+                    asm("{\n\t.reg .b64 x, y, r;\n\tmov.b64 x, {%2, %3};\n\tmov.b64 y, {%4, %4};\n\t"
+                        "mul.rn.f32x2 r, x, y;\n\tmov.b64 {%0, %1}, r;\n\t}"
+                        : "=r"(t0), "=r"(t1) : "r"(h[c]), "r"(h[c + 1]), "r"(ab));
+                    h[c] = __float_as_uint(fmaxf(__uint_as_float(h[c]), __uint_as_float(t0)));
+                    h[c + 1] = __float_as_uint(fmaxf(__uint_as_float(h[c + 1]), __uint_as_float(t1)));
                 }
             }
             tc_st16_nowait(tlane + (uint32_t)(32 * r + 16), h);
@@ -361,12 +366,19 @@ int conv3x3_pair_tmem(const float* x, const float* w1, const float* b1, const fl
     const bool leaky = act1 == UOCR_ACT_LEAKY;
     if (!(act1 == UOCR_ACT_NONE || (leaky && alpha1 >= 0.f && alpha1 <= 1.f))) return UOCR_ERR_UNSUPPORTED;
     // output rows per band: a multiple of PM_R minus the 2 halo rows keeps every step full
-    static const int rb_env = env_int_pm("UOCR_PAIR_RB", 62);
+    // (measured on 64 tiles of 496 x 736: 126-row bands 0.133 ms, 62 rows 0.139, 30 rows 0.155; shorter bands only
+    // when there would otherwise be fewer than ~2 waves of CTAs, 4 resident per SM)
+    static const int rb_env = env_int_pm("UOCR_PAIR_RB", 0);
     PairTcParams p{};
     p.x = x; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y = y;
     p.H = (int)h; p.W = (int)w;
-    p.rb = (int)(h < rb_env ? h : rb_env);
     p.strips = (int)ceil_div(w, PM_OUT);
+    int rb = rb_env;
+    if (rb <= 0) {
+        rb = 126;
+        while (rb > 14 && n * ceil_div(h, rb) * p.strips / 4 < 2 * 4 * 148) rb = rb / 2 - 1;    // 126, 62, 30, 14
+    }
+    p.rb = (int)(h < rb ? h : rb);
     p.bands = (int)ceil_div(h, p.rb);
     p.items = n * p.bands * p.strips;
     p.steps = (p.rb + 2 + PM_R - 1) / PM_R;
