@@ -240,3 +240,22 @@ def test_window_fc_fused(nn, n, w, c, width, n_out):
         lib.uocr_window_fc_fwd(dX.ptr, dW.ptr, wt.ptr if wt is not None else None, y.ptr, n, w, c, width, n_out,
                                ACT_LEAKY, 0.01, MATH_TF32, nn.CP.stream())
         close_tf32(y, want, f'window fc {(n, w, c, width, n_out)} cached={cached}')
+
+
+def test_line_conv_backward_tf32(nn):
+    """5x5 4 -> 4 convolution (Line up_*) in TF32 mode: forward and the input gradient both run on the tcgen05 row-GEMM
+    kernel (the dgrad as a bias-less forward on flipped weights), the weight gradient on the FP32 stencil; vs oracle."""
+    rng = np.random.default_rng(11)
+    X = f32(rng.standard_normal((2, 37, 70, 4)))
+    wt = f32(rng.standard_normal((5, 5, 4, 4)) / 10.0)
+    b = f32(rng.standard_normal(4) * 0.3)
+    layer = nn.layers.Convolutional2D((5, 5), 4, 4, padding=2, w=wt, b=b)
+    y = layer.forward(X)[0]
+    want = O.conv2d_fwd(X, wt, b, 2, 0.0, 1)
+    close_tf32(y, want, 'y')
+    dy = f32(rng.standard_normal(want.shape))
+    dX = layer.backward(dy)[0]
+    odX, odW, odb = O.conv2d_bwd(X, wt, dy, 2, 0.0, 1)
+    close_tf32(dX, odX, 'dX')
+    close_tf32(layer.w.grad, odW, 'dW')
+    close_tf32(layer.b.grad, odb, 'db')

@@ -147,7 +147,11 @@ int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const flo
         t.h = g.ho; t.w = g.wo; t.cin = g.cout; t.cout = g.cin;
         t.ph = g.kh - 1 - g.ph; t.pw = g.kw - 1 - g.pw;
         t.ho = g.h; t.wo = g.w; t.padding_value = 0.f; t.bias = 0; t.ups = 1;
-        rc = conv_fwd_fast(t, 1, UOCR_MATH_FP32, dy, (const float*)wt.ptr, nullptr, dx, UOCR_ACT_NONE, 0.f, st);
+        // TF32 mode: the 5x5 Cin = 4 row GEMM also serves the dgrad of the Line 4 -> 4 layers (no bias); everything
+        // else stays on the FP32 stencils (conv_fwd_tc needs Cin % 32 == 0 and would only see tiny channel counts here)
+        const bool row_tc = math_mode == UOCR_MATH_TF32 && t.cin == 4 && t.kh == 5 && t.kw == 5;
+        rc = conv_fwd_fast(t, 1, row_tc ? UOCR_MATH_TF32 : UOCR_MATH_FP32, dy, (const float*)wt.ptr, nullptr, dx,
+                           UOCR_ACT_NONE, 0.f, st);
         if (rc == UOCR_ERR_UNSUPPORTED)
             rc = conv_fwd_general(t, dy, (const float*)wt.ptr, nullptr, dx, UOCR_ACT_NONE, 0.f, st);
         return rc;

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(RT_THREADS, 4) conv55_row_tc_kernel(const RowT
         float v = 0.f;
         if (n < NZ) {
             if (kq < 5) v = __ldg(p.w + ((ky * 5 + kq) * 4 + kk) * COUT + co) * (1.f + 1.f / 2048.f);
-            else if (kk == 0 && ky == 2) v = __ldg(p.b + co);          // A column 20 is the constant 1
+            else if (kk == 0 && ky == 2 && p.b) v = __ldg(p.b + co);   // A column 20 is the constant 1
         }
         s_b[i] = round_tf32(v);
     }
@@ -227,14 +227,14 @@ __global__ void __launch_bounds__(RT_THREADS, 4) conv55_row_tc_kernel(const RowT
 int conv55_row_tc(const ConvGeom& g, const float* x, const float* w, const float* b, float* y, int act, float alpha,
                   cudaStream_t st) {
     if (g.kh != 5 || g.kw != 5 || g.sh != 1 || g.sw != 1 || g.ph != 2 || g.pw != 2 || g.cin != 4) return UOCR_ERR_UNSUPPORTED;
-    if ((g.cout != 4 && g.cout != 2) || g.padding_value != 0.f || !g.bias || (g.ups != 1 && g.ups != 2))
+    if ((g.cout != 4 && g.cout != 2) || g.padding_value != 0.f || (g.ups != 1 && g.ups != 2))
         return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
     // output rows per band: tall bands amortise the 4 halo rows, short ones give enough CTAs for a few waves
     // (4 resident per SM); measured on the Line shapes: 12 rows beat 28 and 60 there
     static const int rb_env = [] { const char* e = getenv("UOCR_ROWTC_RB"); return e ? atoi(e) : 0; }();
     RowTcParams p{};
-    p.x = x; p.w = w; p.b = b; p.y = y;
+    p.x = x; p.w = w; p.b = g.bias ? b : nullptr; p.y = y;          // no bias: the stride-1 dgrad on flipped weights
     p.H = g.h; p.W = g.w;
     p.strips = (int)ceil_div(g.w, 32);
     int rb = rb_env;
