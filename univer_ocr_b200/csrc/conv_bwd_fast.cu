@@ -371,6 +371,122 @@ __global__ void __launch_bounds__(256) conv55_c1_wgrad_roll_kernel(ConvGeom g, c
     }
 }
 
+// 5 x 5 / stride 1 / padding 2 / Cin = 4 weight gradient (Line up_*, end: Cout = 4 or 2), shared-memory tiled.
+// The generic kernel above re-reads every input window from L1 for each kernel row and each output-channel chunk
+// (147 us for 67 MB: L1-wavefront bound).  Here a CTA stages a 16 x 64 output tile's x (20 x 68 pixels) and dy once
+// (16-byte cp.async, zero fill outside the image = the zero padding) and its five warps each own one kernel ROW ky:
+// lane = output column, 5 (kx) x 4 (ci) x Cout accumulators per thread, 6 conflict-free 128-bit shared loads per 80
+// FMA.  CTAs are persistent over tiles; partial sums go to the workspace in conv_small_wgrad_finalize_kernel's layout
+// (one chunk, civ = 4, cot = Cout).  UPS: x is stored at half resolution (folded Upsample2D(2)).
+constexpr int WT_TY = 16, WT_TX = 64, WT_THREADS = 160;
+
+template <int COUT, bool UPS>
+__global__ void __launch_bounds__(WT_THREADS) conv55_c4_wgrad_tiled_kernel(ConvGeom g, const float* __restrict__ x,
+                                                                           const float* __restrict__ dy,
+                                                                           float* __restrict__ ws, int nblk) {
+    constexpr int XP = WT_TX + 4, XR = WT_TY + 4;
+    constexpr int NACC = 25 * 4 * COUT, NOUT = NACC + COUT;
+    extern __shared__ __align__(16) float wt_smem[];
+    float4* s_x = reinterpret_cast<float4*>(wt_smem);                       // [XR][XP]
+    float* s_dy = wt_smem + XR * XP * 4;                                     // [TY][TX][COUT]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;              // warp = ky
+    const int tiles_x = (g.wo + WT_TX - 1) / WT_TX, tiles_y = (g.ho + WT_TY - 1) / WT_TY;
+    const int64_t ntiles = (int64_t)g.n * tiles_y * tiles_x;
+    const int sw = UPS ? g.w / 2 : g.w, sh = UPS ? g.h / 2 : g.h;           // stored input size
+    float acc[5][4][COUT];
+    float dbacc[COUT];
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) acc[a][b][c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) dbacc[c] = 0.f;
+    const uint32_t sx_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_x));
+    const uint32_t sdy_addr = static_cast<uint32_t>(__cvta_generic_to_shared(s_dy));
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x), ty = (int)((tile / tiles_x) % tiles_y);
+        const int64_t n = tile / ((int64_t)tiles_x * tiles_y);
+        const int oy0 = ty * WT_TY, ox0 = tx * WT_TX;
+        __syncthreads();                                                     // previous tile fully consumed
+        for (int i = threadIdx.x; i < XR * XP; i += WT_THREADS) {
+            const int r = i / XP, c = i - r * XP;
+            const int iy = oy0 - 2 + r, ix = ox0 - 2 + c;
+            const bool in = iy >= 0 && iy < g.h && ix >= 0 && ix < g.w;
+            const float* src = x + ((n * sh + (in ? (UPS ? iy >> 1 : iy) : 0)) * (int64_t)sw + (in ? (UPS ? ix >> 1 : ix) : 0)) * 4;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sx_addr + (uint32_t)i * 16u), "l"(src),
+                         "r"(in ? 16 : 0) : "memory");
+        }
+        for (int i = threadIdx.x; i < WT_TY * WT_TX; i += WT_THREADS) {
+            const int r = i / WT_TX, c = i - r * WT_TX;
+            const int oy = oy0 + r, ox = ox0 + c;
+            const bool in = oy < g.ho && ox < g.wo;
+            const float* src = dy + ((n * g.ho + (in ? oy : 0)) * (int64_t)g.wo + (in ? ox : 0)) * COUT;
+            if (COUT == 4)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(sdy_addr + (uint32_t)i * 16u), "l"(src),
+                             "r"(in ? 16 : 0) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sdy_addr + (uint32_t)i * 8u), "l"(src),
+                             "r"(in ? 8 : 0) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const int ky = warp;
+#pragma unroll 2
+        for (int r = 0; r < WT_TY; ++r) {
+#pragma unroll
+            for (int cg = 0; cg < WT_TX / 32; ++cg) {
+                const int c = lane + 32 * cg;
+                float d[COUT];
+                if (COUT == 4) {
+                    const float4 v = reinterpret_cast<const float4*>(s_dy)[r * WT_TX + c];
+                    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+                } else {
+                    const float2 v = reinterpret_cast<const float2*>(s_dy)[r * WT_TX + c];
+                    d[0] = v.x; d[1] = v.y;
+                }
+                if (ky == 2) {                                               // warp-uniform: one warp also sums dy
+#pragma unroll
+                    for (int co = 0; co < COUT; ++co) dbacc[co] += d[co];
+                }
+                const float4* xrow = s_x + (r + ky) * XP + c;
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const float4 xv = xrow[kx];
+                    const float xc[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+                        for (int co = 0; co < COUT; ++co) acc[kx][ci][co] = fmaf(xc[ci], d[co], acc[kx][ci][co]);
+                }
+            }
+        }
+    }
+    // warp reduction; element order of the finalize kernel: ((ky * 5 + kx) * 4 + ci) * COUT + co, then db[co]
+    const int ky = warp;
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci)
+#pragma unroll
+            for (int co = 0; co < COUT; ++co) {
+                const float t = warp_sum(acc[kx][ci][co]);
+                if (lane == 0) ws[(int64_t)(((ky * 5 + kx) * 4 + ci) * COUT + co) * nblk + blockIdx.x] = t;
+            }
+    if (ky == 2) {
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+            const float t = warp_sum(dbacc[co]);
+            if (lane == 0) ws[(int64_t)(NACC + co) * nblk + blockIdx.x] = t;
+        }
+    }
+    (void)NOUT;
+}
+
+static int wgrad_tiled_grid() { return 148 * 3; }
+
 // one CTA per output element: sums its nblk partials and scatters into dw / db
 __global__ void __launch_bounds__(256) conv_small_wgrad_finalize_kernel(
     const float* __restrict__ ws, int nblk, int kh, int kw, int cin, int civ, int cot, int cout, int bias,
@@ -428,12 +544,24 @@ static void small_wgrad_dims(const ConvGeom& g, const SmallWgradPlan& p, int* nb
     *nout = p.kh * p.kw * p.civ * p.cot + p.cot;
 }
 
+static bool wgrad_tiled_ok(const ConvGeom& g) {
+    return g.kh == 5 && g.kw == 5 && g.sh == 1 && g.sw == 1 && g.ph == 2 && g.pw == 2 && g.cin == 4 &&
+           (g.cout == 4 || g.cout == 2) && g.padding_value == 0.f && (g.ups == 1 || g.ups == 2);
+}
+
 size_t conv_wgrad_fast_workspace(const ConvGeom& g, int) {
     const SmallWgradPlan p = plan_small_wgrad(g);
-    if (!p.ok) return 0;
-    int nblk, chunks, nout;
-    small_wgrad_dims(g, p, &nblk, &chunks, &nout);
-    return sizeof(float) * (size_t)nblk * chunks * nout;
+    size_t need = 0;
+    if (p.ok) {
+        int nblk, chunks, nout;
+        small_wgrad_dims(g, p, &nblk, &chunks, &nout);
+        need = sizeof(float) * (size_t)nblk * chunks * nout;
+    }
+    if (wgrad_tiled_ok(g)) {
+        const size_t t = sizeof(float) * (size_t)wgrad_tiled_grid() * (25 * 4 * g.cout + g.cout);
+        if (t > need) need = t;
+    }
+    return need;
 }
 
 template <int KH, int KW, int SH, int SW, int CIN, int CIV, int COT, int PX, int R>
@@ -449,6 +577,32 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
     if (math_mode == UOCR_MATH_TF32 && g.ups == 1) {
         const int rc = conv_wgrad_tc(g, x, dy, dw, db, accumulate, st);
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    }
+    static const bool tiled = [] { const char* e = getenv("UOCR_WGRAD_TILED"); return !e || e[0] != '0'; }();
+    if (tiled && ws && wgrad_tiled_ok(g) && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15)) {
+        const int64_t ntiles = (int64_t)g.n * ceil_div(g.ho, WT_TY) * ceil_div(g.wo, WT_TX);
+        const int nblk = (int)(ntiles < wgrad_tiled_grid() ? ntiles : wgrad_tiled_grid());
+        const size_t smem = sizeof(float) * ((WT_TY + 4) * (WT_TX + 4) * 4 + WT_TY * WT_TX * g.cout);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(conv55_c4_wgrad_tiled_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(conv55_c4_wgrad_tiled_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(conv55_c4_wgrad_tiled_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            cudaFuncSetAttribute(conv55_c4_wgrad_tiled_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+            configured = true;
+        }
+        if (g.cout == 4) {
+            if (g.ups == 2) conv55_c4_wgrad_tiled_kernel<4, true><<<nblk, WT_THREADS, smem, st>>>(g, x, dy, ws, nblk);
+            else conv55_c4_wgrad_tiled_kernel<4, false><<<nblk, WT_THREADS, smem, st>>>(g, x, dy, ws, nblk);
+        } else {
+            if (g.ups == 2) conv55_c4_wgrad_tiled_kernel<2, true><<<nblk, WT_THREADS, smem, st>>>(g, x, dy, ws, nblk);
+            else conv55_c4_wgrad_tiled_kernel<2, false><<<nblk, WT_THREADS, smem, st>>>(g, x, dy, ws, nblk);
+        }
+        UOCR_LAUNCHED("conv55_c4_wgrad_tiled");
+        const int nout = 25 * 4 * g.cout + g.cout;
+        conv_small_wgrad_finalize_kernel<<<nout, 256, 0, st>>>(ws, nblk, 5, 5, 4, 4, g.cout, g.cout, g.bias, dw, db, accumulate);
+        UOCR_LAUNCHED("conv_small_wgrad_finalize");
+        return UOCR_OK;
     }
     const SmallWgradPlan p = plan_small_wgrad(g);
     if (!p.ok || !ws) return UOCR_ERR_UNSUPPORTED;

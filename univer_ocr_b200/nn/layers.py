@@ -527,9 +527,12 @@ class Convolutional2D(BaseLayer):
 
     def supports_upsampled_input_grad(self):
         """True if the weight gradient can read its input through a folded Upsample2D(2)
-        (conv55_c1_wgrad_roll_kernel<UPS>): 5x5, stride 1, padding 2, 1 -> 1 channels."""
-        return (self.kernel_size == (5, 5) and self.stride == (1, 1) and self.padding == (2, 2)
-                and self.in_channels == 1 and self.out_channels == 1)
+        : 5x5, stride 1, padding 2, 1 -> 1 channels (Paragraph) or 4 -> 4 / 2 channels (Line)."""
+        if self.kernel_size != (5, 5) or self.stride != (1, 1) or self.padding != (2, 2):
+            return False
+        return ((self.in_channels == 1 and self.out_channels == 1)              # conv55_c1_wgrad_roll_kernel<UPS>
+                or (self.in_channels == 4 and self.out_channels in (2, 4)       # conv55_c4_wgrad_tiled_kernel<UPS>
+                    and self.padding_value == 0))
 
     def _backward(self, grad, mem_id=0, need_dx=True):
         X = self._mem[mem_id]
