@@ -35,10 +35,38 @@ class _Runtime:
         lib.uocr_device_count(ctypes.byref(n))
         self.device = dev % max(n.value, 1)
         lib.uocr_set_device(self.device)
+        _bind_to_gpu_numa_node(self.device)
         s = ctypes.c_void_p()
         lib.uocr_stream_create(ctypes.byref(s))
         self.stream = s.value
         return self
+
+
+def _bind_to_gpu_numa_node(device):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that pinned host buffers (first touched by
+    cudaHostAlloc on this thread) land on the GPU's NUMA node: with one process per GPU on a two-socket host the
+    H2D / D2H copies of the end-to-end path otherwise cross the socket interconnect.  Best effort; UOCR_NO_AFFINITY=1
+    disables it."""
+    if os.environ.get('UOCR_NO_AFFINITY') == '1' or not hasattr(os, 'sched_setaffinity'):
+        return
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+        index = device
+        if visible:
+            ids = [v.strip() for v in visible.split(',') if v.strip()]
+            if device < len(ids) and ids[device].isdigit():
+                index = int(ids[device])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * i + b for i, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:                                     # no NVML / not permitted: keep the inherited affinity
+        pass
 
 
 RT = _Runtime()
