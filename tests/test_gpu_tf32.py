@@ -259,3 +259,32 @@ def test_line_conv_backward_tf32(nn):
     close_tf32(dX, odX, 'dX')
     close_tf32(layer.w.grad, odW, 'dW')
     close_tf32(layer.b.grad, odb, 'db')
+
+
+def test_full_page_monochrome_paragraph_tf32(nn):
+    """BASELINE configs[3] geometry: one 2048 x 2048 document -> make_divisible_by -> (1, 2064, 2064, 1) through
+    Monochrome -> Paragraph with the fused tcgen05 / whole-network kernels (TF32 mode) vs the layer-by-layer FP32
+    check mode (Model.fusion off): sigmoid outputs within 2e-3."""
+    from oracle import np_models
+    from univer_ocr_b200 import my_model
+    rng = np.random.default_rng(21)
+    page = my_model.make_divisible_by(f32(rng.uniform(size=(1, 2048, 2048, 1))), 16, 16)
+    assert page.shape == (1, 2064, 2064, 1)
+    outs = {}
+    for mode, fusion in (('fp32', False), ('tf32', True)):
+        nn.CP.set_math_mode(mode)
+        nn.models.Model.fusion = fusion
+        try:
+            mono = my_model.make_monochrome(page.shape)
+            para = my_model.make_paragraph(page.shape)
+        finally:
+            nn.models.Model.fusion = True
+        for name, model in (('monochrome', mono), ('paragraph', para)):
+            w0 = np_models.golden_weights(name, 99)
+            model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})
+        m = mono.predict(page)[0]
+        outs[mode] = (np.asarray(m.get(), dtype=np.float64), np.asarray(para.predict(m)[0].get(), dtype=np.float64))
+    nn.CP.set_math_mode('tf32')
+    for i, what in enumerate(('monochrome', 'paragraph')):
+        err = np.max(np.abs(outs['tf32'][i] - outs['fp32'][i]))
+        assert err <= 2e-3, (what, err)
