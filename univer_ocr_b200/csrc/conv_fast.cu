@@ -313,6 +313,67 @@ static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float
     return UOCR_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Cin = 1 -> Cout = 64 (Char conv_1: 5x3, stride (2, 1)): the layer is bound by its 58.7 MB output write, so the
+// kernel is organised around the STORE: lane = (channel quad, pixel), a warp's 128-bit store covers two pixels x
+// 64 channels = two fully used 256-byte segments (the generic kernel above wrote 16 bytes per lane at a 1 KB
+// stride: half-used sectors, 0.038 ms).  CTA = 128 output pixels of one output row; the KH input rows sit in
+// shared memory (read as broadcasts), a thread owns 4 channels x 8 consecutive pixels with its 15 x 4 weights in
+// registers.
+// ------------------------------------------------------------------------------------------
+template <int KH, int KW, int SH, int SW>
+__global__ void __launch_bounds__(256) conv_c1_wide64_kernel(ConvGeom g, const float* __restrict__ x,
+                                                             const float* __restrict__ w, const float* __restrict__ b,
+                                                             float* __restrict__ y, int act, float alpha) {
+    constexpr int TXB = 128, PXT = 8, NQ = 16;              // pixels per CTA, pixels per thread, channel quads
+    constexpr int IW = (TXB - 1) * SW + KW;                  // input columns a CTA needs
+    constexpr int NIN = (PXT - 1) * SW + KW;                 // ... a thread needs per row
+    __shared__ float s_in[KH][IW + 1];
+    const int ox0 = blockIdx.x * TXB, oy = blockIdx.y;
+    const int64_t n = blockIdx.z;
+    const int iy0 = oy * SH - g.ph, ix0 = ox0 * SW - g.pw;
+    const float* xim = x + n * g.h * (int64_t)g.w;
+    for (int i = threadIdx.x; i < KH * IW; i += 256) {
+        const int r = i / IW, c = i - r * IW;
+        const int iy = iy0 + r, ix = ix0 + c;
+        s_in[r][c] = (iy >= 0 && iy < g.h && ix >= 0 && ix < g.w) ? __ldg(xim + (int64_t)iy * g.w + ix) : g.padding_value;
+    }
+    const int cq = threadIdx.x % NQ, pg = threadIdx.x / NQ;
+    float wr[KH * KW][4];
+#pragma unroll
+    for (int t = 0; t < KH * KW; ++t) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(w + t * 64) + cq);
+        wr[t][0] = v.x; wr[t][1] = v.y; wr[t][2] = v.z; wr[t][3] = v.w;
+    }
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g.bias) bias = __ldg(reinterpret_cast<const float4*>(b) + cq);
+    __syncthreads();
+    float acc[PXT][4];
+#pragma unroll
+    for (int p = 0; p < PXT; ++p) { acc[p][0] = bias.x; acc[p][1] = bias.y; acc[p][2] = bias.z; acc[p][3] = bias.w; }
+    const int px0 = pg * PXT;
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) {
+        float in[NIN];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) in[j] = s_in[ky][px0 * SW + j];
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx)
+#pragma unroll
+            for (int p = 0; p < PXT; ++p)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[p][c] = fmaf(wr[ky * KW + kx][c], in[p * SW + kx], acc[p][c]);
+    }
+    float* yrow = y + ((n * g.ho + oy) * (int64_t)g.wo + ox0 + px0) * 64 + cq * 4;
+#pragma unroll
+    for (int p = 0; p < PXT; ++p) {
+        if (ox0 + px0 + p < g.wo)
+            *reinterpret_cast<float4*>(yrow + (int64_t)p * 64) =
+                make_float4(apply_act_fast(acc[p][0], act, alpha), apply_act_fast(acc[p][1], act, alpha),
+                            apply_act_fast(acc[p][2], act, alpha), apply_act_fast(acc[p][3], act, alpha));
+    }
+}
+
 int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, const float* w,
                   const float* b, float* y, int act, float alpha, cudaStream_t st, const float* w_kmajor) {
     if (math_mode == UOCR_MATH_TF32) {
@@ -336,6 +397,13 @@ int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, con
         (COT_ != 1 || g.cout == 1)) {                                                                   \
         const int rc = launch_c1_fwd<KH_, KW_, SH_, SW_, COT_, PX_>(g, ups, x, w, b, y, act, alpha, st); \
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;                                                      \
+    }
+    if (g.cin == 1 && g.cout == 64 && g.kh == 5 && g.kw == 3 && g.sh == 2 && g.sw == 1 && ups == 1 && g.n <= 65535 &&
+        g.ho <= 65535 && !(reinterpret_cast<uintptr_t>(w) & 15) && !(reinterpret_cast<uintptr_t>(b) & 15)) {     // Char conv_1
+        dim3 grid((unsigned)ceil_div(g.wo, 128), (unsigned)g.ho, (unsigned)g.n);
+        conv_c1_wide64_kernel<5, 3, 2, 1><<<grid, 256, 0, st>>>(g, x, w, b, y, act, alpha);
+        UOCR_LAUNCHED("conv_c1_wide64");
+        return UOCR_OK;
     }
     UOCR_C1(5, 5, 1, 1, 1, 1, 4)             // Paragraph up_*, end
     UOCR_C1(5, 5, 2, 2, 1, 1, 4)             // Paragraph down_*
