@@ -185,10 +185,17 @@ int uocr_hourglass1_fwd(const float* x, const float* const* weights, const float
  * conv_1 plus LeakyRelu._backward (convolutional.py:101-145, layers.py:399-401) and the saved
  * (N,H,W,c_mid) activations they need.  act1: UOCR_ACT_LEAKY (alpha > 0) or UOCR_ACT_NONE. */
 int uocr_conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int32_t c_mid, size_t* bytes);
+/* uocr_conv3x3_pair_bwd_mode: same as uocr_conv3x3_pair_bwd with a math mode; UOCR_MATH_TF32 and c_mid == 16 recompute the
+ * hidden map and its gradient with ONE tcgen05 GEMM per 128 pixels (operands resident in tensor memory) and keep only the
+ * pixel sums on the CUDA cores (csrc/conv_pair_bwd_tc.cu). */
 int uocr_conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
                           float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
                           int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
                           size_t workspace_bytes, void* stream);
+int uocr_conv3x3_pair_bwd_mode(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
+                               float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
+                               int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
+                               size_t workspace_bytes, int math_mode, void* stream);
 
 /* dx = dgrad(dy, w) (overwrites dx).   replaces: _backward_gpu_kernel_dx + the crop of
  * convolutional.py:141-142 / :203-219,239-250. */

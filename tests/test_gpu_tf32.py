@@ -288,3 +288,57 @@ def test_full_page_monochrome_paragraph_tf32(nn):
     for i, what in enumerate(('monochrome', 'paragraph')):
         err = np.max(np.abs(outs['tf32'][i] - outs['fp32'][i]))
         assert err <= 2e-3, (what, err)
+
+
+def test_monochrome_pair_backward_tensor_core(nn):
+    """uocr_conv3x3_pair_bwd_mode in TF32 mode (hidden map and its gradient recomputed by one tcgen05 GEMM per 128
+    pixels, pixel sums on the CUDA cores; csrc/conv_pair_bwd_tc.cu) vs the FP32 CUDA-core kernel and, on the small
+    cases, the float64 oracle: dw1, db1, dw2, db2 within 1e-3 of their range; ragged strips / bands / steps.
+
+    LeakyReLU's derivative jumps at h = 0, so an element whose h is below the TF32 resolution can legitimately fall on
+    either side.  Two modes are checked: (a) UOCR_PAIR_WGRAD_EXACT_MASK=1 -- borderline h recomputed in FP32 -- on data
+    that crosses the kink (random weights, many h near 0) must match the FP32 kernel; (b) the default (branch taken on
+    the TF32 h) on data whose h stays away from 0 (|b1| dominates) must match as well."""
+    import ctypes
+    from univer_ocr_b200._lib import ACT_LEAKY, ACT_NONE, lib
+    rng = np.random.default_rng(29)
+    for exact in (True, False):
+        for (n, h, w), act1 in (((2, 16, 256), ACT_LEAKY), ((3, 21, 150), ACT_LEAKY), ((1, 5, 3), ACT_NONE),
+                                ((2, 1, 1), ACT_LEAKY), ((1, 130, 61), ACT_LEAKY), ((2, 496, 736), ACT_LEAKY)):
+            X = f32(rng.uniform(size=(n, h, w, 1)))
+            if exact:
+                w1 = f32(rng.standard_normal((3, 3, 1, 16)) * 0.4)
+                b1 = f32(rng.standard_normal(16) * 0.2)
+            else:                                   # |h| >= 1.5 - 9 * 0.15: never near the kink, both signs present
+                w1 = f32(rng.uniform(-0.15, 0.15, size=(3, 3, 1, 16)))
+                b1 = f32(np.where(np.arange(16) % 2 == 0, 1.5, -1.5) + rng.uniform(-0.1, 0.1, size=16))
+            w2 = f32(rng.standard_normal((3, 3, 16, 1)) * 0.3)
+            dy = f32(rng.standard_normal((n, h, w, 1)))
+            d = [nn.CP.copy(a) for a in (X, w1, b1, w2, dy)]
+            need = ctypes.c_size_t(0)
+            lib.uocr_conv3x3_pair_bwd_workspace(n, h, w, 16, ctypes.byref(need))
+            outs = []
+            os.environ['UOCR_PAIR_WGRAD_EXACT_MASK'] = '1' if exact else '0'
+            try:
+                for mode in (0, 1):
+                    ws = nn.DeviceArray(((need.value + 3) // 4,))
+                    g = [nn.DeviceArray.zeros(s_) for s_ in ((3, 3, 1, 16), (16,), (3, 3, 16, 1), (1,))]
+                    lib.uocr_conv3x3_pair_bwd_mode(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, None, g[0].ptr,
+                                                   g[1].ptr, g[2].ptr, g[3].ptr, n, h, w, 16, act1, 0.01, 0, ws.ptr,
+                                                   need.value, mode, nn.CP.stream())
+                    outs.append([np.asarray(t.get(), dtype=np.float64) for t in g])
+            finally:
+                os.environ.pop('UOCR_PAIR_WGRAD_EXACT_MASK', None)
+            # sums over a handful of pixels have no averaging of the per-product TF32 rounding: 2e-3 there
+            tol = 2e-3 if n * h * w < 64 else 1e-3
+            for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2'), outs[1], outs[0]):
+                close_tf32(a, b, f'pair bwd tc vs fp32 {name} {(n, h, w)} exact={exact}', tol=tol)
+            if h * w <= 4000:
+                hid = O.conv2d_fwd(X, w1, b1, 1)
+                act = O.leaky_relu_fwd(hid, 0.01) if act1 == ACT_LEAKY else hid
+                dact, odw2, odb2 = O.conv2d_bwd(act, w2, dy, 1, 0.0, 1)
+                dhid = dact * np.where(hid >= 0, 1.0, 0.01) if act1 == ACT_LEAKY else dact
+                _, odw1, odb1 = O.conv2d_bwd(X, w1, dhid, 1, 0.0, 1)
+                for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2'), outs[1], (odw1, odb1, odw2, odb2)):
+                    close_tf32(a, np.asarray(b, dtype=np.float64).reshape(a.shape),
+                               f'pair bwd tc vs oracle {name} {(n, h, w)} exact={exact}', tol=tol)

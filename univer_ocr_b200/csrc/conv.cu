@@ -417,10 +417,31 @@ int uocr_conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int32_t c_m
     return UOCR_OK;
 }
 
+static int pair_bwd_impl(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
+                         float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
+                         int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
+                         size_t workspace_bytes, int math_mode, void* stream);
+
 int uocr_conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
                           float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
                           int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
                           size_t workspace_bytes, void* stream) {
+    return pair_bwd_impl(x, w1, b1, w2, dy, dx, dw1, db1, dw2, db2, n, h, w, c_mid, act1, alpha1, accumulate, workspace,
+                         workspace_bytes, UOCR_MATH_FP32, stream);
+}
+
+int uocr_conv3x3_pair_bwd_mode(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
+                               float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
+                               int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
+                               size_t workspace_bytes, int math_mode, void* stream) {
+    return pair_bwd_impl(x, w1, b1, w2, dy, dx, dw1, db1, dw2, db2, n, h, w, c_mid, act1, alpha1, accumulate, workspace,
+                         workspace_bytes, math_mode, stream);
+}
+
+static int pair_bwd_impl(const float* x, const float* w1, const float* b1, const float* w2, const float* dy,
+                         float* dx, float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h,
+                         int64_t w, int32_t c_mid, int act1, float alpha1, int accumulate, void* workspace,
+                         size_t workspace_bytes, int math_mode, void* stream) {
     UOCR_REQUIRE(x && w1 && b1 && w2 && dy && dw1 && db1 && dw2 && db2, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c_mid > 0 && c_mid <= 256, "bad dimension");
     UOCR_REQUIRE(h < (1 << 30) && w < (1 << 30), "dimension too large");
@@ -432,7 +453,7 @@ int uocr_conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, cons
         return UOCR_ERR_WORKSPACE;
     }
     return conv3x3_pair_bwd(x, w1, b1, w2, dy, dx, dw1, db1, dw2, db2, n, h, w, c_mid, act1, alpha1, accumulate,
-                            (float*)workspace, as_stream(stream));
+                            (float*)workspace, as_stream(stream), math_mode);
 }
 
 int uocr_conv2d_dgrad(const uocr_conv2d_desc* d, const float* dy, const float* w, float* dx,

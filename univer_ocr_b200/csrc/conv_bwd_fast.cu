@@ -886,16 +886,32 @@ __global__ void __launch_bounds__(PB_THREADS) conv3x3_pair_dgrad_kernel(
 
 size_t conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int c1) {
     const int64_t nblk = ceil_div(n * ceil_div(w, PB_CW) * ceil_div(h, PB_R), PB_THREADS);
-    return sizeof(float) * (size_t)nblk * (c1 + 1) * 19;
+    const size_t cuda_cores = sizeof(float) * (size_t)nblk * (c1 + 1) * 19;
+    const size_t tc = c1 == 16 ? conv3x3_pair_wgrad_tc_workspace(n, h, w, c1) : 0;
+    return cuda_cores > tc ? cuda_cores : tc;
 }
 
 int conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* dx,
                      float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h, int64_t w, int c1,
-                     int act1, float alpha1, int accumulate, float* ws, cudaStream_t st) {
+                     int act1, float alpha1, int accumulate, float* ws, cudaStream_t st, int math_mode) {
     const int64_t items = n * ceil_div(w, PB_CW) * ceil_div(h, PB_R);
     const int64_t nblk = ceil_div(items, PB_THREADS);
     if (nblk > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
     const size_t smem = sizeof(float) * 20 * c1;
+    static const bool wgrad_tc = [] { const char* e = getenv("UOCR_PAIR_WGRAD_TC"); return !e || e[0] != '0'; }();
+    int tc_nblk = 0;
+    if (math_mode == UOCR_MATH_TF32 && wgrad_tc &&
+        conv3x3_pair_wgrad_tc(x, w1, b1, w2, dy, ws, n, h, w, c1, act1, alpha1, &tc_nblk, st) == UOCR_OK) {
+        // tensor-core assisted weight gradients (conv_pair_bwd_tc.cu); same workspace layout, same finalize
+        conv3x3_pair_wgrad_finalize_kernel<<<(c1 + 1) * 19, 256, 0, st>>>(ws, tc_nblk, c1, dw1, db1, dw2, db2, accumulate);
+        UOCR_LAUNCHED("conv3x3_pair_wgrad_finalize");
+        if (dx) {
+            conv3x3_pair_dgrad_kernel<PB_CW, PB_R><<<(unsigned)nblk, PB_THREADS, smem, st>>>(
+                x, w1, b1, w2, dy, dx, (int)n, (int)h, (int)w, c1, act1, alpha1);
+            UOCR_LAUNCHED("conv3x3_pair_dgrad");
+        }
+        return UOCR_OK;
+    }
     static const int minb = [] { const char* e = getenv("UOCR_PAIRBWD_MINB"); return e ? atoi(e) : 4; }();
 #define PB_LAUNCH(MB) conv3x3_pair_wgrad_kernel<PB_CW, PB_R, MB><<<(unsigned)nblk, PB_THREADS, smem, st>>>( \
         x, w1, b1, w2, dy, ws, (int)n, (int)h, (int)w, c1, act1, alpha1, (int)nblk)

@@ -45,7 +45,11 @@ int conv3x3_pair_tmem(const float* x, const float* w1, const float* b1, const fl
 size_t conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int c1);
 int conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* dx,
                      float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h, int64_t w, int c1,
-                     int act1, float alpha1, int accumulate, float* ws, cudaStream_t st);
+                     int act1, float alpha1, int accumulate, float* ws, cudaStream_t st, int math_mode = UOCR_MATH_FP32);
+// tensor-core assisted weight gradients of the pair (conv_pair_bwd_tc.cu): partial sums into ws
+size_t conv3x3_pair_wgrad_tc_workspace(int64_t n, int64_t h, int64_t w, int c1);
+int conv3x3_pair_wgrad_tc(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* ws,
+                          int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int* nblk_out, cudaStream_t st);
 int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, float* dx, cudaStream_t st);
 int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* dy, float* dw, float* db, int accumulate,
                   cudaStream_t st);

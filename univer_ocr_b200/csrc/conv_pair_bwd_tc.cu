@@ -1,0 +1,363 @@
+// Weight gradients of the Monochrome conv pair (training), tensor-core assisted.
+//
+//   h = conv3x3(x, w1) + b1,  a = act1(h),  y = conv3x3(a, w2) + b2          1 -> 16 -> 1 channels, padding 1
+//   given dy = dL/dy:   dA = conv3x3^T(dy, w2),  dpre = dA . act1'(h)
+//                       dw2[t, c] = sum_p a[p, c] dy[p - off(t)]      db2 = sum_p dy[p]
+//                       dw1[t, c] = sum_p dpre[p, c] x[p + off(t)]    db1[c] = sum_p dpre[p, c]
+//   replaces: Convolutional2D._backward of conv_2 and conv_1 + LeakyRelu._backward (convolutional.py:101-145,
+//   layers.py:399-401) for make_monochrome (my_model/model.py:119-122), without the (N, H, W, 16) tensors they store.
+//
+// The CUDA-core kernel (conv_bwd_fast.cu) spends 576 FMA per pixel: 288 to RECOMPUTE h and dA for every channel and 288
+// for the four outer-product sums; it runs at 15 cycles per pixel per SM (1.2 ms for 64 tiles, 29 % of a training step).
+// Here the recomputation is ONE tcgen05 GEMM per 128 pixels, with the same TMEM-resident-operand scheme as the forward
+// kernel (conv_pair_tc.cu):
+//   phase 1   lane = pixel.  A row (TMEM, 32 columns) = [3 x 3 window of x + a constant 1 | 3 x 3 window of dy];
+//             B (shared memory, 32 x 32, block diagonal) = [w1 ; b1] (+) [flipped w2];  D row = [h (16) | dA (16)].
+//             The thread reads its D row back, forms a = act1(h) and dpre = dA . act1'(h) and stores them to shared
+//             memory as channel-quad planes.
+//   phase 2   warp = channel quad.  Each warp walks all 128 x 4 pixels of the step and accumulates its 4 channels'
+//             dw1 / dw2 / db1 (76 register accumulators) from a, dpre (two conflict-free 128-bit shared loads per pixel)
+//             and the x / dy windows (shared memory): the pixel sum -- the one contraction no tcgen05 operand layout can
+//             run for a 9 x 16 output -- stays on the CUDA cores, but at 72 FMA per 10 shared loads.
+// CTA = 128 columns x a band of rows, 4 rows per step; x and dy rows live in a 16-row shared-memory ring (next step's rows
+// prefetched with cp.async); MMAs issued by a fifth warp.  Partial sums go to the workspace in the layout of
+// conv3x3_pair_wgrad_finalize_kernel.  TF32 inputs (x, dy, weights rounded to nearest), FP32 accumulation.
+#include "conv_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace uocr {
+
+constexpr int PW_R = 4;                  // hidden rows per step
+constexpr int PW_COLS = 128;             // hidden columns per CTA = UMMA M
+constexpr int PW_THREADS = 160;          // 4 compute warps + 1 MMA-issuing warp
+constexpr int PW_SLOT = 64;              // TMEM columns per row: A at +0 (32), D at +32 (32)
+constexpr int PW_XP = 136;               // ring row pitch: columns c0 - 1 .. c0 + 128 (130 used)
+constexpr int PW_RING = 16;
+
+struct PairWgParams {
+    const float* x; const float* dy; const float* w1; const float* b1; const float* w2; float* ws;
+    int H, W, n;
+    int strips, bands, rb, steps, nblk;
+    int leaky; float alpha1;
+};
+
+__device__ __forceinline__ void pw_bar_compute() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void pw_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ bool pw_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void pw_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    } while (!done);
+}
+// FP32 -> TF32 round to nearest (the tensor core ignores the low 13 mantissa bits)
+__device__ __forceinline__ uint32_t pw_rnd(float v) { return __float_as_uint(v) + 0x1000u; }
+
+template <bool LEAKY, bool EXACT>
+__global__ void __launch_bounds__(PW_THREADS, 2) conv3x3_pair_wgrad_tc_kernel(const PairWgParams p) {
+    extern __shared__ __align__(128) float pw_smem[];
+    float* s_b = pw_smem;                                   // [8 chunks][32 n][4 k]     4 KB
+    float* s_x = s_b + 8 * 32 * 4;                          // [PW_RING][PW_XP]
+    float* s_dy = s_x + PW_RING * PW_XP;
+    float4* s_ad = reinterpret_cast<float4*>(s_dy + PW_RING * PW_XP);     // [PW_R][8 quads][128 px]   64 KB
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ad + PW_R * 8 * PW_COLS);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    float* s_red = reinterpret_cast<float*>(s_tmem + 2);    // 4 floats: db2 partials of the compute warps
+    float* s_w1f = s_red + 4;                               // FP32 w1[9][16], b1[16]: exact h for borderline pixels
+    float* s_thr = s_w1f + 160;                             // [16] 2^-9 max_t |w1[t][c]|, [16] 2^-9 |b1[c]|
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // B[n][k], K-major chunks of 4 k: k = 4 a + b (b < 3) x window row a, k = 3 the constant 1 (b1), k = 12 + 4 a + b
+    // the dy window; n < 16: h channels, n >= 16: dA channels (w2 flipped: window entry (a, b) multiplies tap (2-a, 2-b))
+    for (int i = tid; i < 8 * 32 * 4; i += PW_THREADS) {
+        const int kq = i >> 7, n = (i >> 2) & 31, kk = i & 3;
+        float v = 0.f;
+        if (kq < 3 && n < 16) {
+            if (kk < 3) v = __ldg(p.w1 + (kq * 3 + kk) * 16 + n);
+            else if (kq == 0) v = __ldg(p.b1 + n);
+        } else if (kq >= 3 && kq < 6 && n >= 16 && kk < 3) {
+            v = __ldg(p.w2 + ((2 - (kq - 3)) * 3 + (2 - kk)) * 16 + (n - 16));
+        }
+        s_b[i] = round_tf32(v);
+    }
+    for (int i = tid; i < 160; i += PW_THREADS) s_w1f[i] = i < 144 ? __ldg(p.w1 + i) : __ldg(p.b1 + i - 144);
+    if (tid < 16) {
+        float m = 0.f;
+        for (int t = 0; t < 9; ++t) m = fmaxf(m, fabsf(__ldg(p.w1 + t * 16 + tid)));
+        s_thr[tid] = m * (1.f / 512.f);
+        s_thr[16 + tid] = fabsf(__ldg(p.b1 + tid)) * (1.f / 512.f);
+    }
+    if (tid == 0) {
+        mbar_init(smem_u32(&s_bar[0]), 128);                // A rows stored by every compute thread
+        mbar_init(smem_u32(&s_bar[1]), 1);                  // MMAs committed
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(s_tmem)), "r"((uint32_t)(PW_R * PW_SLOT)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t bars = smem_u32(&s_bar[0]);
+
+    if (warp == 4) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t sb = smem_u32(s_b);
+#pragma unroll 1
+        for (int k = 0; k < p.steps; ++k) {
+            pw_wait(bars, (uint32_t)(k & 1));
+            tc_fence_after();
+            if (pw_elect_one()) {
+#pragma unroll
+                for (int r = 0; r < PW_R; ++r)
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+                        tc_mma_tf32_ts(tmem_base + (uint32_t)(PW_SLOT * r + 32), tmem_base + (uint32_t)(PW_SLOT * r + 8 * m),
+                                       make_kmajor_nosw_desc(sb + (uint32_t)(2 * m) * 512u, 512, 128), idesc, m);
+                tc_commit(bars + 8);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== compute warps =====================
+        const int blk = blockIdx.x;
+        const int strip = blk % p.strips;
+        const int band = (blk / p.strips) % p.bands;
+        const int64_t img = blk / (p.strips * p.bands);
+        const int c0 = strip * PW_COLS, r0 = band * p.rb;
+        const int r_end = min(p.H, r0 + p.rb);
+        const float* xim = p.x + img * (int64_t)p.H * p.W;
+        const float* dyim = p.dy + img * (int64_t)p.H * p.W;
+        const uint32_t tl = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t sx_addr = smem_u32(s_x), sdy_addr = smem_u32(s_dy);
+        // A columns 24 .. 31 are never stored again (zero weights) but must hold finite numbers
+#pragma unroll
+        for (int r = 0; r < PW_R; ++r) {
+            pw_st4(tl + (uint32_t)(PW_SLOT * r + 24), 0u, 0u, 0u, 0u);
+            pw_st4(tl + (uint32_t)(PW_SLOT * r + 28), 0u, 0u, 0u, 0u);
+        }
+        tc_wait_st();
+
+        // ring rows: local index li = image row - (r0 - 1), slot = li % PW_RING; columns cc = image column - (c0 - 1)
+        auto load_rows = [&](int li0, int count) {
+            for (int i = tid; i < count * 130; i += 128) {
+                const int rr = i / 130, cc = i - rr * 130;
+                const int li = li0 + rr, row = r0 - 1 + li, col = c0 - 1 + cc;
+                const bool in = row >= 0 && row < p.H && col >= 0 && col < p.W;
+                const int64_t off = in ? (int64_t)row * p.W + col : 0;
+                const uint32_t so = (uint32_t)((li & (PW_RING - 1)) * PW_XP + cc) * 4u;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sx_addr + so), "l"(xim + off), "r"(in ? 4 : 0) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdy_addr + so), "l"(dyim + off), "r"(in ? 4 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        load_rows(0, PW_R + 2);                             // rows li = 0 .. 5 for step 0
+
+        float gw1[9][4], gw2[9][4], gb1[4];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gw1[t][c] = gw2[t][c] = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gb1[c] = 0.f;
+        float gb2 = 0.f;
+        const bool colvalid = c0 + tid < p.W;
+        const uint32_t one = colvalid ? __float_as_uint(1.f) : 0u;
+
+#pragma unroll 1
+        for (int k = 0; k < p.steps; ++k) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            pw_bar_compute();                               // this step's rows are in the ring; previous phase 2 is done
+            if (k + 1 < p.steps) load_rows(PW_R * (k + 1) + 2, PW_R);       // prefetch: rows li = 4k+6 .. 4k+9
+            // ---------------- phase 1a: windows -> TMEM
+            float s9[PW_R];                                 // sum |x| over the window: scales the TF32 error bound of h
+#pragma unroll
+            for (int r = 0; r < PW_R; ++r) {
+                const int li = PW_R * k + 1 + r;            // hidden row, local
+                const uint32_t ta = tl + (uint32_t)(PW_SLOT * r);
+                s9[r] = 0.f;                                // (dead code unless EXACT)
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float* xr = s_x + ((li - 1 + a) & (PW_RING - 1)) * PW_XP + tid;
+                    const float* dr = s_dy + ((li - 1 + a) & (PW_RING - 1)) * PW_XP + tid;
+                    if (EXACT) s9[r] += fabsf(xr[0]) + fabsf(xr[1]) + fabsf(xr[2]);
+                    pw_st4(ta + 4 * a, pw_rnd(xr[0]), pw_rnd(xr[1]), pw_rnd(xr[2]), a == 0 ? one : 0u);
+                    pw_st4(ta + 12 + 4 * a, pw_rnd(dr[0]), pw_rnd(dr[1]), pw_rnd(dr[2]), 0u);
+                    if (a == 1 && r0 - 1 + li < r_end) gb2 += dr[1];       // dy at the pixel itself (0 outside the image)
+                }
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(bars);
+            // ---------------- phase 1b: [h | dA] -> a, dpre -> shared memory
+            pw_wait(bars + 8, (uint32_t)(k & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int r = 0; r < PW_R; ++r) {
+                uint32_t hv[16], dv[16];
+                tc_ld16_nowait(tl + (uint32_t)(PW_SLOT * r + 32), hv);
+                tc_ld16_nowait(tl + (uint32_t)(PW_SLOT * r + 48), dv);
+                tc_wait_ld();
+                const bool valid = colvalid && (r0 + PW_R * k + r) < r_end;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float a4[4], d4[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float h = __uint_as_float(hv[4 * q + c]);
+                        const float da = __uint_as_float(dv[4 * q + c]);
+                        // LeakyReLU's derivative jumps at h = 0: where the TF32 value is within its own error bound of
+                        // zero, redo this one dot product in FP32 so that the branch is the FP32 kernel's branch
+                        if (LEAKY && EXACT && fabsf(h) < fmaf(s_thr[4 * q + c], s9[r], s_thr[16 + 4 * q + c])) {
+                            const int lih = PW_R * k + 1 + r;
+                            float e = s_w1f[144 + 4 * q + c];
+#pragma unroll
+                            for (int t = 0; t < 9; ++t)
+                                e = fmaf(s_w1f[t * 16 + 4 * q + c],
+                                         s_x[((lih - 1 + t / 3) & (PW_RING - 1)) * PW_XP + tid + t % 3], e);
+                            h = e;
+                        }
+                        float av = h, dp = da;
+                        if (LEAKY) { av = fmaxf(h, h * p.alpha1); dp = h >= 0.f ? da : da * p.alpha1; }
+                        a4[c] = valid ? av : 0.f;
+                        d4[c] = valid ? dp : 0.f;
+                    }
+                    s_ad[(r * 8 + q) * PW_COLS + tid] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                    s_ad[(r * 8 + 4 + q) * PW_COLS + tid] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+                }
+            }
+            pw_bar_compute();
+            // ---------------- phase 2: warp = channel quad; pixel sums on the CUDA cores
+#pragma unroll 1
+            for (int r = 0; r < PW_R; ++r) {
+                const int li = PW_R * k + 1 + r;
+#pragma unroll 1
+                for (int j = 0; j < PW_COLS / 32; ++j) {
+                    const int col = lane + 32 * j;
+                    const float4 a4 = s_ad[(r * 8 + warp) * PW_COLS + col];
+                    const float4 d4 = s_ad[(r * 8 + 4 + warp) * PW_COLS + col];
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) gb1[c] += dv[c];
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        // x[p + off(t)] = x[row + ky - 1][col + kx - 1];  dy[p - off(t)] = dy[row - ky + 1][col - kx + 1]
+                        const float* xr = s_x + ((li + ky - 1) & (PW_RING - 1)) * PW_XP + col;
+                        const float* dr = s_dy + ((li - ky + 1) & (PW_RING - 1)) * PW_XP + col;
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float xv = xr[kx], dyv = dr[2 - kx];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                gw1[ky * 3 + kx][c] = fmaf(xv, dv[c], gw1[ky * 3 + kx][c]);
+                                gw2[ky * 3 + kx][c] = fmaf(dyv, av[c], gw2[ky * 3 + kx][c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---------------- partial sums -> workspace[(c * 19 + k) * nblk + blk]: k < 9 dw1, 9 db1 (c == 16: db2), >= 10 dw2
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int ch = 4 * warp + c;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float s1 = warp_sum(gw1[t][c]), s2 = warp_sum(gw2[t][c]);
+                if (lane == 0) {
+                    p.ws[(int64_t)(ch * 19 + t) * p.nblk + blk] = s1;
+                    p.ws[(int64_t)(ch * 19 + 10 + t) * p.nblk + blk] = s2;
+                }
+            }
+            const float sb = warp_sum(gb1[c]);
+            if (lane == 0) p.ws[(int64_t)(ch * 19 + 9) * p.nblk + blk] = sb;
+        }
+        const float s2 = warp_sum(gb2);
+        if (lane == 0) s_red[warp] = s2;
+        pw_bar_compute();
+        if (tid == 0) p.ws[(int64_t)(16 * 19 + 9) * p.nblk + blk] = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                     ::"r"(tmem_base), "r"((uint32_t)(PW_R * PW_SLOT)) : "memory");
+    }
+}
+
+static void pair_wgrad_tc_geometry(int64_t n, int64_t h, int64_t w, int* strips, int* bands, int* rb, int64_t* nblk) {
+    *strips = (int)ceil_div(w, PW_COLS);
+    // bands: multiples of PW_R rows; enough CTAs for ~3 waves at 2 CTAs per SM, but at least 16 rows per band
+    int r = 256;
+    while (r > 16 && n * (*strips) * ceil_div(h, r) < 3 * 2 * 148) r /= 2;
+    if (r > h) r = (int)(((h + PW_R - 1) / PW_R) * PW_R);
+    *rb = r;
+    *bands = (int)ceil_div(h, r);
+    *nblk = n * (*strips) * (*bands);
+}
+
+size_t conv3x3_pair_wgrad_tc_workspace(int64_t n, int64_t h, int64_t w, int c1) {
+    int strips, bands, rb;
+    int64_t nblk;
+    pair_wgrad_tc_geometry(n, h, w, &strips, &bands, &rb, &nblk);
+    return sizeof(float) * (size_t)nblk * (c1 + 1) * 19;
+}
+
+// dw1 / db1 / dw2 / db2 partial sums into ws (layout of conv3x3_pair_wgrad_finalize_kernel); *nblk_out = partials per element
+int conv3x3_pair_wgrad_tc(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* ws,
+                          int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int* nblk_out, cudaStream_t st) {
+    if (c1 != 16) return UOCR_ERR_UNSUPPORTED;
+    const bool leaky = act1 == UOCR_ACT_LEAKY;
+    if (!(act1 == UOCR_ACT_NONE || (leaky && alpha1 >= 0.f && alpha1 <= 1.f))) return UOCR_ERR_UNSUPPORTED;
+    PairWgParams p{};
+    p.x = x; p.dy = dy; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.ws = ws;
+    p.H = (int)h; p.W = (int)w; p.n = (int)n;
+    int64_t nblk;
+    pair_wgrad_tc_geometry(n, h, w, &p.strips, &p.bands, &p.rb, &nblk);
+    if (nblk > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    p.nblk = (int)nblk;
+    p.steps = (p.rb + PW_R - 1) / PW_R;
+    p.leaky = leaky; p.alpha1 = alpha1;
+    const size_t smem = sizeof(float) * (8 * 32 * 4 + 2 * PW_RING * PW_XP + 192) + sizeof(float4) * PW_R * 8 * PW_COLS + 64;
+    // UOCR_PAIR_WGRAD_EXACT_MASK=1: LeakyReLU's derivative is decided on an FP32 recomputation of h wherever the TF32 value
+    // lies within its own error bound of zero (bit-for-bit the FP32 kernel's branch; ~1.8x slower).  Default: the branch
+    // is taken on the TF32 h, like every other fused conv + LeakyReLU of the TF32 mode -- elements within TF32 resolution
+    // of the kink (about 0.1 % of them on random data) may take either side of the subgradient.
+    const char* exact_env = getenv("UOCR_PAIR_WGRAD_EXACT_MASK");   // read per call: tests switch it
+    const bool exact = exact_env && exact_env[0] == '1';
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(conv3x3_pair_wgrad_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = cudaFuncSetAttribute(conv3x3_pair_wgrad_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e3 = cudaFuncSetAttribute(conv3x3_pair_wgrad_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { set_error("cudaFuncSetAttribute failed"); return UOCR_ERR_CUDA; }
+        configured = true;
+    }
+    if (leaky && exact) conv3x3_pair_wgrad_tc_kernel<true, true><<<(unsigned)nblk, PW_THREADS, smem, st>>>(p);
+    else if (leaky) conv3x3_pair_wgrad_tc_kernel<true, false><<<(unsigned)nblk, PW_THREADS, smem, st>>>(p);
+    else conv3x3_pair_wgrad_tc_kernel<false, false><<<(unsigned)nblk, PW_THREADS, smem, st>>>(p);
+    UOCR_LAUNCHED("conv3x3_pair_wgrad_tc");
+    *nblk_out = (int)nblk;
+    return UOCR_OK;
+}
+
+}  // namespace uocr

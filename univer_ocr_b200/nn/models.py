@@ -458,10 +458,10 @@ class Model(BaseModel):
         dx = DeviceArray(X.shape) if need_dx else None
         tracker = c1.progress_tracker
         tracker.start_tracking(c1.name, 'backward')
-        lib.uocr_conv3x3_pair_bwd(X.ptr, c1.w.value.ptr, c1.b.value.ptr, c2.w.value.ptr, grad.ptr,
-                                  dx.ptr if need_dx else None, c1.w.grad.ptr, c1.b.grad.ptr, c2.w.grad.ptr,
-                                  c2.b.grad.ptr, n, h, w, c1.out_channels, act1, alpha1, 1, ws.ptr, need.value,
-                                  stream())
+        lib.uocr_conv3x3_pair_bwd_mode(X.ptr, c1.w.value.ptr, c1.b.value.ptr, c2.w.value.ptr, grad.ptr,
+                                       dx.ptr if need_dx else None, c1.w.grad.ptr, c1.b.grad.ptr, c2.w.grad.ptr,
+                                       c2.b.grad.ptr, n, h, w, c1.out_channels, act1, alpha1, 1, ws.ptr, need.value,
+                                       CP.math_mode, stream())
         tracker.stop_tracking(c1.name, 'backward')
         return dx
 
