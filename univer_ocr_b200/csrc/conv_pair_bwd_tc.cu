@@ -31,7 +31,8 @@ constexpr int PW_R = 4;                  // hidden rows per step
 constexpr int PW_COLS = 128;             // hidden columns per CTA = UMMA M
 constexpr int PW_THREADS = 160;          // 4 compute warps + 1 MMA-issuing warp
 constexpr int PW_SLOT = 64;              // TMEM columns per row: A at +0 (32), D at +32 (32)
-constexpr int PW_XP = 136;               // ring row pitch: columns c0 - 1 .. c0 + 128 (130 used)
+constexpr int PW_XP = 136;               // ring row pitch: columns c0 - 4 .. c0 + 131 (34 x 16 bytes; c0 - 1 .. c0 + 128 used)
+constexpr int PW_X0 = 3;                 // ring column of image column c0 - 1
 constexpr int PW_RING = 16;
 
 struct PairWgParams {
@@ -155,16 +156,31 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv3x3_pair_wgrad_tc_kernel(co
         }
         tc_wait_st();
 
-        // ring rows: local index li = image row - (r0 - 1), slot = li % PW_RING; columns cc = image column - (c0 - 1)
+        // ring rows: local index li = image row - (r0 - 1), slot = li % PW_RING; ring column = image column - (c0 - 4),
+        // so that a row is 34 aligned 16-byte cp.async copies (W % 4 == 0: a quad is inside or outside the image as a
+        // whole; otherwise element-wise copies)
+        const bool quads = (p.W & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.dy)) & 15) == 0;
         auto load_rows = [&](int li0, int count) {
-            for (int i = tid; i < count * 130; i += 128) {
-                const int rr = i / 130, cc = i - rr * 130;
-                const int li = li0 + rr, row = r0 - 1 + li, col = c0 - 1 + cc;
-                const bool in = row >= 0 && row < p.H && col >= 0 && col < p.W;
-                const int64_t off = in ? (int64_t)row * p.W + col : 0;
-                const uint32_t so = (uint32_t)((li & (PW_RING - 1)) * PW_XP + cc) * 4u;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sx_addr + so), "l"(xim + off), "r"(in ? 4 : 0) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdy_addr + so), "l"(dyim + off), "r"(in ? 4 : 0) : "memory");
+            if (quads) {
+                for (int i = tid; i < count * 34; i += 128) {
+                    const int rr = i / 34, q = i - rr * 34;
+                    const int li = li0 + rr, row = r0 - 1 + li, col = c0 - 4 + 4 * q;
+                    const bool in = row >= 0 && row < p.H && col >= 0 && col < p.W;
+                    const int64_t off = in ? (int64_t)row * p.W + col : 0;
+                    const uint32_t so = (uint32_t)((li & (PW_RING - 1)) * PW_XP + 4 * q) * 4u;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sx_addr + so), "l"(xim + off), "r"(in ? 16 : 0) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sdy_addr + so), "l"(dyim + off), "r"(in ? 16 : 0) : "memory");
+                }
+            } else {
+                for (int i = tid; i < count * 130; i += 128) {
+                    const int rr = i / 130, cc = i - rr * 130;
+                    const int li = li0 + rr, row = r0 - 1 + li, col = c0 - 1 + cc;
+                    const bool in = row >= 0 && row < p.H && col >= 0 && col < p.W;
+                    const int64_t off = in ? (int64_t)row * p.W + col : 0;
+                    const uint32_t so = (uint32_t)((li & (PW_RING - 1)) * PW_XP + PW_X0 + cc) * 4u;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sx_addr + so), "l"(xim + off), "r"(in ? 4 : 0) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sdy_addr + so), "l"(dyim + off), "r"(in ? 4 : 0) : "memory");
+                }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
@@ -181,113 +197,152 @@ __global__ void __launch_bounds__(PW_THREADS, 2) conv3x3_pair_wgrad_tc_kernel(co
         const bool colvalid = c0 + tid < p.W;
         const uint32_t one = colvalid ? __float_as_uint(1.f) : 0u;
 
+        float s9[PW_R];                                     // sum |x| over the window: scales the TF32 error bound of h
+        auto phase_1a = [&](int k) {
+                // ---------------- phase 1a: windows -> TMEM.  The lane walks down its column: the 3 x 3 windows of x and dy
+                // slide through a 3-row register ring (values already rounded to TF32), 6 shared loads per pixel
+                {
+                    uint32_t xw[3][3], dw[3][3];
+                    const int li0 = PW_R * k + 1;
+    #pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const float* xr = s_x + ((li0 - 1 + a) & (PW_RING - 1)) * PW_XP + PW_X0 + tid;
+                        const float* dr = s_dy + ((li0 - 1 + a) & (PW_RING - 1)) * PW_XP + PW_X0 + tid;
+    #pragma unroll
+                        for (int b = 0; b < 3; ++b) { xw[a][b] = pw_rnd(xr[b]); dw[a][b] = pw_rnd(dr[b]); }
+                    }
+    #pragma unroll
+                    for (int r = 0; r < PW_R; ++r) {
+                        const int li = li0 + r;                 // hidden row, local
+                        const uint32_t ta = tl + (uint32_t)(PW_SLOT * r);
+                        {
+                            const float* xr = s_x + ((li + 1) & (PW_RING - 1)) * PW_XP + PW_X0 + tid;
+                            const float* dr = s_dy + ((li + 1) & (PW_RING - 1)) * PW_XP + PW_X0 + tid;
+    #pragma unroll
+                            for (int b = 0; b < 3; ++b) { xw[(r + 2) % 3][b] = pw_rnd(xr[b]); dw[(r + 2) % 3][b] = pw_rnd(dr[b]); }
+                        }
+                        s9[r] = 0.f;                            // (dead code unless EXACT)
+    #pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const uint32_t* xq = xw[(r + a) % 3];
+                            const uint32_t* dq = dw[(r + a) % 3];
+                            if (EXACT) s9[r] += fabsf(__uint_as_float(xq[0])) + fabsf(__uint_as_float(xq[1])) + fabsf(__uint_as_float(xq[2]));
+                            pw_st4(ta + 4 * a, xq[0], xq[1], xq[2], a == 0 ? one : 0u);
+                            pw_st4(ta + 12 + 4 * a, dq[0], dq[1], dq[2], 0u);
+                        }
+                        // dy at the pixel itself (0 outside the image; the +half-ulp of the rounding is below FP32 resolution of the sum)
+                        if (r0 - 1 + li < r_end) gb2 += s_dy[(li & (PW_RING - 1)) * PW_XP + PW_X0 + tid + 1];
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                mbar_arrive(bars);
+        };
+        auto phase_1b = [&](int k) {
+                // ---------------- phase 1b: [h | dA] -> a, dpre -> shared memory
+                pw_wait(bars + 8, (uint32_t)(k & 1));
+                tc_fence_after();
+    #pragma unroll
+                for (int r = 0; r < PW_R; ++r) {
+                    uint32_t hv[16], dv[16];
+                    tc_ld16_nowait(tl + (uint32_t)(PW_SLOT * r + 32), hv);
+                    tc_ld16_nowait(tl + (uint32_t)(PW_SLOT * r + 48), dv);
+                    tc_wait_ld();
+                    const bool valid = colvalid && (r0 + PW_R * k + r) < r_end;      // false only on the last strip / band
+    #pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float a4[4], d4[4];
+    #pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float h = __uint_as_float(hv[4 * q + c]);
+                            const float da = __uint_as_float(dv[4 * q + c]);
+                            // LeakyReLU's derivative jumps at h = 0: where the TF32 value is within its own error bound of
+                            // zero, redo this one dot product in FP32 so that the branch is the FP32 kernel's branch
+                            if (LEAKY && EXACT && fabsf(h) < fmaf(s_thr[4 * q + c], s9[r], s_thr[16 + 4 * q + c])) {
+                                const int lih = PW_R * k + 1 + r;
+                                float e = s_w1f[144 + 4 * q + c];
+    #pragma unroll
+                                for (int t = 0; t < 9; ++t)
+                                    e = fmaf(s_w1f[t * 16 + 4 * q + c],
+                                             s_x[((lih - 1 + t / 3) & (PW_RING - 1)) * PW_XP + PW_X0 + tid + t % 3], e);
+                                h = e;
+                            }
+                            float av = h, dp = da;
+                            if (LEAKY) { av = fmaxf(h, h * p.alpha1); dp = h >= 0.f ? da : da * p.alpha1; }
+                            a4[c] = valid ? av : 0.f;
+                            d4[c] = valid ? dp : 0.f;
+                        }
+                        s_ad[(r * 8 + q) * PW_COLS + tid] = make_float4(a4[0], a4[1], a4[2], a4[3]);
+                        s_ad[(r * 8 + 4 + q) * PW_COLS + tid] = make_float4(d4[0], d4[1], d4[2], d4[3]);
+                    }
+                }
+        };
+        auto phase_2 = [&](int k) {
+                // ---------------- phase 2: warp = channel quad; pixel sums on the CUDA cores.  A lane walks down the
+                // step's rows of one column at a time, so the 3 x 3 windows of x and dy slide in registers (6 new values
+                // per pixel instead of 18 shared loads)
+    #pragma unroll 1
+                for (int j = 0; j < PW_COLS / 32; ++j) {
+                    const int col = lane + 32 * j;
+                    const int li0 = PW_R * k + 1;
+                    float xw[3][3], dw[3][3];                   // rows li - 1, li, li + 1 (static rotation below)
+    #pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        const float* xr = s_x + ((li0 - 1 + a) & (PW_RING - 1)) * PW_XP + PW_X0 + col;
+                        const float* dr = s_dy + ((li0 - 1 + a) & (PW_RING - 1)) * PW_XP + PW_X0 + col;
+    #pragma unroll
+                        for (int b = 0; b < 3; ++b) { xw[a][b] = xr[b]; dw[a][b] = dr[b]; }
+                    }
+    #pragma unroll
+                    for (int r = 0; r < PW_R; ++r) {
+                        const int li = li0 + r;
+                        {   // slot of row li + 1 in the 3-row register ring: (r + 2) % 3
+                            const float* xr = s_x + ((li + 1) & (PW_RING - 1)) * PW_XP + PW_X0 + col;
+                            const float* dr = s_dy + ((li + 1) & (PW_RING - 1)) * PW_XP + PW_X0 + col;
+    #pragma unroll
+                            for (int b = 0; b < 3; ++b) { xw[(r + 2) % 3][b] = xr[b]; dw[(r + 2) % 3][b] = dr[b]; }
+                        }
+                        const float4 a4 = s_ad[(r * 8 + warp) * PW_COLS + col];
+                        const float4 d4 = s_ad[(r * 8 + 4 + warp) * PW_COLS + col];
+                        const float av[4] = {a4.x, a4.y, a4.z, a4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+    #pragma unroll
+                        for (int c = 0; c < 4; ++c) gb1[c] += dv[c];
+    #pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+    #pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                // x[p + off(t)] = x[row + ky - 1][col + kx - 1];  dy[p - off(t)] = dy[row - ky + 1][col - kx + 1]
+                                const float xv = xw[(r + ky) % 3][kx], dyv = dw[(r + 2 - ky) % 3][2 - kx];
+    #pragma unroll
+                                for (int c = 0; c < 4; ++c) {
+                                    gw1[ky * 3 + kx][c] = fmaf(xv, dv[c], gw1[ky * 3 + kx][c]);
+                                    gw2[ky * 3 + kx][c] = fmaf(dyv, av[c], gw2[ky * 3 + kx][c]);
+                                }
+                            }
+                    }
+                }
+        };
+
+        // Software pipeline: the MMAs of step k run while the CUDA cores do phase 2 of step k - 1.
+        //   1a(0) | k = 0 .. steps-1: { phase 2 (k-1) ; bar ; prefetch rows (k+2) ; 1b(k) ; bar ; 1a(k+1) } | phase 2 (steps-1)
+        // Ring rows in use at any time: 4k (1b / exact mask) .. 4k + 13 (prefetch for step k + 2): 14 of the 16 slots.
+        if (p.steps > 1) load_rows(PW_R + 2, PW_R);         // rows of step 1
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        pw_bar_compute();
+        phase_1a(0);
 #pragma unroll 1
         for (int k = 0; k < p.steps; ++k) {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            pw_bar_compute();                               // this step's rows are in the ring; previous phase 2 is done
-            if (k + 1 < p.steps) load_rows(PW_R * (k + 1) + 2, PW_R);       // prefetch: rows li = 4k+6 .. 4k+9
-            // ---------------- phase 1a: windows -> TMEM
-            float s9[PW_R];                                 // sum |x| over the window: scales the TF32 error bound of h
-#pragma unroll
-            for (int r = 0; r < PW_R; ++r) {
-                const int li = PW_R * k + 1 + r;            // hidden row, local
-                const uint32_t ta = tl + (uint32_t)(PW_SLOT * r);
-                s9[r] = 0.f;                                // (dead code unless EXACT)
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float* xr = s_x + ((li - 1 + a) & (PW_RING - 1)) * PW_XP + tid;
-                    const float* dr = s_dy + ((li - 1 + a) & (PW_RING - 1)) * PW_XP + tid;
-                    if (EXACT) s9[r] += fabsf(xr[0]) + fabsf(xr[1]) + fabsf(xr[2]);
-                    pw_st4(ta + 4 * a, pw_rnd(xr[0]), pw_rnd(xr[1]), pw_rnd(xr[2]), a == 0 ? one : 0u);
-                    pw_st4(ta + 12 + 4 * a, pw_rnd(dr[0]), pw_rnd(dr[1]), pw_rnd(dr[2]), 0u);
-                    if (a == 1 && r0 - 1 + li < r_end) gb2 += dr[1];       // dy at the pixel itself (0 outside the image)
-                }
-            }
-            tc_wait_st();
-            tc_fence_before();
-            mbar_arrive(bars);
-            // ---------------- phase 1b: [h | dA] -> a, dpre -> shared memory
-            pw_wait(bars + 8, (uint32_t)(k & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int r = 0; r < PW_R; ++r) {
-                uint32_t hv[16], dv[16];
-                tc_ld16_nowait(tl + (uint32_t)(PW_SLOT * r + 32), hv);
-                tc_ld16_nowait(tl + (uint32_t)(PW_SLOT * r + 48), dv);
-                tc_wait_ld();
-                const bool valid = colvalid && (r0 + PW_R * k + r) < r_end;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float a4[4], d4[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float h = __uint_as_float(hv[4 * q + c]);
-                        const float da = __uint_as_float(dv[4 * q + c]);
-                        // LeakyReLU's derivative jumps at h = 0: where the TF32 value is within its own error bound of
-                        // zero, redo this one dot product in FP32 so that the branch is the FP32 kernel's branch
-                        if (LEAKY && EXACT && fabsf(h) < fmaf(s_thr[4 * q + c], s9[r], s_thr[16 + 4 * q + c])) {
-                            const int lih = PW_R * k + 1 + r;
-                            float e = s_w1f[144 + 4 * q + c];
-#pragma unroll
-                            for (int t = 0; t < 9; ++t)
-                                e = fmaf(s_w1f[t * 16 + 4 * q + c],
-                                         s_x[((lih - 1 + t / 3) & (PW_RING - 1)) * PW_XP + tid + t % 3], e);
-                            h = e;
-                        }
-                        float av = h, dp = da;
-                        if (LEAKY) { av = fmaxf(h, h * p.alpha1); dp = h >= 0.f ? da : da * p.alpha1; }
-                        a4[c] = valid ? av : 0.f;
-                        d4[c] = valid ? dp : 0.f;
-                    }
-                    s_ad[(r * 8 + q) * PW_COLS + tid] = make_float4(a4[0], a4[1], a4[2], a4[3]);
-                    s_ad[(r * 8 + 4 + q) * PW_COLS + tid] = make_float4(d4[0], d4[1], d4[2], d4[3]);
-                }
-            }
-            pw_bar_compute();
-            // ---------------- phase 2: warp = channel quad; pixel sums on the CUDA cores.  A lane walks down the
-            // step's rows of one column at a time, so the 3 x 3 windows of x and dy slide in registers (6 new values
-            // per pixel instead of 18 shared loads)
-#pragma unroll 1
-            for (int j = 0; j < PW_COLS / 32; ++j) {
-                const int col = lane + 32 * j;
-                const int li0 = PW_R * k + 1;
-                float xw[3][3], dw[3][3];                   // rows li - 1, li, li + 1 (static rotation below)
-#pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const float* xr = s_x + ((li0 - 1 + a) & (PW_RING - 1)) * PW_XP + col;
-                    const float* dr = s_dy + ((li0 - 1 + a) & (PW_RING - 1)) * PW_XP + col;
-#pragma unroll
-                    for (int b = 0; b < 3; ++b) { xw[a][b] = xr[b]; dw[a][b] = dr[b]; }
-                }
-#pragma unroll
-                for (int r = 0; r < PW_R; ++r) {
-                    const int li = li0 + r;
-                    {   // slot of row li + 1 in the 3-row register ring: (r + 2) % 3
-                        const float* xr = s_x + ((li + 1) & (PW_RING - 1)) * PW_XP + col;
-                        const float* dr = s_dy + ((li + 1) & (PW_RING - 1)) * PW_XP + col;
-#pragma unroll
-                        for (int b = 0; b < 3; ++b) { xw[(r + 2) % 3][b] = xr[b]; dw[(r + 2) % 3][b] = dr[b]; }
-                    }
-                    const float4 a4 = s_ad[(r * 8 + warp) * PW_COLS + col];
-                    const float4 d4 = s_ad[(r * 8 + 4 + warp) * PW_COLS + col];
-                    const float av[4] = {a4.x, a4.y, a4.z, a4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) gb1[c] += dv[c];
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            // x[p + off(t)] = x[row + ky - 1][col + kx - 1];  dy[p - off(t)] = dy[row - ky + 1][col - kx + 1]
-                            const float xv = xw[(r + ky) % 3][kx], dyv = dw[(r + 2 - ky) % 3][2 - kx];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                gw1[ky * 3 + kx][c] = fmaf(xv, dv[c], gw1[ky * 3 + kx][c]);
-                                gw2[ky * 3 + kx][c] = fmaf(dyv, av[c], gw2[ky * 3 + kx][c]);
-                            }
-                        }
-                }
-            }
+            if (k > 0) phase_2(k - 1);
+            pw_bar_compute();                               // phase 2 (k-1) is done with s_ad and its ring rows
+            if (k + 2 < p.steps) load_rows(PW_R * (k + 2) + 2, PW_R);
+            else asm volatile("cp.async.commit_group;" ::: "memory");       // keeps the group count uniform
+            phase_1b(k);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");           // rows of step k + 1 (all but the newest group)
+            pw_bar_compute();                               // s_ad(k) visible to every warp; rows of step k + 1 landed
+            if (k + 1 < p.steps) phase_1a(k + 1);
         }
+        phase_2(p.steps - 1);
+
         // ---------------- partial sums -> workspace[(c * 19 + k) * nblk + blk]: k < 9 dw1, 9 db1 (c == 16: db2), >= 10 dw2
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
