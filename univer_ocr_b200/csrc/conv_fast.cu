@@ -314,6 +314,160 @@ static int launch_c1_fwd(const ConvGeom& g, int ups, const float* x, const float
 }
 
 // ------------------------------------------------------------------------------------------
+// 5 x 5 / stride 1 / padding 2 / 1 -> 1 channel (Paragraph up_*, end in training; their stride-1 dgrads on flipped
+// weights): the two levels of the fused hourglass kernel (hourglass.cu) as stand-alone layers.
+//   conv55_c1_tile_kernel     : 32 x 128 output block, its 36 x 136 input block staged with 16-byte cp.async (zero fill =
+//                               padding), thread = 2 rows x 4 columns from conflict-free 128-bit shared loads
+//   conv55_c1_ups_tile_kernel : the same convolution over a x2 nearest-upsampled input that is never materialised: four
+//                               parity-specific 3 x 3 kernels with pre-summed weights on the low-resolution block (9 FMA
+//                               per output instead of 25)
+// Both need W % 4 == 0 (W % 8 for the upsampled one), zero padding and 16-byte aligned tensors; otherwise the generic
+// Cin = 1 kernel above runs.
+// ------------------------------------------------------------------------------------------
+constexpr int C55_TH = 32, C55_TW = 128, C55_P = 136;
+
+__global__ void __launch_bounds__(256) conv55_c1_tile_kernel(ConvGeom g, const float* __restrict__ x,
+                                                             const float* __restrict__ w, const float* __restrict__ b,
+                                                             float* __restrict__ y, int act, float alpha) {
+    __shared__ __align__(16) float s_in[(C55_TH + 4) * C55_P];          // origin (oy0 - 2, ox0 - 4)
+    const int ox0 = blockIdx.x * C55_TW, oy0 = blockIdx.y * C55_TH;
+    const float* xim = x + (int64_t)blockIdx.z * g.h * g.w;
+    float* yim = y + (int64_t)blockIdx.z * g.h * g.w;
+    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(s_in));
+    for (int i = threadIdx.x; i < (C55_TH + 4) * (C55_P / 4); i += 256) {
+        const int r = i / (C55_P / 4), q = i - r * (C55_P / 4);
+        const int gy = oy0 - 2 + r, gx = ox0 - 4 + 4 * q;
+        const bool in = (unsigned)gy < (unsigned)g.h && (unsigned)gx < (unsigned)g.w;
+        const float* src = in ? xim + (int64_t)gy * g.w + gx : xim;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(sbase + (uint32_t)(r * C55_P + 4 * q) * 4u), "l"(src), "r"(in ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    float wr[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) wr[i] = __ldg(w + i);
+    const float bias = g.bias ? __ldg(b) : 0.f;
+    __syncthreads();
+    for (int item = threadIdx.x; item < (C55_TH / 2) * (C55_TW / 4); item += 256) {
+        const int r = (item / (C55_TW / 4)) * 2, c0 = (item % (C55_TW / 4)) * 4;
+        float acc[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = bias;
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const float4* row = reinterpret_cast<const float4*>(s_in + (r + rr) * C55_P + c0);
+            const float4 u = row[0], v = row[1], t = row[2];
+            const float in[8] = {u.z, u.w, v.x, v.y, v.z, v.w, t.x, t.y};        // block columns c0 + 2 .. c0 + 9
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int ky = rr - k;
+                if (ky >= 0 && ky < 5) {
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[k][j] = fmaf(wr[ky * 5 + kx], in[j + kx], acc[k][j]);
+                }
+            }
+        }
+        const int gx = ox0 + c0;
+        if (gx < g.w) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int gy = oy0 + r + k;
+                if (gy < g.h)
+                    *reinterpret_cast<float4*>(yim + (int64_t)gy * g.w + gx) =
+                        make_float4(apply_act_fast(acc[k][0], act, alpha), apply_act_fast(acc[k][1], act, alpha),
+                                    apply_act_fast(acc[k][2], act, alpha), apply_act_fast(acc[k][3], act, alpha));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) conv55_c1_ups_tile_kernel(ConvGeom g, const float* __restrict__ x,
+                                                                 const float* __restrict__ w, const float* __restrict__ b,
+                                                                 float* __restrict__ y, int act, float alpha) {
+    constexpr int SH_ = C55_TH / 2 + 2, SP_ = 72;           // low-resolution block: origin (oy0/2 - 1, ox0/2 - 4)
+    __shared__ __align__(16) float s_in[SH_ * SP_];
+    __shared__ float s_f[36];
+    const int ox0 = blockIdx.x * C55_TW, oy0 = blockIdx.y * C55_TH;
+    const int hs = g.h / 2, ws = g.w / 2;                   // stored (low-resolution) size
+    const float* xim = x + (int64_t)blockIdx.z * hs * ws;
+    float* yim = y + (int64_t)blockIdx.z * g.h * g.w;
+    const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(s_in));
+    for (int i = threadIdx.x; i < SH_ * (SP_ / 4); i += 256) {
+        const int r = i / (SP_ / 4), q = i - r * (SP_ / 4);
+        const int gy = oy0 / 2 - 1 + r, gx = ox0 / 2 - 4 + 4 * q;
+        const bool in = (unsigned)gy < (unsigned)hs && (unsigned)gx < (unsigned)ws;
+        const float* src = in ? xim + (int64_t)gy * ws + gx : xim;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(sbase + (uint32_t)(r * SP_ + 4 * q) * 4u), "l"(src), "r"(in ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    if (threadIdx.x < 36) {                                 // parity-folded 3 x 3 kernels (see hourglass.cu)
+        const int i = threadIdx.x, bb = i % 3, a = (i / 3) % 3, px = (i / 9) % 2, py = i / 18;
+        const int ylo = py == 0 ? 2 * a : (a == 0 ? 0 : 2 * a - 1), yhi = py == 0 ? min(2 * a + 1, 4) : (a == 0 ? 0 : 2 * a);
+        const int xlo = px == 0 ? 2 * bb : (bb == 0 ? 0 : 2 * bb - 1), xhi = px == 0 ? min(2 * bb + 1, 4) : (bb == 0 ? 0 : 2 * bb);
+        float t = 0.f;
+        for (int ky = ylo; ky <= yhi; ++ky)
+            for (int kx = xlo; kx <= xhi; ++kx) t += __ldg(w + ky * 5 + kx);
+        s_f[i] = t;
+    }
+    const float bias = g.bias ? __ldg(b) : 0.f;
+    __syncthreads();
+    float wf[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) wf[i] = s_f[i];
+    // item = source row j (output rows 2j, 2j + 1) x 2 source cells n0, n0 + 1 (output columns 2 n0 .. 2 n0 + 3)
+    for (int item = threadIdx.x; item < (C55_TH / 2) * (C55_TW / 4); item += 256) {
+        const int j = item / (C55_TW / 4), n0 = (item % (C55_TW / 4)) * 2;
+        float sv[3][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float* row = s_in + (j + a) * SP_ + n0 + 3;                   // block column of source column n0 - 1
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sv[a][q] = row[q];
+        }
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int px = 0; px < 2; ++px) {
+                    float acc = bias;
+#pragma unroll
+                    for (int a = 0; a < 3; ++a)
+#pragma unroll
+                        for (int bb = 0; bb < 3; ++bb) acc = fmaf(wf[((py * 2 + px) * 3 + a) * 3 + bb], sv[a][i + bb], acc);
+                    o[2 * i + px] = apply_act_fast(acc, act, alpha);
+                }
+            const int gy = oy0 + 2 * j + py, gx = ox0 + 2 * n0;
+            if (gy < g.h && gx < g.w)
+                *reinterpret_cast<float4*>(yim + (int64_t)gy * g.w + gx) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+static int conv55_c1_tiled(const ConvGeom& g, int ups, const float* x, const float* w, const float* b, float* y, int act,
+                           float alpha, cudaStream_t st) {
+    if (g.cin != 1 || g.cout != 1 || g.kh != 5 || g.kw != 5 || g.sh != 1 || g.sw != 1 || g.ph != 2 || g.pw != 2 ||
+        g.padding_value != 0.f || g.n > 65535 || ceil_div(g.h, C55_TH) > 65535)
+        return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)ceil_div(g.w, C55_TW), (unsigned)ceil_div(g.h, C55_TH), (unsigned)g.n);
+    if (ups == 2) {
+        if (g.w % 8 || g.h % 2) return UOCR_ERR_UNSUPPORTED;
+        conv55_c1_ups_tile_kernel<<<grid, 256, 0, st>>>(g, x, w, b, y, act, alpha);
+        UOCR_LAUNCHED("conv55_c1_ups_tile");
+    } else {
+        if (g.w % 4) return UOCR_ERR_UNSUPPORTED;
+        conv55_c1_tile_kernel<<<grid, 256, 0, st>>>(g, x, w, b, y, act, alpha);
+        UOCR_LAUNCHED("conv55_c1_tile");
+    }
+    return UOCR_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // Cin = 1 -> Cout = 64 (Char conv_1: 5x3, stride (2, 1)): the layer is bound by its 58.7 MB output write, so the
 // kernel is organised around the STORE: lane = (channel quad, pixel), a warp's 128-bit store covers two pixels x
 // 64 channels = two fully used 256-byte segments (the generic kernel above wrote 16 bytes per lane at a 1 KB
@@ -397,6 +551,10 @@ int conv_fwd_fast(const ConvGeom& g, int ups, int math_mode, const float* x, con
         (COT_ != 1 || g.cout == 1)) {                                                                   \
         const int rc = launch_c1_fwd<KH_, KW_, SH_, SW_, COT_, PX_>(g, ups, x, w, b, y, act, alpha, st); \
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;                                                      \
+    }
+    {
+        const int rc = conv55_c1_tiled(g, ups, x, w, b, y, act, alpha, st);     // Paragraph up_*, end (+ stride-1 dgrads)
+        if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     }
     if (g.cin == 1 && g.cout == 64 && g.kh == 5 && g.kw == 3 && g.sh == 2 && g.sw == 1 && ups == 1 && g.n <= 65535 &&
         g.ho <= 65535 && !(reinterpret_cast<uintptr_t>(w) & 15) && !(reinterpret_cast<uintptr_t>(b) & 15)) {     // Char conv_1
