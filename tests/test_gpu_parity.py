@@ -558,4 +558,24 @@ def test_paragraph_predict_uses_hourglass_kernel(nn):
         close(got, ref, 1e-4, 2e-6, f'paragraph fused vs layers {shape}')
 
 
-
+@pytest.mark.gpu
+def test_concurrent_branches_match_serial(nn):
+    """pipeline.ConcurrentBranches: the Monochrome -> Paragraph chain, Line and Char forward on three forked CUDA
+    streams (own allocator pools) give bit-identical results to the single-stream order, repeatedly (buffers of one
+    step are recycled by the next)."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.pipeline import ConcurrentBranches
+    rng = np.random.default_rng(31)
+    shapes = {'monochrome': (2, 64, 96, 1), 'paragraph': (2, 64, 96, 1), 'line': (3, 32, 64, 1), 'char': (2, 32, 40, 1)}
+    models = {k: my_model.MAKERS[k](v) for k, v in shapes.items()}
+    page = nn.CP.copy(f32(rng.uniform(size=shapes['monochrome'])))
+    line = nn.CP.copy(f32(rng.uniform(size=shapes['line'])))
+    char = nn.CP.copy(f32(rng.uniform(size=shapes['char'])))
+    want = [host(models['paragraph'].predict(models['monochrome'].predict(page)[0])[0]),
+            host(models['line'].predict(line)[0]), host(models['char'].predict(char)[0])]
+    fork = ConcurrentBranches(3)
+    for _ in range(4):
+        got = fork.run(lambda: models['paragraph'].predict(models['monochrome'].predict(page)[0])[0],
+                       lambda: models['line'].predict(line)[0], lambda: models['char'].predict(char)[0])
+        for g, w_ in zip(got, want):
+            assert np.array_equal(host(g), w_)

@@ -8,6 +8,7 @@ and `DeviceArray` exposes the same protocol, so the two interoperate zero-copy.
 
 Storage is float32 (the reference is float64); see DESIGN.md for the tolerance contract.
 """
+import contextlib
 import ctypes
 import os
 import weakref
@@ -82,16 +83,20 @@ class _Buffer:
 
     def __init__(self, nbytes):
         p = ctypes.c_void_p()
-        lib.uocr_malloc(ctypes.byref(p), max(int(nbytes), 1), stream())
+        st = stream()
+        lib.uocr_malloc(ctypes.byref(p), max(int(nbytes), 1), st)
         self.ptr = p.value
         self.nbytes = int(nbytes)
-        weakref.finalize(self, _free, self.ptr)
+        weakref.finalize(self, _free, self.ptr, st)
 
 
-def _free(ptr):
+def _free(ptr, st):
+    # back to the pool of the stream it was allocated on (reuse is ordered on THAT stream): with several compute
+    # streams (CP.on_stream) a block must not migrate to another stream's free list while its own stream may still
+    # have kernels in flight on it
     try:
         if RT.stream is not None:
-            lib.uocr_free(ptr, RT.stream)
+            lib.uocr_free(ptr, st)
     except Exception:       # interpreter shutdown
         pass
 
@@ -504,6 +509,18 @@ class CP:
     @staticmethod
     def stream():
         return stream()
+
+    @staticmethod
+    @contextlib.contextmanager
+    def on_stream(s):
+        """Everything issued inside the block (kernels, allocations, copies) goes to CUDA stream `s` instead of the
+        process's compute stream; ordering against other streams is the caller's business (events)."""
+        RT.ensure()
+        prev, RT.stream = RT.stream, s
+        try:
+            yield s
+        finally:
+            RT.stream = prev
 
     @staticmethod
     def pinned_empty(shape, dtype=np.float32):

@@ -112,3 +112,38 @@ class InferencePipeline:
             if done is not None:
                 yield done
         yield from self.drain()
+
+
+class ConcurrentBranches:
+    """Runs independent pieces of work (e.g. the forward passes of sub-networks that do not feed each other) on
+    separate CUDA streams, forked from and joined back to the compute stream:
+
+        fork = ConcurrentBranches(3)
+        para, line, char = fork.run(lambda: paragraph(monochrome(x)), lambda: line_net(l), lambda: char_net(c))
+
+    Branch 0 stays on the compute stream; the others get their own stream (and their own allocator pool, so their
+    intermediates are recycled in stream order).  Small-kernel chains (Line, Char: 15-50 us launches that fill only
+    part of the GPU) then overlap with each other and with the big kernels' tails.  Results are valid on the
+    compute stream when `run` returns."""
+
+    def __init__(self, n):
+        CP.use_gpu()
+        self.side = [_new_stream() for _ in range(max(0, n - 1))]
+        self.ev_fork = _new_event()
+        self.ev_join = [_new_event() for _ in self.side]
+
+    def run(self, *branches):
+        assert len(branches) <= len(self.side) + 1
+        main = compute_stream()
+        lib.uocr_event_record(self.ev_fork, main)
+        outs = [None] * len(branches)
+        for i, fn in enumerate(branches[1:]):
+            s = self.side[i]
+            lib.uocr_stream_wait_event(s, self.ev_fork)
+            with CP.on_stream(s):
+                outs[i + 1] = fn()
+            lib.uocr_event_record(self.ev_join[i], s)
+        outs[0] = branches[0]()
+        for i in range(len(branches) - 1):
+            lib.uocr_stream_wait_event(main, self.ev_join[i])
+        return outs
