@@ -382,11 +382,16 @@ def measure_train(args, dist, nn, my_model, models, dev_sets, rng, B, event):
     feeds = {'monochrome': inp['page'], 'paragraph': inp['page'], 'line': inp['line'], 'char': inp['char']}
     stream = nn.CP.stream()
 
+    # the four sub-networks train independently (own parameters, own gradient allreduce): forked streams, joined per step
+    from univer_ocr_b200.pipeline import ConcurrentBranches
+    fork = None if os.environ.get('UOCR_BENCH_SERIAL') == '1' else ConcurrentBranches(len(dps))
+
     def step():
-        out = {}
-        for name, dp in dps.items():
-            out[name] = dp.train(feeds[name], targets[name])
-        return out
+        names = list(dps)
+        if fork is None:
+            return {name: dps[name].train(feeds[name], targets[name]) for name in names}
+        outs = fork.run(*[(lambda name=name: dps[name].train(feeds[name], targets[name])) for name in names])
+        return dict(zip(names, outs))
 
     for _ in range(3):
         losses = step()
