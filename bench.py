@@ -283,6 +283,9 @@ def run_b200(args):
     peaks = load_peaks()
     in_shapes = {'monochrome': (B, *PAGE_HW, 1), 'paragraph': (B, *PAGE_HW, 1),
                  'line': (B, *LINE_HW, 1), 'char': (B, *CHAR_HW, 1)}
+    for i in range(2):                                           # the serial order allocates from the compute stream's
+        step_serial(dev_sets[i % n_sets])                        # pool: fill it before timing layers
+    nn.CP.synchronize()
     tracker = CudaEventTracker()
     work = {}
     for mname, model in models.items():
