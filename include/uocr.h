@@ -322,6 +322,13 @@ int uocr_rmsprop_update(float* w, const float* g, float* a, int64_t n, float lr,
  * hits[r, c] (uint8) = pred[r, c] == max(pred[r, :]) && max != 0   -- the index part of
  * PredToText._func1, interpreter/interpreter.py:596-602 (ties keep every column). */
 int uocr_row_max_hits(const float* pred, uint8_t* hits, int64_t rows, int64_t cols, void* stream);
+/* mask[n, p, c] (uint8) = x[n, p, c] > 0.5 * (mean_p x[n, :, c] + max_p x[n, :, c]) over the
+ * hw positions of each (image, channel): the `thresholded()` of the crop stages,
+ * interpreter/interpreter.py:437-438 (per mask channel) and :549.  Sums in float64, fixed order
+ * (deterministic).  c <= 8; workspace of uocr_threshold_mask_workspace(n, c) bytes. */
+int uocr_threshold_mask_workspace(int64_t n, int64_t c, size_t* bytes);
+int uocr_threshold_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
+                        void* stream);
 
 #ifdef __cplusplus
 }

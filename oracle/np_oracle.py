@@ -436,3 +436,33 @@ def pred_to_ids(pred):
     mx = pred.max(axis=1, keepdims=True)
     hit = (pred == mx) & (mx != 0.0)
     return np.argwhere(hit)[:, 1].astype(np.int64)
+
+
+def thresholded(arr):
+    """interpreter/interpreter.py:437-438 (and :549): `arr > 0.5 * (np.mean(arr) + np.max(arr))`,
+    applied by the reference to one (1, H, W, 1) channel slice at a time; here to every
+    (image, channel) of an NHWC tensor.  Returns a bool array."""
+    arr = np.asarray(arr, dtype=np.float64)
+    out = np.zeros(arr.shape, dtype=bool)
+    for n in range(arr.shape[0]):
+        for c in range(arr.shape[-1]):
+            sl = arr[n, ..., c]
+            out[n, ..., c] = sl > 0.5 * (np.mean(sl) + np.max(sl))
+    return out
+
+
+def pred_to_text(pred, chars, are_similar):
+    """PredToText._func1 (interpreter/interpreter.py:595-614): winners of every row in row order
+    (`pred_to_ids`), id 0 clears the previous character, a character "similar" to the previous
+    one (primitives/__init__.py:53-54; None is similar to nothing) is skipped."""
+    result, prev = '', None
+    for char_id in pred_to_ids(pred):
+        if char_id == 0:
+            prev = None
+            continue
+        cur = chars[char_id]
+        if are_similar(cur, prev):
+            continue
+        result += cur
+        prev = cur
+    return result

@@ -89,3 +89,16 @@ def load_my_model():
     mod = importlib.import_module('web_app.components.my_model.model')
     _loaded['my_model'] = mod
     return mod
+
+
+def load_trainer():
+    """Returns the reference's `web_app.components.my_model.trainer` module (epoch driver:
+    `Losses`, `Trainer`).  Pure Python + NumPy + tqdm, no shims beyond the package shells."""
+    if 'trainer' in _loaded:
+        return _loaded['trainer']
+    if not available():
+        raise RuntimeError(f'reference tree not found at {REFERENCE_ROOT}')
+    _install_shims()
+    mod = importlib.import_module('web_app.components.my_model.trainer')
+    _loaded['trainer'] = mod
+    return mod

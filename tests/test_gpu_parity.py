@@ -388,6 +388,83 @@ def test_row_max_hits_bit_exact(nn):
     assert np.array_equal(got, O.pred_to_ids(pred))
 
 
+
+def test_device_glue_matches_oracle_bit_exact(nn):
+    """make_divisible_by / thresholded / pred_to_text on the device are index
+    and byte work: bit-exact against the oracle and against the strings recorded from the
+    reference's PredToText (tests/golden/glue.json)."""
+    import json
+    import os
+    from univer_ocr_b200 import glue
+    rng = np.random.default_rng(21)
+    for shape in ((2, 480, 720, 1), (3, 33, 47, 3), (1, 16, 32, 2)):
+        a = f32(rng.uniform(size=shape))
+        got = host(glue.make_divisible_by(nn.CP.copy(a), 16, 16))
+        assert np.array_equal(got, O.make_divisible_by(a, 16, 16))
+    for shape in ((4, 496, 736, 1), (5, 128, 256, 2), (3, 7, 5, 8), (1, 1, 1, 1)):
+        a = f32(rng.uniform(size=shape) ** 4)                 # skewed like a predicted mask
+        a[0] = 0.5                                            # a constant image: empty mask
+        mask = glue.thresholded(nn.CP.copy(a)).get()
+        assert mask.dtype == np.uint8 and np.array_equal(mask.astype(bool), O.thresholded(a))
+        assert not mask[0].any()
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'glue.json')) as fp:
+        g = json.load(fp)
+    similar = {k: set(v) for k, v in g['similar'].items()}
+    for case in g['pred_to_text']:
+        text = glue.pred_to_text(nn.CP.copy(np.array(case['pred'])), g['chars'], lambda x, y: x in similar.get(y, ()))
+        assert text == case['text']
+
+
+def test_trainer_epochs_on_device_models(nn):
+    """Epoch driver over real networks: batches of stacked samples through
+    the fused DataParallel step, losses read back once per epoch, device snapshots for the NaN
+    roll-back.  The decision logic itself is pinned to the reference in tests/test_trainer.py."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.nn.optimizers import Adam
+    from univer_ocr_b200.trainer import Trainer
+    rng = np.random.default_rng(8)
+    opt = Adam(lr=0.002)
+    mono = my_model.make_monochrome((1, 32, 48, 1), optimizer=opt)
+    char = my_model.make_char((1, 32, 16, 1), optimizer=opt)
+
+    class DS:
+        def __init__(self, n, seed):
+            r = np.random.default_rng(seed)
+            self.items = []
+            for _ in range(n):
+                x = f32(r.uniform(size=(1, 32, 48, 1)))
+                yc = np.zeros((16, 162))
+                yc[np.arange(16), r.integers(1, 162, size=16)] = 1
+                self.items.append({'mono': (x, f32(x > 0.6)), 'char': (f32(r.uniform(size=(1, 32, 16, 1))), yc)})
+
+        def __len__(self):
+            return len(self.items)
+
+        def get(self, i):
+            return self.items[i]
+
+    saved, lines = [], []
+    trainer = Trainer({'mono': mono, 'char': char}, DS(12, 1), DS(4, 2), optimizer=opt, learning_rate_step=0.9,
+                      batch_size=4, save_weights_func=saved.append, log=lambda *a, **k: lines.append(a))
+    best, best_epoch = trainer.train(3)
+    assert saved and set(saved[-1]) <= {'mono', 'char'}
+    assert np.isfinite(best['mono'][0]) and np.isfinite(best['char'][0])
+    assert best_epoch['mono'] >= 1
+    assert abs(opt.lr - 0.002 * 0.9 ** 3) < 1e-12            # one decay per healthy epoch
+
+    # roll-back path: poison the flat parameter buffer, restore the device snapshot
+    st = trainer.steppers['mono']
+    X = f32(rng.uniform(size=(2, 32, 48, 1)))
+    before = host(mono.predict(X)[0])
+    snap = st.snapshot()
+    st.train(X, f32(X > 0.5))
+    assert np.max(np.abs(host(mono.predict(X)[0]) - before)) > 0
+    st.dp.flat.values.fill(float('nan'))
+    assert mono.nan_weights()
+    st.restore(snap)
+    assert not mono.nan_weights()
+    assert np.array_equal(host(mono.predict(X)[0]), before)
+
 # ----------------------------------------------------------------------------- fused paths
 
 @pytest.mark.parametrize('name', list(MODEL_SHAPES))

@@ -157,6 +157,40 @@ def test_make_divisible_and_pred_ids():
     assert O.pred_to_ids(pred).tolist() == [1, 2, 0, 0]   # ties keep all; all-zero row dropped
 
 
+
+def _glue_golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'glue.json')) as fp:
+        g = json.load(fp)
+    similar = {k: set(v) for k, v in g['similar'].items()}
+    return g, (lambda a, b: a in similar.get(b, ()))
+
+
+def test_pred_to_text_and_padding_match_reference_fixture():
+    """PredToText._func1 strings and make_divisible_by placements recorded from the reference
+    (tests/golden/make_glue_golden.py)."""
+    g, are_similar = _glue_golden()
+    assert len(g['chars']) == 162
+    for case in g['pred_to_text']:
+        assert O.pred_to_text(np.array(case['pred']), g['chars'], are_similar) == case['text']
+    assert len(g['pred_to_text'][1]['text']) > 64            # tie rows emit several characters
+    for pad in g['make_divisible_by']:
+        out = O.make_divisible_by(np.ones(pad['shape']), 16, 16)
+        ys, xs = np.nonzero(out[0, :, :, 0])
+        assert list(out.shape) == pad['out_shape'] and (ys.min(), xs.min()) == (pad['top'], pad['left'])
+
+
+def test_thresholded_is_mean_max_midpoint_per_image_and_channel():
+    rng = np.random.default_rng(3)
+    a = rng.uniform(size=(2, 6, 5, 2))
+    got = O.thresholded(a)
+    for n in range(2):
+        for c in range(2):
+            sl = a[n, :, :, c:c + 1][None]                   # the (1, H, W, 1) slice the reference passes
+            assert np.array_equal(got[n, :, :, c], (sl > 0.5 * (np.mean(sl) + np.max(sl)))[0, :, :, 0])
+    assert not O.thresholded(np.ones((1, 4, 4, 1))).any()    # constant map: nothing exceeds its own max
+
 # ------------------------------------------------------------------ live reference diffs
 
 needs_ref = pytest.mark.skipif(not ref_loader.available(), reason='/root/reference not present')

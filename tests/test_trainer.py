@@ -1,0 +1,144 @@
+"""Epoch driver: `univer_ocr_b200.trainer.Trainer` against traces of the
+reference's `my_model/trainer.py` on scripted models (tests/golden/trainer_traces.json, generated
+by tests/golden/make_trainer_golden.py; compared live as well where /root/reference exists), plus
+the batched / sharded behaviour the reference does not have."""
+import contextlib
+import io
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tests import trainer_cases  # noqa: E402
+
+with open(os.path.join(ROOT, 'tests', 'golden', 'trainer_traces.json')) as fp:
+    GOLDEN = json.load(fp)
+
+
+@pytest.mark.parametrize('scenario', sorted(trainer_cases.SCENARIOS))
+def test_trainer_matches_reference_trace(scenario):
+    got = trainer_cases.run(scenario, trainer_cases.ours_factory)
+    want = GOLDEN[scenario]
+    assert got['trace'] == want['trace']                      # sample order, roll-backs, saves, lr at each save
+    assert got['best'] == want['best'] and got['best_epoch'] == want['best_epoch']
+    assert got['lr'] == want['lr'] and got['weights'] == want['weights']
+
+
+def test_golden_traces_cover_the_rollback_branches():
+    storm = [e for e in GOLDEN['nan_storm']['trace'] if e[0] == 'set_weights']
+    assert len(storm) == 11                                   # 9 x last weights, 1 x start weights, 1 x last
+    assert storm[9][2] == 0.3                                 # the "too many attempts" branch reloads the START weights
+    assert any(e[0] == 'save' for e in GOLDEN['plain']['trace'])
+
+
+def test_trainer_matches_reference_live():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not present')
+    ref = ref_loader.load_trainer()
+    for scenario in trainer_cases.SCENARIOS:
+        with contextlib.redirect_stdout(io.StringIO()):
+            want = trainer_cases.run(scenario, trainer_cases.reference_factory(ref))
+        assert want == GOLDEN[scenario]
+        assert trainer_cases.run(scenario, trainer_cases.ours_factory) == want
+
+
+def test_losses_table_matches_reference_print():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip('reference tree not present')
+    from univer_ocr_b200.trainer import Losses
+    ref = ref_loader.load_trainer()
+    names, cnts = ['monochrome', 'line'], {'monochrome': 1, 'line': 2}
+    tables = []
+    for cls in (ref.Losses, Losses):
+        l = cls(names, cnts)
+        l.reset()
+        l.train({'monochrome': {'output_losses': [1.5]}, 'line': {'output_losses': [0.25, 3.0]}})
+        l.validation({'monochrome': {'output_losses': [2.5]}, 'line': {'output_losses': [0.125, 1.0]}})
+        l.normalize(2, 4)
+        l.next()
+        l.reset()
+        l.train({'monochrome': {'output_losses': [1.0]}, 'line': {'output_losses': [0.5, 2.0]}})
+        l.validation({'monochrome': {'output_losses': [2.0]}, 'line': {'output_losses': [0.25, 0.5]}})
+        l.normalize(2, 4)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            l.print(left_margin=2)
+        tables.append(buf.getvalue())
+    assert tables[0] == tables[1] and 'Avg loss change' in tables[0]
+
+
+class _MeanModel(trainer_cases.ScriptedModel):
+    """A model whose loss averages over the batch (like SoftmaxCE), with a linear update rule so
+    that a stacked batch can be compared with per-sample arithmetic."""
+    mean_over_batch = True
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.seen = []
+
+    def train(self, X, y):
+        self.seen.append(X.shape[0])
+        return super().train(X, y)
+
+
+def test_batched_steps_stack_samples_and_weight_mean_losses():
+    from univer_ocr_b200.trainer import Trainer
+    opt = trainer_cases.ScriptedOptimizer(0.0)                 # lr 0: weights fixed, losses comparable
+    model = _MeanModel('m', 0.5, opt)
+    train_ds = trainer_cases.ScriptedDataset(['m'], 7, 3)
+    val_ds = trainer_cases.ScriptedDataset(['m'], 3, 4)
+    t = Trainer({'m': model}, train_ds, val_ds, optimizer=opt, batch_size=4, log=lambda *a, **k: None)
+    best, epoch = t.train(1)
+    assert model.seen == [4, 3]                                # 7 samples: one full stack, one ragged
+    # the model's loss on a stack uses the stack mean of x; weighting by the stack size keeps the
+    # epoch sum on the per-sample scale: sum_b n_b * (w - mean_b)^2 / n_val
+    xs = [float(np.mean(val_ds.get(i)['m'][0])) for i in range(3)]
+    want = 3 * (0.5 - np.mean(xs)) ** 2 / 3
+    assert abs(best['m'][0] - want) < 1e-12 and epoch == {'m': 1}
+
+
+def _two_rank_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from univer_ocr_b200.trainer import Trainer
+    opt = trainer_cases.ScriptedOptimizer(0.0)
+    trace = []
+    model = trainer_cases.ScriptedModel('m', 0.5, opt, trace=trace)
+    train_ds = trainer_cases.ScriptedDataset(['m'], 6, 3)
+    val_ds = trainer_cases.ScriptedDataset(['m'], 4, 4)
+    saves = []
+    t = Trainer({'m': model}, train_ds, val_ds, optimizer=opt, batch_size=2, save_weights_func=saves.append,
+                shuffle=lambda order: None, log=lambda *a, **k: None)
+    best, _ = t.train(1)
+    out.put((rank, best['m'][0], [e[2] for e in trace if e[0] == 'train'], len(saves)))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_each_batch_and_agree_on_losses():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = 29900 + os.getpid() % 90
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    got = sorted(out.get(timeout=10) for _ in range(2))
+    train_ds = trainer_cases.ScriptedDataset(['m'], 6, 3)
+    val_ds = trainer_cases.ScriptedDataset(['m'], 4, 4)
+    x = [round(float(np.mean(train_ds.get(i)['m'][0])), 9) for i in range(6)]
+    assert got[0][2] == x[0::2] and got[1][2] == x[1::2]       # rank r trains samples r, r + world, ...
+    want = sum((0.5 - float(np.mean(val_ds.get(i)['m'][0]))) ** 2 for i in range(4)) / 4
+    assert abs(got[0][1] - want) < 1e-12 and got[0][1] == got[1][1]   # losses summed over ranks
+    assert (got[0][3], got[1][3]) == (1, 0)                    # only rank 0 saves

@@ -374,6 +374,85 @@ __global__ void __launch_bounds__(kThreads) row_max_hits_kernel(const float* __r
     }
 }
 
+// ---------------------------------------------------------------- mean/max threshold masks
+// mask[n, p, c] = x[n, p, c] > 0.5 * (mean_p x[n, :, c] + max_p x[n, :, c]): the binarisation the
+// crop stages apply to every predicted map (interpreter/interpreter.py:437-438, 549).  Per image
+// kThrBlocks CTAs reduce (sum in float64, max) per channel into a fixed-order partial table, one
+// small kernel folds the partials (deterministic), the third compares.
+constexpr int kThrBlocks = 64;
+constexpr int kThrMaxC = 8;
+
+__global__ void __launch_bounds__(kThreads) threshold_partials_kernel(const float* __restrict__ x,
+                                                                      double* __restrict__ part,
+                                                                      int64_t hw, int c) {
+    __shared__ double s_sum[kThreads / 32][kThrMaxC];
+    __shared__ float s_max[kThreads / 32][kThrMaxC];
+    const int64_t n = blockIdx.y;
+    const float* xi = x + n * hw * c;
+    double sum[kThrMaxC];
+    float mx[kThrMaxC];
+#pragma unroll
+    for (int k = 0; k < kThrMaxC; ++k) { sum[k] = 0.0; mx[k] = -INFINITY; }
+    // a thread always sees the same channel phase: stride is a multiple of c
+    const int64_t total = hw * c;
+    const int64_t stride = (int64_t)gridDim.x * kThreads * c;
+    for (int64_t base = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * c; base < total; base += stride) {
+#pragma unroll
+        for (int k = 0; k < kThrMaxC; ++k)
+            if (k < c) {
+                const float v = xi[base + k];
+                sum[k] += (double)v;
+                mx[k] = fmaxf(mx[k], v);
+            }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < kThrMaxC; ++k)
+        if (k < c) {
+            double s = sum[k];
+            float m = mx[k];
+            for (int o = 16; o; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            }
+            if (lane == 0) { s_sum[warp][k] = s; s_max[warp][k] = m; }
+        }
+    __syncthreads();
+    if (threadIdx.x < c) {
+        double s = 0.0;
+        float m = -INFINITY;
+        for (int w = 0; w < kThreads / 32; ++w) { s += s_sum[w][threadIdx.x]; m = fmaxf(m, s_max[w][threadIdx.x]); }
+        double* out = part + ((n * gridDim.x + blockIdx.x) * c + threadIdx.x) * 2;
+        out[0] = s;
+        out[1] = (double)m;
+    }
+}
+
+__global__ void threshold_finalize_kernel(const double* __restrict__ part, double* __restrict__ thr,
+                                          int64_t groups, int blocks, int c, int64_t hw) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // g = n * c + channel
+    if (g >= groups) return;
+    const int64_t n = g / c, ch = g % c;
+    double s = 0.0, m = -INFINITY;
+    for (int b = 0; b < blocks; ++b) {
+        const double* p = part + ((n * blocks + b) * c + ch) * 2;
+        s += p[0];
+        m = fmax(m, p[1]);
+    }
+    thr[g] = 0.5 * (s / (double)hw + m);
+}
+
+__global__ void __launch_bounds__(kThreads) threshold_apply_kernel(const float* __restrict__ x,
+                                                                   const double* __restrict__ thr,
+                                                                   uint8_t* __restrict__ mask,
+                                                                   int64_t total, int64_t per_image, int c) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * kThreads) {
+        const int64_t n = i / per_image;
+        mask[i] = (double)x[i] > thr[n * c + (i % c)] ? 1 : 0;
+    }
+}
+
 }  // namespace uocr
 
 using namespace uocr;
@@ -596,6 +675,34 @@ int uocr_row_max_hits(const float* pred, uint8_t* hits, int64_t rows, int64_t co
     if (blocks > 148 * 8) blocks = 148 * 8;
     row_max_hits_kernel<<<(int)blocks, kThreads, 0, as_stream(stream)>>>(pred, hits, rows, cols);
     UOCR_LAUNCHED("row_max_hits");
+    return UOCR_OK;
+}
+
+int uocr_threshold_mask_workspace(int64_t n, int64_t c, size_t* bytes) {
+    UOCR_REQUIRE(bytes, "bytes is NULL");
+    *bytes = (n <= 0 || c <= 0) ? 0 : (size_t)(n * kThrBlocks * c * 2 + n * c) * sizeof(double);
+    return UOCR_OK;
+}
+
+int uocr_threshold_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
+                        void* stream) {
+    if (n <= 0 || hw <= 0 || c <= 0) return UOCR_OK;
+    UOCR_REQUIRE(x && mask && workspace, "NULL pointer");
+    UOCR_REQUIRE(c <= kThrMaxC, "threshold_mask supports at most 8 channels");
+    UOCR_REQUIRE(n <= 65535, "threshold_mask: at most 65535 images per call");
+    double* part = static_cast<double*>(workspace);
+    double* thr = part + n * kThrBlocks * c * 2;
+    threshold_partials_kernel<<<dim3(kThrBlocks, (unsigned)n), kThreads, 0, as_stream(stream)>>>(x, part, hw,
+                                                                                               (int)c);
+    UOCR_LAUNCHED("threshold_partials");
+    const int64_t groups = n * c;
+    threshold_finalize_kernel<<<(int)ceil_div(groups, 128), 128, 0, as_stream(stream)>>>(part, thr, groups,
+                                                                                       kThrBlocks, (int)c, hw);
+    UOCR_LAUNCHED("threshold_finalize");
+    const int64_t total = n * hw * c;
+    threshold_apply_kernel<<<ew_grid(total, 4), kThreads, 0, as_stream(stream)>>>(x, thr, mask, total, hw * c,
+                                                                                (int)c);
+    UOCR_LAUNCHED("threshold_apply");
     return UOCR_OK;
 }
 

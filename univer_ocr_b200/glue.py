@@ -1,0 +1,80 @@
+"""Device-side glue between the sub-networks.
+
+In the reference's PREDICT pipeline every prediction goes back to the host as float64 before the
+next stage looks at it (`my_model/model.py:695-714`: `move_from_gpu_*` components), although the
+stages only need (a) the page padded to a multiple of 16, (b) a binarised mask of each predicted
+map, (c) which characters won each window.  These three run on the device here, so what crosses
+the host link is uint8 masks / hit tables (1 byte per element instead of 8):
+
+    make_divisible_by   my_model/model.py:26-34
+    thresholded         interpreter/interpreter.py:437-438, 549   (arr > 0.5 * (mean + max))
+    row_max_hits / pred_to_text   interpreter/interpreter.py:595-614  (PredToText._func1)
+
+The labelling / rotation / zoom stages between them (`scipy.ndimage`) stay on the host (row f4).
+"""
+import ctypes
+
+import numpy as np
+
+from ._lib import lib
+from .nn.gpu import DeviceArray, as_device, stream
+
+
+def make_divisible_by(arr, y, x):
+    """Zero-pads H and W of an NHWC device tensor up to the next multiple of (y, x); a dimension
+    that is already aligned still grows by a full y / x, and the extra rows are split top = add // 2
+    like the reference's `np.pad(((0, 0), (add_y // 2, add_y - add_y // 2), ...))`."""
+    arr = as_device(arr)
+    n, h, w, c = arr.shape
+    add_y, add_x = y - h % y, x - w % x
+    top, left = add_y // 2, add_x // 2
+    out = DeviceArray.empty((n, h + add_y, w + add_x, c))
+    lib.uocr_pad_hw_f32(out.ptr, arr.ptr, n, h, w, c, top, add_y - top, left, add_x - left, 0.0, stream())
+    return out
+
+
+def thresholded(arr):
+    """uint8 mask of `arr > 0.5 * (mean + max)`, mean and max taken per (image, channel) over H x W
+    -- the reference thresholds one (1, H, W, 1) channel slice at a time."""
+    arr = as_device(arr)
+    n, c = arr.shape[0], arr.shape[-1]
+    hw = arr.size // (n * c)
+    mask = DeviceArray.empty(arr.shape, np.uint8)
+    nbytes = ctypes.c_size_t(0)
+    lib.uocr_threshold_mask_workspace(n, c, ctypes.byref(nbytes))
+    work = DeviceArray.empty((nbytes.value,), np.uint8)
+    lib.uocr_threshold_mask(arr.ptr, mask.ptr, n, hw, c, work.ptr, stream())
+    return mask
+
+
+def row_max_hits(pred):
+    """uint8 (rows, classes): 1 where the class ties the row maximum and that maximum is not 0."""
+    pred = as_device(pred)
+    rows, cols = pred.shape
+    hits = DeviceArray.empty((rows, cols), np.uint8)
+    lib.uocr_row_max_hits(pred.ptr, hits.ptr, rows, cols, stream())
+    return hits
+
+
+def hits_to_text(hits, chars, are_similar):
+    """The string part of PredToText._func1 (:602-614) on a host hit table: class ids in row
+    order (ties: every hit of the row, ascending), id 0 resets the repeat filter, a character
+    similar to the previous one is dropped."""
+    rows, cols = np.nonzero(np.asarray(hits))
+    result, prev = '', None
+    for char_id in cols[np.argsort(rows, kind='stable')]:
+        if char_id == 0:
+            prev = None
+            continue
+        cur = chars[char_id]
+        if are_similar(cur, prev):
+            continue
+        result += cur
+        prev = cur
+    return result
+
+
+def pred_to_text(pred, chars, are_similar):
+    """Char-network scores (rows, classes) on the device → text: hit table on the device, 1 byte
+    per score over the host link, string assembly on the host."""
+    return hits_to_text(row_max_hits(pred).get(), chars, are_similar)

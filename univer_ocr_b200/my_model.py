@@ -7,7 +7,6 @@ interchangeable (keys 'Monochrome/conv_1', 'Paragraph/up_2/conv_block/conv_1',
 Only the network definitions live here -- the reference's ModelSystem pipeline, the CPU
 crop/rotate glue and the Trainer are callers of this path, not part of it.
 """
-import json
 
 import numpy as np
 
@@ -163,29 +162,5 @@ MAKERS = {'monochrome': make_monochrome, 'paragraph': make_paragraph, 'line': ma
 
 
 # ---- model_weights.json (my_model/train.py:132-141, my_model/predict.py:12-23) -----------------
-
-def save_weights(models, path):
-    """Read-modify-write merge of the given models' weights into the JSON file, compact
-    separators, float64 repr text -- the reference's format."""
-    try:
-        with open(path, 'r') as fp:
-            weights = json.load(fp)
-    except OSError:
-        weights = {}
-    for model in make_list_if_not(models):
-        weights.update(model.get_weights())
-    with open(path, 'w') as fp:
-        json.dump(weights, fp, separators=(',', ':'))
-    return weights
-
-
-def load_weights(models, path):
-    try:
-        with open(path, 'r') as fp:
-            weights = json.load(fp)
-    except OSError:
-        print('No model_weights.json file found')
-        weights = {}
-    for model in make_list_if_not(models):
-        model.set_weights(weights)
-    return weights
+# JSON stays the source of truth; `weights_io` keeps a hash-checked binary sidecar next to it.
+from .weights_io import load_weights, save_weights  # noqa: E402,F401
