@@ -23,6 +23,7 @@
 // Register tiling: a thread computes 4 (stride-2 levels) or 8 (stride-1 / up levels) outputs of a row from 64-bit
 // shared loads, weights in registers.
 #include "conv_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace uocr {
 
@@ -140,10 +141,11 @@ __device__ __forceinline__ void hg_fold(const float* __restrict__ w25, float* __
     }
 }
 
-template <int TH, int TW>
-__global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const HourglassParams p) {
+template <int TH, int TW, bool TMA>
+__global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const HourglassParams p,
+                                                                       const __grid_constant__ CUtensorMap map_x) {
     using G = HG<TH, TW>;
-    extern __shared__ __align__(16) float hg_smem[];
+    extern __shared__ __align__(128) float hg_smem[];
     float* sX = hg_smem;
     float* sD1 = sX + G::XROWS * G::XP;
     float* sD2 = sD1 + G::D1H * G::D1P;
@@ -157,10 +159,18 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     float* yim = p.y + (int64_t)blockIdx.z * p.H * p.W;
     const int tid = threadIdx.x;
 
-    // ---- level 0: x block -> shared memory with 16-byte cp.async (zero fill outside the image through src-size 0;
-    // gx and W are multiples of 4, so a 16-byte word is entirely inside or outside).  Nothing is staged in registers
-    // and all of a thread's copies are in flight at once (the first version's LDG -> STS loop was the bottleneck).
-    {
+    // ---- level 0: x block -> shared memory.  TMA: ONE thread issues one 3-D box (XP x XH x 1 at (ox0 - 16, oy0 - 14,
+    // image)); out-of-image elements arrive as zeros (= the padding), completion on an mbarrier.  The cp.async variant
+    // (zero fill through src-size 0) spent 18 % of the kernel's instructions on addresses and bounds (ncu source view).
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sF + 2 * 36);          // 8-byte aligned: all segment sizes are even
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(smem_u32(bar), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_arrive_expect_tx(smem_u32(bar), (uint32_t)(G::XH * G::XP * sizeof(float)));
+            tma_load_3d(smem_u32(sX), &map_x, smem_u32(bar), ox0 - 16, oy0 - 14, (int)blockIdx.z);
+        }
+    } else {
         constexpr int QUADS = G::XP / 4;
         const uint32_t sbase = static_cast<uint32_t>(__cvta_generic_to_shared(sX));
         // (r, q) advance by HG_THREADS quads per iteration without a division
@@ -177,14 +187,16 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    for (int i = tid; i < 5 * 26; i += HG_THREADS) {
-        const int l = i / 26, k = i - l * 26;
-        sW[i] = k < 25 ? __ldg(p.w[l] + k) : __ldg(p.b[l]);
+    // weights: static level index (a runtime index into p.w[] forces the whole parameter block into local memory)
+    if (tid < 26) {
+#pragma unroll
+        for (int l = 0; l < 5; ++l) sW[l * 26 + tid] = tid < 25 ? __ldg(p.w[l] + tid) : __ldg(p.b[l]);
     }
     // the two spare rows the last strip of D1 reads must be finite
     for (int i = tid; i < 2 * G::XP; i += HG_THREADS) sX[G::XH * G::XP + i] = 0.f;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    if (TMA) mbar_wait(smem_u32(bar), 0);
     hg_fold(sW + 2 * 26, sF);
     hg_fold(sW + 3 * 26, sF + 36);
     const int hy0 = oy0 / 2, hx0 = ox0 / 2, qy0 = oy0 / 4, qx0 = ox0 / 4;
@@ -242,28 +254,45 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     }
 }
 
+template <bool TMA>
+static int hourglass1_launch(const HourglassParams& p, const CUtensorMap& map, int64_t n, int64_t h, int64_t wd,
+                             cudaStream_t st) {
+    constexpr int TH = 32, TW = 128;
+    const size_t smem = sizeof(float) * HG<TH, TW>::FLOATS;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(hourglass1_fwd_kernel<TH, TW, TMA>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(wd, TW), (unsigned)ceil_div(h, TH), (unsigned)n);
+    if (grid.y > 65535) return UOCR_ERR_UNSUPPORTED;
+    hourglass1_fwd_kernel<TH, TW, TMA><<<grid, HG_THREADS, smem, st>>>(p, map);
+    UOCR_LAUNCHED("hourglass1_fwd");
+    return UOCR_OK;
+}
+
 int hourglass1_fwd(const float* x, const float* const* w, const float* const* b, float* y, int64_t n, int64_t h,
                    int64_t wd, float alpha, int act_end, float alpha_end, cudaStream_t st) {
-    constexpr int TH = 32, TW = 128;
     if (h % 4 || wd % 4 || n > 65535 || alpha < 0.f || alpha > 1.f) return UOCR_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
     HourglassParams p{};
     p.x = x; p.y = y;
     for (int l = 0; l < 5; ++l) { p.w[l] = w[l]; p.b[l] = b[l]; }
     p.H = (int)h; p.W = (int)wd; p.alpha = alpha; p.act_end = act_end; p.alpha_end = alpha_end;
-    const size_t smem = sizeof(float) * HG<TH, TW>::FLOATS;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(hourglass1_fwd_kernel<TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
-        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
-        configured = true;
+    // UOCR_HOURGLASS_TMA=0: cp.async tile fill (the first version; kept for A/B runs)
+    const char* e = getenv("UOCR_HOURGLASS_TMA");
+    CUtensorMap map{};
+    if (!(e && e[0] == '0')) {
+        using G = HG<32, 128>;
+        const uint64_t dims[3] = {(uint64_t)wd, (uint64_t)h, (uint64_t)n};
+        const uint64_t strides[2] = {(uint64_t)wd * 4, (uint64_t)wd * h * 4};
+        const uint32_t box[3] = {(uint32_t)G::XP, (uint32_t)G::XH, 1};
+        if (make_tmap_plain_f32(&map, x, 3, dims, strides, box) == UOCR_OK)
+            return hourglass1_launch<true>(p, map, n, h, wd, st);
     }
-    dim3 grid((unsigned)ceil_div(wd, TW), (unsigned)ceil_div(h, TH), (unsigned)n);
-    if (grid.y > 65535) return UOCR_ERR_UNSUPPORTED;
-    hourglass1_fwd_kernel<TH, TW><<<grid, HG_THREADS, smem, st>>>(p);
-    UOCR_LAUNCHED("hourglass1_fwd");
-    return UOCR_OK;
+    return hourglass1_launch<false>(p, map, n, h, wd, st);
 }
 
 }  // namespace uocr
