@@ -52,6 +52,21 @@ def test_fc_tf32(nn, batch, n_in, n_out):
     close_tf32(fc.w.grad, odW, 'dW')
 
 
+@pytest.mark.parametrize('mode', ['0', '1'])
+def test_fc_tf32_cta_pair_kernel(nn, mode, monkeypatch):
+    """The persistent GEMM as one CTA per SM (UOCR_TC_PAIR=0) and as CTA pairs sharing 256 x 256 tiles through
+    tcgen05 cta_group::2 (=1): same results on a shape with ragged M (tail tile of the second CTA of a pair empty)."""
+    monkeypatch.setenv('UOCR_TC_PAIR', mode)
+    rng = np.random.default_rng(17)
+    batch, n_in, n_out = 16384 + 130, 512, 1024
+    X = f32(rng.standard_normal((batch, n_in)))
+    W = f32(rng.standard_normal((n_in + 1, n_out)) / np.sqrt(n_in))
+    dy = f32(rng.standard_normal((batch, n_out)))
+    fc = nn.layers.FullyConnected(n_in, n_out, w=W)
+    close_tf32(fc.forward(X)[0], O.fc_fwd(X, W), f'y pair={mode}')
+    close_tf32(fc.backward(dy)[0], O.fc_bwd(X, W, dy)[0], f'dX pair={mode}')
+
+
 def test_fc_tf32_rounding_is_unbiased(nn):
     """All-positive operands: truncation to TF32 would bias every product by ~ -2^-10 and the
     sums by ~ -1e-3 relative; round-to-nearest leaves |mean relative error| below 1e-4."""

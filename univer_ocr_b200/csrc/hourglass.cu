@@ -50,25 +50,29 @@ struct HG {
 constexpr int HG_THREADS = 256;
 
 // dst (DH x DW, origin (gy0, gx0) at its resolution, image hl x wl) = act(conv5x5 stride 2 (src) + b); src(2r+ky, 2c+kx).
-// Thread = one output column x 4 rows: neighbouring lanes read neighbouring 8-byte words (no bank conflicts).
-template <int DH, int DW, int DP, int SP>
+// Thread = one output column x R rows: neighbouring lanes read neighbouring 8-byte words (no bank conflicts).  R = 4
+// for the large level; the small one (12 x 36) uses R = 2 so that seven warps share its 222 strips instead of four
+// warps carrying 111 (the level is latency-, not throughput-bound: ncu showed the other warps parked at the barrier).
+template <int DH, int DW, int DP, int SP, int R>
 __device__ __forceinline__ void hg_down(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ wb,
                                         int gy0, int gx0, int hl, int wl, float alpha) {
     float w[25];
 #pragma unroll
     for (int i = 0; i < 25; ++i) w[i] = wb[i];
     const float bias = wb[25];
-    constexpr int STRIPS = (DH + 3) / 4;
+    constexpr int STRIPS = (DH + R - 1) / R;
     for (int item = threadIdx.x; item < STRIPS * DW; item += HG_THREADS) {
-        const int s = item / DW, c = item - s * DW, r0 = 4 * s;
-        float acc[4] = {bias, bias, bias, bias};
+        const int s = item / DW, c = item - s * DW, r0 = R * s;
+        float acc[R];
 #pragma unroll
-        for (int rr = 0; rr < 11; ++rr) {
+        for (int j = 0; j < R; ++j) acc[j] = bias;
+#pragma unroll
+        for (int rr = 0; rr < 2 * R + 3; ++rr) {
             const float2* row = reinterpret_cast<const float2*>(src + (2 * r0 + rr) * SP + 2 * c);
             const float2 a = row[0], b = row[1], e = row[2];
             const float in[5] = {a.x, a.y, b.x, b.y, e.x};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < R; ++j) {
                 const int ky = rr - 2 * j;
                 if (ky >= 0 && ky < 5) {
 #pragma unroll
@@ -78,7 +82,7 @@ __device__ __forceinline__ void hg_down(const float* __restrict__ src, float* __
         }
         const bool colin = (unsigned)(gx0 + c) < (unsigned)wl;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < R; ++j) {
             const float v = fmaxf(acc[j], acc[j] * alpha);
             if (r0 + j < DH) dst[(r0 + j) * DP + c] = (colin && (unsigned)(gy0 + r0 + j) < (unsigned)hl) ? v : 0.f;
         }
@@ -200,9 +204,9 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     hg_fold(sW + 2 * 26, sF);
     hg_fold(sW + 3 * 26, sF + 36);
     const int hy0 = oy0 / 2, hx0 = ox0 / 2, qy0 = oy0 / 4, qx0 = ox0 / 4;
-    hg_down<G::D1H, G::D1W, G::D1P, G::XP>(sX + 2, sD1, sW, hy0 - 6, hx0 - 6, p.H / 2, p.W / 2, p.alpha);
+    hg_down<G::D1H, G::D1W, G::D1P, G::XP, 4>(sX + 2, sD1, sW, hy0 - 6, hx0 - 6, p.H / 2, p.W / 2, p.alpha);
     __syncthreads();
-    hg_down<G::D2H, G::D2W, G::D2P, G::D1P>(sD1, sD2, sW + 26, qy0 - 2, qx0 - 2, p.H / 4, p.W / 4, p.alpha);
+    hg_down<G::D2H, G::D2W, G::D2P, G::D1P, (G::D2H % 2 == 0) ? 2 : 4>(sD1, sD2, sW + 26, qy0 - 2, qx0 - 2, p.H / 4, p.W / 4, p.alpha);
     __syncthreads();
     hg_up<G::U2H, G::U2W, G::U2P, G::D2P>(sD2, sU2, sF, sW[2 * 26 + 25], hy0 - 2, hx0 - 2, p.H / 2, p.W / 2, p.alpha);
     __syncthreads();

@@ -446,13 +446,22 @@ int tc_gemm_tn(const float* A, int64_t lda, const float* Bt, int64_t ldb, float*
 
 constexpr int TCP_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
+// PAIR: two CTAs of a cluster (one TPC) share every tile: UMMA M = 256 with cta_group::2.  CTA r stages rows
+// [128 r, 128 r + 128) of A and rows [nt/2 r, ..) of the B tile (32 KB per stage instead of 48 KB), the leader issues
+// the MMAs for both tensor cores, every CTA drains its own 128 accumulator rows.  Shared-memory traffic per MMA drops
+// from 12 KB read + 12 KB written to 8 + 8 KB per SM, which is what capped the single-CTA kernel.
+// `m_tiles` counts tiles of 128 (256 for PAIR) rows.
+template <bool PAIR>
 __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                            const __grid_constant__ CUtensorMap map_b,
                                                                            const TcParams p, int m_tiles, int n_tiles) {
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const int cta = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int ncta = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t a_bytes = TC_BM * TC_BK * 4;
-    const uint32_t b_bytes = (uint32_t)p.nt * TC_BK * 4;
+    const uint32_t b_bytes = (uint32_t)(PAIR ? p.nt / 2 : p.nt) * TC_BK * 4;
     const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
     uint64_t* full = bars;
@@ -480,17 +489,24 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(smem_u32(&tmem_full[b]), 1);
-            mbar_init(smem_u32(&tmem_empty[b]), 8);
+            mbar_init(smem_u32(&tmem_empty[b]), PAIR ? 16 : 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -498,40 +514,46 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;                                    // running K-block counter across tiles
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int m0 = (tile % m_tiles) * TC_BM, n0 = (tile / m_tiles) * p.nt;
+            for (int tile = cta; tile < total_tiles; tile += ncta) {
+                const int mt = (tile % m_tiles) * (PAIR ? 2 : 1) + (int)rank;        // this CTA's 128-row tile
+                const int m0 = mt * TC_BM, n0 = (tile / m_tiles) * p.nt + (PAIR ? (int)rank * (p.nt / 2) : 0);
                 // Every CTA walks the K blocks from a different starting block (the sum does not care about
                 // the order): the ~148 CTAs that share one B tile then read different lines of it at any
                 // moment instead of hammering the same L2 slices.
-                const int rot = (int)(blockIdx.x % (unsigned)p.num_kb);
+                const int rot = cta % p.num_kb;
                 for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
                     const int s = it % p.stages;
                     const uint32_t phase = (it / p.stages) & 1;
                     mbar_wait(smem_u32(&empty[s]), phase ^ 1);
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                    const uint32_t bar = smem_u32(&full[s]);
-                    mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
+                    // PAIR: both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
+                    const uint32_t bar = PAIR ? mapa_rank(smem_u32(&full[s]), 0) : smem_u32(&full[s]);
+                    if (!PAIR) mbar_arrive_expect_tx(bar, a_bytes + b_bytes);
+                    else if (rank == 0) mbar_arrive_expect_tx(smem_u32(&full[s]), 2 * (a_bytes + b_bytes));
                     const int kbr = kb + rot >= p.num_kb ? kb + rot - p.num_kb : kb + rot;
                     const int kk = kbr * TC_BK;
                     if (p.win_w) {                         // 128 consecutive window positions of one image: a 3-D box
-                        const int mt = tile % m_tiles;
                         const int k = kbr / p.win_cblocks, cb = kbr - k * p.win_cblocks;
-                        tma_load_3d(sa, &map_a, bar, cb * TC_BK, (mt % p.win_tiles_per_img) * TC_BM + k - p.win_half,
-                                    mt / p.win_tiles_per_img);
+                        const int wx = (mt % p.win_tiles_per_img) * TC_BM + k - p.win_half, wn = mt / p.win_tiles_per_img;
+                        if (PAIR) tma_load_3d_pair(sa, &map_a, bar, cb * TC_BK, wx, wn);
+                        else tma_load_3d(sa, &map_a, bar, cb * TC_BK, wx, wn);
+                    } else if (PAIR) {
+                        tma_load_2d_pair(sa, &map_a, bar, kk, m0);
                     } else {
                         tma_load_2d(sa, &map_a, bar, kk, m0);
                     }
-                    tma_load_2d(sa + a_bytes, &map_b, bar, kk, n0);
+                    if (PAIR) tma_load_2d_pair(sa + a_bytes, &map_b, bar, kk, n0);
+                    else tma_load_2d(sa + a_bytes, &map_b, bar, kk, n0);
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt >> 3) << 17) |
-                                   ((uint32_t)(TC_BM >> 4) << 24);
+                                   ((uint32_t)((PAIR ? 2 * TC_BM : TC_BM) >> 4) << 24);
             int it = 0, local = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            for (int tile = cta; tile < total_tiles; tile += ncta, ++local) {
                 const int buf = local & 1;
                 mbar_wait(smem_u32(&tmem_empty[buf]), ((local >> 1) & 1) ^ 1);   // epilogue drained this buffer
                 tc_fence_after();
@@ -545,12 +567,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                     const uint64_t da = make_kmajor_sw128_desc(sa);
                     const uint64_t db = make_kmajor_sw128_desc(sa + a_bytes);
 #pragma unroll
-                    for (int k = 0; k < TC_BK / 8; ++k)
-                        tc_mma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
-                                    (kb > 0 || k > 0) ? 1u : 0u);
-                    tc_commit(smem_u32(&empty[s]));
+                    for (int k = 0; k < TC_BK / 8; ++k) {
+                        if (PAIR) tc_mma_tf32_pair(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                                   (kb > 0 || k > 0) ? 1u : 0u);
+                        else tc_mma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
+                                         (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    if (PAIR) tc_commit_pair(smem_u32(&empty[s]));      // frees the stage in both CTAs
+                    else tc_commit(smem_u32(&empty[s]));
                 }
-                tc_commit(smem_u32(&tmem_full[buf]));
+                if (PAIR) tc_commit_pair(smem_u32(&tmem_full[buf]));
+                else tc_commit(smem_u32(&tmem_full[buf]));
             }
         }
     } else {
@@ -567,9 +594,14 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         const int sub_r = lane >> 2, sub_g = lane & 3;       // store phase: row within a group of 8, granule
         const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
         int local = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        // the accumulator buffer is released to the MMA issuer, which lives in the leader CTA
+        auto release = [&](int buf) {
+            if (PAIR) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[buf]), 0));
+            else mbar_arrive(smem_u32(&tmem_empty[buf]));
+        };
+        for (int tile = cta; tile < total_tiles; tile += ncta, ++local) {
             const int buf = local & 1;
-            const int64_t row0 = (int64_t)(tile % m_tiles) * TC_BM + q * 32;   // first row of this warp
+            const int64_t row0 = ((int64_t)(tile % m_tiles) * (PAIR ? 2 : 1) + rank) * TC_BM + q * 32;   // first row of this warp
             const int n0 = (tile / m_tiles) * p.nt;
             mbar_wait(smem_u32(&tmem_full[buf]), (local >> 1) & 1);
             tc_fence_after();
@@ -581,7 +613,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                     tc_ld16_nowait(tq + (uint32_t)((hc + 2) * 16), nxt);
                 } else {                                     // this warp has read all its columns of the buffer
                     tc_fence_before();
-                    if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf]));
+                    if (lane == 0) release(buf);
                 }
                 const int c = n0 + hc * 16;
                 const int ncols = (int)min((int64_t)16, p.N - c);
@@ -620,7 +652,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                 }
             };
             if (half < nhc) tc_ld16_nowait(tq + (uint32_t)(half * 16), va);
-            else { tc_fence_before(); if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[buf])); }
+            else { tc_fence_before(); if (lane == 0) release(buf); }
             for (int hc = half; hc < nhc; hc += 4) {
                 handle(va, vb, hc);
                 if (hc + 2 < nhc) handle(vb, va, hc + 2);
@@ -629,10 +661,12 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();           // the leader's MMAs read the peer's shared memory until the last commit
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
 }
 
@@ -659,7 +693,15 @@ static int tc_gemm_tn_persistent_impl(const float* A, int64_t lda, const WindowG
     }
     p.nt = N >= 256 ? 256 : (int)(((N + 15) / 16) * 16);
     p.bias = bias; p.act = act; p.alpha = alpha; p.accumulate = accumulate;
-    const size_t a_bytes = TC_BM * TC_BK * 4, b_bytes = (((size_t)p.nt * TC_BK * 4) + 1023) & ~(size_t)1023;
+    // CTA pairs (cta_group::2) need full 256-column tiles.  Measured (tools/gemmbench.py): no gain where the fixed
+    // costs dominate (dense_1 forward, 16 K blocks x 3.5 tiles per CTA: 47 us either way), +5 % with K = 1024
+    // (its dgrad), +10 % at 14 tiles per CTA (504 -> 556 TFLOP/s).  UOCR_TC_PAIR = 0 / 1 forces never / always.
+    const char* pe = getenv("UOCR_TC_PAIR");
+    const int pair_mode = pe ? atoi(pe) : -1;
+    const bool pair_fits = p.nt == 256 && M >= 4096;
+    const bool pair = pair_fits && (pair_mode > 0 || (pair_mode < 0 && (K >= 1024 || M * N >= ((int64_t)1 << 25))));
+    const size_t a_bytes = TC_BM * TC_BK * 4;
+    const size_t b_bytes = (((size_t)(pair ? p.nt / 2 : p.nt) * TC_BK * 4) + 1023) & ~(size_t)1023;
     p.stages = (int)((196 * 1024) / (a_bytes + b_bytes));
     if (p.stages > 8) p.stages = 8;
     if (p.stages < 2) return UOCR_ERR_UNSUPPORTED;
@@ -680,22 +722,49 @@ static int tc_gemm_tn_persistent_impl(const float* A, int64_t lda, const WindowG
     }
     if (rc) return rc;
     const uint64_t db[2] = {(uint64_t)K, (uint64_t)N}, sb[1] = {(uint64_t)ldb * 4};
-    const uint32_t bb[2] = {TC_BK, (uint32_t)p.nt};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)(pair ? p.nt / 2 : p.nt)};
     rc = make_tmap(&mb, Bt, 2, db, sb, bb);
     if (rc) return rc;
-    static int num_sms = 0;
+    static int num_sms = 0, num_pairs = 0;
     if (!num_sms) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_gemm_persistent_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024);
         if (e != cudaSuccess) { num_sms = 0; set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
     }
-    const int m_tiles = (int)ceil_div(M, TC_BM), n_tiles = (int)ceil_div(N, p.nt);
+    const int n_tiles = (int)ceil_div(N, p.nt);
+    if (pair) {
+        const int m_tiles = (int)ceil_div(M, 2 * TC_BM);
+        const int64_t tiles = (int64_t)m_tiles * n_tiles;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(TCP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+        if (!num_pairs) {
+            cfg.gridDim = dim3((unsigned)num_sms & ~1u);
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, tc_gemm_persistent_kernel<true>, &cfg) != cudaSuccess || n <= 0) {
+                cudaGetLastError();
+                n = num_sms / 2;
+            }
+            num_pairs = n < num_sms / 2 ? n : num_sms / 2;
+        }
+        cfg.gridDim = dim3(2u * (unsigned)(tiles < num_pairs ? tiles : num_pairs));
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_persistent_kernel<true>, ma, mb, p, m_tiles, n_tiles);
+        if (e != cudaSuccess) { set_error("cluster launch: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        UOCR_LAUNCHED("tc_gemm_persistent_pair_tf32");
+        return UOCR_OK;
+    }
+    const int m_tiles = (int)ceil_div(M, TC_BM);
     const int64_t tiles = (int64_t)m_tiles * n_tiles;
     const unsigned grid = (unsigned)(tiles < num_sms ? tiles : num_sms);
-    tc_gemm_persistent_kernel<<<grid, TCP_THREADS, smem, st>>>(ma, mb, p, m_tiles, n_tiles);
+    tc_gemm_persistent_kernel<false><<<grid, TCP_THREADS, smem, st>>>(ma, mb, p, m_tiles, n_tiles);
     UOCR_LAUNCHED("tc_gemm_persistent_tf32");
     return UOCR_OK;
 }
