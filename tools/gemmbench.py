@@ -13,7 +13,10 @@ def ev():
     e = ctypes.c_void_p(); lib.uocr_event_create(ctypes.byref(e)); return e.value
 
 
-for (M, K, N) in [(16384, 512, 1024), (16384, 1024, 512), (65536, 1024, 1024), (16384, 1024, 128)]:
+SHAPES = [(16384, 512, 1024), (16384, 1024, 512), (65536, 1024, 1024), (16384, 1024, 128)]
+if len(sys.argv) > 1:
+    SHAPES = [tuple(int(v) for v in sys.argv[1].split('x'))]
+for (M, K, N) in SHAPES:
     X = nn.CP.copy(rng.standard_normal((M, K)).astype(np.float32))
     W = nn.CP.copy((rng.standard_normal((K + 1, N)) / np.sqrt(K)).astype(np.float32))
     wt = nn.DeviceArray((N, K)); lib.uocr_weights_to_kmajor(W.ptr, wt.ptr, K, N, nn.CP.stream())

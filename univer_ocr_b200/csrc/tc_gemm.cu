@@ -515,8 +515,11 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         if (lane == 0) {
             int it = 0;                                    // running K-block counter across tiles
             for (int tile = cta; tile < total_tiles; tile += ncta) {
-                const int mt = (tile % m_tiles) * (PAIR ? 2 : 1) + (int)rank;        // this CTA's 128-row tile
-                const int m0 = mt * TC_BM, n0 = (tile / m_tiles) * p.nt + (PAIR ? (int)rank * (p.nt / 2) : 0);
+                // N index fastest: the CTAs that run at the same time share a few row blocks of A, which then
+                // comes from DRAM once (B, the weights, is L2-resident anyway).  With the M index fastest a 268 MB
+                // A was streamed from DRAM once per N tile (ncu: 1.09 GB read, L2 hit rate 44 %, DRAM 73 % busy).
+                const int mt = (tile / n_tiles) * (PAIR ? 2 : 1) + (int)rank;        // this CTA's 128-row tile
+                const int m0 = mt * TC_BM, n0 = (tile % n_tiles) * p.nt + (PAIR ? (int)rank * (p.nt / 2) : 0);
                 // Every CTA walks the K blocks from a different starting block (the sum does not care about
                 // the order): the ~148 CTAs that share one B tile then read different lines of it at any
                 // moment instead of hammering the same L2 slices.
@@ -601,8 +604,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         };
         for (int tile = cta; tile < total_tiles; tile += ncta, ++local) {
             const int buf = local & 1;
-            const int64_t row0 = ((int64_t)(tile % m_tiles) * (PAIR ? 2 : 1) + rank) * TC_BM + q * 32;   // first row of this warp
-            const int n0 = (tile / m_tiles) * p.nt;
+            const int64_t row0 = ((int64_t)(tile / n_tiles) * (PAIR ? 2 : 1) + rank) * TC_BM + q * 32;   // first row of this warp
+            const int n0 = (tile % n_tiles) * p.nt;
             mbar_wait(smem_u32(&tmem_full[buf]), (local >> 1) & 1);
             tc_fence_after();
             const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.nt);
