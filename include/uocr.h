@@ -88,7 +88,11 @@ int uocr_event_sync(void* event);                   /* blocks the host   */
 int uocr_event_elapsed_ms(void* start, void* stop, float* ms);
 int uocr_stream_wait_event(void* stream, void* event);
 
-/* CUDA-graph capture of a launch sequence (one inference or train step) */
+/* CUDA-graph capture of a launch sequence (one inference step): everything issued on `stream` (and on streams
+ * forked from it through events) between _begin and _end becomes one replayable graph.  Blocks freed with
+ * uocr_free while capturing stay reserved for the graph (its kernels carry their addresses) until
+ * uocr_graph_destroy; uocr_launch_count advances by the captured kernel count on every uocr_graph_launch.
+ * The sequence must not synchronise, read back, or depend on host data that changes between replays. */
 int uocr_graph_begin(void* stream);
 int uocr_graph_end(void* stream, void** graph_exec);
 int uocr_graph_launch(void* graph_exec, void* stream);

@@ -656,3 +656,51 @@ def test_concurrent_branches_match_serial(nn):
                        lambda: models['line'].predict(line)[0], lambda: models['char'].predict(char)[0])
         for g, w_ in zip(got, want):
             assert np.array_equal(host(g), w_)
+
+
+def test_captured_step_replays_match_eager_and_follow_inputs_and_weights(nn):
+    """pipeline.CapturedStep: the forked three-stream forward captured into one CUDA graph.  Replays must (a) equal
+    the eager result bit for bit, (b) see new data copied into the SAME input buffers, (c) keep working while other
+    allocations churn the pool (the graph's blocks are held by the allocator), (d) re-capture after a parameter
+    change, and (e) account for the kernels they run in uocr_launch_count."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200._lib import launch_count
+    from univer_ocr_b200.pipeline import CapturedStep, ConcurrentBranches
+    rng = np.random.default_rng(32)
+    shapes = {'monochrome': (2, 64, 96, 1), 'paragraph': (2, 64, 96, 1), 'line': (3, 32, 64, 1), 'char': (2, 32, 40, 1)}
+    models = {k: my_model.MAKERS[k](v) for k, v in shapes.items()}
+    for k, m in models.items():                               # signed weights: the default init saturates the sigmoids
+        m.set_weights({key: {n: ((v - v.mean()) if n == 'w' else v * 0).tolist() for n, v in p.items()}
+                       for key, p in np_models.golden_weights(k, 5).items()})
+    host_in = {k: f32(rng.uniform(size=shapes[k])) for k in ('monochrome', 'line', 'char')}
+    page, line, char = (nn.CP.copy(host_in[k]) for k in ('monochrome', 'line', 'char'))
+    fork = ConcurrentBranches(3)
+
+    def forward():
+        return fork.run(lambda: models['paragraph'].predict(models['monochrome'].predict(page)[0])[0],
+                        lambda: models['line'].predict(line)[0], lambda: models['char'].predict(char)[0])
+
+    want = [host(o) for o in forward()]
+    step = CapturedStep(forward)
+    n0 = launch_count()
+    got = step()
+    per_replay = launch_count() - n0
+    assert all(np.array_equal(host(g), w_) for g, w_ in zip(got, want))
+    n1 = launch_count()
+    step()
+    assert launch_count() - n1 >= 10 and launch_count() - n1 <= per_replay     # a replay = the captured kernels
+    # (b) + (c): new data in place, allocator churn in between
+    page.set(f32(rng.uniform(size=shapes['monochrome'])))
+    line.set(f32(rng.uniform(size=shapes['line'])))
+    junk = [nn.CP.copy(f32(rng.uniform(size=(64, 64, 7)))) for _ in range(20)]
+    del junk
+    want2 = [host(o) for o in forward()]
+    got2 = step()
+    assert all(np.array_equal(host(g), w_) for g, w_ in zip(got2, want2))
+    assert not np.array_equal(want2[1], want[1]) and not np.array_equal(want2[0], want[0])
+    # (d) parameter change -> re-capture with the new weights
+    conv = models['line'].layers['Line/end/conv_1']
+    conv.b.value = host(conv.b.value) + 0.5
+    want3 = host(forward()[1])
+    assert np.array_equal(host(step()[1]), want3) and not np.array_equal(want3, want2[1])
+    step.close()

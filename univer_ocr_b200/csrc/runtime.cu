@@ -6,6 +6,7 @@
 
 #include <map>
 #include <mutex>
+#include <vector>
 #include <unordered_map>
 
 #include "common.cuh"
@@ -38,6 +39,12 @@ static std::mutex g_pool_mutex;
 static std::map<PoolKey, std::multimap<size_t, void*>> g_free;      // parked blocks by size
 static std::unordered_map<void*, std::pair<size_t, int>> g_live;    // ptr -> (rounded size, device)
 static size_t g_reserved = 0;
+// While a launch sequence is being captured into a CUDA graph, blocks that are freed must not be handed out again:
+// the graph's kernels carry their addresses and will use them on every replay.  They are parked in g_held and
+// belong to the captured graph until it is destroyed.
+struct HeldBlock { void* ptr; size_t size; int dev; cudaStream_t st; };
+static bool g_hold = false;
+static std::vector<HeldBlock> g_held;
 
 static size_t round_size(size_t bytes) {
     if (bytes < 512) return 512;
@@ -89,10 +96,18 @@ int pool_free(void* ptr, cudaStream_t st) {
         set_error("uocr_free: pointer %p was not allocated by uocr_malloc", ptr);
         return UOCR_ERR_INVALID;
     }
-    g_free[PoolKey{it->second.second, st}].emplace(it->second.first, ptr);
+    if (g_hold) g_held.push_back(HeldBlock{ptr, it->second.first, it->second.second, st});
+    else g_free[PoolKey{it->second.second, st}].emplace(it->second.first, ptr);
     g_live.erase(it);
     return UOCR_OK;
 }
+
+struct CapturedGraph {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<HeldBlock> held;
+    uint64_t launches = 0;
+};
+static uint64_t g_capture_launch0 = 0;
 
 int pool_trim() {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
@@ -283,34 +298,71 @@ int uocr_stream_wait_event(void* stream, void* event) {
 
 int uocr_graph_begin(void* stream) {
     UOCR_REQUIRE(stream, "graph capture needs a non-default stream");
-    UOCR_CUDA(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeThreadLocal));
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        UOCR_REQUIRE(!g_hold, "a graph capture is already in progress");
+        g_hold = true;
+        g_held.clear();
+    }
+    g_capture_launch0 = g_launches.load(std::memory_order_relaxed);
+    // relaxed: a pool miss during capture may call cudaMalloc (no work is enqueued by it)
+    cudaError_t e = cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed);
+    if (e != cudaSuccess) {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        g_hold = false;
+        set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+        return UOCR_ERR_CUDA;
+    }
     return UOCR_OK;
+}
+
+static void release_held(std::vector<HeldBlock>& held) {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (const HeldBlock& b : held) g_free[PoolKey{b.dev, b.st}].emplace(b.size, b.ptr);
+    held.clear();
 }
 
 int uocr_graph_end(void* stream, void** graph_exec) {
     UOCR_REQUIRE(stream && graph_exec, "NULL argument");
     cudaGraph_t graph = nullptr;
-    UOCR_CUDA(cudaStreamEndCapture(as_stream(stream), &graph));
-    cudaGraphExec_t exec = nullptr;
-    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
+    cudaError_t e = cudaStreamEndCapture(as_stream(stream), &graph);
+    CapturedGraph* cg = new CapturedGraph();
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        cg->held.swap(g_held);
+        g_hold = false;
+    }
+    cg->launches = g_launches.load(std::memory_order_relaxed) - g_capture_launch0;
+    if (e == cudaSuccess) {
+        e = cudaGraphInstantiate(&cg->exec, graph, 0);
+        cudaGraphDestroy(graph);
+    }
     if (e != cudaSuccess) {
-        set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        set_error("graph capture / instantiate: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        release_held(cg->held);
+        delete cg;
         return UOCR_ERR_CUDA;
     }
-    *graph_exec = exec;
+    *graph_exec = cg;
     return UOCR_OK;
 }
 
 int uocr_graph_launch(void* graph_exec, void* stream) {
     UOCR_REQUIRE(graph_exec, "graph_exec is NULL");
-    UOCR_CUDA(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)));
+    CapturedGraph* cg = static_cast<CapturedGraph*>(graph_exec);
+    UOCR_CUDA(cudaGraphLaunch(cg->exec, as_stream(stream)));
+    g_launches.fetch_add(cg->launches, std::memory_order_relaxed);     // the kernels the replay runs
     return UOCR_OK;
 }
 
 int uocr_graph_destroy(void* graph_exec) {
     if (!graph_exec) return UOCR_OK;
-    UOCR_CUDA(cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(graph_exec)));
+    CapturedGraph* cg = static_cast<CapturedGraph*>(graph_exec);
+    cudaError_t e = cudaGraphExecDestroy(cg->exec);
+    release_held(cg->held);                 // the caller has synchronised: nothing replays any more
+    delete cg;
+    if (e != cudaSuccess) { set_error("cudaGraphExecDestroy: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
     return UOCR_OK;
 }
 

@@ -49,6 +49,7 @@ class Losses:
         self.train_losses = None
         self.val_losses = None
         self.best_loss_epoch = {name: 0 for name in self.model_names}
+        self._pending = []
 
     def _new_losses(self, value):
         return {name: [value] * self.outputs_cnts[name] for name in self.model_names}
@@ -56,6 +57,7 @@ class Losses:
     def reset(self):
         self.train_losses = self._new_losses(0)
         self.val_losses = self._new_losses(0)
+        self._pending = []
 
     def next(self):
         self.train_prev_losses = self.train_losses
@@ -67,7 +69,10 @@ class Losses:
                 continue
             out_losses = update[name]['output_losses']
             for i in range(self.outputs_cnts[name]):
-                target[name][i] = target[name][i] + out_losses[i] * weight
+                if isinstance(out_losses[i], (int, float)):
+                    target[name][i] = target[name][i] + out_losses[i] * weight
+                else:                                    # device-resident value: no read-back (= sync) per step
+                    self._pending.append((target, name, i, out_losses[i], weight))
 
     def train(self, update, weight=1):
         self._add(self.train_losses, update, weight)
@@ -76,7 +81,11 @@ class Losses:
         self._add(self.val_losses, update, weight)
 
     def materialize(self, reduce_fn=None):
-        """Reads the device-resident sums back (once) and, with `reduce_fn`, sums them over ranks."""
+        """Adds the device-resident values of the epoch (read back here, in step order) and, with `reduce_fn`,
+        sums the tables over ranks."""
+        for target, name, i, loss, weight in self._pending:
+            target[name][i] = target[name][i] + float(loss) * weight
+        self._pending = []
         flat = [float(v) for table in (self.train_losses, self.val_losses)
                 for name in self.model_names for v in table[name]]
         if reduce_fn is not None:
@@ -191,7 +200,10 @@ class Trainer:
 
     `models`: {name: model}.  Data sets: `len(ds)` samples, `ds.get(i)` → {name: (X, y)} where X / y
     are arrays (or lists of arrays for multi-input / multi-output models) with a leading batch
-    axis; a model missing from the dict sits that sample out.  `save_weights_func(names)` is called
+    axis; a model missing from the dict sits that sample out.  Stacking 64 page tiles on the host
+    costs ~20 ms, twenty times the GPU's training step, so a data set may instead offer
+    `ds.get_batch(indices)` → {name: (X, y)} already stacked -- host or device arrays
+    (`tools/train_synthetic.py` keeps its samples in HBM and gathers with device copies).  `save_weights_func(names)` is called
     on rank 0 with the models whose validation loss improved (`my_model/train.py:132-141`)."""
 
     MAX_RELOAD_ATTEMPTS = 10                            # trainer.py:262
@@ -248,9 +260,15 @@ class Trainer:
     def _batches(self, dataset, order):
         """Yields ({name: (X, y, n_samples)}, samples consumed so far): `batch_size` samples per
         step, this rank's share [rank::world] of each."""
+        batched = getattr(dataset, 'get_batch', None)
         for start in range(0, len(order), self.batch_size):
             chunk = order[start:start + self.batch_size]
             mine = chunk[self.rank::self.world]
+            if batched is not None:
+                # the data set stacks (and may keep its samples on the device): {name: (X, y)} for these indices
+                got = batched(mine)
+                yield {name: (X, y, len(mine)) for name, (X, y) in got.items() if name in self.models}, start + len(chunk)
+                continue
             samples = [dataset.get(i) for i in mine]
             batch = {}
             for name in self.models:
