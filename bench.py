@@ -215,9 +215,18 @@ def run_b200(args):
     # (pipeline.CapturedStep; UOCR_BENCH_GRAPH=0 issues the 14 launches one by one instead)
     use_graph = os.environ.get('UOCR_BENCH_GRAPH', '1') != '0'
     eager_step = step
+    graph_note = None
     if use_graph:
         from univer_ocr_b200.pipeline import CapturedStep
         captured = {id(inp): CapturedStep(lambda inp=inp: eager_step(inp)) for inp in dev_sets}
+        try:                                             # capture now; a failure falls back to eager launches, loudly
+            for graph in captured.values():
+                graph()
+            nn.CP.synchronize()
+        except Exception as exc:                         # noqa: BLE001
+            graph_note = f'graph capture failed, launching kernel by kernel: {exc}'
+            print(graph_note, file=sys.stderr, flush=True)
+            captured, use_graph = {}, False
 
         def step(inp):
             graph = captured.get(id(inp))
@@ -270,7 +279,7 @@ def run_b200(args):
     # forward of batch i and D2H of batch i-1 overlap on three streams; every batch is still
     # uploaded from and downloaded to host memory inside the timed region, fill and drain included
     from univer_ocr_b200.pipeline import InferencePipeline
-    pipe = InferencePipeline(step, depth=3)
+    pipe = InferencePipeline(eager_step, depth=3, graph=use_graph)
     for i in range(6):
         pipe.submit(host_sets[i % n_sets], i)
     for _ in pipe.drain():
@@ -356,12 +365,12 @@ def run_b200(args):
                                '(64,32,256,1), per GPU; pages sharded across GPUs, no collective',
                    'batch_per_gpu': B, 'math_mode': args.math, 'weights': 'random init (kaiming_uniform, seeded)',
                    'streams': 'Monochrome->Paragraph, Line and Char forward on three forked CUDA streams joined per step' if fork is not None else 'one stream',
-                   'launch': 'one CUDA graph replay per step (captured per resident input set)' if use_graph else 'kernel by kernel',
+                   'launch': 'one CUDA graph replay per step (captured per resident input set)' if use_graph else (graph_note or 'kernel by kernel'),
                    'l2_policy': 'inputs rotate over 2 resident sets (206 MB) and each step streams '
                                 '~3.3 GB of intermediates: working set >> 126 MB L2'},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': e2e_s * 1e3,
-                'api': 'univer_ocr_b200.pipeline.InferencePipeline(depth=3): pinned host in -> H2D -> forward -> D2H -> pinned host out',
+                'api': 'univer_ocr_b200.pipeline.InferencePipeline(depth=3%s): pinned host in -> H2D -> forward -> D2H -> pinned host out' % (', graph=True' if use_graph else ''),
                 'timing': 'host wall clock over K submitted batches incl. pipeline fill and drain, max over ranks',
                 'sync_value': B * dist.world / sync_s, 'sync_ms_per_step': sync_s * 1e3},
         'gpu_launches': int(launches),

@@ -563,9 +563,10 @@ def test_fused_data_parallel_step_matches_model_train(nn, golden, name):
     close(model.predict(g['X'])[0], g['pred2'], 1e-3, 1e-5, 'pred2')
 
 
-def test_inference_pipeline_matches_direct_predict(nn):
-    """pipeline.InferencePipeline (three streams, slots, events) returns, in order, exactly what a
-    synchronous predict returns for every submitted batch."""
+@pytest.mark.parametrize('graph', [False, True], ids=['eager', 'graph'])
+def test_inference_pipeline_matches_direct_predict(nn, graph):
+    """pipeline.InferencePipeline (three streams, slots, events; per-slot CUDA-graph replay with graph=True) returns,
+    in order, exactly what a synchronous predict returns for every submitted batch."""
     from univer_ocr_b200 import my_model
     from univer_ocr_b200.pipeline import InferencePipeline
     np.random.seed(3)
@@ -577,7 +578,7 @@ def test_inference_pipeline_matches_direct_predict(nn):
         buf[...] = rng.uniform(size=buf.shape)
         batches.append({'x': buf})
     want = [model.predict(np.asarray(b['x']))[0].get() for b in batches]
-    pipe = InferencePipeline(lambda inp: model.predict(inp['x']), depth=3)
+    pipe = InferencePipeline(lambda inp: model.predict(inp['x']), depth=3, graph=graph)
     got = {}
     for tag, outs in pipe.run(batches):
         got[tag] = outs[0].copy()

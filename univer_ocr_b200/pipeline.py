@@ -41,6 +41,7 @@ class _Slot:
         self.ev_h2d, self.ev_comp, self.ev_d2h = _new_event(), _new_event(), _new_event()
         self.busy = False
         self.tag = None
+        self.graph = None           # CapturedStep of this slot's forward (InferencePipeline(graph=True))
 
 
 class InferencePipeline:
@@ -52,8 +53,11 @@ class InferencePipeline:
             consume(outs)                         # `depth` further batches have been submitted)
     """
 
-    def __init__(self, fn, depth=3):
+    def __init__(self, fn, depth=3, graph=False):
+        """`graph=True`: every slot replays its forward as one CUDA graph (`CapturedStep` over the slot's fixed
+        input buffers) instead of issuing it kernel by kernel."""
         self.fn = fn
+        self.graph = bool(graph)
         self.depth = max(2, int(depth))
         CP.use_gpu()
         self.s_in, self.s_out = _new_stream(), _new_stream()
@@ -85,7 +89,12 @@ class InferencePipeline:
         lib.uocr_event_record(slot.ev_h2d, self.s_in)
         # compute
         lib.uocr_stream_wait_event(comp, slot.ev_h2d)
-        outs = list(self.fn(slot.dev_in))
+        if self.graph:
+            if slot.graph is None:
+                slot.graph = CapturedStep(lambda s=slot: self.fn(s.dev_in))
+            outs = list(slot.graph())
+        else:
+            outs = list(self.fn(slot.dev_in))
         lib.uocr_event_record(slot.ev_comp, comp)
         # copy-out
         if slot.host_out is None:
