@@ -421,6 +421,27 @@ def measure_train(args, dist, nn, my_model, models, dev_sets, rng, B, event):
     for _ in range(3):
         losses = step()
     nn.CP.synchronize()
+    # the training step is a fixed launch sequence over fixed buffers as well (parameters, gradients and Adam state are
+    # updated in place) and replays correctly from a CUDA graph (tests/test_gpu_parity.py, 2.85 -> 2.76 ms at one GPU).
+    # Opt-in only (UOCR_BENCH_TRAIN_GRAPH=1): with world > 1 the captured sequence contains torch's NCCL allreduce, and
+    # one of two 2-rank experiments with a captured allreduce deadlocked, so every N is measured kernel by kernel.
+    launch_mode = 'kernel by kernel'
+    if os.environ.get('UOCR_BENCH_TRAIN_GRAPH', '0') == '1':
+        from univer_ocr_b200.pipeline import CapturedStep
+
+        def bump():
+            nn.CP.weights_generation += 1
+
+        eager_train_step = step
+        graph = CapturedStep(eager_train_step, warmup=0, track_weights=False, after_replay=bump)
+        try:
+            graph()
+            nn.CP.synchronize()
+            step = graph
+            launch_mode = 'one CUDA graph replay per step'
+        except Exception as exc:                         # noqa: BLE001
+            print(f'train-step graph capture failed, launching kernel by kernel: {exc}', file=sys.stderr, flush=True)
+            step = eager_train_step
     dist.barrier()
     e0, e1 = event(), event()
     launches0 = launch_count()
@@ -441,6 +462,7 @@ def measure_train(args, dist, nn, my_model, models, dev_sets, rng, B, event):
             'value': B * dist.world / (ms_per_step / 1e3), 'unit': UNIT, 'ms_per_step': ms_per_step,
             'steps': steps, 'batch_per_gpu': B, 'global_batch': B * dist.world,
             'allreduce_bytes_per_step': 4 * n_params if dist.world > 1 else 0, 'gpu_launches': int(launches),
+            'launch': launch_mode,
             'losses': {k: float(v['output_losses'][0]) for k, v in losses.items()}}
 
 

@@ -705,3 +705,43 @@ def test_captured_step_replays_match_eager_and_follow_inputs_and_weights(nn):
     want3 = host(forward()[1])
     assert np.array_equal(host(step()[1]), want3) and not np.array_equal(want3, want2[1])
     step.close()
+
+
+def test_captured_training_step_matches_eager_steps(nn):
+    """DataParallel.train captured into a CUDA graph (CapturedStep(track_weights=False)): parameters, gradients and
+    Adam state are updated in place, so N replays must leave the same weights and losses as N eager steps
+    (tolerance 1e-5 of the largest weight: split-K atomics reorder FP32 sums between any two runs)."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.nn.optimizers import Adam
+    from univer_ocr_b200.parallel import DataParallel
+    from univer_ocr_b200.pipeline import CapturedStep
+    rng = np.random.default_rng(41)
+    for name, shape in (('line', (3, 32, 64, 1)), ('char', (2, 32, 40, 1))):
+        w0 = {key: {n: ((v - v.mean()) if n == 'w' else v * 0).tolist() for n, v in p.items()}
+              for key, p in np_models.golden_weights(name, 7).items()}
+        X = nn.CP.copy(f32(rng.uniform(size=shape)))
+        runs = []
+        for mode in ('eager', 'graph'):
+            opt = Adam(lr=0.002)
+            model = my_model.MAKERS[name](shape, optimizer=opt)
+            model.set_weights(w0)
+            dp = DataParallel(model, optimizer=opt)
+            out_shape = model.get_output_shapes([shape])[0]
+            if name == 'char':
+                yh = np.zeros(out_shape)
+                yh[np.arange(out_shape[0]), np.arange(out_shape[0]) % out_shape[1]] = 1
+            else:
+                yh = (np.arange(int(np.prod(out_shape))).reshape(out_shape) % 3 == 0).astype(np.float64)
+            y = nn.CP.copy(yh)
+            dp.train(X, y)                                            # one eager step for both (lazy initialisation)
+            step = (lambda: dp.train(X, y)) if mode == 'eager' else CapturedStep(
+                lambda: dp.train(X, y), warmup=0, track_weights=False)
+            gen0 = nn.CP.weights_generation
+            for _ in range(3):
+                losses = step()
+            runs.append((host(dp.flat.values), float(losses['output_losses'][0]), float(losses['regularization_loss'])))
+            if mode == 'graph':
+                step.close()
+        (we, le, re_), (wg, lg, rg) = runs
+        assert np.max(np.abs(we - wg)) <= 1e-5 * np.max(np.abs(we)), name
+        assert abs(le - lg) <= 1e-5 * abs(le) and abs(re_ - rg) <= 1e-5 * max(abs(re_), 1e-12), (name, le, lg, re_, rg)

@@ -174,10 +174,19 @@ class CapturedStep:
     stream capture -- forked streams (`ConcurrentBranches`) join the capture through their events.  Every block the
     sequence allocates and frees stays reserved for the graph (libuocr's allocator holds it, see uocr_graph_begin),
     so its memory footprint is the SUM of its intermediates.  `fn` must not synchronise, read values back or upload
-    host data.  A parameter change (`CP.weights_generation`) triggers a re-capture on the next call."""
+    host data.  A parameter change (`CP.weights_generation`) triggers a re-capture on the next call.
 
-    def __init__(self, fn, warmup=2):
+    A training step can be captured too (`track_weights=False`: it updates the flat parameter buffers in place, so the
+    graph stays valid): `after_replay` then has to do what the eager step does on the host besides launching kernels --
+    for `DataParallel.train` that is bumping `CP.weights_generation` so that inference-side weight caches notice.
+    Loss scalars returned by `fn` are device-resident (`LazyScalar`); read them after the replay of interest, each
+    object caches its first read.  Keep collectives out of a captured step: single-process training replays correctly
+    (tests/test_gpu_parity.py), but with torch's NCCL allreduce inside the captured sequence one of two 2-rank
+    experiments deadlocked, so `bench.py` measures multi-rank training kernel by kernel."""
+
+    def __init__(self, fn, warmup=2, track_weights=True, after_replay=None):
         self.fn, self.warmup = fn, warmup
+        self.track_weights, self.after_replay = track_weights, after_replay
         self._exec, self._generation, self.out = None, None, None
 
     def _capture(self):
@@ -193,10 +202,12 @@ class CapturedStep:
         self._exec, self.out, self._generation = exec_.value, out, CP.weights_generation
 
     def __call__(self):
-        if self._exec is None or self._generation != CP.weights_generation:
+        if self._exec is None or (self.track_weights and self._generation != CP.weights_generation):
             self.close()
             self._capture()
         lib.uocr_graph_launch(self._exec, compute_stream())
+        if self.after_replay is not None:
+            self.after_replay()
         return self.out
 
     def close(self):
