@@ -142,3 +142,50 @@ def test_two_ranks_shard_each_batch_and_agree_on_losses():
     want = sum((0.5 - float(np.mean(val_ds.get(i)['m'][0]))) ** 2 for i in range(4)) / 4
     assert abs(got[0][1] - want) < 1e-12 and got[0][1] == got[1][1]   # losses summed over ranks
     assert (got[0][3], got[1][3]) == (1, 0)                    # only rank 0 saves
+
+
+def test_prefetch_overlaps_host_batching_with_training_and_keeps_order():
+    import time
+    from univer_ocr_b200.trainer import Trainer
+
+    class SlowDataset(trainer_cases.ScriptedDataset):
+        def get(self, i):
+            time.sleep(0.01)
+            return super().get(i)
+
+    class SlowModel(trainer_cases.ScriptedModel):
+        def train(self, X, y):
+            time.sleep(0.02)
+            return super().train(X, y)
+
+    def run(prefetch):
+        opt = trainer_cases.ScriptedOptimizer(0.01)
+        trace = []
+        model = SlowModel('m', 0.5, opt, trace=trace)
+        t = Trainer({'m': model}, SlowDataset(['m'], 16, 3), trainer_cases.ScriptedDataset(['m'], 2, 4), optimizer=opt,
+                    batch_size=2, prefetch=prefetch, shuffle=lambda order: order.reverse(), log=lambda *a, **k: None)
+        t0 = time.perf_counter()
+        best, _ = t.train(1)
+        return time.perf_counter() - t0, [e[2] for e in trace if e[0] == 'train'], best
+
+    t_serial, order_serial, best_serial = run(0)
+    t_prefetch, order_prefetch, best_prefetch = run(2)
+    assert order_prefetch == order_serial and best_prefetch == best_serial      # same batches, same order
+    assert t_serial > 0.30 and t_prefetch < t_serial - 0.08                       # 8 x (2 x 10 ms) of fetching hidden
+
+
+def test_prefetch_propagates_dataset_errors():
+    from univer_ocr_b200.trainer import Trainer
+
+    class Broken(trainer_cases.ScriptedDataset):
+        def get(self, i):
+            if i == 5:
+                raise KeyError('sample 5 is missing')
+            return super().get(i)
+
+    opt = trainer_cases.ScriptedOptimizer(0.01)
+    t = Trainer({'m': trainer_cases.ScriptedModel('m', 0.5, opt)}, Broken(['m'], 8, 3),
+                trainer_cases.ScriptedDataset(['m'], 2, 4), optimizer=opt, batch_size=2, shuffle=lambda order: None,
+                log=lambda *a, **k: None)
+    with pytest.raises(KeyError):
+        t.train(1)

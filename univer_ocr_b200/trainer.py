@@ -200,8 +200,9 @@ class Trainer:
 
     `models`: {name: model}.  Data sets: `len(ds)` samples, `ds.get(i)` → {name: (X, y)} where X / y
     are arrays (or lists of arrays for multi-input / multi-output models) with a leading batch
-    axis; a model missing from the dict sits that sample out.  Stacking 64 page tiles on the host
-    costs ~20 ms, twenty times the GPU's training step, so a data set may instead offer
+    axis; a model missing from the dict sits that sample out; the next `prefetch` batches are
+    fetched and stacked by a background thread.  Stacking 64 page tiles on the host still costs
+    ~20 ms, twenty times the GPU's training step, so a data set may instead offer
     `ds.get_batch(indices)` → {name: (X, y)} already stacked -- host or device arrays
     (`tools/train_synthetic.py` keeps its samples in HBM and gathers with device copies).  `save_weights_func(names)` is called
     on rank 0 with the models whose validation loss improved (`my_model/train.py:132-141`)."""
@@ -210,7 +211,7 @@ class Trainer:
 
     def __init__(self, models, train_dataset, validation_dataset, progress_tracker=None,
                  optimizer=None, learning_rate_step=0.995, save_weights_func=None,
-                 batch_size=1, fused_update=True, shuffle=None, log=print):
+                 batch_size=1, fused_update=True, shuffle=None, log=print, prefetch=2):
         self.models = models
         self.train_dataset = train_dataset
         self.validation_dataset = validation_dataset
@@ -221,6 +222,7 @@ class Trainer:
         self.batch_size = int(batch_size)
         self.shuffle = shuffle if shuffle is not None else random.shuffle   # trainer.py:3
         self.log = log
+        self.prefetch = int(prefetch)
         self.world, self.rank, self._dist, self._torch = 1, 0, None, None
         try:
             import torch.distributed as dist
@@ -258,6 +260,45 @@ class Trainer:
         return cat([p[0] for p in parts]), cat([p[1] for p in parts])
 
     def _batches(self, dataset, order):
+        """`_host_batches` with the next `prefetch` batches fetched and stacked by a background thread while the
+        current one trains (host data sets only: `get_batch` data sets do their own staging)."""
+        source = self._host_batches(dataset, order)
+        if self.prefetch <= 0 or hasattr(dataset, 'get_batch') or len(order) <= self.batch_size:
+            yield from source
+            return
+        import queue
+        import threading
+        ready, stop, end = queue.Queue(maxsize=self.prefetch), threading.Event(), object()
+
+        def produce():
+            try:
+                for item in source:
+                    while not stop.is_set():
+                        try:
+                            ready.put(item, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                ready.put(end)
+            except BaseException as exc:                 # noqa: BLE001 -- re-raised in the consumer
+                ready.put(exc)
+
+        worker = threading.Thread(target=produce, name='uocr-trainer-prefetch', daemon=True)
+        worker.start()
+        try:
+            while True:
+                item = ready.get()
+                if item is end:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+        finally:
+            stop.set()
+
+    def _host_batches(self, dataset, order):
         """Yields ({name: (X, y, n_samples)}, samples consumed so far): `batch_size` samples per
         step, this rank's share [rank::world] of each."""
         batched = getattr(dataset, 'get_batch', None)
