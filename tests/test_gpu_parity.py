@@ -745,3 +745,27 @@ def test_captured_training_step_matches_eager_steps(nn):
         (we, le, re_), (wg, lg, rg) = runs
         assert np.max(np.abs(we - wg)) <= 1e-5 * np.max(np.abs(we)), name
         assert abs(le - lg) <= 1e-5 * abs(le) and abs(re_ - rg) <= 1e-5 * max(abs(re_), 1e-12), (name, le, lg, re_, rg)
+
+
+def test_tiled_pooling_and_upsample2_fast_paths_bit_exact(nn):
+    """The streaming fast paths (kernel == stride pooling without padding; Upsample2D(2) with C % 4 == 0 or C == 1)
+    against the oracle at every vector width, with floor-mode leftover rows / columns, exact ties and odd shapes that
+    fall back to the general kernels.  Outputs, tie masks and upsampling are selections: bit-exact; pooling / upsample
+    gradients are exact too (one division / three additions in the oracle's order) up to the float32 rounding of it."""
+    rng = np.random.default_rng(77)
+    for shape, k in (((3, 40, 52, 16), 2), ((2, 31, 29, 6), 3), ((2, 10, 14, 3), 2), ((2, 9, 12, 8), 3), ((1, 7, 5, 4), 2)):
+        X = f32(np.round(rng.standard_normal(shape) * 2) / 2)              # many exact ties
+        layer = nn.layers.MaxPool2D(k)
+        y = layer.forward(X)[0]
+        oy, mask = O.maxpool2d_fwd(X, k)
+        assert np.array_equal(host(y), oy), (shape, k)
+        assert np.array_equal(layer._mem[0][0].get(), mask.astype(np.uint8)), (shape, k)
+        dy = f32(rng.standard_normal(oy.shape))
+        close(layer.backward(dy)[0], O.maxpool2d_bwd(dy, mask, X.shape, k), 1e-6, 1e-7, f'maxpool dX {shape} k{k}')
+    for shape in ((2, 12, 20, 4), (3, 10, 16, 1), (2, 6, 7, 1), (1, 5, 9, 8), (2, 4, 6, 3)):
+        X = f32(rng.standard_normal(shape))
+        up = nn.layers.Upsample2D(2)
+        y = up.forward(X)[0]
+        assert np.array_equal(host(y), O.upsample2d_fwd(X, 2)), shape
+        dy = f32(rng.standard_normal(host(y).shape))
+        close(up.backward(dy)[0], O.upsample2d_bwd(dy, 2), 1e-6, 1e-6, f'upsample dX {shape}')

@@ -453,6 +453,197 @@ __global__ void __launch_bounds__(kThreads) threshold_apply_kernel(const float* 
     }
 }
 
+// ---------------------------------------------------------------- fast paths: tiled pooling / x2 upsampling
+// The general kernels above take any geometry with 64-bit index chains and one scalar per thread (maxpool backward:
+// 3 % of HBM peak).  The shapes that matter -- non-overlapping windows (kernel == stride, no padding, floor mode) and
+// Upsample2D(2) -- are pure streaming: one thread per window / source cell and V channels (128-, 64- or 32-bit
+// accesses), 32-bit indices, every byte touched once.
+template <int V> struct VecT;
+template <> struct VecT<1> { typedef float F; typedef uint8_t B; };
+template <> struct VecT<2> { typedef float2 F; typedef uchar2 B; };
+template <> struct VecT<4> { typedef float4 F; typedef uchar4 B; };
+
+template <int V, int K>
+__global__ void __launch_bounds__(kThreads) maxpool_tile_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                    uint8_t* __restrict__ mask, int n, int h, int w,
+                                                                    int c, int ho, int wo) {
+    typedef typename VecT<V>::F F;
+    typedef typename VecT<V>::B B;
+    const int cg = c / V;
+    const int64_t total = (int64_t)n * ho * wo * cg;
+    const int64_t mw = (int64_t)K * wo;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int g = (int)(i % cg);
+        int64_t t = i / cg;
+        const int ox = (int)(t % wo); t /= wo;
+        const int oy = (int)(t % ho);
+        const int64_t b = t / ho;
+        float v[K][K][V], m[V];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const F f = *reinterpret_cast<const F*>(x + ((b * h + oy * K + ky) * w + ox * K + kx) * c + g * V);
+                const float* fp = reinterpret_cast<const float*>(&f);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    v[ky][kx][j] = fp[j];
+                    m[j] = (ky == 0 && kx == 0) ? fp[j] : fmaxf(m[j], fp[j]);       // same tap order as the general kernel
+                }
+            }
+        F out;
+        float* op = reinterpret_cast<float*>(&out);
+#pragma unroll
+        for (int j = 0; j < V; ++j) op[j] = m[j];
+        *reinterpret_cast<F*>(y + i * V) = out;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                B hit;
+                uint8_t* hp = reinterpret_cast<uint8_t*>(&hit);
+#pragma unroll
+                for (int j = 0; j < V; ++j) hp[j] = v[ky][kx][j] == m[j] ? 1 : 0;
+                *reinterpret_cast<B*>(mask + ((b * (K * ho) + oy * K + ky) * mw + ox * K + kx) * c + g * V) = hit;
+            }
+    }
+}
+
+// dx of a tiled pooling: every input position belongs to exactly one window.  Rows / columns beyond ho*K, wo*K (floor
+// mode leftovers) are zeroed by the caller.
+template <int V, int K>
+__global__ void __launch_bounds__(kThreads) maxpool_tile_bwd_kernel(const float* __restrict__ dy,
+                                                                    const uint8_t* __restrict__ mask,
+                                                                    float* __restrict__ dx, int n, int h, int w, int c,
+                                                                    int ho, int wo) {
+    typedef typename VecT<V>::F F;
+    typedef typename VecT<V>::B B;
+    const int cg = c / V;
+    const int64_t total = (int64_t)n * ho * wo * cg;
+    const int64_t mw = (int64_t)K * wo;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int g = (int)(i % cg);
+        int64_t t = i / cg;
+        const int ox = (int)(t % wo); t /= wo;
+        const int oy = (int)(t % ho);
+        const int64_t b = t / ho;
+        uint8_t hit[K][K][V];
+        int cnt[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) cnt[j] = 0;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const B mb = *reinterpret_cast<const B*>(mask + ((b * (K * ho) + oy * K + ky) * mw + ox * K + kx) * c + g * V);
+                const uint8_t* mp = reinterpret_cast<const uint8_t*>(&mb);
+#pragma unroll
+                for (int j = 0; j < V; ++j) { hit[ky][kx][j] = mp[j]; cnt[j] += mp[j]; }
+            }
+        const F gv = *reinterpret_cast<const F*>(dy + i * V);
+        const float* gp = reinterpret_cast<const float*>(&gv);
+        float share[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) share[j] = cnt[j] ? gp[j] / (float)cnt[j] : 0.f;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                F out;
+                float* op = reinterpret_cast<float*>(&out);
+#pragma unroll
+                for (int j = 0; j < V; ++j) op[j] = hit[ky][kx][j] ? share[j] : 0.f;
+                *reinterpret_cast<F*>(dx + ((b * h + oy * K + ky) * w + ox * K + kx) * c + g * V) = out;
+            }
+    }
+}
+
+// Upsample2D(2), C % 4 == 0: thread = one source pixel x 4 channels -> the same 128-bit word to 2 x 2 output pixels
+__global__ void __launch_bounds__(kThreads) upsample2_c4_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y,
+                                                                    int64_t total, int h, int w, int cg) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int g = (int)(i % cg);
+        int64_t t = i / cg;
+        const int ix = (int)(t % w); t /= w;
+        const int iy = (int)(t % h);
+        const int64_t b = t / h;
+        const float4 v = x[i];
+        float4* o = y + ((b * 2 * h + 2 * iy) * (2 * w) + 2 * ix) * cg + g;
+        o[0] = v; o[cg] = v;
+        o += (int64_t)2 * w * cg;
+        o[0] = v; o[cg] = v;
+    }
+}
+// Upsample2D(2), C == 1, W even: thread = two source pixels -> (a, a, b, b) as one 128-bit store in each of two rows
+__global__ void __launch_bounds__(kThreads) upsample2_c1_fwd_kernel(const float2* __restrict__ x, float4* __restrict__ y,
+                                                                    int64_t total, int h, int w2) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int jx = (int)(i % w2);
+        int64_t t = i / w2;
+        const int iy = (int)(t % h);
+        const int64_t b = t / h;
+        const float2 v = x[i];
+        const float4 o = make_float4(v.x, v.x, v.y, v.y);
+        float4* dst = y + ((b * 2 * h + 2 * iy) * w2 + jx);
+        dst[0] = o;
+        dst[w2] = o;
+    }
+}
+// backward of the above: sums of 2 x 2 blocks
+__global__ void __launch_bounds__(kThreads) upsample2_c4_bwd_kernel(const float4* __restrict__ dy, float4* __restrict__ dx,
+                                                                    int64_t total, int h, int w, int cg) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int g = (int)(i % cg);
+        int64_t t = i / cg;
+        const int ix = (int)(t % w); t /= w;
+        const int iy = (int)(t % h);
+        const int64_t b = t / h;
+        const float4* s = dy + ((b * 2 * h + 2 * iy) * (2 * w) + 2 * ix) * cg + g;
+        const float4 a = s[0], c2 = s[cg];
+        s += (int64_t)2 * w * cg;
+        const float4 d = s[0], e = s[cg];
+        // the general kernel's order: (0,0) + (0,1) + (1,0) + (1,1)
+        dx[i] = make_float4(((a.x + c2.x) + d.x) + e.x, ((a.y + c2.y) + d.y) + e.y, ((a.z + c2.z) + d.z) + e.z,
+                            ((a.w + c2.w) + d.w) + e.w);
+    }
+}
+__global__ void __launch_bounds__(kThreads) upsample2_c1_bwd_kernel(const float4* __restrict__ dy, float2* __restrict__ dx,
+                                                                    int64_t total, int h, int w2) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += (int64_t)gridDim.x * kThreads) {
+        const int jx = (int)(i % w2);
+        int64_t t = i / w2;
+        const int iy = (int)(t % h);
+        const int64_t b = t / h;
+        const float4* s = dy + ((b * 2 * h + 2 * iy) * w2 + jx);
+        const float4 r0 = s[0], r1 = s[w2];
+        dx[i] = make_float2(((r0.x + r0.y) + r1.x) + r1.y, ((r0.z + r0.w) + r1.z) + r1.w);
+    }
+}
+
+template <int K>
+static bool maxpool_tile_launch(bool fwd, const float* a, float* out, uint8_t* mask_w, const uint8_t* mask_r, int64_t n,
+                                int64_t h, int64_t w, int64_t c, int64_t ho, int64_t wo, cudaStream_t st) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out);
+    const uintptr_t alm = reinterpret_cast<uintptr_t>(fwd ? mask_w : mask_r);
+    const int v = (c % 4 == 0 && al % 16 == 0 && alm % 4 == 0) ? 4 : (c % 2 == 0 && al % 8 == 0 && alm % 2 == 0) ? 2 : 1;
+    const int64_t total = n * ho * wo * (c / v);
+    const int grid = ew_grid(total, 1);
+#define UOCR_POOL_CASE(V)                                                                                            \
+    if (fwd) maxpool_tile_fwd_kernel<V, K><<<grid, kThreads, 0, st>>>(a, out, mask_w, (int)n, (int)h, (int)w, (int)c,  \
+                                                                       (int)ho, (int)wo);                              \
+    else maxpool_tile_bwd_kernel<V, K><<<grid, kThreads, 0, st>>>(a, mask_r, out, (int)n, (int)h, (int)w, (int)c,      \
+                                                                   (int)ho, (int)wo)
+    if (v == 4) { UOCR_POOL_CASE(4); } else if (v == 2) { UOCR_POOL_CASE(2); } else { UOCR_POOL_CASE(1); }
+#undef UOCR_POOL_CASE
+    return true;
+}
+
+// non-overlapping windows entirely inside the image: kernel == stride in {2, 3}, no padding, no ceil-mode overhang
+static bool maxpool_is_tiled(int64_t h, int64_t w, int kh, int kw, int ph, int pw, int sh, int sw, int64_t ho, int64_t wo) {
+    return kh == kw && (kh == 2 || kh == 3) && sh == kh && sw == kw && ph == 0 && pw == 0 && ho * kh <= h && wo * kw <= w &&
+           h < (1 << 30) && w < (1 << 30);
+}
+
 }  // namespace uocr
 
 using namespace uocr;
@@ -583,8 +774,19 @@ int uocr_upsample2d_fwd(const float* x, float* y, int64_t n, int64_t h, int64_t 
                         int32_t sy, int32_t sx, void* stream) {
     UOCR_REQUIRE(x && y, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && sy > 0 && sx > 0, "non-positive dimension");
-    upsample_fwd_kernel<<<ew_grid(n * h * w * c * sy * sx, 4), kThreads, 0, as_stream(stream)>>>(
-        x, y, n, h, w, c, sy, sx);
+    const bool al = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    if (sy == 2 && sx == 2 && al && c % 4 == 0 && h < (1 << 30) && w < (1 << 30)) {
+        const int64_t total = n * h * w * (c / 4);
+        upsample2_c4_fwd_kernel<<<ew_grid(total, 1), kThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), total, (int)h, (int)w, (int)(c / 4));
+    } else if (sy == 2 && sx == 2 && al && c == 1 && w % 2 == 0 && h < (1 << 30) && w < (1 << 30)) {
+        const int64_t total = n * h * (w / 2);
+        upsample2_c1_fwd_kernel<<<ew_grid(total, 1), kThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float2*>(x), reinterpret_cast<float4*>(y), total, (int)h, (int)(w / 2));
+    } else {
+        upsample_fwd_kernel<<<ew_grid(n * h * w * c * sy * sx, 4), kThreads, 0, as_stream(stream)>>>(
+            x, y, n, h, w, c, sy, sx);
+    }
     UOCR_LAUNCHED("upsample2d_fwd");
     return UOCR_OK;
 }
@@ -593,8 +795,18 @@ int uocr_upsample2d_bwd(const float* dy, float* dx, int64_t n, int64_t h, int64_
                         int32_t sy, int32_t sx, void* stream) {
     UOCR_REQUIRE(dy && dx, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && sy > 0 && sx > 0, "non-positive dimension");
-    upsample_bwd_kernel<<<ew_grid(n * h * w * c, 2), kThreads, 0, as_stream(stream)>>>(dy, dx, n, h, w,
-                                                                                       c, sy, sx);
+    const bool al = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    if (sy == 2 && sx == 2 && al && c % 4 == 0 && h < (1 << 30) && w < (1 << 30)) {
+        const int64_t total = n * h * w * (c / 4);
+        upsample2_c4_bwd_kernel<<<ew_grid(total, 1), kThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dx), total, (int)h, (int)w, (int)(c / 4));
+    } else if (sy == 2 && sx == 2 && al && c == 1 && w % 2 == 0 && h < (1 << 30) && w < (1 << 30)) {
+        const int64_t total = n * h * (w / 2);
+        upsample2_c1_bwd_kernel<<<ew_grid(total, 1), kThreads, 0, as_stream(stream)>>>(
+            reinterpret_cast<const float4*>(dy), reinterpret_cast<float2*>(dx), total, (int)h, (int)(w / 2));
+    } else {
+        upsample_bwd_kernel<<<ew_grid(n * h * w * c, 2), kThreads, 0, as_stream(stream)>>>(dy, dx, n, h, w, c, sy, sx);
+    }
     UOCR_LAUNCHED("upsample2d_bwd");
     return UOCR_OK;
 }
@@ -616,8 +828,13 @@ int uocr_maxpool2d_fwd(const float* x, float* y, uint8_t* mask, int64_t n, int64
     UOCR_REQUIRE(x && y && mask, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && ho > 0 && wo > 0, "non-positive dimension");
     UOCR_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0, "bad pooling geometry");
-    maxpool_fwd_kernel<<<ew_grid(n * ho * wo * c, 1), kThreads, 0, as_stream(stream)>>>(
-        x, y, mask, n, h, w, c, kh, kw, ph, pw, sh, sw, ho, wo);
+    if (maxpool_is_tiled(h, w, kh, kw, ph, pw, sh, sw, ho, wo)) {
+        if (kh == 2) maxpool_tile_launch<2>(true, x, y, mask, nullptr, n, h, w, c, ho, wo, as_stream(stream));
+        else maxpool_tile_launch<3>(true, x, y, mask, nullptr, n, h, w, c, ho, wo, as_stream(stream));
+    } else {
+        maxpool_fwd_kernel<<<ew_grid(n * ho * wo * c, 1), kThreads, 0, as_stream(stream)>>>(
+            x, y, mask, n, h, w, c, kh, kw, ph, pw, sh, sw, ho, wo);
+    }
     UOCR_LAUNCHED("maxpool2d_fwd");
     return UOCR_OK;
 }
@@ -628,8 +845,15 @@ int uocr_maxpool2d_bwd(const float* dy, const uint8_t* mask, float* dx, int64_t 
     UOCR_REQUIRE(dy && mask && dx, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && ho > 0 && wo > 0, "non-positive dimension");
     UOCR_REQUIRE(kh > 0 && kw > 0 && sh > 0 && sw > 0 && ph >= 0 && pw >= 0, "bad pooling geometry");
-    maxpool_bwd_kernel<<<ew_grid(n * h * w * c, 1), kThreads, 0, as_stream(stream)>>>(
-        dy, mask, dx, n, h, w, c, kh, kw, ph, pw, sh, sw, ho, wo);
+    if (maxpool_is_tiled(h, w, kh, kw, ph, pw, sh, sw, ho, wo)) {
+        if (ho * kh != h || wo * kw != w)                   // floor-mode leftovers belong to no window
+            UOCR_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * n * h * w * c, as_stream(stream)));
+        if (kh == 2) maxpool_tile_launch<2>(false, dy, dx, nullptr, mask, n, h, w, c, ho, wo, as_stream(stream));
+        else maxpool_tile_launch<3>(false, dy, dx, nullptr, mask, n, h, w, c, ho, wo, as_stream(stream));
+    } else {
+        maxpool_bwd_kernel<<<ew_grid(n * h * w * c, 1), kThreads, 0, as_stream(stream)>>>(
+            dy, mask, dx, n, h, w, c, kh, kw, ph, pw, sh, sw, ho, wo);
+    }
     UOCR_LAUNCHED("maxpool2d_bwd");
     return UOCR_OK;
 }
