@@ -129,6 +129,105 @@ static int launch_small_dgrad(const ConvGeom& g, const float* dy, const float* w
     return UOCR_OK;
 }
 
+// dgrad for Cin == 1, Cout % 64 == 0 (Char conv_1: 5x3, stride (2,1), 1 <- 64): dx(n, iy, ix) is a dot product over
+// the taps that reach the pixel and all output channels.  Warp = one input pixel, lane = a channel pair (64-bit
+// coalesced loads of dy, weights in shared memory), one shuffle reduction per pixel.  Any kernel / stride / padding.
+// (Plain Model.train computes this gradient like the reference does although nothing consumes it; the general
+// gather kernel needed 0.9 ms for it at batch 64.)
+__global__ void __launch_bounds__(256) conv_dgrad_cin1_warp_kernel(ConvGeom g, const float* __restrict__ dy,
+                                                                   const float* __restrict__ w,
+                                                                   float* __restrict__ dx) {
+    extern __shared__ float s_wd[];                          // (kh*kw, cout)
+    for (int i = threadIdx.x; i < g.kh * g.kw * g.cout; i += 256) s_wd[i] = w[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t pixels = (int64_t)g.n * g.h * g.w;
+    const int64_t warps = (int64_t)gridDim.x * 8;
+    for (int64_t p = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); p < pixels; p += warps) {
+        const int ix = (int)(p % g.w);
+        const int iy = (int)((p / g.w) % g.h);
+        const int64_t n = p / ((int64_t)g.w * g.h);
+        float acc = 0.f;
+        for (int ky = 0; ky < g.kh; ++ky) {
+            const int ty = iy + g.ph - ky;
+            if (ty < 0 || ty % g.sh) continue;
+            const int oy = ty / g.sh;
+            if (oy >= g.ho) continue;
+            for (int kx = 0; kx < g.kw; ++kx) {
+                const int tx = ix + g.pw - kx;
+                if (tx < 0 || tx % g.sw) continue;
+                const int ox = tx / g.sw;
+                if (ox >= g.wo) continue;
+                const float* d = dy + ((n * g.ho + oy) * g.wo + ox) * g.cout;
+                const float* ww = s_wd + (ky * g.kw + kx) * g.cout;
+                for (int c0 = 2 * lane; c0 < g.cout; c0 += 64) {
+                    const float2 dv = *reinterpret_cast<const float2*>(d + c0);
+                    const float2 wv = *reinterpret_cast<const float2*>(ww + c0);
+                    acc = fmaf(dv.x, wv.x, acc);
+                    acc = fmaf(dv.y, wv.y, acc);
+                }
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) dx[p] = acc;
+    }
+}
+
+// Same gradient organised from the OUTPUT side (taps as the N dimension of a small GEMM): lane = one output pixel,
+// Z[tap] = dy(pixel, :) . w(tap, :) for all KH*KW taps from one pass over the pixel's channel vector (weights broadcast
+// from shared memory), then Z[tap] is added to the input pixel that tap reaches.  Each dy element is read once;
+// dx must be zeroed by the caller.  The float atomics make the summation order of the <= KH*KW terms per input pixel
+// run-dependent (as in the split-K GEMMs).
+template <int KH, int KW>
+__global__ void __launch_bounds__(128) conv_dgrad_cin1_scatter_kernel(ConvGeom g, const float* __restrict__ dy,
+                                                                      const float* __restrict__ w,
+                                                                      float* __restrict__ dx) {
+    constexpr int NT = KH * KW, NTP = (NT + 3) & ~3;
+    extern __shared__ __align__(16) float s_ws[];            // (cout, NTP): the taps of a channel are contiguous
+    for (int i = threadIdx.x; i < NTP * g.cout; i += 128) {
+        const int c = i / NTP, t = i - c * NTP;
+        s_ws[i] = t < NT ? w[t * g.cout + c] : 0.f;
+    }
+    __syncthreads();
+    const int64_t pixels = (int64_t)g.n * g.ho * g.wo;
+    for (int64_t p = (int64_t)blockIdx.x * 128 + threadIdx.x; p < pixels; p += (int64_t)gridDim.x * 128) {
+        const int ox = (int)(p % g.wo);
+        const int oy = (int)((p / g.wo) % g.ho);
+        const int64_t n = p / ((int64_t)g.wo * g.ho);
+        float z[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) z[t] = 0.f;
+        const float4* d = reinterpret_cast<const float4*>(dy + p * g.cout);
+        for (int c4 = 0; c4 < g.cout / 4; ++c4) {
+            const float4 v = d[c4];
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4* ws4 = reinterpret_cast<const float4*>(s_ws + (c4 * 4 + j) * NTP);
+#pragma unroll
+                for (int q = 0; q < NTP / 4; ++q) {
+                    const float4 wv = ws4[q];                // broadcast: every lane reads the same 16 bytes
+                    const float wq[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (4 * q + r < NT) z[4 * q + r] = fmaf(vv[j], wq[r], z[4 * q + r]);
+                }
+            }
+        }
+        float* xrow = dx + n * g.h * g.w;
+#pragma unroll
+        for (int ky = 0; ky < KH; ++ky) {
+            const int iy = oy * g.sh + ky - g.ph;
+            if (iy < 0 || iy >= g.h) continue;
+#pragma unroll
+            for (int kx = 0; kx < KW; ++kx) {
+                const int ix = ox * g.sw + kx - g.pw;
+                if (ix >= 0 && ix < g.w) atomicAdd(xrow + (int64_t)iy * g.w + ix, z[ky * KW + kx]);
+            }
+        }
+    }
+}
+
 int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const float* w, float* dx,
                     cudaStream_t st) {
     if (math_mode == UOCR_MATH_TF32) {
@@ -166,6 +265,25 @@ int conv_dgrad_fast(const ConvGeom& g, int math_mode, const float* dy, const flo
         UOCR_DG(5, 5, 2, 2, 2, 4, 4, 4)      // Line down_2
     }
 #undef UOCR_DG
+    if (g.cin == 1 && g.kh == 5 && g.kw == 3 && g.cout % 4 == 0 && g.cout <= 256 &&
+        (reinterpret_cast<uintptr_t>(dy) & 15) == 0) {       // Char conv_1
+        UOCR_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * g.n * g.h * g.w, st));
+        const int64_t pixels = (int64_t)g.n * g.ho * g.wo;
+        int64_t blocks = ceil_div(pixels, 128);
+        if (blocks > 148 * 64) blocks = 148 * 64;
+        conv_dgrad_cin1_scatter_kernel<5, 3><<<(int)blocks, 128, sizeof(float) * 16 * g.cout, st>>>(g, dy, w, dx);
+        UOCR_LAUNCHED("conv_dgrad_cin1_scatter");
+        return UOCR_OK;
+    }
+    if (g.cin == 1 && g.cout % 64 == 0 && (int64_t)g.kh * g.kw * g.cout <= 8192 &&
+        (reinterpret_cast<uintptr_t>(dy) & 7) == 0) {
+        const int64_t pixels = (int64_t)g.n * g.h * g.w;
+        int64_t blocks = ceil_div(pixels, 8 * 4);            // ~4 pixels per warp
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        conv_dgrad_cin1_warp_kernel<<<(int)blocks, 256, sizeof(float) * g.kh * g.kw * g.cout, st>>>(g, dy, w, dx);
+        UOCR_LAUNCHED("conv_dgrad_cin1_warp");
+        return UOCR_OK;
+    }
     return UOCR_ERR_UNSUPPORTED;
 }
 
