@@ -290,6 +290,12 @@ int uocr_fc_bwd(const float* x, const float* w, const float* dy, float* dx, floa
 int uocr_seg_loss_workspace(int64_t n, int64_t c, size_t* bytes);
 int uocr_seg_loss(int kind, const float* pred, const float* gt, float* grad, float* loss,
                   int64_t n, int64_t hw, int64_t c, void* workspace, void* stream);
+/* The gradient pass on its own, from the per-(n, c) coefficients a uocr_seg_loss call (grad may have been NULL) left
+ * in `workspace`: out = a[n,c] * gt + b[n,c]  (losses.py:24), and with x_pre != NULL multiplied by the Sigmoid
+ * derivative exp(-x) / (1 + exp(-x))^2 of the pre-activation tensor the prediction was computed from
+ * (layers.py:413-415): loss gradient + Sigmoid._backward of a network's last layer in one pass over memory. */
+int uocr_seg_grad(const float* gt, const float* x_pre, float* out, int64_t n, int64_t hw, int64_t c,
+                  const void* workspace, void* stream);
 /* row softmax cross-entropy, (B, C); loss = -sum(gt * log p) / B, grad = (p - gt) / B;
  * 0 * log 0 -> NaN as in the reference.   replaces: losses.py:60-73 */
 int uocr_softmax_ce(const float* logits, const float* gt, float* grad, float* loss, int64_t batch,

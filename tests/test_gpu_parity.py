@@ -769,3 +769,35 @@ def test_tiled_pooling_and_upsample2_fast_paths_bit_exact(nn):
         assert np.array_equal(host(y), O.upsample2d_fwd(X, 2)), shape
         dy = f32(rng.standard_normal(host(y).shape))
         close(up.backward(dy)[0], O.upsample2d_bwd(dy, 2), 1e-6, 1e-6, f'upsample dX {shape}')
+
+
+def test_c_abi_rejects_bad_arguments_with_messages(nn):
+    """Error convention of the boundary (include/uocr.h): a negative return code + uocr_last_error() text, nothing
+    launched, and the library stays usable afterwards."""
+    import ctypes
+    from univer_ocr_b200._lib import UocrError, launch_count, lib
+    st = nn.CP.stream()
+    x = nn.CP.copy(np.ones((1, 4, 4, 1), dtype=np.float32))
+    y = nn.DeviceArray((1, 8, 8, 1))
+    before = launch_count()
+    with pytest.raises(UocrError, match='NULL'):
+        lib.uocr_upsample2d_fwd(None, y.ptr, 1, 4, 4, 1, 2, 2, st)
+    with pytest.raises(UocrError, match='non-positive'):
+        lib.uocr_upsample2d_fwd(x.ptr, y.ptr, 1, 0, 4, 1, 2, 2, st)
+    with pytest.raises(UocrError, match='at most 8 channels'):
+        work = nn.DeviceArray((1024,), np.uint8)
+        lib.uocr_threshold_mask(x.ptr, y.ptr, 1, 1, 16, work.ptr, st)
+    with pytest.raises(UocrError, match='kernel larger'):
+        ho, wo = ctypes.c_int64(0), ctypes.c_int64(0)
+        lib.uocr_maxpool2d_out_hw(2, 2, 3, 3, 0, 0, 1, 1, 0, ctypes.byref(ho), ctypes.byref(wo))
+    with pytest.raises(UocrError, match='multiples of 4'):
+        ptrs = ctypes.c_void_p * 5
+        w5 = [nn.CP.copy(np.zeros((5, 5, 1, 1), dtype=np.float32)) for _ in range(5)]
+        b5 = [nn.CP.copy(np.zeros((1,), dtype=np.float32)) for _ in range(5)]
+        bad = nn.CP.copy(np.ones((1, 6, 6, 1), dtype=np.float32))
+        out = nn.DeviceArray((1, 6, 6, 1))
+        lib.uocr_hourglass1_fwd(bad.ptr, ptrs(*[a.ptr for a in w5]), ptrs(*[a.ptr for a in b5]), out.ptr, 1, 6, 6,
+                                0.01, 0, 0.0, st)
+    assert launch_count() == before                         # nothing was launched by the rejected calls
+    lib.uocr_upsample2d_fwd(x.ptr, y.ptr, 1, 4, 4, 1, 2, 2, st)
+    assert np.array_equal(y.get(), np.ones((1, 8, 8, 1), dtype=np.float32))

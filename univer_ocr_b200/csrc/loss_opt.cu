@@ -100,33 +100,48 @@ __global__ void __launch_bounds__(kThreads) seg_finalize_kernel(int kind, const 
     if (threadIdx.x == 0) loss[0] = (float)acc;
 }
 
-// pass 2: grad = a[n,c] * gt + b[n,c].  grid = (chunks, N)
+// pass 2: grad = a[n,c] * gt + b[n,c]  (SIG: times the Sigmoid derivative e / (e + 1)^2, e = exp(-x), of the
+// pre-activation x the prediction came from -- loss gradient and Sigmoid backward in one pass).  grid = (chunks, N)
+template <bool SIG>
 __global__ void __launch_bounds__(kThreads) seg_grad_kernel(const float* __restrict__ gt,
                                                             const float* __restrict__ coef,
+                                                            const float* __restrict__ xpre,
                                                             float* __restrict__ grad, int64_t hw, int c) {
     const int n = blockIdx.y;
     const int64_t len = hw * c;
     const float* g = gt + (int64_t)n * len;
+    const float* xp = SIG ? xpre + (int64_t)n * len : nullptr;
     float* o = grad + (int64_t)n * len;
     const float* cf = coef + (int64_t)n * c * 2;
-    if (c == 1 && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(o)) & 15) == 0) {
+    auto one = [&](float a, float b, float gv, float xv) {
+        const float gr = fmaf(a, gv, b);
+        if (!SIG) return gr;
+        const float e = expf(-xv);                           // same expression as SigmoidBwd (elementwise.cu)
+        const float d = e + 1.f;
+        return gr * e / (d * d);
+    };
+    const bool al = ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(o) |
+                      (SIG ? reinterpret_cast<uintptr_t>(xp) : 0)) & 15) == 0;
+    if (c == 1 && al) {
         const float a = cf[0], b = cf[1];
         const int64_t n4 = len / 4;
         const float4* g4 = reinterpret_cast<const float4*>(g);
+        const float4* x4 = reinterpret_cast<const float4*>(xp);
         float4* o4 = reinterpret_cast<float4*>(o);
         for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n4;
              i += (int64_t)gridDim.x * kThreads) {
             const float4 v = g4[i];
-            o4[i] = make_float4(fmaf(a, v.x, b), fmaf(a, v.y, b), fmaf(a, v.z, b), fmaf(a, v.w, b));
+            const float4 xv = SIG ? x4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            o4[i] = make_float4(one(a, b, v.x, xv.x), one(a, b, v.y, xv.y), one(a, b, v.z, xv.z), one(a, b, v.w, xv.w));
         }
         for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < len;
              i += (int64_t)gridDim.x * kThreads)
-            o[i] = fmaf(a, g[i], b);
+            o[i] = one(a, b, g[i], SIG ? xp[i] : 0.f);
     } else {
         for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < len;
              i += (int64_t)gridDim.x * kThreads) {
             const int ch = (int)(i % c);
-            o[i] = fmaf(cf[2 * ch], g[i], cf[2 * ch + 1]);
+            o[i] = one(cf[2 * ch], cf[2 * ch + 1], g[i], SIG ? xp[i] : 0.f);
         }
     }
 }
@@ -318,13 +333,24 @@ int uocr_seg_loss(int kind, const float* pred, const float* gt, float* grad, flo
     UOCR_LAUNCHED("seg_sums");
     seg_finalize_kernel<<<1, kThreads, 0, st>>>(kind, sums, coef, nc, loss);
     UOCR_LAUNCHED("seg_finalize");
-    if (grad) {
-        int64_t gchunks = ceil_div(hw * c, (int64_t)kThreads * 16);
-        if (gchunks > cap) gchunks = cap;
-        if (gchunks < 1) gchunks = 1;
-        seg_grad_kernel<<<dim3((unsigned)gchunks, (unsigned)n), kThreads, 0, st>>>(gt, coef, grad, hw, (int)c);
-        UOCR_LAUNCHED("seg_grad");
-    }
+    if (grad) return uocr_seg_grad(gt, nullptr, grad, n, hw, c, workspace, stream);
+    return UOCR_OK;
+}
+
+int uocr_seg_grad(const float* gt, const float* x_pre, float* out, int64_t n, int64_t hw, int64_t c,
+                  const void* workspace, void* stream) {
+    UOCR_REQUIRE(gt && out && workspace, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && hw > 0 && c > 0 && n < 65536 && c < 65536, "bad dimension");
+    cudaStream_t st = as_stream(stream);
+    const float* coef = reinterpret_cast<const float*>(reinterpret_cast<const double*>(workspace) + 3 * n * c);
+    const int64_t cap = ceil_div(148 * 8, n);
+    int64_t gchunks = ceil_div(hw * c, (int64_t)kThreads * 16);
+    if (gchunks > cap) gchunks = cap;
+    if (gchunks < 1) gchunks = 1;
+    const dim3 grid((unsigned)gchunks, (unsigned)n);
+    if (x_pre) seg_grad_kernel<true><<<grid, kThreads, 0, st>>>(gt, coef, x_pre, out, hw, (int)c);
+    else seg_grad_kernel<false><<<grid, kThreads, 0, st>>>(gt, coef, nullptr, out, hw, (int)c);
+    UOCR_LAUNCHED("seg_grad");
     return UOCR_OK;
 }
 

@@ -547,4 +547,7 @@ def as_device(x):
     """Layer inputs may be DeviceArrays, foreign CUDA arrays or host data (uploaded)."""
     if isinstance(x, DeviceArray):
         return x
+    materialize = getattr(x, 'materialize', None)          # lazy device values (losses.LazySegGrad)
+    if materialize is not None:
+        return materialize()
     return CP.copy(x)

@@ -372,6 +372,22 @@ class Sigmoid(BaseLayer):
         lib.uocr_sigmoid_fwd(X.ptr, y.ptr, X.size, stream())
         return y
 
+    @track_method('backward')
+    def backward(self, grads):
+        """A Dice / Jaccard gradient that has not been written out yet (losses.LazySegGrad) is combined with this
+        layer's derivative in one pass; anything else takes the reference's route."""
+        grads = make_list_if_not(grads)
+        through = getattr(grads[0], 'through_sigmoid', None) if len(grads) == 1 else None
+        X = self._mem.get(0)
+        if through is not None and isinstance(X, DeviceArray) and X.shape == tuple(grads[0].shape) and len(X.shape) == 4:
+            dx = through(X)
+            if dx is not None:
+                self.clear_memory()
+                return [dx]
+        result = [self._backward(as_device(grad), mem_id) for mem_id, grad in enumerate(grads)]
+        self.clear_memory()
+        return result
+
     def _backward(self, grad, mem_id=0):
         X = self._mem[mem_id]
         if isinstance(X, FromOutput):
