@@ -179,8 +179,11 @@ def main():
         pred = nn.CP.copy(rng.uniform(0.01, 0.99, size=(N, 496, 736, 1)).astype(np.float32))
         gt = nn.CP.copy((rng.uniform(size=(N, 496, 736, 1)) < 0.2).astype(np.float32))
         loss = nn.losses.SegmentationDice2D()
-        ms, best = timeit(lambda: loss(pred, gt))
+        ms, best = timeit(lambda: loss(pred, gt)[1].materialize())       # loss + the plain gradient tensor
         report('dice fwd+bwd (N,496,736,1)', ms, best, {'bound': 'hbm', 'bytes': 20 * pred.size, 'flops': 0})
+        xpre = nn.CP.copy(rng.standard_normal((N, 496, 736, 1)).astype(np.float32))
+        ms, best = timeit(lambda: loss(pred, gt)[1].through_sigmoid(xpre))
+        report('dice fwd + (dice, sigmoid) bwd fused', ms, best, {'bound': 'hbm', 'bytes': 24 * pred.size, 'flops': 0})
     if not args.only or 'adam' in args.only:
         n = 803395
         p = L.Param(rng.standard_normal(n).astype(np.float32), optimizer=nn.optimizers.Adam())
