@@ -113,7 +113,7 @@ def _two_rank_worker(rank, world, port, out):
     opt = trainer_cases.ScriptedOptimizer(0.0)
     trace = []
     model = trainer_cases.ScriptedModel('m', 0.5, opt, trace=trace)
-    train_ds = trainer_cases.ScriptedDataset(['m'], 6, 3)
+    train_ds = trainer_cases.ScriptedDataset(['m'], 7, 3)         # 7 samples, stacks of 2: the last, single sample is dropped
     val_ds = trainer_cases.ScriptedDataset(['m'], 4, 4)
     saves = []
     t = Trainer({'m': model}, train_ds, val_ds, optimizer=opt, batch_size=2, save_weights_func=saves.append,
@@ -135,10 +135,10 @@ def test_two_ranks_shard_each_batch_and_agree_on_losses():
         p.join(timeout=120)
         assert p.exitcode == 0
     got = sorted(out.get(timeout=10) for _ in range(2))
-    train_ds = trainer_cases.ScriptedDataset(['m'], 6, 3)
+    train_ds = trainer_cases.ScriptedDataset(['m'], 7, 3)
     val_ds = trainer_cases.ScriptedDataset(['m'], 4, 4)
     x = [round(float(np.mean(train_ds.get(i)['m'][0])), 9) for i in range(6)]
-    assert got[0][2] == x[0::2] and got[1][2] == x[1::2]       # rank r trains samples r, r + world, ...
+    assert got[0][2] == x[0:6:2] and got[1][2] == x[1:6:2]     # rank r trains samples r, r + world, ...; both run 3 steps
     want = sum((0.5 - float(np.mean(val_ds.get(i)['m'][0]))) ** 2 for i in range(4)) / 4
     assert abs(got[0][1] - want) < 1e-12 and got[0][1] == got[1][1]   # losses summed over ranks
     assert (got[0][3], got[1][3]) == (1, 0)                    # only rank 0 saves

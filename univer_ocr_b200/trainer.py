@@ -234,6 +234,7 @@ class Trainer:
             pass
         assert self.batch_size % self.world == 0, (
             f'batch_size {self.batch_size} must be divisible by the world size {self.world}')
+        assert min(len(train_dataset), len(validation_dataset)) >= self.world, 'fewer samples than ranks'
         self.steppers = {name: _Stepper(model, optimizer, fused_update) for name, model in models.items()}
 
     # ---- plumbing -------------------------------------------------------------------
@@ -304,6 +305,12 @@ class Trainer:
         batched = getattr(dataset, 'get_batch', None)
         for start in range(0, len(order), self.batch_size):
             chunk = order[start:start + self.batch_size]
+            if self.world > 1 and len(chunk) % self.world:
+                # every rank must take part in every step (the gradient allreduce is a collective): the last, ragged
+                # stack keeps a multiple of the world size; `_usable` is what the epoch's losses are normalised by
+                chunk = chunk[:len(chunk) - len(chunk) % self.world]
+                if not chunk:
+                    return
             mine = chunk[self.rank::self.world]
             if batched is not None:
                 # the data set stacks (and may keep its samples on the device): {name: (X, y)} for these indices
@@ -333,6 +340,13 @@ class Trainer:
             for name in update:                          # one weight per model
                 (losses.train if training else losses.validation)({name: update[name]}, weights[name])
             self._message('train_iteration' if training else 'val_iteration', {'current': done, 'total': total})
+
+    def _usable(self, n):
+        """Samples of an n-sample data set that a pass consumes (all of them on one rank)."""
+        if self.world == 1:
+            return n
+        full, rest = divmod(n, self.batch_size)
+        return full * self.batch_size + rest - rest % self.world
 
     def _nan_weights(self):
         return any(model.nan_weights() for model in self.models.values())
@@ -376,7 +390,7 @@ class Trainer:
             assert n_val > 0, 'Validation dataset must have at least 1 element'
             self._run(self.validation_dataset, val_order, False, losses)
             losses.materialize(self._reduce)
-            losses.normalize(n_train, n_val)
+            losses.normalize(self._usable(n_train), self._usable(n_val))
 
             if self.optimizer is not None:
                 reload_attempts += 1
