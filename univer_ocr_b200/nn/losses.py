@@ -44,10 +44,10 @@ class LazySegGrad:
     def __radd__(self, other):                              # Model.backward sums fan-out gradients: 0 + g
         if isinstance(other, (int, float)) and other == 0:
             return self
-        return other + self.materialize()
+        return as_device(other) + self.materialize()
 
     def __add__(self, other):
-        return self.materialize() + other
+        return self.materialize() + as_device(other)
 
     def __getattr__(self, name):                            # .get(), .ptr, .size, .reshape, ... of the dense tensor
         if name.startswith('_'):
