@@ -801,3 +801,27 @@ def test_c_abi_rejects_bad_arguments_with_messages(nn):
     assert launch_count() == before                         # nothing was launched by the rejected calls
     lib.uocr_upsample2d_fwd(x.ptr, y.ptr, 1, 4, 4, 1, 2, 2, st)
     assert np.array_equal(y.get(), np.ones((1, 8, 8, 1), dtype=np.float32))
+
+
+def test_maxpool_full_tile_properties(nn):
+    """MaxPool2D(2) / (3) at the microbench's full tile sizes, through properties that need no oracle pass over
+    190 M elements: every output equals the maximum of its window and is marked at least once; the gradient of a
+    window is shared among its marked positions, so block sums of dX reproduce dy (exactly when a window has one
+    winner, to rounding otherwise) and positions outside every window get 0."""
+    rng = np.random.default_rng(91)
+    for shape, k in (((8, 496, 736, 16), 2), ((16, 240, 320, 6), 3)):
+        X = rng.standard_normal(shape).astype(np.float32)
+        layer = nn.layers.MaxPool2D(k)
+        y = layer.forward(X)[0].get()
+        n, h, w, c = shape
+        ho, wo = h // k, w // k
+        blocks = X[:, :ho * k, :wo * k, :].reshape(n, ho, k, wo, k, c)
+        assert np.array_equal(y, blocks.max(axis=(2, 4)))
+        mask = layer._mem[0][0].get().reshape(n, ho, k, wo, k, c)
+        assert mask.sum(axis=(2, 4)).min() >= 1
+        assert np.array_equal(mask.astype(bool), blocks == y[:, :, None, :, None, :])
+        dy = rng.standard_normal(y.shape).astype(np.float32)
+        dX = layer.backward(dy)[0].get()
+        got = dX[:, :ho * k, :wo * k, :].reshape(n, ho, k, wo, k, c).sum(axis=(2, 4), dtype=np.float64)
+        assert np.max(np.abs(got - dy)) <= 1e-6 * np.max(np.abs(dy))
+        assert not dX[:, ho * k:, :, :].any() and not dX[:, :, wo * k:, :].any()
