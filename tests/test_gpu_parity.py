@@ -825,3 +825,34 @@ def test_maxpool_full_tile_properties(nn):
         got = dX[:, :ho * k, :wo * k, :].reshape(n, ho, k, wo, k, c).sum(axis=(2, 4), dtype=np.float64)
         assert np.max(np.abs(got - dy)) <= 1e-6 * np.max(np.abs(dy))
         assert not dX[:, ho * k:, :, :].any() and not dX[:, :, wo * k:, :].any()
+
+
+def test_page_stage_pads_predicts_and_binarises_on_device(nn, tmp_path):
+    """predict.PageStage: make_divisible_by -> Monochrome -> Paragraph -> thresholded, weights from model_weights.json,
+    against the oracle chain on the same file."""
+    from univer_ocr_b200 import weights_io
+    from univer_ocr_b200.predict import PageStage
+    w = {}
+    for name in ('monochrome', 'paragraph'):
+        for key, p in np_models.golden_weights(name, 13).items():
+            w[key] = {n: ((v - v.mean()) if n == 'w' else v * 0) for n, v in p.items()}    # signed: no saturation
+    path = tmp_path / 'model_weights.json'
+    weights_io.write(path, w)
+    rng = np.random.default_rng(55)
+    pages = f32(rng.uniform(size=(2, 100, 150, 1)))
+    stage = PageStage(weights_path=path)
+    out = stage(pages)
+    padded = O.make_divisible_by(pages, 16, 16)
+    assert out['padded'].shape == (2, 112, 160, 1) and np.array_equal(host(out['padded']), padded)
+    wf = weights_io.read(path)
+    mono = np_models.forward(np_models.net_spec('monochrome'), {k: v for k, v in wf.items() if k.startswith('Mono')}, padded)
+    para = np_models.forward(np_models.net_spec('paragraph'), {k: v for k, v in wf.items() if k.startswith('Para')}, mono)
+    close(out['monochrome_pred'], mono, 1e-4, 1e-5, 'monochrome_pred')
+    close(out['paragraph_pred'], para, 1e-4, 1e-5, 'paragraph_pred')
+    got = PageStage.to_host(out)
+    assert got['paragraph_mask'].dtype == np.uint8 and got['monochrome_pred'].dtype == np.float32
+    assert np.array_equal(got['paragraph_mask'].astype(bool), O.thresholded(host(out['paragraph_pred'])))
+    assert 0 < got['paragraph_mask'].mean() < 1
+    # second call with another page size builds (and caches) another pair of networks
+    out2 = stage(f32(rng.uniform(size=(1, 64, 64, 1))))
+    assert out2['paragraph_mask'].shape == (1, 80, 80, 1) and len(stage._models) == 2
