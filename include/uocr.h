@@ -101,12 +101,39 @@ int uocr_graph_destroy(void* graph_exec);
 /* number of kernels this library has launched in this process (all threads) */
 int uocr_launch_count(uint64_t* count);
 
+/* ------------------------------------------------------------------ collectives (data-parallel training)
+ * The reference has no distributed backend at all ("Distributed communication backend: none");
+ * these entry points are what north_star's "NCCL gradient allreduce over NVLink overlapped with backward" binds
+ * (SURVEY.md 8b names them).  One communicator per process (= per GPU).  NCCL is resolved at run time with
+ * dlopen -- a libnccl.so.2 already mapped into the process is reused, else `uocr_nccl_load(path)`'s library,
+ * else the system one -- so libuocr.so carries no link-time dependency on a particular NCCL build.
+ *   uocr_nccl_unique_id : rank 0 creates the 128-byte id; the caller ships it to the other ranks (file, env, ...)
+ *   uocr_nccl_init      : collective over all `world` ranks; binds the communicator to the CURRENT device
+ *   uocr_allreduce_sum_f32 / uocr_broadcast_f32 : in place, asynchronous on `stream` (capturable into a CUDA graph)
+ *   uocr_allreduce_f64  : op 0 = sum, 1 = max, 2 = min (epoch-loss sums, max-over-ranks timings, barriers)
+ * Every rank must issue the same collectives in the same order.  UOCR_ERR_COMM on NCCL errors. */
+#define UOCR_ERR_COMM        -5   /* NCCL error / not initialised, see uocr_last_error()   */
+#define UOCR_NCCL_UNIQUE_ID_BYTES 128
+int uocr_nccl_load(const char* path);
+int uocr_nccl_version(int* version);
+int uocr_nccl_unique_id(void* id_out);
+int uocr_nccl_init(int rank, int world, const void* unique_id);
+int uocr_nccl_rank(int* rank, int* world);
+int uocr_nccl_finalize(void);
+int uocr_allreduce_sum_f32(float* data, int64_t count, void* stream);
+int uocr_allreduce_f64(double* data, int64_t count, int op, void* stream);
+int uocr_broadcast_f32(float* data, int64_t count, int root, void* stream);
+
 /* ------------------------------------------------------------------ array helpers
  * the whole-array NumPy/CuPy expressions the reference's graph executor and Param use */
 int uocr_fill_f32(float* dst, float value, int64_t n, void* stream);
 int uocr_f64_to_f32(float* dst, const double* src, int64_t n, void* stream);
 int uocr_f32_to_f64(double* dst, const float* src, int64_t n, void* stream);
 int uocr_u8_to_f32(float* dst, const uint8_t* src, float scale, int64_t n, void* stream); /* encode_layers: /255, train_data_generator.py:24-37 */
+/* dst = float32(src / divisor), correctly rounded (== np.float32(u / 255.0) for all 256 pixel values; a multiply by
+ * 1/255 is not): uint8 image planes are uploaded as bytes and widened on the device -- 4x less host-link traffic than
+ * the reference's float arrays (encode_layers, train_data_generator.py:24-37).  16-byte aligned pointers. */
+int uocr_u8_div_f32(float* dst, const uint8_t* src, float divisor, int64_t n, void* stream);
 /* y = a * x + b * y   (fan-out gradient sum models.py:218; `param.grad += grad` layers.py:153) */
 int uocr_axpby_f32(float* y, const float* x, float a, float b, int64_t n, void* stream);
 int uocr_mul_f32(float* out, const float* a, const float* b, int64_t n, void* stream);

@@ -93,17 +93,30 @@ def init_weights(spec, rng):
     return weights
 
 
+# per-network scale of the centred golden weights: chosen so that the sigmoid / softmax outputs on
+# U[0,1) inputs are spread over (0, 1) instead of pinned at 1 (round-1 VERDICT: with the raw
+# all-positive init the Line / Paragraph predictions were 1.0 everywhere, sigma' ~ 1e-16, and the
+# whole-network train goldens could not see a wrong backward)
+GOLDEN_SCALE = {'monochrome': 5.0, 'paragraph': 5.5, 'line': 3.5, 'char': 2.5}
+
+
 def golden_weights(name, seed):
-    """The float32-representable start weights of the `models` golden cases.  The reference's
-    kaiming_uniform is all-positive, which saturates Char's softmax (loss = NaN from 0 * log 0,
-    losses.py:71); and makes every layer a sum of ~10^3 same-sign terms.  The Char conv / FC
-    weights are therefore centred and scaled by 2.5 (activations stay O(1)), so the golden Char
-    case exercises finite, well-conditioned losses (the NaN case is covered by `sce_nan`)."""
+    """The float32-representable start weights of the `models` golden cases (and of smoke() and the
+    training leg of bench.py).  The reference's kaiming_uniform is all-positive
+    (initializers.py:22-25), which saturates every network's output: Char's softmax (loss = NaN
+    from 0 * log 0, losses.py:71) and the three segmentation networks' sigmoids (prediction == 1.0
+    everywhere, so the data gradient vanishes against the L2 term).  All weights are therefore
+    centred (mean removed per tensor) and scaled per network (GOLDEN_SCALE) so that activations
+    stay O(1) and predictions are spread over (0, 1); the segmentation networks' biases are centred
+    too.  The NaN case is covered by `sce_nan`."""
     spec = net_spec(name)
     w = init_weights(spec, np.random.default_rng(int(seed)))
-    if name == 'char':
-        for key in w:
-            w[key]['w'] = (w[key]['w'] - w[key]['w'].mean()) * 2.5
+    scale = GOLDEN_SCALE[name]
+    for key in w:
+        w[key]['w'] = (w[key]['w'] - w[key]['w'].mean()) * scale
+        if name != 'char' and 'b' in w[key]:
+            b = w[key]['b']
+            w[key]['b'] = (b - b.mean()) * scale if b.size > 1 else b * 0.25
     return {k: {n: v.astype(np.float32).astype(np.float64) for n, v in p.items()} for k, p in w.items()}
 
 

@@ -102,3 +102,37 @@ def load_trainer():
     mod = importlib.import_module('web_app.components.my_model.trainer')
     _loaded['trainer'] = mod
     return mod
+
+
+def load_my_model_on(nn_package, alias='uocr_dropin'):
+    """The reference's UNMODIFIED `my_model/model.py` (and `nn/model_system.py`, `interpreter/`) imported a second
+    time, under the package name `<alias>.components`, with `..nn` resolving to `nn_package` (e.g.
+    `univer_ocr_b200.nn`) wherever that package has a module of the same name, and to the reference's own file
+    otherwise (model_system.py, which only orchestrates).  This is route A of INTEGRATION.md executed literally:
+    the reference's builders construct their networks out of the drop-in layer classes.
+
+    Returns the imported `<alias>.components.my_model.model` module."""
+    key = f'dropin:{alias}'
+    if key in _loaded:
+        return _loaded[key]
+    if not available():
+        raise RuntimeError(f'reference tree not found at {REFERENCE_ROOT}')
+    _install_shims()
+    comp_dir = os.path.join(REFERENCE_ROOT, 'web_app', 'components')
+    for pkg, path in ((alias, os.path.join(REFERENCE_ROOT, 'web_app')), (f'{alias}.components', comp_dir)):
+        mod = types.ModuleType(pkg)
+        mod.__path__ = [path]
+        sys.modules[pkg] = mod
+    nn_alias = types.ModuleType(f'{alias}.components.nn')
+    nn_alias.__path__ = [os.path.join(comp_dir, 'nn')]             # fallback: the reference's own files
+    sys.modules[nn_alias.__name__] = nn_alias
+    prefix = nn_package.__name__ + '.'
+    for name, module in list(sys.modules.items()):
+        if name.startswith(prefix) and module is not None:
+            sub = name[len(prefix):]
+            sys.modules[f'{nn_alias.__name__}.{sub}'] = module      # the drop-in's module wins
+            if '.' not in sub:
+                setattr(nn_alias, sub, module)
+    mod = importlib.import_module(f'{alias}.components.my_model.model')
+    _loaded[key] = mod
+    return mod

@@ -178,15 +178,32 @@ def main():
             y[np.arange(y.shape[0]), rng.integers(0, y.shape[1], size=y.shape[0])] = 1
         else:
             y = (rng.uniform(size=pred0.shape) < 0.2).astype(np.float64)
+        if name != 'char':          # the point of golden_weights: predictions spread over (0, 1), not pinned at 1
+            assert 0.02 < pred0.mean() < 0.98 and pred0.std() > 0.03, (name, pred0.mean(), pred0.std())
         out.update({f'{name}__seed': np.int64(seed), f'{name}__X': X, f'{name}__y': y,
                     f'{name}__pred0': pred0})
+        picks = {}
+        for key, param in model.params().items():
+            size = int(np.asarray(param.value).size)
+            picks[key] = np.random.default_rng(seed + 1).integers(0, size, size=min(size, 96))
         for step in (1, 2):
-            losses = model.train(X, y)
+            # Model.train (nn/models.py:250-254) taken apart so that the gradients can be recorded BEFORE Adam
+            # consumes them (they include the L2 term, models.py:246): Adam without bias correction maps any
+            # gradient to ~3.16 * lr * sign(g) on the first step, so updated weights alone cannot pin a backward
+            losses = model.compute_loss_and_gradients(X, y)
+            for key, param in model.params().items():
+                g = np.asarray(param.grad, dtype=np.float64).ravel()
+                tag = key.replace('/', '.')
+                out[f'{name}__grad{step}__{tag}__val'] = g[picks[key]]
+                out[f'{name}__grad{step}__{tag}__l2'] = np.float64(np.sqrt((g * g).sum()))
+                out[f'{name}__grad{step}__{tag}__max'] = np.float64(np.abs(g).max())
+            model.update_grads()
+            model.clear_grads()
             out[f'{name}__loss{step}'] = np.float64(losses['output_losses'][0])
             out[f'{name}__reg{step}'] = np.float64(losses['regularization_loss'])
         for key, param in model.params().items():
             v = np.asarray(param.value).ravel()
-            pick = np.random.default_rng(seed + 1).integers(0, v.size, size=min(v.size, 96))
+            pick = picks[key]
             tag = key.replace('/', '.')
             out[f'{name}__after__{tag}__idx'] = pick
             out[f'{name}__after__{tag}__val'] = v[pick]

@@ -246,20 +246,47 @@ def test_dice_large_tile(nn):
 
 # ----------------------------------------------------------------------------- whole sub-models
 
+def _check_golden_grads(model, g, step, rtol, atol_frac):
+    """Parameter gradients (incl. the L2 term) as the reference had them BEFORE Adam (make_golden.py)."""
+    for key, param in model.params().items():
+        tag = key.replace('/', '.')
+        got = host(param.grad).ravel()
+        want = g[f'grad{step}__{tag}__val']
+        gmax = float(g[f'grad{step}__{tag}__max'])
+        np.testing.assert_allclose(got[g[f'after__{tag}__idx']], want, rtol=rtol, atol=atol_frac * gmax,
+                                   err_msg=f'grad{step} {key}')
+        l2 = float(np.sqrt((got * got).sum()))
+        assert abs(l2 - float(g[f'grad{step}__{tag}__l2'])) <= max(rtol, atol_frac) * float(g[f'grad{step}__{tag}__l2']), key
+
+
+@pytest.mark.parametrize('fused', [False, True], ids=['per_param', 'fused_update'])
 @pytest.mark.parametrize('name', list(MODEL_SHAPES))
-def test_submodel_train_golden(nn, golden, name):
-    """Two Model.train steps of each my_model sub-network (fwd + loss + bwd + L2 + Adam) vs the
-    reference.  Predictions rtol 1e-4; updated weights rtol 1e-3 with an absolute floor of
-    1e-5 (Adam without bias correction amplifies sign flips of near-zero gradients)."""
+def test_submodel_train_golden(nn, golden, name, fused):
+    """Two Model.train steps of each my_model sub-network (fwd + loss + bwd + L2 + Adam) vs the reference, on
+    un-saturated golden weights (predictions spread over (0, 1): the data gradient is visible next to the L2 term).
+    Predictions rtol 1e-4; parameter gradients BEFORE Adam rtol 2e-4 + 5e-6 of the tensor's largest gradient;
+    updated weights rtol 1e-3 with an absolute floor of 1e-5 (Adam without bias correction amplifies sign flips of
+    near-zero gradients).  `fused`: the steps go through Model.train's flat-buffer update (the default route) instead
+    of compute_loss_and_gradients + update_grads + clear_grads; the gradients are then compared on a replica."""
     from univer_ocr_b200 import my_model
     g = golden('models').case(name)
+    if name != 'char':
+        assert 0.02 < float(g['pred0'].mean()) < 0.98 and float(g['pred0'].std()) > 0.03
+    assert float(g['loss1']) != float(g['loss2'])
     w0 = np_models.golden_weights(name, g['seed'])
     opt = nn.optimizers.Adam(lr=0.0015)
     model = my_model.MAKERS[name](MODEL_SHAPES[name], optimizer=opt)
+    model.fused_update = fused
     model.set_weights({k: {n: f32(v).tolist() for n, v in p.items()} for k, p in w0.items()})
     close(model.predict(g['X'])[0], g['pred0'], 1e-4, 2e-6, 'pred0')
     for step in (1, 2):
-        losses = model.train(g['X'], g['y'])
+        if fused:
+            losses = model.train(g['X'], g['y'])
+        else:
+            losses = model.compute_loss_and_gradients(g['X'], g['y'])
+            _check_golden_grads(model, g, step, 2e-4, 5e-6)
+            model.update_grads()
+            model.clear_grads()
         got = float(losses['output_losses'][0])
         assert abs(got - float(g[f'loss{step}'])) <= 2e-5 * abs(float(g[f'loss{step}'])), (got, g[f'loss{step}'])
         reg = float(losses['regularization_loss'])
@@ -552,8 +579,22 @@ def test_fused_data_parallel_step_matches_model_train(nn, golden, name):
     model = my_model.MAKERS[name](MODEL_SHAPES[name], optimizer=opt)
     model.set_weights({k: {n: f32(v).tolist() for n, v in p.items()} for k, p in w0.items()})
     dp = DataParallel(model, optimizer=opt)
+    seen = []
+
+    def check_grads():                                    # data gradients before the fused L2 + Adam: golden minus 2*l2*w
+        for key, param in model.params().items():
+            tag = key.replace('/', '.')
+            l2 = 0.01 if '/conv_' in key else 0.0          # my_model/model.py:37-39: L2(0.01) on every conv param
+            idx = g[f'after__{tag}__idx']
+            want = g[f'grad{len(seen) + 1}__{tag}__val'] - 2 * l2 * host(param.value).ravel()[idx]
+            gmax = float(g[f'grad{len(seen) + 1}__{tag}__max'])
+            np.testing.assert_allclose(host(param.grad).ravel()[idx], want, rtol=2e-4, atol=5e-6 * gmax, err_msg=key)
+        seen.append(1)
+
+    dp.after_reduce = check_grads
     for step in (1, 2):
         losses = dp.train(g['X'], g['y'])
+        assert len(seen) == step
         assert same_scalar(losses['output_losses'][0], g[f'loss{step}'], 2e-5)
         assert same_scalar(losses['regularization_loss'], g[f'reg{step}'], 2e-5)
     for key, param in model.params().items():

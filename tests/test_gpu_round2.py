@@ -1,0 +1,314 @@
+"""Round-2 parity additions (VERDICT r1 "what's weak" 1-3):
+
+  * whole TRAIN STEP parity in the mode the bench times: TF32 `DataParallel.train`, two steps per sub-network,
+    against `np_models.train_step` -- gradients compared BEFORE Adam, on un-saturated weights;
+  * `Model.train`'s fused flat-buffer route == the reference's per-parameter route;
+  * repeated `compute_loss_and_gradients` on the fused Monochrome pair does not accumulate (reference clears
+    each layer's gradients in forward, nn/models.py:188);
+  * `set_weights` after a model was adopted by flat buffers keeps training on the loaded weights;
+  * SigmoidCrossEntropy stays finite for confident logits where float64 is finite (losses.py:45-57);
+  * the end-to-end payload forms: uint8 pages -> float32 / 255 bit-exact, thresholded masks and row-max hits of
+    the pipeline outputs bit-exact against the oracle.
+
+TF32 tolerance (north_star: 1e-3 relative with TF32): per tensor |got - want| <= tol * max|want|.
+"""
+import numpy as np
+import pytest
+
+from oracle import np_models, np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TRAIN_SHAPES = {'monochrome': (2, 64, 96, 1), 'paragraph': (2, 64, 96, 1), 'line': (2, 64, 128, 1),
+                'char': (2, 32, 64, 1)}
+
+
+@pytest.fixture()
+def nn():
+    import univer_ocr_b200.nn as nn_
+    nn_.CP.use_gpu()
+    keep = nn_.CP.math_mode
+    yield nn_
+    nn_.CP.math_mode = keep
+
+
+def f32(a):
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
+def host(a):
+    return np.asarray(a.get() if hasattr(a, 'get') else a, dtype=np.float64)
+
+
+def rel_max(got, want):
+    want = np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(host(got).reshape(want.shape) - want)) / max(float(np.max(np.abs(want))), 1e-30))
+
+
+def _problem(name, seed):
+    rng = np.random.default_rng(seed)
+    spec, kind = np_models.net_spec(name), np_models.loss_kind(name)
+    w = np_models.golden_weights(name, seed)
+    X = f32(rng.uniform(size=TRAIN_SHAPES[name]))
+    pred = np_models.forward(spec, w, X)
+    if kind == 'dice':
+        y = (rng.uniform(size=pred.shape) < 0.2).astype(np.float64)
+    else:
+        y = np.zeros(pred.shape)
+        y[np.arange(y.shape[0]), rng.integers(0, y.shape[1], size=y.shape[0])] = 1
+    return spec, kind, w, X, y, pred
+
+
+def _as_lists(w):
+    return {k: {n: v.tolist() for n, v in p.items()} for k, p in w.items()}
+
+
+# ----------------------------------------------------------------------------- TF32 train-step parity
+
+@pytest.mark.parametrize('mode,tol', [('fp32', 2e-4), ('tf32', 2e-3)])
+@pytest.mark.parametrize('name', list(TRAIN_SHAPES))
+def test_data_parallel_train_step_vs_oracle(nn, name, mode, tol):
+    """Two `DataParallel.train` steps (the step bench.py times) vs `np_models.train_step` (reference
+    nn/models.py:232-254, losses.py:9-25,60-73).  Checked per step: the loss, the regularisation loss and EVERY
+    parameter gradient before the update (data gradient = oracle gradient minus its L2 term), per tensor within
+    `tol` of the tensor's largest gradient; after both steps the updated weights (<= 1 % of the elements may differ by
+    more than 1e-3 |w| + 1e-4: Adam without bias correction maps a gradient to ~3.16 lr sign(g), so an element whose
+    gradient is within rounding of zero can land on the other side) and the predictions."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.parallel import DataParallel
+    nn.CP.set_math_mode(mode)
+    spec, kind, w, X, y, pred0 = _problem(name, 321)
+    if kind == 'dice':
+        assert 0.02 < pred0.mean() < 0.98 and pred0.std() > 0.03          # not the saturated regime
+    opt = nn.optimizers.Adam(lr=0.0015)
+    model = my_model.MAKERS[name](TRAIN_SHAPES[name], optimizer=opt)
+    model.set_weights(_as_lists(w))
+    dp = DataParallel(model, optimizer=opt)
+    state = np_models.new_adam_state(w)
+    errs = {}
+
+    def check_grads():
+        for key, param in model.params().items():
+            lkey, pname = key.rsplit('/', 1)
+            l2 = np_models.L2_STRENGTH if '/conv_' in key else 0.0
+            want = want_grads[lkey][pname] - 2 * l2 * w_before[lkey][pname]
+            errs[f'step{step} {key}'] = rel_max(param.grad, want)
+
+    dp.after_reduce = check_grads
+    for step in (1, 2):
+        w_before = {k: {n: v.copy() for n, v in p.items()} for k, p in w.items()}
+        want_losses, want_grads, _, _ = np_models.train_step(spec, kind, w, state, X, y, lr=0.0015)
+        got = dp.train(X, y)
+        gl, wl = float(got['output_losses'][0]), float(want_losses['output_losses'][0])
+        assert abs(gl - wl) <= tol * abs(wl), (step, gl, wl)
+        gr, wr = float(got['regularization_loss']), float(want_losses['regularization_loss'])
+        assert abs(gr - wr) <= max(tol, 1e-4) * abs(wr) + 1e-7, (step, gr, wr)
+    assert len(errs) == 2 * len(model.params())
+    bad = {k: v for k, v in errs.items() if v > tol}
+    assert not bad, f'{name} {mode}: gradients beyond {tol} of their tensor max: {bad}'
+    for key, param in model.params().items():
+        lkey, pname = key.rsplit('/', 1)
+        want = w[lkey][pname]
+        diff = np.abs(host(param.value) - want)
+        frac = float(np.mean(diff > 1e-3 * np.abs(want) + 1e-4))
+        assert frac <= 0.01, (key, frac)
+    ptol = 5e-3 if mode == 'tf32' else 1e-3
+    assert rel_max(model.predict(X)[0], np_models.forward(spec, w, X)) <= ptol
+
+
+# ----------------------------------------------------------------------------- fused Model.train == per-parameter
+
+@pytest.mark.parametrize('name', list(TRAIN_SHAPES))
+def test_model_train_fused_route_equals_reference_route(nn, name):
+    """`Model.train` defaults to the flat-buffer update (one fused L2 + Adam launch per regularisation group); with
+    `fused_update = False` it runs compute_loss_and_gradients -> update_grads -> clear_grads like the reference
+    (nn/models.py:250-254).  Same losses and weights after three steps (FP32: 1e-6 relative)."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200._lib import launch_count
+    nn.CP.set_math_mode('fp32')
+    _, _, w, X, y, _ = _problem(name, 77)
+    results, launches = {}, {}
+    for fused in (True, False):
+        opt = nn.optimizers.Adam(lr=0.0015)
+        model = my_model.MAKERS[name](TRAIN_SHAPES[name], optimizer=opt)
+        model.fused_update = fused
+        model.set_weights(_as_lists(w))
+        model.train(X, y)                                           # warm-up (flat buffers are created here)
+        before = launch_count()
+        losses = [model.train(X, y) for _ in range(2)]
+        launches[fused] = launch_count() - before
+        results[fused] = ([float(l['output_losses'][0]) for l in losses],
+                          [float(l['regularization_loss']) for l in losses],
+                          {k: host(p.value) for k, p in model.params().items()})
+        assert model._flat is not None if fused else model._flat is None
+    for a, b in zip(results[True][0] + results[True][1], results[False][0] + results[False][1]):
+        assert abs(a - b) <= 1e-5 * abs(b), (a, b)
+    for key in results[True][2]:
+        np.testing.assert_allclose(results[True][2][key], results[False][2][key], rtol=1e-5, atol=1e-7, err_msg=key)
+    n_params = len(results[True][2])
+    assert launches[True] <= launches[False] - 2 * n_params          # >= 2 launches per parameter tensor saved per step
+
+
+def test_fused_route_shares_adam_state_with_the_per_parameter_protocol(nn):
+    """A model adopted by flat buffers still honours the reference's per-parameter calls on the SAME state: one fused
+    step followed by compute_loss_and_gradients + update_grads + clear_grads equals two per-parameter steps."""
+    from univer_ocr_b200 import my_model
+    nn.CP.set_math_mode('fp32')
+    _, _, w, X, y, _ = _problem('line', 5)
+    weights = {}
+    for mixed in (True, False):
+        opt = nn.optimizers.Adam(lr=0.0015)
+        model = my_model.make_line(TRAIN_SHAPES['line'], optimizer=opt)
+        model.fused_update = mixed
+        model.set_weights(_as_lists(w))
+        model.train(X, y)
+        model.compute_loss_and_gradients(X, y)
+        model.update_grads()
+        model.clear_grads()
+        weights[mixed] = {k: host(p.value) for k, p in model.params().items()}
+    for key in weights[True]:
+        np.testing.assert_allclose(weights[True][key], weights[False][key], rtol=1e-5, atol=1e-7, err_msg=key)
+
+
+# ----------------------------------------------------------------------------- ADVICE r1
+
+def test_repeated_compute_loss_and_gradients_does_not_accumulate_in_the_fused_pair(nn):
+    """ADVICE r1 (nn/models.py:324): the reference clears each layer's gradients in forward (models.py:188), so two
+    compute_loss_and_gradients calls in a row leave the gradients of ONE call -- also for Monochrome, whose
+    conv -> LeakyRelu -> conv runs as one fused step."""
+    from univer_ocr_b200 import my_model
+    for mode in ('fp32', 'tf32'):
+        nn.CP.set_math_mode(mode)
+        _, _, w, X, y, _ = _problem('monochrome', 9)
+        grads = {}
+        for fusion in (True, False):
+            model = my_model.make_monochrome(TRAIN_SHAPES['monochrome'], optimizer=nn.optimizers.Adam(lr=0.001))
+            if not fusion:
+                model.fusion = False
+                model.initialize(model.input_shapes)
+            model.set_weights(_as_lists(w))
+            model.compute_loss_and_gradients(X, y)
+            once = {k: host(p.grad) for k, p in model.params().items()}
+            model.compute_loss_and_gradients(X, y)
+            twice = {k: host(p.grad) for k, p in model.params().items()}
+            for k in once:
+                np.testing.assert_allclose(twice[k], once[k], rtol=1e-6, atol=1e-9, err_msg=f'{mode} {fusion} {k}')
+            grads[fusion] = twice
+        tol = 1e-4 if mode == 'fp32' else 2e-3
+        for k in grads[True]:
+            assert rel_max(grads[True][k], grads[False][k]) <= tol, (mode, k)
+
+
+def test_set_weights_after_flat_adoption_keeps_training_on_the_loaded_weights(nn):
+    """ADVICE r1 (parallel.py:63): `set_weights` on a model whose parameters are views of flat buffers copies INTO the
+    views, so the fused update keeps driving the tensors the layers read."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200.parallel import DataParallel
+    nn.CP.set_math_mode('fp32')
+    spec, kind, w, X, y, _ = _problem('paragraph', 21)
+    opt = nn.optimizers.Adam(lr=0.0015)
+    model = my_model.make_paragraph(TRAIN_SHAPES['paragraph'], optimizer=opt)
+    dp = DataParallel(model, optimizer=opt)
+    dp.train(X, y)                                                   # some step on the random initial weights
+    model.set_weights(_as_lists(w))                                  # e.g. weights_io.load_weights / a roll-back
+    assert dp.flat.attached()
+    for p in model.params().values():                                # fresh Adam state for the comparison below
+        for st in opt.groups[id(p)][1].values():
+            st.fill(0)
+    assert rel_max(model.predict(X)[0], np_models.forward(spec, w, X)) <= 1e-4
+    state = np_models.new_adam_state(w)
+    np_models.train_step(spec, kind, w, state, X, y, lr=0.0015)
+    before = host(model.predict(X)[0])
+    dp.train(X, y)
+    after = host(model.predict(X)[0])
+    assert np.max(np.abs(after - before)) > 1e-4                     # the step moved the model ...
+    assert rel_max(after, np_models.forward(spec, w, X)) <= 1e-3     # ... to where the oracle's step moves it
+    # a param whose tensor is re-bound behind the owner's back is re-adopted on the next step
+    key, param = next(iter(model.params().items()))
+    param._value, param._pinned = param._value.copy(), False
+    assert not dp.flat.attached()
+    dp.train(X, y)
+    assert dp.flat.attached()
+
+
+def test_sigmoid_cross_entropy_confident_logits_stay_finite(nn):
+    """ADVICE r1 (loss_opt.cu:210): logits of +-20 with matching targets are finite in the float64 reference
+    (losses.py:45-57) and must be here; beyond float64's own saturation (x > 36.74 with target 1) the reference's
+    0 * log 0 = NaN is kept."""
+    logits = f32(np.array([[20.0, -20.0, 17.5, -30.0, 0.3, -2.0], [25.0, -18.0, 3.0, -17.0, 35.0, -36.0]]))
+    gt = (logits > 0).astype(np.float64)
+    loss, grad = nn.losses.SigmoidCrossEntropy()(logits, gt)
+    want_loss, want_grad = O.sigmoid_ce_loss(logits, gt)
+    assert np.isfinite(want_loss) and abs(float(loss) - want_loss) <= 1e-5 * abs(want_loss)
+    np.testing.assert_allclose(host(grad), want_grad, rtol=1e-4, atol=1e-9)
+    wrong = 1.0 - gt                                                 # confidently wrong: large finite loss
+    loss, _ = nn.losses.SigmoidCrossEntropy()(logits, wrong)
+    want_loss, _ = O.sigmoid_ce_loss(logits, wrong)
+    assert np.isfinite(want_loss) and abs(float(loss) - want_loss) <= 1e-5 * abs(want_loss)
+    sat = logits.copy()
+    sat[0, 0] = 40.0
+    with np.errstate(all='ignore'):
+        want_loss, _ = O.sigmoid_ce_loss(sat, gt)
+    loss, _ = nn.losses.SigmoidCrossEntropy()(sat, gt)
+    assert np.isnan(want_loss) and np.isnan(float(loss))
+
+
+# ----------------------------------------------------------------------------- end-to-end payload forms
+
+def test_uint8_pixels_widen_bit_exactly_for_all_256_values(nn):
+    """`glue.pixels_to_unit` (uocr_u8_div_f32) == float32(u / 255.0), the float32 storage of the reference's
+    `encode_layers` planes (train_data_generator.py:24-37), for every pixel value, at aligned and ragged sizes."""
+    from univer_ocr_b200 import glue
+    rng = np.random.default_rng(4)
+    for shape in ((256,), (2, 496, 736, 1), (3, 7, 5, 1), (1, 1, 17, 1)):
+        u = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        u.reshape(-1)[:min(256, u.size)] = np.arange(min(256, u.size), dtype=np.uint8)     # every value at least once
+        got = glue.pixels_to_unit(u).get()
+        want = (u.astype(np.float64) / 255.0).astype(np.float32)
+        assert got.dtype == np.float32 and np.array_equal(got, want), shape
+    wrong = (np.arange(256, dtype=np.float32) * np.float32(1 / 255)) != (np.arange(256) / 255.0).astype(np.float32)
+    assert wrong.sum() > 100          # why the kernel divides: the multiply-by-reciprocal form is off for 126 values
+
+
+@pytest.mark.parametrize('graph', [False, True], ids=['eager', 'graph'])
+def test_pipeline_ships_uint8_in_and_masks_and_hits_out(nn, graph):
+    """The e2e form bench.py times: uint8 planes up, `thresholded` masks (interpreter.py:437-447) and the PredToText
+    hit table (:596-602) down.  Bit-exact against the oracle's rules applied to the device's own float32 maps, and
+    the float maps themselves within the FP32 tolerance of the oracle on u / 255 inputs."""
+    from univer_ocr_b200 import glue, my_model
+    from univer_ocr_b200.pipeline import InferencePipeline
+    nn.CP.set_math_mode('fp32')
+    rng = np.random.default_rng(8)
+    shapes = {'line': (3, 32, 64, 1), 'char': (3, 32, 40, 1)}
+    models, weights = {}, {}
+    for name in shapes:
+        weights[name] = np_models.golden_weights(name, 31)
+        models[name] = my_model.MAKERS[name](shapes[name])
+        models[name].set_weights(_as_lists(weights[name]))
+
+    def step(inp):
+        line = models['line'].predict(glue.pixels_to_unit(inp['line']))[0]
+        char = models['char'].predict(glue.pixels_to_unit(inp['char']))[0]
+        return glue.thresholded(line), glue.row_max_hits(char), line, char
+
+    batches = []
+    for _ in range(5):
+        b = {}
+        for name, shape in shapes.items():
+            buf = nn.CP.pinned_empty(shape, np.uint8)
+            buf[...] = rng.integers(0, 256, size=shape, dtype=np.uint8)
+            b[name] = buf
+        batches.append(b)
+    pipe = InferencePipeline(step, depth=3, graph=graph)
+    seen = 0
+    for tag, outs in pipe.run(batches):
+        mask, hits, line, char = [np.array(o) for o in outs]
+        assert mask.dtype == np.uint8 and hits.dtype == np.uint8 and line.dtype == np.float32
+        assert np.array_equal(mask.astype(bool), O.thresholded(line))
+        rowmax = char.max(axis=1, keepdims=True)
+        assert np.array_equal(hits.astype(bool), (char == rowmax) & (rowmax != 0))
+        x_line = (np.asarray(batches[tag]['line'], dtype=np.float64) / 255.0).astype(np.float32).astype(np.float64)
+        want = np_models.forward(np_models.net_spec('line'), weights['line'], x_line)
+        assert rel_max(line, want) <= 1e-4
+        seen += 1
+    assert seen == 5

@@ -337,8 +337,8 @@ def test_monochrome_pair_backward_tensor_core(nn):
             try:
                 for mode in (0, 1):
                     ws = nn.DeviceArray(((need.value + 3) // 4,))
-                    g = [nn.DeviceArray.zeros(s_) for s_ in ((3, 3, 1, 16), (16,), (3, 3, 16, 1), (1,))]
-                    lib.uocr_conv3x3_pair_bwd_mode(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, None, g[0].ptr,
+                    g = [nn.DeviceArray.zeros(s_) for s_ in ((3, 3, 1, 16), (16,), (3, 3, 16, 1), (1,), (n, h, w, 1))]
+                    lib.uocr_conv3x3_pair_bwd_mode(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, g[4].ptr, g[0].ptr,
                                                    g[1].ptr, g[2].ptr, g[3].ptr, n, h, w, 16, act1, 0.01, 0, ws.ptr,
                                                    need.value, mode, nn.CP.stream())
                     outs.append([np.asarray(t.get(), dtype=np.float64) for t in g])
@@ -346,14 +346,15 @@ def test_monochrome_pair_backward_tensor_core(nn):
                 os.environ.pop('UOCR_PAIR_WGRAD_EXACT_MASK', None)
             # sums over a handful of pixels have no averaging of the per-product TF32 rounding: 2e-3 there
             tol = 2e-3 if n * h * w < 64 else 1e-3
-            for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2'), outs[1], outs[0]):
+            # dx (conv3x3_pair_dgrad in the TF32 dispatch) is checked too: round 1 passed dx = NULL here
+            for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2', 'dx'), outs[1], outs[0]):
                 close_tf32(a, b, f'pair bwd tc vs fp32 {name} {(n, h, w)} exact={exact}', tol=tol)
             if h * w <= 4000:
                 hid = O.conv2d_fwd(X, w1, b1, 1)
                 act = O.leaky_relu_fwd(hid, 0.01) if act1 == ACT_LEAKY else hid
                 dact, odw2, odb2 = O.conv2d_bwd(act, w2, dy, 1, 0.0, 1)
                 dhid = dact * np.where(hid >= 0, 1.0, 0.01) if act1 == ACT_LEAKY else dact
-                _, odw1, odb1 = O.conv2d_bwd(X, w1, dhid, 1, 0.0, 1)
-                for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2'), outs[1], (odw1, odb1, odw2, odb2)):
+                odx, odw1, odb1 = O.conv2d_bwd(X, w1, dhid, 1, 0.0, 1)
+                for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2', 'dx'), outs[1], (odw1, odb1, odw2, odb2, odx)):
                     close_tf32(a, np.asarray(b, dtype=np.float64).reshape(a.shape),
                                f'pair bwd tc vs oracle {name} {(n, h, w)} exact={exact}', tol=tol)

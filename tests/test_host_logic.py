@@ -238,3 +238,80 @@ def test_progress_tracker_protocol():
     assert events == ['forward', 'forward']
     summary = tracker.get_summary()['thing'][0]
     assert summary['name'] == 'forward' and summary['done'] and summary['counter'] == 1
+
+
+# ----------------------------------------------------------------------------- data-parallel host logic
+
+def _char_like_ranges():
+    """Flat layout of make_char as nn.flat.FlatParameters builds it: the L2 group (convs) first, then the
+    unregularised FullyConnected layers, each group in evaluation order."""
+    sizes = [('conv_1', 5 * 3 * 1 * 64 + 64), ('conv_2', 5 * 3 * 64 * 64 + 64), ('conv_3', 5 * 3 * 64 * 64 + 64),
+             ('dense_1', 513 * 1024), ('dense_2', 1025 * 128), ('dense_3', 129 * 162)]
+    ranges, off = {}, 0
+    for name, n in sizes:
+        n_al = (n + 3) // 4 * 4
+        ranges[name] = (off, off + n_al)
+        off += n_al
+    return ranges, off
+
+
+def test_bucket_scheduler_sends_every_gradient_once_largest_layers_first():
+    from univer_ocr_b200.nn.flat import BucketScheduler
+    ranges, total = _char_like_ranges()
+    sched = BucketScheduler(ranges, bucket_elems=(256 << 10) // 4)
+    backward_order = ['dense_3', 'leaky_relu_2', 'dense_2', 'leaky_relu_1', 'dense_1', 'flatten', 'fixed_width',
+                      'conv_3', 'conv_2', 'conv_1']
+    sent, timeline = [], []
+    for name in backward_order:
+        out = sched.layer_done(name)
+        sent += out
+        timeline.append((name, out))
+    sent += sched.finish()
+    covered = sorted(sent)
+    assert covered[0][0] == 0 and covered[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))           # a partition: no gap, no overlap
+    # dense_3 alone (20 898 gradients) stays below the 64 Ki-element threshold and rides with dense_2
+    assert timeline[0][1] == [] and timeline[2][1] == [(ranges['dense_2'][0], ranges['dense_3'][1])]
+    assert timeline[4][1] == [ranges['dense_1']]                             # 2.1 MB leave as soon as dense_1 is done
+    # the conv group is not adjacent to anything pending and conv_1 (1 024 gradients) only leaves at the end
+    assert sent[-1][0] == 0
+    # a second step starts clean
+    sched.reset()
+    assert sched.layer_done('dense_1') == [ranges['dense_1']]
+    assert sched.layer_done('dense_1') == []                                 # reported twice: sent once
+
+
+def test_bucket_scheduler_flushes_a_non_adjacent_range_and_unreported_layers():
+    from univer_ocr_b200.nn.flat import BucketScheduler
+    sched = BucketScheduler({'a': (0, 8), 'b': (8, 16), 'c': (16, 24), 'frozen': (24, 24)}, bucket_elems=1000)
+    assert sched.layer_done('c') == []
+    assert sched.layer_done('a') == [(16, 24)]                               # not adjacent to c: c leaves, a is pending
+    assert sched.layer_done('unknown_activation') == [] and sched.layer_done('frozen') == []
+    assert sorted(sched.finish()) == [(0, 8), (8, 16)]                       # pending a + b, which never reported
+
+
+def test_rendezvous_file_is_unique_per_launch(monkeypatch):
+    from univer_ocr_b200 import comm
+    a = comm.rendezvous_file({'MASTER_PORT': '29501', 'TORCHELASTIC_RUN_ID': 'none'})
+    b = comm.rendezvous_file({'MASTER_PORT': '29502', 'TORCHELASTIC_RUN_ID': 'none'})
+    assert a != b and str(os.getppid()) in a                                 # ranks of one launch share their parent
+    assert comm.rendezvous_file({'UOCR_RDZV_FILE': '/tmp/x.id'}) == '/tmp/x.id'
+    single = comm.init(0, 1)
+    assert (single.rank, single.world) == (0, 1) and single.allreduce_host([1.5, 2.0], 'max') == [1.5, 2.0]
+    assert single.broadcast_ints([3, 1, 2]) == [3, 1, 2]
+    comm.use(None)
+
+
+def test_package_does_not_import_torch():
+    """north_star: no PyTorch in the path.  Nothing under univer_ocr_b200/ may import torch (bench.py's launcher glue
+    and the tests are the only users)."""
+    import re
+    pkg = os.path.join(ROOT, 'univer_ocr_b200')
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                text = open(os.path.join(dirpath, f)).read()
+                if re.search(r'^\s*(import torch|from torch)', text, re.M):
+                    offenders.append(os.path.join(dirpath, f))
+    assert offenders == []

@@ -136,10 +136,19 @@ def test_submodel_train_golden(golden, name):
     w = np_models.golden_weights(name, g['seed'])
     state = np_models.new_adam_state(w)
     close(np_models.forward(spec, w, g['X']), g['pred0'])
+    if name != 'char':                                  # un-saturated: the data gradient is visible next to the L2 term
+        assert 0.02 < g['pred0'].mean() < 0.98 and g['pred0'].std() > 0.03
+    assert abs(float(g['loss1']) - float(g['loss2'])) > 1e-4 * abs(float(g['loss1']))
     for step in (1, 2):
-        losses, _, _, _ = np_models.train_step(spec, kind, w, state, g['X'], g['y'], lr=0.0015)
+        losses, grads, _, _ = np_models.train_step(spec, kind, w, state, g['X'], g['y'], lr=0.0015)
         close(losses['output_losses'][0], g[f'loss{step}'], rtol=1e-9)
         close(losses['regularization_loss'], g[f'reg{step}'], rtol=1e-9)
+        for key, p in grads.items():                    # gradients (incl. L2) as the reference had them BEFORE Adam
+            for n, gr in p.items():
+                tag = f'grad{step}__{key}.{n}'.replace('/', '.')
+                idx = g[f'after__{key}.{n}__idx'.replace('/', '.')]
+                close(gr.ravel()[idx], g[f'{tag}__val'], rtol=1e-8, atol=1e-9 * float(g[f'{tag}__max']))
+                close(np.sqrt((gr * gr).sum()), g[f'{tag}__l2'], rtol=1e-8)
     for key, p in w.items():
         for n, v in p.items():
             tag = f'after__{key.replace("/", ".")}/{n}'.replace('/', '.')

@@ -104,11 +104,13 @@ def test_batched_steps_stack_samples_and_weight_mean_losses():
     assert abs(best['m'][0] - want) < 1e-12 and epoch == {'m': 1}
 
 
-def _two_rank_worker(rank, world, port, out):
+def _two_rank_worker(rank, world, port, out, mode):
     sys.path.insert(0, ROOT)
+    import random
     import torch.distributed as dist
     os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
+    from tests.gloo_comm import GlooComm
     from univer_ocr_b200.trainer import Trainer
     opt = trainer_cases.ScriptedOptimizer(0.0)
     trace = []
@@ -116,25 +118,34 @@ def _two_rank_worker(rank, world, port, out):
     train_ds = trainer_cases.ScriptedDataset(['m'], 7, 3)         # 7 samples, stacks of 2: the last, single sample is dropped
     val_ds = trainer_cases.ScriptedDataset(['m'], 4, 4)
     saves = []
+    kwargs = {}
+    if mode == 'fixed':
+        kwargs['shuffle'] = lambda order: None
+    else:                                                         # the default random.shuffle, seeded DIFFERENTLY per rank
+        random.seed(1000 + rank)
     t = Trainer({'m': model}, train_ds, val_ds, optimizer=opt, batch_size=2, save_weights_func=saves.append,
-                shuffle=lambda order: None, log=lambda *a, **k: None)
+                log=lambda *a, **k: None, comm=GlooComm(), **kwargs)
     best, _ = t.train(1)
     out.put((rank, best['m'][0], [e[2] for e in trace if e[0] == 'train'], len(saves)))
     dist.destroy_process_group()
 
 
-def test_two_ranks_shard_each_batch_and_agree_on_losses():
+def _run_two_ranks(mode, port_base):
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     out = ctx.Queue()
-    port = 29900 + os.getpid() % 90
-    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, out)) for r in range(2)]
+    port = port_base + os.getpid() % 90
+    procs = [ctx.Process(target=_two_rank_worker, args=(r, 2, port, out, mode)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    got = sorted(out.get(timeout=10) for _ in range(2))
+    return sorted(out.get(timeout=10) for _ in range(2))
+
+
+def test_two_ranks_shard_each_batch_and_agree_on_losses():
+    got = _run_two_ranks('fixed', 29900)
     train_ds = trainer_cases.ScriptedDataset(['m'], 7, 3)
     val_ds = trainer_cases.ScriptedDataset(['m'], 4, 4)
     x = [round(float(np.mean(train_ds.get(i)['m'][0])), 9) for i in range(6)]
@@ -142,6 +153,50 @@ def test_two_ranks_shard_each_batch_and_agree_on_losses():
     want = sum((0.5 - float(np.mean(val_ds.get(i)['m'][0]))) ** 2 for i in range(4)) / 4
     assert abs(got[0][1] - want) < 1e-12 and got[0][1] == got[1][1]   # losses summed over ranks
     assert (got[0][3], got[1][3]) == (1, 0)                    # only rank 0 saves
+
+
+def test_two_ranks_agree_on_the_shuffled_order():
+    """Per-process random.shuffle (differently seeded ranks): rank 0's permutation is broadcast, so the two ranks'
+    slices are disjoint and together cover the 6 samples an epoch consumes (7 samples, stacks of 2, world 2)."""
+    got = _run_two_ranks('random', 29800)
+    train_ds = trainer_cases.ScriptedDataset(['m'], 7, 3)
+    x = [round(float(np.mean(train_ds.get(i)['m'][0])), 9) for i in range(7)]
+    seen = got[0][2] + got[1][2]
+    assert len(got[0][2]) == len(got[1][2]) == 3
+    assert len(set(seen)) == 6 and set(seen) <= set(x)         # a partition: nothing trained twice, one sample left out
+    assert got[0][1] == got[1][1]
+
+
+def test_multi_rank_rejects_samples_that_miss_a_model():
+    from univer_ocr_b200.trainer import Trainer
+
+    class TwoRanks:
+        rank, world = 0, 2
+
+        def allreduce_host(self, values, op='sum'):
+            return list(values)
+
+        def broadcast_ints(self, values, root=0):
+            return list(values)
+
+    opt = trainer_cases.ScriptedOptimizer(0.0)
+    models = {'a': trainer_cases.ScriptedModel('a', 0.5, opt), 'b': trainer_cases.ScriptedModel('b', 0.5, opt)}
+    full = trainer_cases.ScriptedDataset(['a', 'b'], 4, 3)
+
+    class Ragged:
+        def __len__(self):
+            return 4
+
+        def get(self, i):
+            sample = full.get(i)
+            if i == 2:
+                del sample['b']
+            return sample
+
+    t = Trainer(models, Ragged(), full, optimizer=opt, batch_size=2, log=lambda *a, **k: None, comm=TwoRanks(),
+                shuffle=lambda order: None, prefetch=0)
+    with pytest.raises(ValueError, match='every model in every sample'):
+        t.train(1)
 
 
 def test_prefetch_overlaps_host_batching_with_training_and_keeps_order():

@@ -60,13 +60,8 @@ def main():
         lib.uocr_event_elapsed_ms(e0, e1, ctypes.byref(ms))
         best = min(best, ms.value)
     if world > 1:
-        import torch
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0))))
-        t = torch.tensor([best], device='cuda')
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        best = float(t.item())
-        dist.destroy_process_group()
+        from univer_ocr_b200 import comm as comm_
+        best = comm_.init_from_env().allreduce_host([best], 'max')[0]
     if rank == 0:
         pages = -(-mine // args.batch) * args.batch * world
         print(json.dumps({'config': 'full-page 2064x2064 Monochrome->Paragraph, pages sharded round-robin',

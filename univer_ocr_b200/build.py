@@ -76,7 +76,7 @@ def build(force=False, verbose=False, extra_flags=()):
                 print(f'--- {os.path.basename(obj)}\n{log}')
     objs = [o for o, _ in results]
     if force or any(j[2] for j in jobs) or not os.path.exists(LIB_PATH):
-        cmd = [nvcc, '-shared', '-o', LIB_PATH, *objs, '-lcudart', '-Xlinker', '--no-undefined']
+        cmd = [nvcc, '-shared', '-o', LIB_PATH, *objs, '-lcudart', '-ldl', '-Xlinker', '--no-undefined']
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f'link failed:\n{res.stdout}\n{res.stderr}')

@@ -130,6 +130,32 @@ __global__ void __launch_bounds__(kThreads) convert_kernel(TO* __restrict__ dst,
         dst[i] = static_cast<TO>(src[i]) * static_cast<TO>(scale);
 }
 
+// uint8 image planes -> float32 pixel / divisor (the reference's `encode_layers`: PNG planes / 255 in float64,
+// train_data_generator.py:24-37).  dst must equal float32(float64(u) / divisor): a multiplication by 1/255 is off by
+// one ulp for 126 of the 256 values, an IEEE division is exact for all of them (tests/test_gpu_round2.py), so the
+// 256 quotients are formed once per CTA with __fdiv_rn and looked up: 16 pixels per thread, one 128-bit load and four
+// 128-bit stores.
+__global__ void __launch_bounds__(kThreads) u8_div_kernel(float* __restrict__ dst, const uint8_t* __restrict__ src,
+                                                          float divisor, int64_t n) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = __fdiv_rn((float)threadIdx.x, divisor);            // kThreads == 256
+    __syncthreads();
+    const int64_t n16 = n / 16;
+    const uint4* src16 = reinterpret_cast<const uint4*>(src);
+    float4* dst4 = reinterpret_cast<float4*>(dst);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n16; i += (int64_t)gridDim.x * kThreads) {
+        const uint4 v = __ldg(src16 + i);
+        const uint32_t words[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t wd = words[k];
+            dst4[i * 4 + k] = make_float4(lut[wd & 255u], lut[(wd >> 8) & 255u], lut[(wd >> 16) & 255u], lut[wd >> 24]);
+        }
+    }
+    for (int64_t i = n16 * 16 + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        dst[i] = lut[src[i]];
+}
+
 __global__ void __launch_bounds__(kThreads) nan_flag_kernel(const float* __restrict__ x, int64_t n,
                                                             int32_t* flag) {
     bool bad = false;
@@ -679,6 +705,18 @@ int uocr_u8_to_f32(float* dst, const uint8_t* src, float scale, int64_t n, void*
     UOCR_REQUIRE(dst && src, "NULL pointer");
     convert_kernel<float, uint8_t><<<ew_grid(n, 4), kThreads, 0, as_stream(stream)>>>(dst, src, scale, n);
     UOCR_LAUNCHED("u8_to_f32");
+    return UOCR_OK;
+}
+
+int uocr_u8_div_f32(float* dst, const uint8_t* src, float divisor, int64_t n, void* stream) {
+    if (n <= 0) return UOCR_OK;
+    UOCR_REQUIRE(dst && src, "NULL pointer");
+    UOCR_REQUIRE(divisor != 0.f, "divisor is 0");
+    UOCR_REQUIRE((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0,
+                 "dst and src must be 16-byte aligned");
+    static_assert(kThreads == 256, "u8_div_kernel builds its 256-entry table with one thread per entry");
+    u8_div_kernel<<<ew_grid(n, 16), kThreads, 0, as_stream(stream)>>>(dst, src, divisor, n);
+    UOCR_LAUNCHED("u8_div_f32");
     return UOCR_OK;
 }
 

@@ -205,9 +205,17 @@ __global__ void __launch_bounds__(kThreads) sigmoid_ce_kernel(const float* __res
     float acc = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * kThreads) {
-        const float p = 1.f / (1.f + expf(-logits[i]));
+        const float x = logits[i];
+        const float p = 1.f / (1.f + expf(-x));
         const float g = gt[i];
-        acc += g * logf(p) + (1.f - g) * logf(1.f - p);          // losses.py:54
+        // log p = -softplus(-x), log(1 - p) = -softplus(x): logf(1 - p) on the FP32 p is -inf from x ~ 16.6 on, where
+        // the float64 reference is still finite.  The reference's own 0 * -inf = NaN / -inf are kept where FLOAT64
+        // produces them: p == 1.0 for x > 36.74 (1 + e^-x rounds to 1), p == 0.0 for x < -745.13 (e^-x overflows).
+        const float t = log1pf(expf(-fabsf(x)));
+        float logp = -(fmaxf(-x, 0.f) + t), logq = -(fmaxf(x, 0.f) + t);
+        if (x > 36.7368f) { logp = 0.f; logq = -INFINITY; }
+        if (x < -745.13f) { logp = -INFINITY; logq = 0.f; }
+        acc += g * logp + (1.f - g) * logq;                      // losses.py:54
         if (grad) grad[i] = (g * (p - 1.f) + (1.f - g) * p) * inv_b;   // losses.py:56
     }
     acc = block_sum(acc, red);

@@ -6,6 +6,7 @@ stages only need (a) the page padded to a multiple of 16, (b) a binarised mask o
 map, (c) which characters won each window.  These three run on the device here, so what crosses
 the host link is uint8 masks / hit tables (1 byte per element instead of 8):
 
+    pixels_to_unit      my_model/train_data_generator.py:24-37  (uint8 planes / 255, widened on the device)
     make_divisible_by   my_model/model.py:26-34
     thresholded         interpreter/interpreter.py:437-438, 549   (arr > 0.5 * (mean + max))
     row_max_hits / pred_to_text   interpreter/interpreter.py:595-614  (PredToText._func1)
@@ -30,6 +31,17 @@ def make_divisible_by(arr, y, x):
     top, left = add_y // 2, add_x // 2
     out = DeviceArray.empty((n, h + add_y, w + add_x, c))
     lib.uocr_pad_hw_f32(out.ptr, arr.ptr, n, h, w, c, top, add_y - top, left, add_x - left, 0.0, stream())
+    return out
+
+
+def pixels_to_unit(arr, divisor=255.0):
+    """uint8 image planes (device or host, any shape) -> float32 `pixel / 255`, bit-identical to the float32 storage of
+    the reference's `encode_layers` output (`train_data_generator.py:24-37`: PNG planes / 255 in float64).  Uploading
+    the bytes and widening them here moves a quarter of the float32 payload over the host link."""
+    arr = as_device(arr) if isinstance(arr, DeviceArray) else DeviceArray.from_host(np.asarray(arr, np.uint8), np.uint8)
+    assert arr.dtype == np.uint8, f'expected uint8 pixels, got {arr.dtype}'
+    out = DeviceArray.empty(arr.shape, np.float32)
+    lib.uocr_u8_div_f32(out.ptr, arr.ptr, float(divisor), arr.size, stream())
     return out
 
 

@@ -14,7 +14,7 @@ from .nn.help_func import make_list_if_not
 from .nn.layers import (Concat, Conv2DToBatchedFixedWidthed, Convolutional2D, Flatten,
                         FullyConnected, LeakyRelu, Sigmoid, Upsample2D)
 from .nn.losses import SegmentationDice2D, SoftmaxCrossEntropy
-from .nn.models import HourglassFusion, Model
+from .nn.models import Model
 from .nn.optimizers import Adam
 from .nn.regularizations import L2
 
@@ -108,10 +108,8 @@ def _make_hourglass(name, input_shape, channels, out_channels, optimizer):
         0: 'end',
     }
     model = wrap(name, Model(layers=layers, relations=relations), loss=SegmentationDice2D())
-    if channels == 1 and out_channels == 1:
-        model.infer_fusion = HourglassFusion(name)      # whole-network inference kernel (Paragraph)
-    model.initialize(input_shape)
-    return model
+    model.initialize(input_shape)       # Paragraph (1 -> 1 channels): Model recognises the hourglass and attaches
+    return model                        # its whole-network inference kernel (nn.models.HourglassFusion.detect)
 
 
 def make_paragraph(input_shape, optimizer=None):

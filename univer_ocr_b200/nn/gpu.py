@@ -356,6 +356,11 @@ class LazyScalar:
             self._dev = None
         return self._val
 
+    def peek(self):
+        """The value on the device right now, without caching it: a step replayed from a CUDA graph hands back the
+        same LazyScalar objects every time, over buffers the replay rewrites."""
+        return self._dev.item() if self._dev is not None else self._val
+
     def _f(op):
         def fn(self, other):
             return getattr(float(self), op)(float(other))
@@ -464,7 +469,11 @@ class CP:
     """Same surface as the reference's `CP` (nn/gpu.py:5-29)."""
     cp = _DeviceNamespace
     is_gpu_used = True
-    math_mode = MATH_FP32
+    # TF32 (tcgen05 tensor-core kernels, FP32 accumulate, 1e-3 tolerance contract) is the default on sm_100 devices:
+    # a drop-in user gets the fast path without knowing about `set_math_mode`.  `set_math_mode('fp32')` (or
+    # UOCR_MATH=fp32) selects the FP32-FFMA check mode; the first `use_gpu()` settles the default (`_math_mode_set`).
+    math_mode = MATH_TF32
+    _math_mode_set = False
     # bumped by everything that changes parameter values (Param.value = ..., optimizer updates, the flat-buffer
     # DataParallel update): layers key their cached K-major weight copies on it
     weights_generation = 0
@@ -473,6 +482,15 @@ class CP:
     def use_gpu():
         RT.ensure()
         CP.is_gpu_used = True
+        if not CP._math_mode_set:
+            CP._math_mode_set = True
+            env = os.environ.get('UOCR_MATH')
+            if env in ('fp32', 'tf32'):
+                CP.math_mode = {'fp32': MATH_FP32, 'tf32': MATH_TF32}[env]
+            else:
+                major = ctypes.c_int(0)
+                lib.uocr_device_info(RT.device, None, 0, None, ctypes.byref(major), None, None, None)
+                CP.math_mode = MATH_TF32 if major.value == 10 else MATH_FP32     # tcgen05 kernels are sm_100a only
 
     @staticmethod
     def use_cpu():
@@ -484,6 +502,7 @@ class CP:
         """'fp32' -- FFMA everywhere (check mode); 'tf32' -- tcgen05 TF32 tensor-core kernels for
         the dense contractions (Char 64->64 convolutions, FullyConnected), FP32 accumulate."""
         CP.math_mode = {'fp32': MATH_FP32, 'tf32': MATH_TF32}[mode]
+        CP._math_mode_set = True
 
     @staticmethod
     def copy(obj):

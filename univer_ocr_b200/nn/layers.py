@@ -58,33 +58,88 @@ _DEFAULT_OPTIMIZER = Adam()     # the reference's default argument is one shared
 
 
 class Param:
-    """A trainable tensor with its gradient and optimiser hook (layers.py:10-21)."""
+    """A trainable tensor with its gradient and optimiser hook (layers.py:10-21).
+
+    Once `nn.flat.FlatParameters` has adopted the parameter (`pin`), `value` and `grad` are views into the model's
+    flat buffers and assignments copy INTO those views instead of re-binding the attribute, so `set_weights`,
+    roll-backs and user code that writes `param.grad = ...` keep operating on the memory the fused update reads."""
 
     def __init__(self, value, optimizer=None):
         self._value = None
+        self._grad = None
+        self._pinned = False
+        self._pending = None                 # host values not uploaded yet (see `value`)
         self.value = value
-        self.grad = DeviceArray.zeros(self._value.shape)
         self.optimizer = optimizer
         self.optimizer.add_param(self)
 
+    @staticmethod
+    def _coerce(new):
+        return new if isinstance(new, DeviceArray) else CP.copy(np.asarray(new, dtype=np.float64))
+
+    def _assign(self, slot, new):
+        cur = getattr(self, slot)
+        new = self._coerce(new)
+        if self._pinned and cur is not None and new.shape == cur.shape:
+            if new.ptr != cur.ptr:
+                lib.uocr_memcpy_d2d(cur.ptr, new.ptr, cur.nbytes, stream())
+        else:
+            if self._pinned and slot == '_value':
+                self._pinned = False                    # shape changed: the flat owner re-adopts on its next update
+            setattr(self, slot, new)
+
+    # Host values handed to a parameter that has no device tensor yet (construction: initialiser draws, `w=` / `b=`
+    # arguments) are uploaded on first use, and the zero gradient is allocated on first use: building a network and
+    # analysing it (`get_all_output_shapes`, `count_parameters`, receptive fields, fusion plans) needs no device.
+    @property
+    def shape(self):
+        return self._pending.shape if self._pending is not None else self._value.shape
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64))
+
     @property
     def value(self):
+        if self._pending is not None:
+            host, self._pending = self._pending, None
+            self._value = CP.copy(host)
         return self._value
 
     @value.setter
     def value(self, new):
-        self._value = new if isinstance(new, DeviceArray) else CP.copy(np.asarray(new, dtype=np.float64))
+        if self._value is None and not isinstance(new, DeviceArray):
+            self._pending = np.asarray(new, dtype=np.float64)
+        else:
+            self._pending = None
+            self._assign('_value', new)
         CP.weights_generation += 1
+
+    @property
+    def grad(self):
+        if self._grad is None:
+            self._grad = DeviceArray.zeros(self.shape)
+        return self._grad
+
+    @grad.setter
+    def grad(self, new):
+        self._assign('_grad', new)
+
+    def pin(self, value_view, grad_view):
+        """Re-binds value / grad to views of a flat buffer (their contents were copied by the caller)."""
+        self._value, self._grad, self._pinned = value_view, grad_view, True
 
     def update_grad(self):
         self.optimizer.update(self)
         CP.weights_generation += 1
 
     def clear_grad(self):
-        if self.grad.shape != self._value.shape:
-            self.grad = DeviceArray.zeros(self._value.shape)
+        if self._grad is None:
+            return                               # allocated as zeros on first use
+        if self._grad.shape != self.shape:
+            self._grad = DeviceArray.zeros(self.shape)
         else:
-            self.grad.fill(0)
+            self._grad.fill(0)
 
 
 class BaseLayer:
@@ -161,20 +216,20 @@ class BaseLayer:
             error = None
             if np.any(np.isnan(new)):
                 error = 'NaN found in loaded weights'
-            elif new.shape != param.value.shape:
-                error = f'Shapes don`t match: {new.shape} != {param.value.shape}'
+            elif new.shape != param.shape:
+                error = f'Shapes don`t match: {new.shape} != {param.shape}'
             if error is not None:
                 print(f'{self.name}/{name}: {error}, skipping')
                 continue
-            param.value = CP.copy(new)
+            param.value = new                    # uploaded now if the parameter already lives on the device
 
     def nan_weights(self):
         return any(param.value.isnan_any() for param in self.params().values())
 
     def count_parameters(self, param=None):
         if param is not None:
-            return self.params()[param].value.size
-        return sum(p.value.size for p in self.params().values())
+            return self.params()[param].size
+        return sum(p.size for p in self.params().values())
 
     def regularize(self, loss_dev=None):
         """grad += regulariser gradient for EVERY param of the layer (w and b), returns the

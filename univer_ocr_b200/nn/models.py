@@ -206,6 +206,10 @@ class Model(BaseModel):
             print(f'These layers have never been visited: {never}')
         self._plan_train = self._make_plan(training=True)
         self._plan_infer = self._make_plan(training=False)
+        if self.fusion and self.infer_fusion is None:
+            # whole-network inference kernels are recognised from the topology, so networks built by the reference's
+            # own my_model/model.py (which knows nothing about them) get them as well
+            self.infer_fusion = HourglassFusion.detect(self)
         self._fusion_planned = bool(self.fusion)                    # like the plans: fixed at initialize
         self.is_initialized = True
 
@@ -321,6 +325,10 @@ class Model(BaseModel):
             elif kind == 'winfc':
                 self._run_winfc(step, value_of, outputs)
             else:
+                if clear_grads:                                    # reference :188, for every member of the fused pair
+                    for member in step[1:]:
+                        if member is not None:
+                            self.layers[member].clear_grads()
                 self._run_pair(step, value_of, outputs, training)
         for key in self._output_keys():
             outputs[key] = value_of(self.relations[key][0])
@@ -406,9 +414,13 @@ class Model(BaseModel):
         outputs[a2_name if a2_name is not None else c2_name] = y
 
     @track_method('backward')
-    def backward(self, grads):
+    def backward(self, grads, on_layer_done=None):
+        """`on_layer_done(name)` is called as soon as the parameter gradients of layer `name` are final (its backward
+        kernels are queued on the current stream) -- the data-parallel step starts that layer's gradient allreduce
+        there, while the rest of backward runs."""
         grads = make_list_if_not(grads)
         produced = {}                                               # layer -> list of input grads
+        done = on_layer_done if on_layer_done is not None else (lambda name: None)
 
         def incoming(name):
             parts = []
@@ -432,6 +444,7 @@ class Model(BaseModel):
                     produced[name] = [None] * len(self.relations[name])
                 else:
                     produced[name] = make_list_if_not(layer.backward(incoming(name)))
+                done(name)
             elif name == step[3]:                                   # conv_2: keep its output gradient
                 stash[step[1]] = incoming(name)
                 produced[name] = [None]
@@ -441,6 +454,8 @@ class Model(BaseModel):
                 first = all(isinstance(src, int) for src in self.relations[name])
                 produced[name] = [self._pair_backward(step, stash.pop(name),
                                                       need_dx=self.compute_input_grads or not first)]
+                done(step[3])
+                done(name)
         for key in range(self.inputs_count):
             self.input_grads[key] = incoming(key) if self.compute_input_grads else None
         return [self.input_grads[k] for k in range(self.inputs_count)]
@@ -470,6 +485,8 @@ class Model(BaseModel):
 
     def compute_loss_and_gradients(self, X, y):
         X, y = make_list_if_not(X), make_list_if_not(y)
+        if self._flat:
+            self._flat.clean = False                                # gradients are about to be left in param.grad
         predicted = self.forward(X)
         losses, gradients = [], []
         for key in range(self.outputs_count):
@@ -479,7 +496,62 @@ class Model(BaseModel):
         self.backward(gradients)
         return {'output_losses': losses, 'regularization_loss': self.regularize()}
 
+    # `Model.train` (reference :250-254) = compute_loss_and_gradients -> update_grads -> clear_grads: per parameter
+    # tensor one regulariser kernel, one Adam kernel and one memset (the reference: ~12 CuPy kernels and a host sync
+    # each).  When the model is what my_model builds -- one shared Adam, L2 or no regulariser, everything trainable
+    # (`FlatParameters.eligible`) -- the same step runs on flat buffers: forward + loss + backward, then ONE fused
+    # L2 + Adam launch per regularisation group and ONE memset.  Same numbers (tests/test_gpu_parity.py); set
+    # `fused_update = False` (class or instance) for the per-parameter route.
+    fused_update = True
+    _flat = None
+
+    def fused_optimizer(self):
+        """The shared Adam instance if this model qualifies for the fused update right now, else None."""
+        from .flat import FlatParameters
+        if not self.is_initialized:
+            return None
+        return FlatParameters.eligible(self)
+
+    def flat_parameters(self):
+        """The model's `FlatParameters` (created on first use), or None if it does not qualify."""
+        if self._flat is None:
+            from .flat import FlatParameters
+            if self.fused_optimizer() is None:
+                return None
+            self._flat = FlatParameters(self)
+        return self._flat
+
+    def train_fused(self, X, y, reduce_gradients=None, grad_scale=1.0, on_layer_done=None):
+        """One training step on the flat buffers.  `reduce_gradients()` runs between backward and the update (the
+        data-parallel allreduce); returns the same dict as `train`."""
+        opt, flat = self.fused_optimizer(), self.flat_parameters()
+        assert flat is not None and opt is not None, 'model does not qualify for the fused update'
+        if not flat.attached():
+            flat.adopt()
+        if not flat.clean:
+            flat.zero_grads()
+        X, y = make_list_if_not(X), make_list_if_not(y)
+        keep, self.compute_input_grads = self.compute_input_grads, False    # `train` never surfaces dL/dX (:250-254)
+        try:
+            predicted = self.forward(X, clear_grads=False)
+            losses, gradients = [], []
+            for key in range(self.outputs_count):
+                loss, grad = self._loss_for(key)(predicted[key], y[key])
+                losses.append(loss)
+                gradients.append(grad)
+            flat.clean = False
+            self.backward(gradients, on_layer_done=on_layer_done)
+        finally:
+            self.compute_input_grads = keep
+        if reduce_gradients is not None:
+            reduce_gradients()
+        reg = flat.update(opt, grad_scale)
+        self.input_grads = {}
+        return {'output_losses': losses, 'regularization_loss': reg}
+
     def train(self, X, y):
+        if self.fused_update and self.fused_optimizer() is not None:
+            return self.train_fused(X, y)
         losses = self.compute_loss_and_gradients(X, y)
         self.update_grads()
         self.clear_grads()
@@ -704,6 +776,17 @@ class HourglassFusion:
                       f'{p}/up_2/upsample', f'{p}/up_2/conv_block/conv_1', f'{p}/up_2/conv_block/leaky_relu_1',
                       f'{p}/up_1/upsample', f'{p}/up_1/conv_block/conv_1', f'{p}/up_1/conv_block/leaky_relu_1',
                       f'{p}/end/conv_1', f'{p}/end/sigmoid']
+
+    @classmethod
+    def detect(cls, model):
+        """A HourglassFusion for `model` if its flattened layers are exactly the single-channel hourglass, else None."""
+        tail = '/down_1/conv_1'
+        for name in model.layers:
+            if name.endswith(tail):
+                fusion = cls(name[:-len(tail)])
+                if fusion._blocks(model) is not None:
+                    return fusion
+        return None
 
     def _blocks(self, model):
         """[(conv, act)] in kernel order, or None if the network is not the expected hourglass."""

@@ -1,103 +1,67 @@
-"""Batch-sharded data-parallel training step and the fused parameter update.
+"""Batch-sharded data-parallel training step.
 
-The reference trains with batch 1 on one device and, per step, runs for EVERY parameter tensor
-`regularizer(w)` (+ a host sync for the loss), `grad += reg_grad`, then ~9 CuPy kernels of Adam
-(`nn/layers/layers.py:147-155`, `nn/optimizers.py:56-61`), then re-allocates zero gradients
-(`layers.py:20-21`).  Here all parameters of a model live in ONE flat device buffer (values,
-gradients, Adam velocity / accumulator), every `Param.value / .grad` is a view into it, and one
-step is
+One process per GPU; every rank runs the step on its shard of the batch:
 
-    forward + loss + backward (gradients accumulate into the flat buffer)
-    [world > 1]  ONE NCCL sum-allreduce over the flat gradient buffer (NVLink / NVSwitch)
+    forward + loss + backward     gradients accumulate into the model's flat gradient buffer (nn/flat.py)
+      |  while backward runs: as soon as a layer's parameter gradients are final, the contiguous flat range they
+      |  complete is sum-allreduced over NVLink / NVSwitch on the communicator's SIDE stream (buckets grow in
+      |  reverse layer order, so the Char head's FullyConnected gradients -- 99 % of my_model's 3.2 MB -- are on
+      |  the wire while the convolutions' backward is still computing)
+    join: the compute stream waits for the last bucket
     ONE fused kernel per regularisation group: g*scale + 2*l2*w -> Adam -> w   (+ reg loss)
     ONE memset of the flat gradient buffer
 
-Gradient scaling: the Dice / Jaccard losses sum over the batch (`losses.py:23`), so shard
-gradients are summed without scaling; SoftmaxCE / SigmoidCE divide by the LOCAL batch
-(`losses.py:69-72`), so their summed gradients are scaled by 1 / world (= local / global batch).
-The L2 gradient depends on the weights only, so it is added once, after the allreduce.
+The collectives go through libuocr's own NCCL binding (`comm.Communicator` over `uocr_allreduce_sum_f32`); no
+PyTorch anywhere.  The whole step -- collectives included -- is a fixed launch sequence over fixed buffers and
+can be replayed from one CUDA graph (`pipeline.CapturedStep`).
+
+Gradient scaling: the Dice / Jaccard losses sum over the batch (`losses.py:23`), so shard gradients are summed
+without scaling; SoftmaxCE / SigmoidCE divide by the LOCAL batch (`losses.py:69-72`), so their summed gradients are
+scaled by 1 / world (= local / global batch).  The L2 gradient depends on the weights only, so it is added once,
+after the allreduce (inside the fused update).
 """
-import numpy as np
+import ctypes
 
-from .nn import optimizers
-from .nn.gpu import CP, DeviceArray, LazyScalar, stream
-from .nn.losses import SegmentationDice2D, SegmentationJaccard2D
-from .nn.regularizations import L2
+from . import comm as comm_
 from ._lib import lib
+from .nn import optimizers
+from .nn.flat import BucketScheduler, FlatParameters          # noqa: F401  (FlatParameters: public name)
+from .nn.gpu import CP, LazyScalar
+from .nn.losses import SegmentationDice2D, SegmentationJaccard2D
 
 
-class FlatParameters:
-    """Moves a model's parameters into flat buffers, grouped by L2 strength so that each group
-    is one contiguous range (one fused update launch)."""
-
-    def __init__(self, model):
-        self.model = model
-        groups = {}
-        for lname, layer in model.layers.items():
-            reg = getattr(layer, 'regularizer', None)
-            if reg is not None and not isinstance(reg, L2):
-                raise NotImplementedError('fused update supports L2 or no regulariser')
-            l2 = float(reg.reg_strength) if reg is not None else 0.0
-            if not layer.trainable:
-                continue
-            for pname, param in layer.params().items():
-                groups.setdefault(l2, []).append((f'{lname}/{pname}', param))
-        self.entries = []                       # (key, param, offset, size)
-        self.groups = []                        # (l2, offset, size)
-        offset = 0
-        for l2 in sorted(groups, reverse=True):
-            start = offset
-            for key, param in groups[l2]:
-                size = param.value.size
-                size_al = (size + 3) // 4 * 4   # keep every tensor 16-byte aligned
-                self.entries.append((key, param, offset, size))
-                offset += size_al
-            self.groups.append((l2, start, offset - start))
-        self.total = offset
-        self.values = DeviceArray.zeros((self.total,))
-        self.grads = DeviceArray.zeros((self.total,))
-        self.velocity = DeviceArray.zeros((self.total,))
-        self.accumulated = DeviceArray.zeros((self.total,))
-        self.adopt()
-
-    def adopt(self):
-        """(Re-)installs the views; call again after `set_weights` replaced parameter tensors."""
-        for key, param, offset, size in self.entries:
-            view = self.values.flat_view(offset, size, param.value.shape)
-            if param.value.ptr != view.ptr:
-                lib.uocr_memcpy_d2d(view.ptr, param.value.ptr, view.nbytes, stream())
-                param._value = view
-            gview = self.grads.flat_view(offset, size, param.value.shape)
-            if param.grad.ptr != gview.ptr:
-                param.grad = gview
-        lib.uocr_memset(self.grads.ptr, 0, self.grads.nbytes, stream())
+def _new_event():
+    e = ctypes.c_void_p()
+    lib.uocr_event_create(ctypes.byref(e))
+    return e.value
 
 
 class DataParallel:
     """One training step of `model` on this rank's shard of the batch.
 
-        dp = DataParallel(model, optimizer)        # world / rank from torch.distributed if initialised
-        losses = dp.train(X_shard, y_shard)        # same dict as Model.train
+        comm.init_from_env()                        # once per process (torchrun's RANK / WORLD_SIZE / LOCAL_RANK)
+        dp = DataParallel(model, optimizer)
+        losses = dp.train(X_shard, y_shard)         # same dict as Model.train
 
-    With world == 1 this is simply the fused single-GPU step."""
+    With world == 1 this is simply the fused single-GPU step (what `Model.train` itself runs).
+    `overlap=False` issues ONE allreduce over the whole flat buffer after backward, on the compute stream."""
 
-    def __init__(self, model, optimizer=None, process_group=None):
+    def __init__(self, model, optimizer=None, comm=None, overlap=True, bucket_bytes=256 << 10):
         self.model = model
-        model.compute_input_grads = False            # a training step never reads dL/dX
-        self.flat = FlatParameters(model)
         self.optimizer = optimizer if optimizer is not None else self._find_optimizer(model)
         if not isinstance(self.optimizer, optimizers.Adam):
             raise NotImplementedError('DataParallel fuses the Adam update (the only optimiser my_model uses)')
-        self.world, self.rank, self._torch, self._dist, self._tensor = 1, 0, None, None, None
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                import torch
-                self._torch, self._dist = torch, dist
-                self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
-                self.group = process_group
-        except ImportError:
-            pass
+        self.flat = model.flat_parameters()
+        if self.flat is None or model.fused_optimizer() is not self.optimizer:
+            raise NotImplementedError('DataParallel needs a model whose parameters share this Adam instance, '
+                                      'regularised by L2 or nothing (nn.flat.FlatParameters.eligible)')
+        self.comm = comm if comm is not None else comm_.current()
+        self.world, self.rank = self.comm.world, self.comm.rank
+        self.overlap = bool(overlap) and self.world > 1
+        self.scheduler = BucketScheduler(self.flat.layer_ranges, max(1, int(bucket_bytes) // 4))
+        self._ev_ready, self._ev_joined = (_new_event(), _new_event()) if self.world > 1 else (None, None)
+        self.buckets_last_step = []                     # [(lo, hi)] of the last step, in issue order
+        self.after_reduce = None                        # optional callable: sees the summed gradients before the update
         losses = model.loss if isinstance(model.loss, list) else [model.loss]
         summed = all(isinstance(l, (SegmentationDice2D, SegmentationJaccard2D)) for l in losses)
         self.grad_scale = 1.0 if summed else 1.0 / self.world
@@ -107,56 +71,65 @@ class DataParallel:
     @staticmethod
     def _find_optimizer(model):
         for layer in model.layers.values():
-            if layer.params():
-                return layer.optimizer
+            for param in layer.params().values():
+                return param.optimizer
         raise ValueError('model has no parameters')
 
-    def _as_tensor(self, arr):
-        """Zero-copy torch view of a DeviceArray (through __cuda_array_interface__)."""
-        return self._torch.as_tensor(arr, device=f'cuda:{self._torch.cuda.current_device()}')
-
-    def _on_compute_stream(self):
-        return self._torch.cuda.stream(self._torch.cuda.ExternalStream(stream()))
-
     def broadcast_parameters(self, src=0):
-        with self._on_compute_stream():
-            self._dist.broadcast(self._as_tensor(self.flat.values), src=src, group=self.group)
+        """Rank `src`'s parameters (and Adam state) on every rank."""
+        st = CP.stream()
+        for buf in (self.flat.values, self.flat.velocity, self.flat.accumulated):
+            self.comm.broadcast(buf, src, stream=st)
+        CP.weights_generation += 1
+
+    # ---- gradient reduction -----------------------------------------------------------
+    def _send(self, lo, hi):
+        """Sum-allreduce flat.grads[lo:hi] on the communicator's stream, after everything queued so far on the
+        current compute stream (the kernels that produced those gradients)."""
+        side = self.comm.stream
+        lib.uocr_event_record(self._ev_ready, CP.stream())
+        lib.uocr_stream_wait_event(side, self._ev_ready)
+        self.comm.allreduce_sum(self.flat.grads, lo, hi - lo, stream=side)
+        self.buckets_last_step.append((lo, hi))
+
+    def _layer_done(self, name):
+        for lo, hi in self.scheduler.layer_done(name):
+            self._send(lo, hi)
 
     def allreduce_gradients(self):
+        """After backward: flush what the buckets still hold and make the compute stream wait for the wire."""
         if self.world == 1:
             return
-        if self._tensor is None:
-            self._tensor = self._as_tensor(self.flat.grads)
-        with self._on_compute_stream():        # NCCL orders itself after the backward kernels
-            self._dist.all_reduce(self._tensor, op=self._dist.ReduceOp.SUM, group=self.group)
+        if not self.overlap:
+            self.comm.allreduce_sum(self.flat.grads, stream=CP.stream())
+            self.buckets_last_step = [(0, self.flat.total)]
+            return
+        for lo, hi in self.scheduler.finish():
+            self._send(lo, hi)
+        lib.uocr_event_record(self._ev_joined, self.comm.stream)
+        lib.uocr_stream_wait_event(CP.stream(), self._ev_joined)
+
+    def _reduce(self):
+        self.allreduce_gradients()
+        if self.after_reduce is not None:
+            self.after_reduce()
 
     def update(self):
-        """Fused L2 + Adam over the flat buffers, then zero the gradients.  Returns the
-        regularisation loss (of the pre-update weights, like `Model.regularize`)."""
-        opt, flat = self.optimizer, self.flat
-        reg_loss = DeviceArray.zeros((1,))
-        for l2, offset, size in flat.groups:
-            if size == 0:
-                continue
-            lib.uocr_adam_update(flat.values.ptr + 4 * offset, flat.grads.ptr + 4 * offset,
-                                 flat.velocity.ptr + 4 * offset, flat.accumulated.ptr + 4 * offset, size,
-                                 float(opt.lr), float(opt.beta1), float(opt.beta2), optimizers.EPS,
-                                 float(self.grad_scale), l2, reg_loss.ptr if l2 else None, stream())
-        lib.uocr_memset(flat.grads.ptr, 0, flat.grads.nbytes, stream())
-        CP.weights_generation += 1                      # the parameter views changed under the layers
-        return LazyScalar(reg_loss)
+        """Fused L2 + Adam over the flat buffers, then zero the gradients -> regularisation loss."""
+        reg = self.flat.update(self.optimizer, self.grad_scale)
+        return reg if isinstance(reg, LazyScalar) else LazyScalar(_zero_scalar())
 
     def train(self, X, y):
-        model = self.model
-        X = X if isinstance(X, list) else [X]
-        y = y if isinstance(y, list) else [y]
-        predicted = model.forward(X, clear_grads=False)
-        losses, gradients = [], []
-        for key in range(model.outputs_count):
-            loss, grad = model._loss_for(key)(predicted[key], y[key])
-            losses.append(loss)
-            gradients.append(grad)
-        model.backward(gradients)
-        self.allreduce_gradients()
-        reg = self.update()
-        return {'output_losses': losses, 'regularization_loss': reg}
+        self.scheduler.reset()
+        self.buckets_last_step = []
+        hook = self._layer_done if self.overlap else None
+        out = self.model.train_fused(X, y, reduce_gradients=self._reduce, grad_scale=self.grad_scale,
+                                     on_layer_done=hook)
+        if not isinstance(out['regularization_loss'], LazyScalar):
+            out['regularization_loss'] = LazyScalar(_zero_scalar())
+        return out
+
+
+def _zero_scalar():
+    from .nn.gpu import DeviceArray
+    return DeviceArray.zeros((1,))

@@ -51,7 +51,12 @@ class InferencePipeline:
         pipe = InferencePipeline(step_fn, depth=3)
         for tag, outs in pipe.run(batches):      # outs: list of pinned host arrays (valid until
             consume(outs)                         # `depth` further batches have been submitted)
-    """
+
+    Inputs and outputs keep their dtypes: a uint8 host array is uploaded as bytes into a uint8 device buffer (the
+    reference's inputs are 8-bit PNG planes, `train_data_generator.py:24-37`; `fn` widens them with
+    `glue.pixels_to_unit`), and whatever `fn` returns -- float32 maps, `glue.thresholded` uint8 masks,
+    `glue.row_max_hits` uint8 tables -- is downloaded as is.  So a step can ship what the next host stage consumes
+    (masks: `interpreter/interpreter.py:437-447`; hit tables: `:596-602`) instead of float32 everywhere."""
 
     def __init__(self, fn, depth=3, graph=False):
         """`graph=True`: every slot replays its forward as one CUDA graph (`CapturedStep` over the slot's fixed
@@ -63,6 +68,11 @@ class InferencePipeline:
         self.s_in, self.s_out = _new_stream(), _new_stream()
         self.slots = [_Slot() for _ in range(self.depth)]
         self.next = 0
+
+    @staticmethod
+    def _dtype_of(host_array):
+        """Device dtype of an input: uint8 stays uint8 (image bytes), everything else is float32 storage."""
+        return np.uint8 if np.asarray(host_array).dtype == np.uint8 else np.float32
 
     def _retire(self, slot):
         """Blocks until the slot's results are on the host and returns (tag, outputs)."""
@@ -78,12 +88,15 @@ class InferencePipeline:
         self.next += 1
         done = self._retire(slot) if slot.busy else None
         if slot.dev_in is None:
-            slot.dev_in = {k: DeviceArray(v.shape, np.float32) for k, v in host_inputs.items()}
+            # owned by the copy-in stream's pool for the pipeline's lifetime: a block recycled from the COMPUTE stream's
+            # free list could still be read by kernels queued there when the first H2D (on s_in) overwrites it
+            with CP.on_stream(self.s_in):
+                slot.dev_in = {k: DeviceArray(v.shape, self._dtype_of(v)) for k, v in host_inputs.items()}
         comp = compute_stream()
         # copy-in: the previous forward that read these device buffers must have finished
         lib.uocr_stream_wait_event(self.s_in, slot.ev_comp)
         for k, v in host_inputs.items():
-            src = np.ascontiguousarray(v, dtype=np.float32)
+            src = np.ascontiguousarray(v, dtype=slot.dev_in[k].dtype)
             assert src.shape == slot.dev_in[k].shape, f'{k}: {src.shape} != {slot.dev_in[k].shape}'
             lib.uocr_memcpy_h2d(slot.dev_in[k].ptr, src.ctypes.data, src.nbytes, self.s_in)
         lib.uocr_event_record(slot.ev_h2d, self.s_in)
@@ -98,7 +111,7 @@ class InferencePipeline:
         lib.uocr_event_record(slot.ev_comp, comp)
         # copy-out
         if slot.host_out is None:
-            slot.host_out = [CP.pinned_empty(o.shape, np.float32) for o in outs]
+            slot.host_out = [CP.pinned_empty(o.shape, o.dtype) for o in outs]
         lib.uocr_stream_wait_event(self.s_out, slot.ev_comp)
         for o, h in zip(outs, slot.host_out):
             lib.uocr_memcpy_d2h(h.ctypes.data, o.ptr, o.nbytes, self.s_out)

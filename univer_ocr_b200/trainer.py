@@ -16,8 +16,11 @@ What is different, on purpose:
   host between the networks, out of scope here) and calls `gc.collect()` after each
   (`trainer.py:231-232`).  Here every model gets its own batches: a data set's `get(i)` returns
   `{model_name: (X, y)}` with a leading batch axis, `batch_size` of them are stacked per step and,
-  with `torch.distributed` initialised, each rank trains its slice of the stack through
-  `parallel.DataParallel` (one NCCL allreduce over the flat gradient buffer per step);
+  with a multi-rank communicator (`univer_ocr_b200.comm`, NCCL through libuocr -- no PyTorch), each rank trains
+  its slice of the stack through `parallel.DataParallel` (bucketed NCCL allreduce of the flat gradient buffer,
+  overlapped with backward); rank 0's shuffled orders are broadcast so that the ranks' slices partition each
+  batch, and at world > 1 every sample must carry every model (a rank that skipped a model's step would leave
+  the others waiting in that model's allreduce);
 * loss values stay on the device during an epoch (`LazyScalar`), the epoch's sums are read back
   once and summed over ranks, so every rank takes the same NaN / best-weights decisions;
 * roll-back snapshots of `Model`s are device copies of the flat parameter buffer (3.2 MB) instead
@@ -152,7 +155,7 @@ def _mean_over_batch(model):
 class _Stepper:
     """One model behind the trainer: how to step it, snapshot it and roll it back."""
 
-    def __init__(self, model, optimizer, fused_update):
+    def __init__(self, model, optimizer, fused_update, comm=None):
         self.model, self.dp = model, None
         is_native = False
         try:
@@ -163,7 +166,7 @@ class _Stepper:
         self.mean_loss = _mean_over_batch(model) if is_native else bool(getattr(model, 'mean_over_batch', False))
         if is_native and fused_update:
             from .parallel import DataParallel
-            self.dp = DataParallel(model, optimizer)
+            self.dp = DataParallel(model, optimizer, comm=comm)
 
     def train(self, X, y):
         return (self.dp or self.model).train(X, y)
@@ -174,22 +177,13 @@ class _Stepper:
     def snapshot(self):
         if self.dp is None:
             return self.model.get_weights()
-        from .nn.gpu import DeviceArray, stream
-        from ._lib import lib
-        flat = self.dp.flat
-        copy = DeviceArray.zeros((flat.total,))
-        lib.uocr_memcpy_d2d(copy.ptr, flat.values.ptr, flat.values.nbytes, stream())
-        return copy
+        return self.dp.flat.snapshot()
 
     def restore(self, snapshot):
         if self.dp is None:
             self.model.set_weights(snapshot)
             return
-        from .nn.gpu import CP, stream
-        from ._lib import lib
-        flat = self.dp.flat
-        lib.uocr_memcpy_d2d(flat.values.ptr, snapshot.ptr, flat.values.nbytes, stream())
-        CP.weights_generation += 1
+        self.dp.flat.restore(snapshot)
 
 
 class Trainer:
@@ -211,7 +205,7 @@ class Trainer:
 
     def __init__(self, models, train_dataset, validation_dataset, progress_tracker=None,
                  optimizer=None, learning_rate_step=0.995, save_weights_func=None,
-                 batch_size=1, fused_update=True, shuffle=None, log=print, prefetch=2):
+                 batch_size=1, fused_update=True, shuffle=None, log=print, prefetch=2, comm=None):
         self.models = models
         self.train_dataset = train_dataset
         self.validation_dataset = validation_dataset
@@ -223,19 +217,15 @@ class Trainer:
         self.shuffle = shuffle if shuffle is not None else random.shuffle   # trainer.py:3
         self.log = log
         self.prefetch = int(prefetch)
-        self.world, self.rank, self._dist, self._torch = 1, 0, None, None
-        try:
-            import torch.distributed as dist
-            if dist.is_available() and dist.is_initialized():
-                import torch
-                self._dist, self._torch = dist, torch
-                self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        except ImportError:
-            pass
+        if comm is None:
+            from . import comm as comm_
+            comm = comm_.current()
+        self.comm = comm                                # rank / world / allreduce_host / broadcast_ints
+        self.world, self.rank = comm.world, comm.rank
         assert self.batch_size % self.world == 0, (
             f'batch_size {self.batch_size} must be divisible by the world size {self.world}')
         assert min(len(train_dataset), len(validation_dataset)) >= self.world, 'fewer samples than ranks'
-        self.steppers = {name: _Stepper(model, optimizer, fused_update) for name, model in models.items()}
+        self.steppers = {name: _Stepper(model, optimizer, fused_update, comm) for name, model in models.items()}
 
     # ---- plumbing -------------------------------------------------------------------
     def _message(self, *args):
@@ -243,13 +233,14 @@ class Trainer:
             self.progress_tracker.message(*args)
 
     def _reduce(self, values):
-        if self.world == 1:
-            return values
-        backend = self._dist.get_backend()
-        device = f'cuda:{self._torch.cuda.current_device()}' if backend == 'nccl' else 'cpu'
-        t = self._torch.tensor(values, dtype=self._torch.float64, device=device)
-        self._dist.all_reduce(t)
-        return t.cpu().tolist()
+        return values if self.world == 1 else self.comm.allreduce_host(values, 'sum')
+
+    def _shuffle(self, order):
+        """The reference's in-place `random.shuffle` (`trainer.py:207,211`); with several ranks, rank 0's permutation
+        is the epoch's order everywhere -- per-process shuffles would make the ranks' [rank::world] slices overlap."""
+        self.shuffle(order)
+        if self.world > 1:
+            order[:] = self.comm.broadcast_ints(order, root=0)
 
     @staticmethod
     def _stack(parts):
@@ -321,6 +312,10 @@ class Trainer:
             batch = {}
             for name in self.models:
                 parts = [s[name] for s in samples if name in s]
+                if self.world > 1 and len(parts) != len(samples):
+                    raise ValueError(f'data-parallel training needs every model in every sample: {name!r} is missing '
+                                     f'from {len(samples) - len(parts)} of this rank\'s {len(samples)} samples (a rank '
+                                     f'that skips a model\'s step leaves the others waiting in its allreduce)')
                 if parts:
                     X, y = self._stack(parts)
                     batch[name] = (X, y, len(parts))
@@ -384,9 +379,9 @@ class Trainer:
             ts = dt.now()
             losses.reset()
 
-            self.shuffle(train_order)
+            self._shuffle(train_order)
             self._run(self.train_dataset, train_order, True, losses)
-            self.shuffle(val_order)
+            self._shuffle(val_order)
             assert n_val > 0, 'Validation dataset must have at least 1 element'
             self._run(self.validation_dataset, val_order, False, losses)
             losses.materialize(self._reduce)
