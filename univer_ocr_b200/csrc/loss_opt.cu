@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(kThreads) sigmoid_ce_kernel(const float* __res
         if (x > 36.7368f) { logp = 0.f; logq = -INFINITY; }
         if (x < -745.13f) { logp = -INFINITY; logq = 0.f; }
         acc += g * logp + (1.f - g) * logq;                      // losses.py:54
-        if (grad) grad[i] = (g * (p - 1.f) + (1.f - g) * p) * inv_b;   // losses.py:56
+        // losses.py:56: g (p - 1) + (1 - g) p, with p - 1 formed as -sigmoid(-x): on the FP32 p it cancels to 0 from
+        // x ~ 17 on, where the float64 reference still has -e^-x
+        if (grad) grad[i] = ((1.f - g) * p - g / (1.f + expf(x))) * inv_b;
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) atomicAdd(loss, -acc * inv_b);
