@@ -402,9 +402,13 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
     const char* pair_env = getenv("UOCR_PAIR_TC");       // read per call: tests switch between the variants
     const int pair_tc = pair_env ? atoi(pair_env) : 2;
     if (math_mode == UOCR_MATH_TF32 && pair_tc) {
-        const int rc = pair_tc == 2
-            ? conv3x3_pair_tmem(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream))
-            : conv3x3_pair_tc(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream));
+        int rc = UOCR_ERR_UNSUPPORTED;
+        if (pair_tc == 3)      // GEMM 1 straight from the image rows in shared memory (conv_pair_rows_tc.cu)
+            rc = conv3x3_pair_rows(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream));
+        if (rc == UOCR_ERR_UNSUPPORTED)
+            rc = pair_tc >= 2
+                ? conv3x3_pair_tmem(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream))
+                : conv3x3_pair_tc(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2, as_stream(stream));
         if (rc != UOCR_ERR_UNSUPPORTED) return rc;
     }
     return conv3x3_pair_fwd(x, w1, b1, w2, b2, y, n, h, w, c_mid, act1, alpha1, act2, alpha2,

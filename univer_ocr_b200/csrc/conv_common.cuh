@@ -42,6 +42,11 @@ int conv55_row_tc(const ConvGeom& g, const float* x, const float* w, const float
 int conv3x3_pair_tmem(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
                       int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
                       cudaStream_t st);
+// GEMM 1 reads the image rows in shared memory directly (overlapping descriptor rows), warp-specialised persistent
+// kernel (conv_pair_rows_tc.cu); needs w % 4 == 0
+int conv3x3_pair_rows(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
+                      int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
+                      cudaStream_t st);
 size_t conv3x3_pair_bwd_workspace(int64_t n, int64_t h, int64_t w, int c1);
 int conv3x3_pair_bwd(const float* x, const float* w1, const float* b1, const float* w2, const float* dy, float* dx,
                      float* dw1, float* db1, float* dw2, float* db2, int64_t n, int64_t h, int64_t w, int c1,

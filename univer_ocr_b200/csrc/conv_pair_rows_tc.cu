@@ -1,0 +1,531 @@
+// Monochrome conv pair, third tensor-core formulation: the 1 -> 16 convolution reads its A operand STRAIGHT FROM THE
+// IMAGE ROWS in shared memory (no im2col, no per-pixel register work), warp-specialised and persistent.
+//
+//   y = act2(conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2)        1 -> 16 -> 1 channels, padding 1, stride 1
+//   replaces: make_monochrome's conv_1 -> leaky_relu_1 -> conv_2 -> sigmoid (my_model/model.py:119-122), i.e.
+//   Convolutional2D._forward (convolutional.py:62-99) twice + LeakyRelu/Sigmoid._forward (layers.py:390-415).
+//
+// conv3x3_pair_tmem_kernel (conv_pair_tc.cu) builds the 3 x 3 window of every hidden pixel in registers and stores it
+// into tensor memory: ~125 SASS instructions per pixel and thread, 0.137 ms for 64 tiles (ncu: issue-bound on the CUDA
+// cores, tensor pipe 20 %).  Here the CUDA cores only do what no tensor core can: LeakyReLU and the final shift-add.
+//
+// GEMM 1 (space-to-depth along x).  A shared-memory matrix descriptor is address arithmetic: row m of the A operand
+// starts SBO/8 = 16 bytes after row m - 1.  With a row of the image lying contiguously in shared memory, "row m" of A
+// is therefore the 12 floats x[4m .. 4m + 11] -- rows OVERLAP, nothing is copied.  Position m owns the four hidden
+// pixels 4m + c0 + phase (phase = 0..3, c0 = 3 or 5 chosen per tile so that TMA box origins stay 16-byte aligned),
+// whose 3-wide windows all lie inside those 12 floats:
+//     H[m, (phase, c)] = sum_{ky, f} x[row + ky - 1, 4m + f] . B1[(ky, f), (phase, c)]        M = 128, N = 64, K = 36 + 4
+// B1 holds w1[ky, kx, c] at f = c0 + phase + kx - 1 and zeros elsewhere; the bias rides on a constant chunk {1,0,0,0}
+// that every row reads (the descriptor's K stride, LBO, may point anywhere).  K = 40 = five tcgen05.mma 128x64x8:
+// three take chunks 0-1 of one image row each, one pairs chunk 2 of rows 0 and 1 (LBO = row pitch of the ring), one
+// pairs chunk 2 of row 2 with the constant chunk.  The M = 128 rows are two independent x tiles of 64 positions
+// (62 valid: 248 hidden pixels, 246 outputs), so three tiles cover the 736-pixel page tile with 1 % waste.
+// ACT     four warps read H (tcgen05.ld, lane = position, 64 columns), apply LeakyReLU, zero hidden pixels that lie
+//         outside the image (conv_2's zero padding) and store A2 in place.
+// GEMM 2  as in conv_pair_tc.cu: Z[m, (phase, tap)] = sum_c A2[m, (phase, c)] . w2[tap, c]   (A from TMEM, 8 MMAs
+//         128x16x8 per row), the nine taps stay in N and are combined afterwards:
+// EPI     four warps keep rolling vertical sums (3 output rows x 4 pixels x 3 kx per thread), exchange the two
+//         horizontal neighbours by warp shuffle (and through shared memory across the one warp boundary inside a
+//         tile), add b2, apply act2 and store.
+// One persistent CTA per SM: TMA warp (image rows -> 8-slot ring, zero fill outside the image = conv_1's padding,
+// rounded to TF32 by the TMA unit), MMA warp, 4 ACT warps, 4 EPI warps; 4 hidden rows in flight in the 512 TMEM columns
+// (64 H/A2 + 64 Z each); mbarrier pipeline full/empty (ring), h_full, a2_full, z_full, z_empty.
+//
+// Numerics: as conv_pair_tc.cu -- x and weights rounded to TF32, H consumed as TF32 by truncation inside the tensor
+// core and made unbiased by scaling w1 and b1 with (1 + 2^-11); FP32 accumulation.  Tolerance in tests: 1e-3.
+#include <cuda.h>
+
+#include "conv_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace uocr {
+
+int make_tmap_plain_tf32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box);      // tc_gemm.cu
+
+namespace {
+
+constexpr int PR_THREADS = 320;          // warps 0-3 ACT, 4-7 EPI, 8 TMA, 9 MMA
+constexpr int PR_RING = 8;               // image rows in the shared-memory ring (+ 1 mirror slot)
+constexpr int PR_SLOT = 2048;            // bytes per ring slot: 2 tiles x 256 floats
+constexpr int PR_OUT = 246;              // output columns per tile
+constexpr int PR_TSLOTS = 4;             // hidden rows in flight in tensor memory
+constexpr int PR_LAG = 2;                // GEMM 2 of hidden row r is issued after GEMM 1 of row r + PR_LAG
+
+struct PairRowsParams {
+    const float* w1; const float* b1; const float* w2; const float* b2; float* y;
+    int N, H, W;
+    int xt, nb, rb, npair;               // x tiles, bands, rows per band, image pairs
+    int total;                           // work units = nb * xt * npair
+    float alpha1, alpha2;
+    int dbg;                             // timing experiments only (UOCR_PAIR_ROWS_DBG): results are wrong when set
+};
+
+struct __align__(128) PairRowsSmem {
+    float ring[(PR_RING + 1) * PR_SLOT / 4];   // slot s: tile 0 floats [0, 256), tile 1 floats [256, 512)
+    float ones[128 * 4];                       // {1, 0, 0, 0} per A row: the K chunk that carries b1
+    float b1[2][10 * 64 * 4];                  // per c0 variant: chunk kc (16 B) of row n = (phase, c) at kc * 1024 + n * 16
+    float b2[256];                             // chunk kq of row n = tap at kq * 256 + n * 16
+    float xch[2][2][2];                        // [tile][row parity][0: left warp's V0, 1: right warp's V2]
+    uint64_t full[PR_RING], empty[PR_RING];
+    uint64_t hfull[PR_TSLOTS], a2full[PR_TSLOTS], zfull[PR_TSLOTS], zempty[PR_TSLOTS];
+    uint64_t drain;                            // the MMA warp's last commit: nothing asynchronous outlives the CTA
+    uint32_t tmem;
+};
+
+struct WorkUnit {
+    int y0, rows;        // first output row of the band, output rows
+    int t, n0, n1;       // x tile, the two images (n1 may be >= N: idle half)
+    int S, c0;           // image x of ring float 0; hidden pixel of position m, phase f: x = S + 4 m + c0 + f
+};
+
+__device__ __forceinline__ WorkUnit pr_decode(const PairRowsParams& p, int w) {
+    WorkUnit u;
+    const int pi = w % p.npair;
+    const int rest = w / p.npair;
+    u.t = rest % p.xt;
+    const int b = rest / p.xt;
+    u.y0 = b * p.rb;
+    u.rows = min(p.rb, p.H - u.y0);
+    u.n0 = 2 * pi;
+    u.n1 = 2 * pi + 1;
+    // hidden pixel 0 of the tile is image x = PR_OUT t - 1; ring float 0 must sit at a multiple of 4 (TMA box origin)
+    u.c0 = (u.t & 1) ? 5 : 3;
+    u.S = PR_OUT * u.t - 1 - u.c0;
+    return u;
+}
+
+// plain try_wait spin.  (A suspend-time hint turns the failed probe into NANOSLEEP.SYNCS, whose wake-up costs ~1 us:
+// fine where 16 rows per SM hide it (conv_pair_tc.cu), fatal here where a row's stages are chained -- measured 1715
+// cycles per row with the hint.)
+__device__ __forceinline__ void pr_wait(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+__device__ __forceinline__ void pr_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    tc_ld16_nowait(taddr, r);
+}
+__device__ __forceinline__ void pr_st16(uint32_t taddr, const float* v) {
+    tc_st16_nowait(taddr, reinterpret_cast<const uint32_t*>(v));
+}
+
+__device__ __forceinline__ bool pr_elect() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// ------------------------------------------------------------------ TMA warp (convergent; one elected lane issues)
+__device__ void pr_producer(const PairRowsParams& p, const CUtensorMap* map, PairRowsSmem& sm) {
+    const uint32_t ring = smem_u32(sm.ring);
+    uint32_t ut = 0;                                       // input rows issued so far (all work units)
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+        const WorkUnit u = pr_decode(p, w);
+        const int nin = u.rows + 4;                        // image rows y0 - 2 .. y0 + rows + 1
+        for (int r = 0; r < nin; ++r, ++ut) {
+            const uint32_t slot = ut % PR_RING;
+            pr_wait(smem_u32(&sm.empty[slot]), ((ut / PR_RING) & 1u) ^ 1u);
+            if (pr_elect()) {
+                const uint32_t bar = smem_u32(&sm.full[slot]);
+                const bool mirror = slot == 0;             // also at the end of the ring: slots (RING - 1, RING) are adjacent
+                mbar_arrive_expect_tx(bar, mirror ? 2u * PR_SLOT : (uint32_t)PR_SLOT);
+                const int y = u.y0 - 2 + r;
+                const uint32_t dst = ring + slot * PR_SLOT;
+                tma_load_3d(dst, map, bar, u.S, y, u.n0);          // out-of-image rows / columns / images: zeros
+                tma_load_3d(dst + 1024, map, bar, u.S, y, u.n1);
+                if (mirror) {
+                    const uint32_t dst2 = ring + PR_RING * PR_SLOT;
+                    tma_load_3d(dst2, map, bar, u.S, y, u.n0);
+                    tma_load_3d(dst2 + 1024, map, bar, u.S, y, u.n1);
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ MMA warp (convergent; one elected lane issues)
+// The issuing lane's instruction stream is the pipeline's pacemaker (13 MMAs and 3 commits per hidden row), so it is
+// kept short: descriptors are a constant plus the 16-byte-unit start address, everything is warp-uniform (the first
+// version ran under `if (lane == 0)`: the compiler wrapped every UTCHMMA in an ELECT loop, ~250 dependent
+// instructions = 1700 cycles per row, 5x the tensor time).
+__device__ void pr_mma(const PairRowsParams& p, PairRowsSmem& sm, uint32_t tmem) {
+    const uint32_t ring = smem_u32(sm.ring), ones = smem_u32(sm.ones), sb2 = smem_u32(sm.b2);
+    // instruction descriptors: D FP32, A / B TF32, K-major both, M = 128, N = 64 / 16
+    const uint32_t id64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t id16 = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t da_row = make_kmajor_nosw_desc(0, 16, 128);         // + start: chunks 0, 1 of one image row
+    const uint64_t da_pair = make_kmajor_nosw_desc(0, PR_SLOT, 128);   // + start: chunk 2 of two adjacent ring slots
+    const uint64_t da_bias = make_kmajor_nosw_desc(0, 0, 128);         // + start + LBO: chunk 2 of a row, then `ones`
+    const uint64_t db2_0 = make_kmajor_nosw_desc(sb2, 256, 128), db2_1 = make_kmajor_nosw_desc(sb2 + 512, 256, 128);
+    uint32_t ut = 0, k1 = 0, k2 = 0;                       // input rows consumed, hidden rows through GEMM 1 / GEMM 2
+    uint32_t wu = 0;                                       // image rows whose TMA completion has been observed
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+        const WorkUnit u = pr_decode(p, w);
+        const uint32_t sb1 = smem_u32(sm.b1[u.c0 == 5 ? 1 : 0]);
+        const uint64_t db_ky0 = make_kmajor_nosw_desc(sb1 + 0 * 1024, 1024, 128);
+        const uint64_t db_ky1 = make_kmajor_nosw_desc(sb1 + 3 * 1024, 1024, 128);
+        const uint64_t db_ky2 = make_kmajor_nosw_desc(sb1 + 6 * 1024, 1024, 128);
+        const uint64_t db_c2 = make_kmajor_nosw_desc(sb1 + 2 * 1024, 3 * 1024, 128);
+        const uint64_t db_bias = make_kmajor_nosw_desc(sb1 + 8 * 1024, 1024, 128);
+        const int nh = u.rows + 2;                         // hidden rows y0 - 1 .. y0 + rows
+        for (int r = 0; r < nh + PR_LAG; ++r) {
+            if (r < nh) {
+                const int i = u.y0 - 1 + r;
+                const bool valid = i >= 0 && i < p.H;
+                const uint32_t u0 = ut + (uint32_t)r;
+                // every image row is waited for exactly once, in order (`wu` = next row not yet waited for): rows r and
+                // r + 1 were needed by earlier hidden rows; a row is also waited for before its slot is released below,
+                // even if only an out-of-image hidden row would have read it
+                const uint32_t need = valid ? u0 + 2u : u0;
+                while (wu <= need) {
+                    pr_wait(smem_u32(&sm.full[wu % PR_RING]), (wu / PR_RING) & 1u);
+                    ++wu;
+                }
+                tc_fence_after();
+                if (pr_elect()) {
+                    if (valid) {
+                        const uint32_t d1 = tmem + 128u * (k1 % PR_TSLOTS);
+                        const uint64_t a0 = (uint64_t)((ring + (u0 % PR_RING) * PR_SLOT) >> 4);
+                        const uint64_t a1 = (uint64_t)((ring + ((u0 + 1u) % PR_RING) * PR_SLOT) >> 4);
+                        const uint64_t a2 = (uint64_t)((ring + ((u0 + 2u) % PR_RING) * PR_SLOT) >> 4);
+                        tc_mma_tf32(d1, da_row + a0, db_ky0, id64, 0);
+                        tc_mma_tf32(d1, da_row + a1, db_ky1, id64, 1);
+                        tc_mma_tf32(d1, da_row + a2, db_ky2, id64, 1);
+                        // chunk 2 of rows 0 and 1 (physically adjacent slots: the ring's last slot is mirrored behind it)
+                        tc_mma_tf32(d1, da_pair + a0 + 2u, db_c2, id64, 1);
+                        // chunk 2 of row 2 + the constant chunk that carries b1 (LBO = distance to `ones`)
+                        tc_mma_tf32(d1, da_bias + (a2 + 2u) + ((uint64_t)((ones >> 4) - (uint32_t)(a2 + 2u)) << 16), db_bias,
+                                    id64, 1);
+                        tc_commit(smem_u32(&sm.hfull[k1 % PR_TSLOTS]));
+                    }
+                    // image row r of the unit is not read by any later hidden row
+                    tc_commit(smem_u32(&sm.empty[u0 % PR_RING]));
+                }
+                __syncwarp();
+                if (valid) ++k1;
+            }
+            const int r2 = r - PR_LAG;
+            if (r2 >= 0) {
+                const int i = u.y0 - 1 + r2;
+                if (i >= 0 && i < p.H) {
+                    const uint32_t s = k2 % PR_TSLOTS, par = (k2 / PR_TSLOTS) & 1u;
+                    pr_wait(smem_u32(&sm.a2full[s]), par);
+                    pr_wait(smem_u32(&sm.zempty[s]), par ^ 1u);
+                    tc_fence_after();
+                    if (pr_elect()) {
+                        const uint32_t base = tmem + 128u * s;
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) {
+                            tc_mma_tf32_ts(base + 64u + 16u * f, base + 16u * f, db2_0, id16, 0);
+                            tc_mma_tf32_ts(base + 64u + 16u * f, base + 16u * f + 8u, db2_1, id16, 1);
+                        }
+                        tc_commit(smem_u32(&sm.zfull[s]));
+                    }
+                    __syncwarp();
+                    ++k2;
+                }
+            }
+        }
+        // the unit's last two image rows.  Every row the TMA warp loads is waited for here, also rows that only an
+        // out-of-image hidden row would have read: a CTA must not exit (and hand its shared memory to the next CTA)
+        // while a bulk copy into it is still in flight -- that was an intermittent "unspecified launch failure".
+        while (wu <= ut + (uint32_t)nh + 1u) {
+            pr_wait(smem_u32(&sm.full[wu % PR_RING]), (wu / PR_RING) & 1u);
+            ++wu;
+        }
+        if (pr_elect()) {
+            tc_commit(smem_u32(&sm.empty[(ut + (uint32_t)nh) % PR_RING]));
+            tc_commit(smem_u32(&sm.empty[(ut + (uint32_t)nh + 1u) % PR_RING]));
+        }
+        __syncwarp();
+        ut += (uint32_t)(nh + 2);
+    }
+    // ... nor while a tcgen05.commit still has to arrive on one of its barriers
+    if (pr_elect()) tc_commit(smem_u32(&sm.drain));
+    __syncwarp();
+    pr_wait(smem_u32(&sm.drain), 0);
+}
+
+// ------------------------------------------------------------------ ACT warps: H -> LeakyReLU -> A2 (in place)
+template <bool LEAKY>
+__device__ void pr_act(const PairRowsParams& p, PairRowsSmem& sm, uint32_t tmem, int q, int lane) {
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const int j = (q & 1) * 32 + lane;                     // position inside the tile
+    uint32_t k = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+        const WorkUnit u = pr_decode(p, w);
+        const int x0 = u.S + u.c0 + 4 * j;                 // image x of this thread's first hidden pixel
+        uint32_t inside = 0;                               // hidden pixels outside the image are conv_2's zero padding
+#pragma unroll
+        for (int f = 0; f < 4; ++f) inside |= (x0 + f >= 0 && x0 + f < p.W) ? (1u << f) : 0u;
+        const int nh = u.rows + 2;
+        for (int r = 0; r < nh; ++r) {
+            const int i = u.y0 - 1 + r;
+            if (i < 0 || i >= p.H) continue;
+            const uint32_t s = k % PR_TSLOTS;
+            pr_wait(smem_u32(&sm.hfull[s]), (k / PR_TSLOTS) & 1u);
+            tc_fence_after();
+            float h[64];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pr_ld16(tl + 128u * s + 16u * g, h + 16 * g);
+            tc_wait_ld();
+            if (LEAKY && !(p.dbg & 8)) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c) h[c] = fmaxf(h[c], h[c] * p.alpha1);
+            }
+            if (inside != 15u) {
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if (!((inside >> f) & 1u)) {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) h[16 * f + c] = 0.f;
+                    }
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pr_st16(tl + 128u * s + 16u * g, h + 16 * g);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.a2full[s]));
+            ++k;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ EPI warps: Z -> shift-add -> act2 -> y
+struct EpiState {
+    float acc[3][4][3];                  // [output row % 3][pixel of the thread][kx]
+};
+
+// hidden row r of the unit (ring phase PH = r % 3, compile time).  `valid`: the row lies inside the image and its Z
+// tile is in tensor memory; otherwise it contributes zeros.  Completes output row r - 2 of the band.
+template <int PH, bool SIGMOID>
+__device__ __forceinline__ void pr_epi_row(const PairRowsParams& p, PairRowsSmem& sm, EpiState& st, uint32_t tl,
+                                           uint32_t& k, uint32_t& xcount, bool valid, int r, int nrows, int q, int lane,
+                                           int tile, float bias2, uint32_t store_mask, float* __restrict__ yrow) {
+    float z[4][9];
+    if (valid) {
+        const uint32_t s = k % PR_TSLOTS;
+        pr_wait(smem_u32(&sm.zfull[s]), (k / PR_TSLOTS) & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            uint32_t* zr = reinterpret_cast<uint32_t*>(z[f]);
+            tc_ld8_nowait(tl + 128u * s + 64u + 16u * f, zr);
+            tc_ld1_nowait(tl + 128u * s + 64u + 16u * f + 8u, zr + 8);
+        }
+        tc_wait_ld();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&sm.zempty[s]));
+        ++k;
+    } else {
+#pragma unroll
+        for (int f = 0; f < 4; ++f)
+#pragma unroll
+            for (int t = 0; t < 9; ++t) z[f][t] = 0.f;
+    }
+    // hidden row i feeds output rows i + 1 (ky = 0), i (ky = 1), i - 1 (ky = 2)
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            st.acc[(PH + 2) % 3][f][kx] = z[f][kx];
+            st.acc[(PH + 1) % 3][f][kx] += z[f][3 + kx];
+            st.acc[PH][f][kx] += z[f][6 + kx];
+        }
+    if (r < 2) return;                                     // warp-uniform
+    // y[q] = b2 + V0[q - 1] + V1[q] + V2[q + 1]; V of the neighbouring positions by shuffle, across the warp boundary
+    // inside a tile (positions 31 | 32) through shared memory
+    float left = __shfl_up_sync(0xffffffffu, st.acc[PH][3][0], 1);
+    float right = __shfl_down_sync(0xffffffffu, st.acc[PH][0][2], 1);
+    const int par = (int)(xcount++ & 1u);
+    if ((q & 1) == 0) { if (lane == 31) sm.xch[tile][par][0] = st.acc[PH][3][0]; }
+    else { if (lane == 0) sm.xch[tile][par][1] = st.acc[PH][0][2]; }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + tile) : "memory");
+    if ((q & 1) == 0) { if (lane == 31) right = sm.xch[tile][par][1]; }
+    else { if (lane == 0) left = sm.xch[tile][par][0]; }
+    const int orow = r - 2;
+    if (orow < nrows) {
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const float l = f == 0 ? left : st.acc[PH][f - 1][0];
+            const float rr = f == 3 ? right : st.acc[PH][f + 1][2];
+            float v = st.acc[PH][f][1] + l + rr + bias2;
+            if (SIGMOID) v = __fdividef(1.f, 1.f + __expf(-v));
+            else if (p.alpha2 != 1.f) v = v >= 0.f ? v : v * p.alpha2;
+            if ((store_mask >> f) & 1u) yrow[f] = v;
+        }
+    }
+}
+
+template <bool SIGMOID>
+__device__ void pr_epi(const PairRowsParams& p, PairRowsSmem& sm, uint32_t tmem, int q, int lane) {
+    const uint32_t tl = tmem + ((uint32_t)(q * 32) << 16);
+    const int tile = q >> 1;
+    const int j = (q & 1) * 32 + lane;
+    const float bias2 = __ldg(p.b2);
+    uint32_t k = 0, xcount = 0;
+    for (int w = blockIdx.x; w < p.total; w += gridDim.x) {
+        const WorkUnit u = pr_decode(p, w);
+        const int n = tile ? u.n1 : u.n0;
+        const int x0 = u.S + u.c0 + 4 * j;
+        // hidden pixel hp = 4 j + f of the tile is an output iff 1 <= hp <= PR_OUT, inside the image, real image
+        uint32_t store_mask = 0;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+            const int hp = 4 * j + f;
+            if (n < p.N && hp >= 1 && hp <= PR_OUT && x0 + f < p.W) store_mask |= 1u << f;
+        }
+        EpiState st;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) st.acc[a][f][kx] = 0.f;
+        const int nh = u.rows + 2;
+        // &y[n, y0 - 2, x0]: row r completes output row y0 + r - 2 (never dereferenced where store_mask is 0)
+        float* yrow = p.y + ((int64_t)(n < p.N ? n : 0) * p.H + (u.y0 - 2)) * (int64_t)p.W + x0;
+#define PR_ROW(PH, R)                                                                                              \
+        {                                                                                                          \
+            const int i_ = u.y0 - 1 + (R);                                                                         \
+            pr_epi_row<PH, SIGMOID>(p, sm, st, tl, k, xcount, i_ >= 0 && i_ < p.H, (R), u.rows, q, lane, tile, bias2, \
+                                    store_mask, yrow + (int64_t)(R) * p.W);                                        \
+        }
+        for (int r = 0; r < nh; r += 3) {
+            PR_ROW(0, r)
+            if (r + 1 < nh) PR_ROW(1, r + 1)
+            if (r + 2 < nh) PR_ROW(2, r + 2)
+        }
+#undef PR_ROW
+    }
+}
+
+template <bool LEAKY, bool SIGMOID>
+__global__ void __launch_bounds__(PR_THREADS, 1) conv3x3_pair_rows_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                          const PairRowsParams p) {
+    __shared__ PairRowsSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    // ---- operands: B1 (two c0 variants), B2, the constant chunk
+    for (int i = tid; i < 2 * 10 * 64 * 4; i += PR_THREADS) {
+        const int var = i / 2560, rest = i % 2560;
+        const int kc = rest / 256, n = (rest % 256) >> 2, e = rest & 3;        // chunk, row n = (phase, c), element
+        const int c0 = var ? 5 : 3, f = n >> 4, c = n & 15;
+        float v = 0.f;
+        if (kc < 9) {
+            const int ky = kc / 3, fr = 4 * (kc % 3) + e;                       // float 4 m + fr of image row ky
+            const int kx = fr - (c0 + f) + 1;
+            if (kx >= 0 && kx < 3) v = __ldg(p.w1 + (ky * 3 + kx) * 16 + c);
+        } else if (e == 0) {
+            v = __ldg(p.b1 + c);
+        }
+        // scaled so that the tensor core's truncation of H to TF32 (GEMM 2's A operand) is unbiased
+        sm.b1[var][kc * 256 + n * 4 + e] = round_tf32(v * (1.f + 1.f / 2048.f));
+    }
+    for (int i = tid; i < 256; i += PR_THREADS) {
+        const int kq = i >> 6, n = (i & 63) >> 2, kk = i & 3;
+        sm.b2[i] = n < 9 ? round_tf32(__ldg(p.w2 + n * 16 + kq * 4 + kk)) : 0.f;
+    }
+    for (int i = tid; i < 512; i += PR_THREADS) sm.ones[i] = (i & 3) == 0 ? 1.f : 0.f;
+    if (tid == 0) {
+        for (int s = 0; s < PR_RING; ++s) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), 1);
+        }
+        for (int s = 0; s < PR_TSLOTS; ++s) {
+            mbar_init(smem_u32(&sm.hfull[s]), 1);
+            mbar_init(smem_u32(&sm.a2full[s]), 128);
+            mbar_init(smem_u32(&sm.zfull[s]), 1);
+            mbar_init(smem_u32(&sm.zempty[s]), 128);
+        }
+        mbar_init(smem_u32(&sm.drain), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // operands are read by the async proxy
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&sm.tmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem;
+
+    if (warp == 8) {
+        pr_producer(p, &map_x, sm);
+    } else if (warp == 9) {
+        pr_mma(p, sm, tmem);
+    } else if (warp < 4) {
+        pr_act<LEAKY>(p, sm, tmem, warp, lane);
+    } else {
+        pr_epi<SIGMOID>(p, sm, tmem, warp - 4, lane);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace
+
+int conv3x3_pair_rows(const float* x, const float* w1, const float* b1, const float* w2, const float* b2, float* y,
+                      int64_t n, int64_t h, int64_t w, int c1, int act1, float alpha1, int act2, float alpha2,
+                      cudaStream_t st) {
+    if (c1 != 16 || w % 4 || w < 8 || n > 0x3fffffff) return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return UOCR_ERR_UNSUPPORTED;
+    const bool leaky = act1 == UOCR_ACT_LEAKY;
+    if (!(act1 == UOCR_ACT_NONE || (leaky && alpha1 >= 0.f && alpha1 <= 1.f))) return UOCR_ERR_UNSUPPORTED;
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    PairRowsParams p{};
+    p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.y = y;
+    p.N = (int)n; p.H = (int)h; p.W = (int)w;
+    p.xt = (int)ceil_div(w, PR_OUT);
+    p.npair = (int)ceil_div(n, 2);
+    // bands: every unit costs rows + 2 hidden rows; choose the band count that minimises waves x (rows + 2)
+    int best_nb = 1;
+    double best_cost = 1e300;
+    for (int nb = 1; nb <= 32 && nb <= h; ++nb) {
+        const int64_t rb = ceil_div(h, nb);
+        const int64_t units = (int64_t)ceil_div(h, rb) * p.xt * p.npair;
+        const double cost = (double)ceil_div(units, sms) * (double)(rb + 2 + 6);      // + 6: pipeline fill per unit
+        if (cost < best_cost) { best_cost = cost; best_nb = nb; }
+    }
+    p.rb = (int)ceil_div(h, best_nb);
+    p.nb = (int)ceil_div(h, p.rb);
+    const int64_t total = (int64_t)p.nb * p.xt * p.npair;
+    if (total > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    p.total = (int)total;
+    p.alpha1 = alpha1;
+    p.alpha2 = act2 == UOCR_ACT_LEAKY ? alpha2 : 1.f;
+    { const char* e = getenv("UOCR_PAIR_ROWS_DBG"); p.dbg = e ? atoi(e) : 0; }
+    CUtensorMap map;
+    const uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)n};
+    const uint64_t strides[2] = {(uint64_t)w * 4, (uint64_t)w * h * 4};
+    const uint32_t box[3] = {256, 1, 1};
+    int rc = make_tmap_plain_tf32(&map, x, 3, dims, strides, box);
+    if (rc) return rc;
+    unsigned grid = (unsigned)(total < sms ? total : sms);
+    { const char* e = getenv("UOCR_PAIR_ROWS_GRID"); if (e && atoi(e) > 0 && (unsigned)atoi(e) < grid) grid = (unsigned)atoi(e); }
+    if (act2 == UOCR_ACT_SIGMOID) {
+        if (leaky) conv3x3_pair_rows_kernel<true, true><<<grid, PR_THREADS, 0, st>>>(map, p);
+        else conv3x3_pair_rows_kernel<false, true><<<grid, PR_THREADS, 0, st>>>(map, p);
+    } else {
+        if (leaky) conv3x3_pair_rows_kernel<true, false><<<grid, PR_THREADS, 0, st>>>(map, p);
+        else conv3x3_pair_rows_kernel<false, false><<<grid, PR_THREADS, 0, st>>>(map, p);
+    }
+    UOCR_LAUNCHED("conv3x3_pair_rows");
+    return UOCR_OK;
+}
+
+}  // namespace uocr

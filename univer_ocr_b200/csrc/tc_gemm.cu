@@ -94,6 +94,22 @@ int make_tmap_plain_f32(CUtensorMap* map, const void* base, int rank, const uint
     return UOCR_OK;
 }
 
+// plain (no swizzle) boxes whose elements the TMA unit rounds to TF32 (round to nearest): image rows that a tcgen05.mma
+// reads directly as its A operand (conv_pair_rows_tc.cu)
+int make_tmap_plain_tf32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable"); return UOCR_ERR_UNSUPPORTED; }
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    CUresult r = fn(map, tmap_dtype(), (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (plain tf32) failed (%d)", (int)r); return UOCR_ERR_UNSUPPORTED; }
+    return UOCR_OK;
+}
+
 constexpr int TC_BM = 128;           // UMMA M
 constexpr int TC_BK = 32;            // contraction elements per stage
 constexpr int TC_THREADS = 192;
