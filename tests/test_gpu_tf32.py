@@ -128,16 +128,20 @@ def test_char_model_tf32_matches_fp32(nn):
 
 
 def test_monochrome_pair_on_tensor_cores(nn):
-    """uocr_conv3x3_pair_fwd in TF32 mode (both convolutions as tcgen05.mma with TMEM-resident A
-    operands, csrc/conv_pair_tc.cu) vs the float64 oracle: |err| <= 1e-3 * max (outputs are sigmoid
-    values in (0, 1)) for aligned and ragged sizes (strip / band / step remainders, single-pixel
-    rows and columns), plus agreement with the FP32 pair kernel."""
+    """uocr_conv3x3_pair_fwd in TF32 mode vs the float64 oracle: |err| <= 1e-3 * max (outputs are sigmoid values in
+    (0, 1)) for aligned and ragged sizes (tile / strip / band / step remainders, single-pixel rows and columns,
+    odd image counts, several work units per persistent CTA), plus agreement with the FP32 pair kernel.  Variants:
+    `rows` (default, csrc/conv_pair_rows_tc.cu: GEMM 1 reads the image rows in shared memory through overlapping
+    descriptor rows; needs W % 4 == 0, otherwise the next variant runs), `tmem` (csrc/conv_pair_tc.cu: windows
+    stored to tensor memory), `smem` (the earlier shared-memory MMA variant, a measured negative result)."""
     import ctypes
     from univer_ocr_b200._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
     rng = np.random.default_rng(17)
     for (n, h, w), act2 in (((2, 16, 256), ACT_SIGMOID), ((3, 21, 150), ACT_SIGMOID), ((1, 5, 3), ACT_NONE),
                             ((2, 1, 1), ACT_NONE), ((1, 63, 31), ACT_SIGMOID), ((1, 130, 61), ACT_NONE),
-                            ((5, 3, 240), ACT_SIGMOID), ((2, 496, 736), ACT_SIGMOID)):
+                            ((5, 3, 240), ACT_SIGMOID), ((2, 496, 736), ACT_SIGMOID), ((3, 33, 244), ACT_SIGMOID),
+                            ((2, 40, 248), ACT_NONE), ((1, 7, 492), ACT_SIGMOID), ((1, 130, 1000), ACT_SIGMOID),
+                            ((5, 3, 12), ACT_NONE), ((1, 2, 8), ACT_SIGMOID), ((9, 300, 736), ACT_SIGMOID)):
         X = f32(rng.uniform(size=(n, h, w, 1)))
         w1 = f32(rng.standard_normal((3, 3, 1, 16)) * 0.4)
         b1 = f32(rng.standard_normal(16) * 0.2)
@@ -151,9 +155,14 @@ def test_monochrome_pair_on_tensor_cores(nn):
         outs = {}
         # math mode 0 = FP32 pair kernel; mode 1 with UOCR_PAIR_TC = 2 (default): both convs as tcgen05.mma with
         # TMEM-resident operands; = 1: the earlier shared-memory MMA variant (kept as a measured negative result)
-        for key, mode, variant in (('fp32', 0, None), ('tmem', 1, '2'), ('smem', 1, '1')):
+        for key, mode, variant, grid in (('fp32', 0, None, None), ('rows', 1, '3', None), ('rows_1cta', 1, '3', '1'),
+                                         ('rows_5cta', 1, '3', '5'), ('tmem', 1, '2', None), ('smem', 1, '1', None)):
+            if key.startswith('rows_') and n * h * w > 2000000:
+                continue                                # the capped-grid runs exist for the multi-unit bookkeeping
             if variant is not None:
                 os.environ['UOCR_PAIR_TC'] = variant
+            if grid is not None:
+                os.environ['UOCR_PAIR_ROWS_GRID'] = grid      # few persistent CTAs: many work units per CTA
             try:
                 y = nn.DeviceArray((n, h, w, 1))
                 lib.uocr_conv3x3_pair_fwd(d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, y.ptr, n, h, w, 16,
@@ -161,7 +170,10 @@ def test_monochrome_pair_on_tensor_cores(nn):
                 outs[key] = np.asarray(y.get(), dtype=np.float64)
             finally:
                 os.environ.pop('UOCR_PAIR_TC', None)
-        for key in ('tmem', 'smem'):
+                os.environ.pop('UOCR_PAIR_ROWS_GRID', None)
+        for key in outs:
+            if key == 'fp32':
+                continue
             close_tf32(outs[key], want, f'{key} pair {(n, h, w)}')
             close_tf32(outs[key], outs['fp32'], f'{key} vs fp32 pair {(n, h, w)}')
 

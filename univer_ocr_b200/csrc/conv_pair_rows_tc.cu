@@ -58,7 +58,6 @@ struct PairRowsParams {
     int xt, nb, rb, npair;               // x tiles, bands, rows per band, image pairs
     int total;                           // work units = nb * xt * npair
     float alpha1, alpha2;
-    int dbg;                             // timing experiments only (UOCR_PAIR_ROWS_DBG): results are wrong when set
 };
 
 struct __align__(128) PairRowsSmem {
@@ -194,13 +193,19 @@ __device__ void pr_mma(const PairRowsParams& p, PairRowsSmem& sm, uint32_t tmem,
         const uint64_t db_c2 = make_kmajor_nosw_desc(sb1 + 2 * 1024, 3 * 1024, 128);
         const uint64_t db_bias = make_kmajor_nosw_desc(sb1 + 8 * 1024, 1024, 128);
         const int nh = u.rows + 2;                         // hidden rows y0 - 1 .. y0 + rows
-        for (int r = 0; r < nh; ++r) {
-            const int i = u.y0 - 1 + r;
-            const bool valid = i >= 0 && i < p.H;
-            const bool mine = valid ? (int)(kv & 3u) == j : j == 0;
-            const uint32_t kvr = kv;
-            if (valid) ++kv;
-            if (!mine) continue;
+        // rows of the unit inside the image: [r_lo, r_hi); the (at most two) rows outside belong to warp 0
+        const int r_lo = u.y0 == 0 ? 1 : 0, r_hi = min(nh, p.H - u.y0 + 1);
+        // this warp's rows: valid row r has running index kv + (r - r_lo); the first one with index = j mod 4, then
+        // every fourth; warp 0 also takes the row above (r = 0) / below (r = r_hi) the image where the unit has one
+        const int below = (j == 0 && r_hi < nh) ? r_hi : nh;
+        int first = r_lo + (int)((uint32_t)(j - (int)(kv & 3u)) & 3u);
+        if (first >= r_hi) first = below;
+        int r = (j == 0 && r_lo == 1) ? 0 : first;
+        while (r < nh) {
+            const bool valid = r >= r_lo && r < r_hi;
+            const uint32_t kvr = kv + (uint32_t)(r - r_lo);
+            int r_next = r < r_lo ? first : (valid ? r + 4 : nh);
+            if (valid && r_next >= r_hi) r_next = below;
             if (pending) {                                 // same slot: before GEMM 1 overwrites its H / A2 columns
                 pr_conv2(sm, tmem, j, pkv, db2_0, db2_1, id16);
                 pending = false;
@@ -240,7 +245,9 @@ __device__ void pr_mma(const PairRowsParams& p, PairRowsSmem& sm, uint32_t tmem,
             }
             __syncwarp();
             if (valid) { pending = true; pkv = kvr; }
+            r = r_next;
         }
+        kv += (uint32_t)(r_hi - r_lo);
         ut += (uint32_t)(nh + 2);
     }
     if (pending) pr_conv2(sm, tmem, j, pkv, db2_0, db2_1, id16);
@@ -572,7 +579,6 @@ int conv3x3_pair_rows(const float* x, const float* w1, const float* b1, const fl
     p.total = (int)total;
     p.alpha1 = alpha1;
     p.alpha2 = act2 == UOCR_ACT_LEAKY ? alpha2 : 1.f;
-    { const char* e = getenv("UOCR_PAIR_ROWS_DBG"); p.dbg = e ? atoi(e) : 0; }
     CUtensorMap map;
     const uint64_t dims[3] = {(uint64_t)w, (uint64_t)h, (uint64_t)n};
     const uint64_t strides[2] = {(uint64_t)w * 4, (uint64_t)w * h * 4};
@@ -580,6 +586,7 @@ int conv3x3_pair_rows(const float* x, const float* w1, const float* b1, const fl
     int rc = make_tmap_plain_tf32(&map, x, 3, dims, strides, box);
     if (rc) return rc;
     unsigned grid = (unsigned)(total < sms ? total : sms);
+    // tests: fewer persistent CTAs than work units (UOCR_PAIR_ROWS_GRID), to exercise the multi-unit bookkeeping on small inputs
     { const char* e = getenv("UOCR_PAIR_ROWS_GRID"); if (e && atoi(e) > 0 && (unsigned)atoi(e) < grid) grid = (unsigned)atoi(e); }
     if (act2 == UOCR_ACT_SIGMOID) {
         if (leaky) conv3x3_pair_rows_kernel<true, true><<<grid, PR_THREADS, 0, st>>>(map, p);
