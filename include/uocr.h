@@ -208,6 +208,12 @@ int uocr_conv3x3_pair_fwd(const float* x, const float* w1, const float* b1, cons
  * its input shape); UOCR_ERR_UNSUPPORTED otherwise.  FP32 FFMA in every math mode. */
 int uocr_hourglass1_fwd(const float* x, const float* const* weights, const float* const* biases, float* y,
                         int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end, void* stream);
+/* the same with a math mode: UOCR_MATH_TF32 runs the network's full-resolution levels as tcgen05.mma straight from the
+ * intermediate maps in shared memory (TF32 operands, FP32 accumulators in tensor memory; tolerance 1e-3 of the output
+ * range); UOCR_MATH_FP32 is uocr_hourglass1_fwd. */
+int uocr_hourglass1_fwd_mode(const float* x, const float* const* weights, const float* const* biases, float* y,
+                             int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end,
+                             int math_mode, void* stream);
 
 /* Backward of the same pair in TRAINING (y = conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2, the final
  * activation handled by its own layer): dw1/db1/dw2/db2 (+)= parameter gradients, dx = input gradient

@@ -372,3 +372,41 @@ def test_monochrome_pair_backward_tensor_core(nn):
                 for name, a, b in zip(('dw1', 'db1', 'dw2', 'db2', 'dx'), outs[1], (odw1, odb1, odw2, odb2, odx)):
                     close_tf32(a, np.asarray(b, dtype=np.float64).reshape(a.shape),
                                f'pair bwd tc vs oracle {name} {(n, h, w)} exact={exact}', tol=tol)
+
+
+def test_hourglass_tensor_core_levels_vs_oracle(nn, monkeypatch):
+    """uocr_hourglass1_fwd_mode in TF32 mode with UOCR_HOURGLASS_TC=1: the Paragraph network's `end` level as
+    tcgen05.mma straight from the U1 block in shared memory (csrc/hourglass.cu; slower than the FFMA level, kept as a
+    measured negative result and therefore off by default) -- vs the float64 oracle chain of five conv layers and vs
+    the FP32 kernel, for block-aligned, ragged, tiny and full-tile sizes.  Tolerance 1e-3 of the output range (2e-3 for
+    the un-squashed linear output, whose range is the sum of five layers' gains)."""
+    monkeypatch.setenv('UOCR_HOURGLASS_TC', '1')
+    import ctypes
+    from univer_ocr_b200._lib import ACT_NONE, ACT_SIGMOID, lib
+    rng = np.random.default_rng(321)
+    for (n, h, w), act_end in (((2, 32, 128), ACT_SIGMOID), ((1, 36, 140), ACT_NONE), ((3, 4, 4), ACT_SIGMOID),
+                               ((2, 8, 300), ACT_NONE), ((1, 132, 12), ACT_SIGMOID), ((2, 496, 736), ACT_SIGMOID),
+                               ((1, 64, 2064), ACT_SIGMOID)):
+        X = f32(rng.uniform(size=(n, h, w, 1)))
+        ws = [f32(rng.standard_normal((5, 5, 1, 1)) * 0.25) for _ in range(5)]
+        bs = [f32(rng.standard_normal(1) * 0.3) for _ in range(5)]
+        t = O.leaky_relu_fwd(O.conv2d_fwd(X, ws[0], bs[0], 2, stride=2), 0.01)
+        t = O.leaky_relu_fwd(O.conv2d_fwd(t, ws[1], bs[1], 2, stride=2), 0.01)
+        t = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(t, 2), ws[2], bs[2], 2), 0.01)
+        t = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(t, 2), ws[3], bs[3], 2), 0.01)
+        want = O.conv2d_fwd(t, ws[4], bs[4], 2)
+        if act_end == ACT_SIGMOID:
+            want = O.sigmoid_fwd(want)
+        dX = nn.CP.copy(X)
+        dw = [nn.CP.copy(a) for a in ws]
+        db = [nn.CP.copy(a) for a in bs]
+        ptrs = ctypes.c_void_p * 5
+        outs = {}
+        for mode in (0, 1):
+            y = nn.DeviceArray.full((n, h, w, 1), -3.0)
+            lib.uocr_hourglass1_fwd_mode(dX.ptr, ptrs(*[a.ptr for a in dw]), ptrs(*[a.ptr for a in db]), y.ptr, n, h, w,
+                                         0.01, act_end, 0.0, mode, nn.CP.stream())
+            outs[mode] = np.asarray(y.get(), dtype=np.float64)
+        tol = 1e-3 if act_end == ACT_SIGMOID else 2e-3
+        close_tf32(outs[1], want, f'hourglass tf32 vs oracle {(n, h, w)}', tol=tol)
+        close_tf32(outs[1], outs[0], f'hourglass tf32 vs fp32 {(n, h, w)}', tol=tol)

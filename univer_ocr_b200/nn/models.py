@@ -834,6 +834,6 @@ class HourglassFusion:
         last = blocks[4][1]
         last.progress_tracker.start_tracking(last.name, 'forward')
         y = DeviceArray((n, h, w, 1))
-        lib.uocr_hourglass1_fwd(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], stream())
+        lib.uocr_hourglass1_fwd_mode(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], CP.math_mode, stream())
         last.progress_tracker.stop_tracking(last.name, 'forward')
         return [y]
