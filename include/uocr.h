@@ -365,6 +365,14 @@ int uocr_rmsprop_update(float* w, const float* g, float* a, int64_t n, float lr,
  * hits[r, c] (uint8) = pred[r, c] == max(pred[r, :]) && max != 0   -- the index part of
  * PredToText._func1, interpreter/interpreter.py:596-602 (ties keep every column). */
 int uocr_row_max_hits(const float* pred, uint8_t* hits, int64_t rows, int64_t cols, void* stream);
+/* labels (int32, n x h x w) = connected components of every image of a uint8 mask, counts[n] = their number:
+ * foreground = pixels strictly above the image's mean, 4-neighbourhood, labels 1..count in raster order of each
+ * component's first pixel -- bit-identical to `ndimage.label(layer > np.mean(layer))` of label_layer
+ * (interpreter/interpreter.py:16-22) on a (1, H, W, 1) layer, the first step of every crop stage (:437-470).
+ * h * w < 2^31; workspace of uocr_label_components_workspace(n, h, w) bytes. */
+int uocr_label_components_workspace(int64_t n, int64_t h, int64_t w, size_t* bytes);
+int uocr_label_components(const uint8_t* mask, int32_t* labels, int32_t* counts, int64_t n, int64_t h, int64_t w,
+                          void* workspace, void* stream);
 /* mask[n, p, c] (uint8) = x[n, p, c] > 0.5 * (mean_p x[n, :, c] + max_p x[n, :, c]) over the
  * hw positions of each (image, channel): the `thresholded()` of the crop stages,
  * interpreter/interpreter.py:437-438 (per mask channel) and :549.  Sums in float64, fixed order

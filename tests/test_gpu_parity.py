@@ -898,6 +898,13 @@ def test_page_stage_pads_predicts_and_binarises_on_device(nn, tmp_path):
     assert got['paragraph_mask'].dtype == np.uint8 and got['monochrome_pred'].dtype == np.float32
     assert np.array_equal(got['paragraph_mask'].astype(bool), O.thresholded(host(out['paragraph_pred'])))
     assert 0 < got['paragraph_mask'].mean() < 1
+    # ... and its connected components, numbered like the reference's label_layer (scipy.ndimage.label of `> mean`)
+    from scipy import ndimage
+    labels, counts = host(out['paragraph_labels']), host(out['paragraph_count'])
+    for i in range(labels.shape[0]):
+        layer = got['paragraph_mask'][i:i + 1]
+        want, cnt = ndimage.label(layer > np.mean(layer))
+        assert cnt == int(counts[i]) and np.array_equal(labels[i:i + 1], want)
     # second call with another page size builds (and caches) another pair of networks
     out2 = stage(f32(rng.uniform(size=(1, 64, 64, 1))))
     assert out2['paragraph_mask'].shape == (1, 80, 80, 1) and len(stage._models) == 2

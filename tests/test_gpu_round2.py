@@ -357,3 +357,68 @@ def test_pipeline_ships_uint8_in_and_masks_and_hits_out(nn, graph):
         assert rel_max(line, want) <= 1e-4
         seen += 1
     assert seen == 5
+
+
+# ----------------------------------------------------------------------------- crop stages: labelling on the device
+
+def _label_reference(mask):
+    """label_layer's labelling (interpreter/interpreter.py:16-22) per image: ndimage.label(layer > mean(layer)) on the
+    (1, H, W, 1) layer -- SciPy is the reference's own dependency for this step."""
+    from scipy import ndimage
+    out = np.zeros(mask.shape, dtype=np.int32)
+    counts = []
+    for n in range(mask.shape[0]):
+        layer = mask[n:n + 1]
+        lab, cnt = ndimage.label(layer > np.mean(layer))
+        out[n:n + 1] = lab
+        counts.append(cnt)
+    return out, np.array(counts, dtype=np.int32)
+
+
+def test_label_components_bit_exact_vs_scipy(nn):
+    """uocr_label_components == scipy.ndimage.label (default structure) on random masks of every density, adversarial
+    shapes for a union-find (spirals, combs, checkerboards: many merges / long chains), all-ones (the reference's
+    `> mean` makes that EMPTY), all-zeros, single pixels, non-binary uint8 layers, page-tile and full-page sizes."""
+    from univer_ocr_b200 import glue
+    rng = np.random.default_rng(77)
+    cases = []
+    for shape in ((1, 1, 1, 1), (2, 1, 9, 1), (2, 7, 1, 1), (3, 13, 11, 1), (2, 64, 300, 1), (1, 257, 1025, 1)):
+        for dens in (0.15, 0.5, 0.62, 0.9):
+            cases.append((rng.uniform(size=shape) < dens).astype(np.uint8))
+    h, w = 96, 130
+    spiral = np.zeros((h, w), np.uint8)
+    t, b, l, r = 0, h - 1, 0, w - 1
+    while t <= b and l <= r:                                    # a one-pixel-wide rectangular spiral: ONE component
+        spiral[t, l:r + 1] = 1
+        spiral[t:b + 1, r] = 1
+        if t + 2 <= b:
+            spiral[b, l + 2:r + 1] = 1
+            spiral[t + 2:b + 1, l + 2] = 1
+        t, b, l, r = t + 2, b - 2, l + 2, r - 2
+        if t <= b and l <= r:
+            spiral[t, l] = 1
+    comb = np.zeros((h, w), np.uint8)
+    comb[:, ::2] = 1                                            # vertical teeth ...
+    comb[-1, :] = 1                                             # ... joined only at the bottom row
+    checker = (np.indices((h, w)).sum(axis=0) % 2).astype(np.uint8)       # no two foreground pixels touch
+    stripes = np.zeros((h, w), np.uint8)
+    stripes[::2, :] = 1
+    for img in (spiral, comb, checker, stripes, np.ones((h, w), np.uint8), np.zeros((h, w), np.uint8)):
+        cases.append(img[None, :, :, None])
+    cases.append(rng.integers(0, 256, size=(2, 40, 50, 1), dtype=np.uint8))         # not binary: > mean still defines it
+    pred = rng.uniform(size=(2, 496, 736, 1)) ** 6                                  # blobs like a thresholded mask
+    cases.append((pred > 0.5 * (pred.mean() + pred.max())).astype(np.uint8))
+    cases.append((rng.uniform(size=(1, 2064, 2064, 1)) < 0.55).astype(np.uint8))    # near the percolation threshold
+    for mask in cases:
+        want, want_counts = _label_reference(mask)
+        labels, counts = glue.label_components(mask)
+        got = labels.get()
+        assert got.dtype == np.int32 and got.shape == mask.shape
+        assert np.array_equal(counts.get(), want_counts), (mask.shape, counts.get(), want_counts)
+        assert np.array_equal(got, want), f'labels differ for shape {mask.shape}'
+    # the reference's interface: a list of per-object boolean masks
+    mask = cases[10][:1]
+    objs = glue.label_layer(mask)
+    from scipy import ndimage
+    lab, cnt = ndimage.label(mask > np.mean(mask))
+    assert len(objs) == cnt and all(np.array_equal(o, lab == i + 1) for i, o in enumerate(objs))

@@ -10,8 +10,10 @@ the host link is uint8 masks / hit tables (1 byte per element instead of 8):
     make_divisible_by   my_model/model.py:26-34
     thresholded         interpreter/interpreter.py:437-438, 549   (arr > 0.5 * (mean + max))
     row_max_hits / pred_to_text   interpreter/interpreter.py:595-614  (PredToText._func1)
+    label_components / label_layer   interpreter/interpreter.py:16-22  (ndimage.label of the crop stages)
 
-The labelling / rotation / zoom stages between them (`scipy.ndimage`) stay on the host (row f4).
+Of the stages between them (row f4) the connected-component labelling runs on the device as well; rotation and zoom
+(`scipy.ndimage.rotate / zoom`) stay on the host.
 """
 import ctypes
 
@@ -57,6 +59,34 @@ def thresholded(arr):
     work = DeviceArray.empty((nbytes.value,), np.uint8)
     lib.uocr_threshold_mask(arr.ptr, mask.ptr, n, hw, c, work.ptr, stream())
     return mask
+
+
+def label_components(mask):
+    """Connected components of every image of a uint8 mask (N, H, W) or (N, H, W, 1) -> (labels int32 of the same
+    shape, counts int32 (N,)), both on the device: foreground = strictly above the image's mean, 4-neighbourhood,
+    labels 1..count in raster order of each component's first pixel -- `ndimage.label(layer > np.mean(layer))` of the
+    reference's `label_layer` (`interpreter/interpreter.py:16-22`), bit for bit."""
+    mask = as_device(mask) if isinstance(mask, DeviceArray) else DeviceArray.from_host(np.asarray(mask, np.uint8), np.uint8)
+    assert mask.dtype == np.uint8, f'expected a uint8 mask, got {mask.dtype}'
+    shape = mask.shape
+    assert len(shape) == 3 or (len(shape) == 4 and shape[3] == 1), f'expected (N, H, W[, 1]), got {shape}'
+    n, h, w = shape[:3]
+    nbytes = ctypes.c_size_t(0)
+    lib.uocr_label_components_workspace(n, h, w, ctypes.byref(nbytes))
+    work = DeviceArray.empty((nbytes.value,), np.uint8)
+    labels = DeviceArray.empty(shape, np.int32)
+    counts = DeviceArray.empty((n,), np.int32)
+    lib.uocr_label_components(mask.ptr, labels.ptr, counts.ptr, n, h, w, work.ptr, stream())
+    return labels, counts
+
+
+def label_layer(mask):
+    """The reference's `label_layer` (`interpreter/interpreter.py:16-22`) for ONE (1, H, W, 1) mask: a list of
+    full-size boolean arrays, one per object.  The labelling runs on the device; the per-object masks are expanded on
+    the host (that list is the reference's interface -- device-side consumers use `label_components`)."""
+    labels, counts = label_components(mask)
+    host = labels.get()
+    return [host == l_id + 1 for l_id in range(int(counts.get()[0]))]
 
 
 def row_max_hits(pred):

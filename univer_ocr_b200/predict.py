@@ -4,8 +4,9 @@ Reference (`my_model/predict.py:12-23`, `my_model/model.py:695-699`): load `mode
 multiple of 16 (`make_divisible_by`), run Monochrome, feed its prediction to Paragraph, move BOTH float64 maps to the
 host, where `CropAndRotateParagraphs` starts by binarising the paragraph map (`interpreter/interpreter.py:437-447`).
 Here the padding, the two networks (Monochrome conv pair on tcgen05, Paragraph as one fused kernel) and the binarisation
-run back to back on the device; what the crop stage needs crosses the host link as one float32 map + a uint8 mask
-(5 bytes per pixel instead of 16).  The labelling / rotation stages that follow are host code (row f4, out of scope).
+and the connected-component labelling of that mask (`label_layer`, `interpreter/interpreter.py:16-22`) run back to
+back on the device; what the crop stage needs crosses the host link as one float32 map + a uint8 mask or an int32
+label map (5-8 bytes per pixel instead of 16).  The rotation / zoom stages that follow are host code (rest of row f4).
 """
 import numpy as np
 
@@ -42,8 +43,12 @@ class PageStage:
         mono, para = self.models_for(x.shape)
         monochrome_pred = mono.predict(x)[0]
         paragraph_pred = para.predict(monochrome_pred)[0]
+        paragraph_mask = glue.thresholded(paragraph_pred)
+        # what CropAndRotateParagraphs does first with that mask (interpreter/interpreter.py:437-447 -> label_layer :16-22)
+        paragraph_labels, paragraph_count = glue.label_components(paragraph_mask)
         return {'padded': x, 'monochrome_pred': monochrome_pred, 'paragraph_pred': paragraph_pred,
-                'paragraph_mask': glue.thresholded(paragraph_pred)}
+                'paragraph_mask': paragraph_mask, 'paragraph_labels': paragraph_labels,
+                'paragraph_count': paragraph_count}
 
     @staticmethod
     def to_host(result, want=('monochrome_pred', 'paragraph_mask')):
