@@ -373,6 +373,12 @@ int uocr_row_max_hits(const float* pred, uint8_t* hits, int64_t rows, int64_t co
 int uocr_label_components_workspace(int64_t n, int64_t h, int64_t w, size_t* bytes);
 int uocr_label_components(const uint8_t* mask, int32_t* labels, int32_t* counts, int64_t n, int64_t h, int64_t w,
                           void* workspace, void* stream);
+/* stats[n][l - 1][0..6] (int64) = pixel count, sum of y, sum of x, y_min, y_max, x_min, x_max of component l of image n
+ * (l = 1..max_labels; components beyond max_labels are ignored; absent components: count 0, min > max): the bounding
+ * box ndimage.find_objects returns for an object mask and the exact integer sums ndimage.center_of_mass divides
+ * (interpreter/interpreter.py:36-38, 125-148, 230, 303, 341, 496-497). */
+int uocr_label_stats(const int32_t* labels, int64_t* stats, int64_t n, int64_t h, int64_t w, int64_t max_labels,
+                     void* stream);
 /* mask[n, p, c] (uint8) = x[n, p, c] > 0.5 * (mean_p x[n, :, c] + max_p x[n, :, c]) over the
  * hw positions of each (image, channel): the `thresholded()` of the crop stages,
  * interpreter/interpreter.py:437-438 (per mask channel) and :549.  Sums in float64, fixed order

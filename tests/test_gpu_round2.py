@@ -422,3 +422,31 @@ def test_label_components_bit_exact_vs_scipy(nn):
     from scipy import ndimage
     lab, cnt = ndimage.label(mask > np.mean(mask))
     assert len(objs) == cnt and all(np.array_equal(o, lab == i + 1) for i, o in enumerate(objs))
+
+
+def test_label_stats_match_find_objects_and_center_of_mass(nn):
+    """uocr_label_stats: per-object bounding boxes == ndimage.find_objects and centres of mass == ndimage.center_of_mass
+    of every object mask `labels == l` (what the crop stages compute object by object on the host,
+    interpreter/interpreter.py:36-38, 125-148), exactly -- the device accumulates integer sums."""
+    from scipy import ndimage
+    from univer_ocr_b200 import glue
+    rng = np.random.default_rng(5)
+    for shape, dens in (((2, 33, 47, 1), 0.3), ((1, 128, 256, 1), 0.5), ((3, 496, 736, 1), None), ((1, 9, 5, 1), 1.0)):
+        if dens is None:
+            pred = rng.uniform(size=shape) ** 6
+            mask = (pred > 0.5 * (pred.mean() + pred.max())).astype(np.uint8)
+        else:
+            mask = (rng.uniform(size=shape) < dens).astype(np.uint8)
+            mask[:, 0, 0, :] = 0                                 # keep the all-ones image from being "empty under > mean"
+        labels, counts = glue.label_components(mask)
+        got = glue.label_stats(labels, counts)
+        host_labels = labels.get()
+        for i in range(shape[0]):
+            lab = host_labels[i, :, :, 0]
+            boxes = ndimage.find_objects(lab)
+            assert len(got[i]) == len(boxes) == int(counts.get()[i])
+            centres = ndimage.center_of_mass(lab > 0, lab, range(1, len(boxes) + 1)) if boxes else []
+            for l, obj in enumerate(got[i]):
+                assert obj['slices'] == boxes[l], (shape, i, l)
+                assert obj['count'] == int((lab == l + 1).sum())
+                assert obj['center_of_mass'] == tuple(float(v) for v in centres[l]), (shape, i, l, obj, centres[l])

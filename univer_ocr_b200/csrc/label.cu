@@ -216,6 +216,64 @@ __global__ void __launch_bounds__(256) label_paint_kernel(const int32_t* __restr
     }
 }
 
+// ---- per-component statistics: what the crop stages take from each object mask (`labels == l`): its bounding box
+// (ndimage.find_objects, interpreter.py:125-148, 230, 303, 341, 496-497) and its centre of mass
+// (ndimage.center_of_mass, :36-38, 142-144).  stats[n][l - 1][0..6] = count, sum_y, sum_x, y_min, y_max, x_min, x_max.
+// Lanes of a warp that hold the same label are combined first (__match_any_sync): one set of atomics per label and warp.
+constexpr int LB_STATS = 7;
+
+__global__ void __launch_bounds__(256) label_stats_init_kernel(long long* __restrict__ stats, int64_t entries) {
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < entries; i += (int64_t)gridDim.x * 256) {
+        long long* s = stats + i * LB_STATS;
+        s[0] = 0; s[1] = 0; s[2] = 0;
+        s[3] = 0x7fffffffffffffffll; s[4] = -1; s[5] = 0x7fffffffffffffffll; s[6] = -1;
+    }
+}
+
+__global__ void __launch_bounds__(256) label_stats_kernel(const int32_t* __restrict__ labels, long long* __restrict__ stats,
+                                                          int h, int w, int64_t max_labels, int64_t total) {
+    const int64_t px = (int64_t)h * w;
+    const int lane = threadIdx.x & 31;
+    // whole warps iterate together (the loop bound is rounded up per warp), idle lanes carry label 0
+    for (int64_t g0 = ((int64_t)blockIdx.x * 256 + (threadIdx.x & ~31)); g0 < total; g0 += (int64_t)gridDim.x * 256) {
+        const int64_t g = g0 + lane;
+        int32_t l = 0;
+        int y = 0, x = 0;
+        int64_t n = 0;
+        if (g < total) {
+            l = labels[g];
+            n = g / px;
+            const int64_t p = g - n * px;
+            y = (int)(p / w);
+            x = (int)(p - (int64_t)y * w);
+        }
+        if (l > max_labels) l = 0;
+        // key = (image, label): lanes of one warp can straddle two images
+        const long long key = l > 0 ? (n << 32) | (long long)l : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (l <= 0) continue;
+        const int leader = __ffs(peers) - 1;
+        long long cnt = 0, sy = 0, sx = 0;
+        int y0 = y, y1 = y, x0 = x, x1 = x;
+        for (unsigned m = peers; m; m &= m - 1) {
+            const int src = __ffs(m) - 1;
+            const int oy = __shfl_sync(peers, y, src), ox = __shfl_sync(peers, x, src);
+            ++cnt; sy += oy; sx += ox;
+            y0 = min(y0, oy); y1 = max(y1, oy); x0 = min(x0, ox); x1 = max(x1, ox);
+        }
+        if (lane == leader) {
+            long long* s = stats + (n * max_labels + (l - 1)) * LB_STATS;
+            atomicAdd(reinterpret_cast<unsigned long long*>(s + 0), (unsigned long long)cnt);
+            atomicAdd(reinterpret_cast<unsigned long long*>(s + 1), (unsigned long long)sy);
+            atomicAdd(reinterpret_cast<unsigned long long*>(s + 2), (unsigned long long)sx);
+            atomicMin(s + 3, (long long)y0);
+            atomicMax(s + 4, (long long)y1);
+            atomicMin(s + 5, (long long)x0);
+            atomicMax(s + 6, (long long)x1);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace uocr
 
@@ -261,6 +319,22 @@ int uocr_label_components(const uint8_t* mask, int32_t* labels, int32_t* counts,
     UOCR_LAUNCHED("label_rank");
     label_paint_kernel<<<flat_blocks, 256, 0, st>>>(parent, labels, px, total);
     UOCR_LAUNCHED("label_paint");
+    return UOCR_OK;
+}
+
+int uocr_label_stats(const int32_t* labels, int64_t* stats, int64_t n, int64_t h, int64_t w, int64_t max_labels,
+                     void* stream) {
+    UOCR_REQUIRE(labels && stats, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && max_labels > 0 && h <= 0x7fffffff && w <= 0x7fffffff, "bad dimension");
+    UOCR_REQUIRE(h * w < (1ll << 31) && max_labels < (1ll << 31), "image too large for 32-bit pixel indices");
+    cudaStream_t st = as_stream(stream);
+    const int64_t entries = n * max_labels, total = n * h * w;
+    const int init_blocks = (int)(ceil_div(entries, 256) < 148 * 8 ? ceil_div(entries, 256) : 148 * 8);
+    label_stats_init_kernel<<<init_blocks, 256, 0, st>>>(reinterpret_cast<long long*>(stats), entries);
+    UOCR_LAUNCHED("label_stats_init");
+    const int blocks = (int)(ceil_div(total, 256) < 148 * 32 ? ceil_div(total, 256) : 148 * 32);
+    label_stats_kernel<<<blocks, 256, 0, st>>>(labels, reinterpret_cast<long long*>(stats), (int)h, (int)w, max_labels, total);
+    UOCR_LAUNCHED("label_stats");
     return UOCR_OK;
 }
 

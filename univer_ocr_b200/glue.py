@@ -80,6 +80,28 @@ def label_components(mask):
     return labels, counts
 
 
+def label_stats(labels, counts):
+    """Per-object bounding boxes and centres of mass of a device label map (N, H, W[, 1]) from `label_components`:
+    -> list (per image) of lists (per object, in label order) of dicts {'slices': (slice_y, slice_x) as
+    `ndimage.find_objects` returns them, 'center_of_mass': (y, x) as `ndimage.center_of_mass` of the object's mask,
+    'count': pixels}.  The sums are accumulated as integers on the device; one small table crosses the host link."""
+    n, h, w = labels.shape[:3]
+    host_counts = np.asarray(counts.get(), dtype=np.int64)
+    max_labels = max(int(host_counts.max()) if host_counts.size else 0, 1)
+    stats = DeviceArray.empty((n, max_labels, 7), np.int64)
+    lib.uocr_label_stats(labels.ptr, stats.ptr, n, h, w, max_labels, stream())
+    table = stats.get()
+    out = []
+    for i in range(n):
+        objs = []
+        for l in range(int(host_counts[i])):
+            cnt, sy, sx, y0, y1, x0, x1 = (int(v) for v in table[i, l])
+            objs.append({'slices': (slice(y0, y1 + 1), slice(x0, x1 + 1)),
+                         'center_of_mass': (sy / cnt, sx / cnt), 'count': cnt})
+        out.append(objs)
+    return out
+
+
 def label_layer(mask):
     """The reference's `label_layer` (`interpreter/interpreter.py:16-22`) for ONE (1, H, W, 1) mask: a list of
     full-size boolean arrays, one per object.  The labelling runs on the device; the per-object masks are expanded on
