@@ -214,6 +214,13 @@ int uocr_hourglass1_fwd(const float* x, const float* const* weights, const float
 int uocr_hourglass1_fwd_mode(const float* x, const float* const* weights, const float* const* biases, float* y,
                              int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end,
                              int math_mode, void* stream);
+/* The four-channel hourglass (make_line, my_model/model.py:194-248: 1 -> 4 -> 4 -> 4 -> 4 -> 2 channels, otherwise the
+ * topology above) in ONE tensor-core kernel: every level is tcgen05.mma (TF32 operands, FP32 accumulators in tensor
+ * memory) reading the previous level's block in shared memory in place.  weights: (5,5,1,4), (5,5,4,4) x 3, (5,5,4,2);
+ * biases (4) x 4, (2); x: (N, H, W, 1), y: (N, H, W, 2), H % 4 == 0 and W % 4 == 0.  A TF32 kernel (tolerance 1e-3 of
+ * the output range); callers in UOCR_MATH_FP32 mode run the layers one by one instead. */
+int uocr_hourglass4_fwd(const float* x, const float* const* weights, const float* const* biases, float* y,
+                        int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end, void* stream);
 
 /* Backward of the same pair in TRAINING (y = conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2, the final
  * activation handled by its own layer): dw1/db1/dw2/db2 (+)= parameter gradients, dx = input gradient

@@ -11,6 +11,10 @@ namespace uocr {
 int make_tmap_plain_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box);
 
+// the same, but the TMA unit rounds the elements to TF32 (image rows a tcgen05.mma reads directly as its A operand)
+int make_tmap_plain_tf32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box);
+
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -769,6 +769,9 @@ class HourglassFusion:
     plan) whenever the topology, the hyper-parameters or the input geometry are not the ones the
     kernel implements."""
 
+    CHANNELS_1 = [(1, 1)] * 5                                     # make_paragraph: uocr_hourglass1_fwd
+    CHANNELS_4 = [(1, 4), (4, 4), (4, 4), (4, 4), (4, 2)]         # make_line (my_model/model.py:194-248): uocr_hourglass4_fwd
+
     def __init__(self, prefix):
         p = prefix
         self.chain = [f'{p}/down_1/conv_1', f'{p}/down_1/leaky_relu_1',
@@ -809,10 +812,12 @@ class HourglassFusion:
                 if type(ups) is not Upsample2D or ups.scale_factor != (2, 2):
                     return None
             if (type(conv) is not Convolutional2D or conv.kernel_size != (5, 5) or conv.padding != (2, 2)
-                    or conv.stride != stride or conv.in_channels != 1 or conv.out_channels != 1
-                    or conv.padding_value != 0 or not conv.bias):
+                    or conv.stride != stride or conv.padding_value != 0 or not conv.bias):
                 return None
             out.append((conv, act))
+        channels = [(conv.in_channels, conv.out_channels) for conv, _ in out]
+        if channels not in (self.CHANNELS_1, self.CHANNELS_4):
+            return None
         return out
 
     def __call__(self, model, inputs):
@@ -827,13 +832,19 @@ class HourglassFusion:
         if (end is None or any(a is None or a[0] != ACT_LEAKY or a[1] > 1 for a in inner)
                 or len({a[1] for a in inner}) != 1):
             return None
+        four = blocks[1][0].in_channels == 4
+        if four and CP.math_mode != MATH_TF32:             # the four-channel kernel is tensor-core (TF32) only
+            return None
         n, h, w, _ = X.shape
         ptrs = ctypes.c_void_p * 5
         wp = ptrs(*[conv.w.value.ptr for conv, _ in blocks])
         bp = ptrs(*[conv.b.value.ptr for conv, _ in blocks])
         last = blocks[4][1]
         last.progress_tracker.start_tracking(last.name, 'forward')
-        y = DeviceArray((n, h, w, 1))
-        lib.uocr_hourglass1_fwd_mode(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], CP.math_mode, stream())
+        y = DeviceArray((n, h, w, blocks[4][0].out_channels))
+        if four:
+            lib.uocr_hourglass4_fwd(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], stream())
+        else:
+            lib.uocr_hourglass1_fwd_mode(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], CP.math_mode, stream())
         last.progress_tracker.stop_tracking(last.name, 'forward')
         return [y]
