@@ -221,6 +221,13 @@ int uocr_hourglass1_fwd_mode(const float* x, const float* const* weights, const 
  * the output range); callers in UOCR_MATH_FP32 mode run the layers one by one instead. */
 int uocr_hourglass4_fwd(const float* x, const float* const* weights, const float* const* biases, float* y,
                         int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end, void* stream);
+/* The kernel reads the five weight tensors in a packed tensor-core operand layout (*floats of uocr_hourglass4_packed_floats
+ * floats, 16-byte aligned, TF32-rounded, the two up levels pre-summed per output parity): uocr_hourglass4_fwd packs them
+ * on every call; callers that keep the packed image until the weights change call these two instead. */
+int uocr_hourglass4_packed_floats(int64_t* floats);
+int uocr_hourglass4_pack(const float* const* weights, float* packed, void* stream);
+int uocr_hourglass4_fwd_packed(const float* x, const float* packed, const float* const* biases, float* y,
+                               int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end, void* stream);
 
 /* Backward of the same pair in TRAINING (y = conv3x3(act1(conv3x3(x, w1) + b1), w2) + b2, the final
  * activation handled by its own layer): dw1/db1/dw2/db2 (+)= parameter gradients, dx = input gradient

@@ -410,3 +410,100 @@ def test_hourglass_tensor_core_levels_vs_oracle(nn, monkeypatch):
         tol = 1e-3 if act_end == ACT_SIGMOID else 2e-3
         close_tf32(outs[1], want, f'hourglass tf32 vs oracle {(n, h, w)}', tol=tol)
         close_tf32(outs[1], outs[0], f'hourglass tf32 vs fp32 {(n, h, w)}', tol=tol)
+
+
+def _line_oracle(X, ws, bs, act_end, alpha=0.01, alpha_end=0.0):
+    """make_line's forward (my_model/model.py:194-248) from the oracle's layers."""
+    from univer_ocr_b200._lib import ACT_LEAKY, ACT_SIGMOID
+    t = O.leaky_relu_fwd(O.conv2d_fwd(X, ws[0], bs[0], 2, stride=2), alpha)
+    t = O.leaky_relu_fwd(O.conv2d_fwd(t, ws[1], bs[1], 2, stride=2), alpha)
+    t = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(t, 2), ws[2], bs[2], 2), alpha)
+    t = O.leaky_relu_fwd(O.conv2d_fwd(O.upsample2d_fwd(t, 2), ws[3], bs[3], 2), alpha)
+    want = O.conv2d_fwd(t, ws[4], bs[4], 2)
+    if act_end == ACT_SIGMOID:
+        want = O.sigmoid_fwd(want)
+    elif act_end == ACT_LEAKY:
+        want = O.leaky_relu_fwd(want, alpha_end)
+    return want
+
+
+def test_line_network_one_kernel_vs_oracle(nn):
+    """uocr_hourglass4_fwd: the whole Line network (1 -> 4 -> 4 -> 4 -> 4 -> 2 channels) as ONE tensor-core kernel
+    (csrc/hourglass4_tc.cu) vs the float64 oracle chain of five conv layers, through the C ABI with raw pointers: the
+    Line tile (2, 128, 256), sizes that end inside a 16 x 128 block, sizes smaller than one block, a page-wide strip, and
+    every end activation.  Signed weights (un-saturated sigmoids); tolerance 1e-3 of the output range for the sigmoid
+    output, 2e-3 for the un-squashed outputs (five layers of gain).  The packed-weights entry gives the same bits."""
+    import ctypes
+    from univer_ocr_b200._lib import ACT_LEAKY, ACT_NONE, ACT_SIGMOID, lib
+    rng = np.random.default_rng(77)
+    ptrs = ctypes.c_void_p * 5
+    for (n, h, w), act_end in (((2, 128, 256), ACT_SIGMOID), ((1, 16, 128), ACT_NONE), ((3, 4, 4), ACT_SIGMOID),
+                               ((2, 20, 36), ACT_LEAKY), ((1, 52, 300), ACT_SIGMOID), ((1, 132, 12), ACT_NONE),
+                               ((2, 8, 2064), ACT_SIGMOID), ((1, 496, 736), ACT_SIGMOID)):
+        X = f32(rng.uniform(size=(n, h, w, 1)))
+        chans = [(1, 4), (4, 4), (4, 4), (4, 4), (4, 2)]
+        ws = [f32(rng.standard_normal((5, 5, ci, co)) * (0.6 / np.sqrt(ci * 6.0))) for ci, co in chans]
+        bs = [f32(rng.standard_normal(co) * 0.2) for _, co in chans]
+        want = _line_oracle(X, ws, bs, act_end, alpha_end=0.2)
+        dX, dw, db = nn.CP.copy(X), [nn.CP.copy(a) for a in ws], [nn.CP.copy(a) for a in bs]
+        y = nn.DeviceArray.full((n, h, w, 2), -3.0)
+        lib.uocr_hourglass4_fwd(dX.ptr, ptrs(*[a.ptr for a in dw]), ptrs(*[a.ptr for a in db]), y.ptr, n, h, w,
+                                0.01, act_end, 0.2, nn.CP.stream())
+        got = np.asarray(y.get(), dtype=np.float64)
+        assert np.isfinite(got).all()
+        if act_end == ACT_SIGMOID:
+            assert 0.05 < want.mean() < 0.95 and want.std() > 0.02, 'saturated test case'
+        close_tf32(got, want, f'line one-kernel vs oracle {(n, h, w)}', tol=1e-3 if act_end == ACT_SIGMOID else 2e-3)
+        count = ctypes.c_int64()
+        lib.uocr_hourglass4_packed_floats(ctypes.byref(count))
+        packed = nn.DeviceArray((count.value,))
+        lib.uocr_hourglass4_pack(ptrs(*[a.ptr for a in dw]), packed.ptr, nn.CP.stream())
+        y2 = nn.DeviceArray.full((n, h, w, 2), -3.0)
+        lib.uocr_hourglass4_fwd_packed(dX.ptr, packed.ptr, ptrs(*[a.ptr for a in db]), y2.ptr, n, h, w, 0.01, act_end, 0.2,
+                                       nn.CP.stream())
+        assert np.array_equal(y2.get(), y.get())
+    # error convention: geometry the kernel does not implement
+    from univer_ocr_b200._lib import UocrError
+    with pytest.raises(UocrError) as err:
+        lib.uocr_hourglass4_fwd(dX.ptr, ptrs(*[a.ptr for a in dw]), ptrs(*[a.ptr for a in db]), y.ptr, 1, 6, 8,
+                                0.01, ACT_SIGMOID, 0.0, nn.CP.stream())
+    assert err.value.code == -3 and 'multiples of 4' in str(err.value)
+
+
+def test_line_model_uses_the_one_kernel_path(nn):
+    """my_model.make_line in TF32 mode: Model.predict goes through HourglassFusion -> uocr_hourglass4_fwd_packed (one
+    launch + one pack launch on the first call / after a weight change) and agrees with the layer-by-layer FP32 path;
+    in FP32 mode the fusion steps aside."""
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200._lib import launch_count
+    shape = (2, 128, 256, 1)
+    model = my_model.make_line(shape)
+    for key, p in model.params().items():                                 # centred: the default init saturates the sigmoid
+        v = np.asarray(p.value.get(), dtype=np.float64)
+        p.value = (v - v.mean()) * 3.5 if v.size > 2 else v * 0.25
+    x = f32(np.random.default_rng(3).uniform(size=shape))
+    nn.CP.set_math_mode('tf32')
+    try:
+        assert model.infer_fusion is not None
+        n0 = launch_count()
+        y1 = model.predict(x)[0].get()
+        first = launch_count() - n0
+        n0 = launch_count()
+        y2 = model.predict(x)[0].get()
+        second = launch_count() - n0
+        assert np.array_equal(y1, y2)
+        assert second == 1 and first == 2, (first, second)
+        # a weight change re-packs
+        for key, p in model.params().items():
+            if key.endswith('end/conv_1/w'):
+                p.value = np.asarray(p.value.get()) * 0.5
+        y3 = model.predict(x)[0].get()
+        assert not np.array_equal(y1, y3)
+        nn.CP.set_math_mode('fp32')
+        n0 = launch_count()
+        ref = model.predict(x)[0].get()
+        assert launch_count() - n0 >= 5                                # layer by layer
+    finally:
+        nn.CP.set_math_mode('tf32')
+    assert 0.05 < ref.mean() < 0.95
+    close_tf32(np.asarray(y3, dtype=np.float64), np.asarray(ref, dtype=np.float64), 'line model fused vs fp32', tol=1e-3)

@@ -59,14 +59,14 @@ constexpr int OFF_P00 = 25728;                    // 13184 + 20 * 624 = 25664, r
 constexpr int P0_BYTES = H4_P0_ROWS * H4_POS * 16, P1_BYTES = H4_P1_ROWS * H4_POS * 16;
 constexpr int OFF_P10 = OFF_P00 + 2 * P0_BYTES;
 constexpr int OFF_R0_END = OFF_P10 + 2 * P1_BYTES;                         // 49440
-constexpr int OFF_U1 = 0;                         // aliases the x block and the D1 planes (dead after down_2)
+// D2, U2 and U1 alias the x block and the D1 planes: a level's epilogue starts only after all of the level's MMAs have
+// completed, so the block a level WRITES may overwrite the block it READ (and everything older).  70 KB: 3 CTAs / SM.
+constexpr int OFF_U1 = 0, OFF_D2 = 0, OFF_U2 = 0;
 constexpr int U1_BYTES = H4_U1H * H4_PU1 * 16;
-static_assert(OFF_U1 + U1_BYTES + 64 <= OFF_R0_END, "U1 fits over the x block and the D1 planes");
-constexpr int OFF_D2 = OFF_R0_END;
 constexpr int D2_BYTES = H4_D2H * H4_POS * 16;
-constexpr int OFF_U2 = OFF_D2 + D2_BYTES + 64;
 constexpr int U2_BYTES = H4_U2H * H4_PU2 * 16;
-constexpr int OFF_B = OFF_U2 + U2_BYTES + 64;
+static_assert(OFF_U1 + U1_BYTES + 64 <= OFF_R0_END, "U1 fits over the x block and the D1 planes");
+constexpr int OFF_B = OFF_R0_END;
 constexpr int OFF_BIAS = OFF_B + H4_BFLOATS * 4;
 constexpr int OFF_BAR = OFF_BIAS + 96;
 constexpr int OFF_TMEM = OFF_BAR + 64;
@@ -81,8 +81,6 @@ struct Hourglass4Params {
     int H, W;
     float alpha;
     int act_end; float alpha_end;
-    int dbg, xw;
-    int stop;                                     // debugging: leave after this level (0 = after the prologue)
 };
 
 // ---- B operand image.  Every MMA tile is K-major [chunk c: 2][n: 16][e: 4] (k = 4 c + e); weights are (5,5,Cin,Cout).
@@ -139,17 +137,29 @@ __device__ __forceinline__ void h4_level_sync() {
     tc_fence_after();
 }
 
-__device__ __forceinline__ float4 h4_act4(const uint32_t* v, const float* bias, float alpha, bool in) {
-    float o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float t = __uint_as_float(v[k]) + bias[k];
-        o[k] = in ? round_tf32(fmaxf(t, t * alpha)) : 0.f;
-    }
-    return make_float4(o[0], o[1], o[2], o[3]);
+// + bias, LeakyReLU, round to TF32 (round to nearest, ties away: add half an ulp of the 10-bit mantissa and cut; the mask
+// doubles as the "inside the image" select), as one 16-byte shared-memory store.  Branch-free: the first version (a
+// conditional around every value, biases read from shared memory) spent 8 k cycles in up_1's epilogue alone.
+__device__ __forceinline__ void h4_store4(uint32_t addr, const uint32_t* v, const float4 b, float alpha, bool in) {
+    const uint32_t msk = in ? 0xffffe000u : 0u;
+    const float t0 = __uint_as_float(v[0]) + b.x, t1 = __uint_as_float(v[1]) + b.y;
+    const float t2 = __uint_as_float(v[2]) + b.z, t3 = __uint_as_float(v[3]) + b.w;
+    const uint32_t o0 = (__float_as_uint(fmaxf(t0, t0 * alpha)) + 0x1000u) & msk;
+    const uint32_t o1 = (__float_as_uint(fmaxf(t1, t1 * alpha)) + 0x1000u) & msk;
+    const uint32_t o2 = (__float_as_uint(fmaxf(t2, t2 * alpha)) + 0x1000u) & msk;
+    const uint32_t o3 = (__float_as_uint(fmaxf(t3, t3 * alpha)) + 0x1000u) & msk;
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+}
+__device__ __forceinline__ void h4_zero16(uint32_t addr) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ float4 h4_lds4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+    return r;
 }
 
-__global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hourglass4Params p,
+__global__ void __launch_bounds__(H4_THREADS, 3) hourglass4_fwd_kernel(const Hourglass4Params p,
                                                                        const __grid_constant__ CUtensorMap map_even,
                                                                        const __grid_constant__ CUtensorMap map_odd) {
     extern __shared__ __align__(128) uint8_t h4_smem[];
@@ -165,33 +175,27 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
 #pragma unroll
         for (int l = 0; l < 6; ++l) mbar_init(bar + 8 * l, l == 0 ? 1u : (uint32_t)(l == 1 ? H4_T1 : l == 2 ? H4_T2 : l == 3 ? H4_T3 : l == 4 ? H4_T4 : H4_T5));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (!(p.dbg & 1)) {
-        mbar_arrive_expect_tx(bar, (uint32_t)(((p.dbg & 8) ? 0 : H4_XE_ROWS) + ((p.dbg & 4) ? 0 : H4_XO_ROWS)) * p.xw * 4);
-        // block row 2 i (+ 1) = row (oy0 - 14) / 2 + i of the even- (odd-) row view of the image; zeros outside it
-        if (!(p.dbg & 8)) tma_load_3d(sm + OFF_XE, &map_even, bar, ox0 - 16, (oy0 - 14) / 2, img);
-        if (!(p.dbg & 4)) tma_load_3d(sm + OFF_XO, &map_odd, bar, ox0 - 16, (oy0 - 14) / 2, img);
-        }
+        mbar_arrive_expect_tx(bar, (uint32_t)((H4_XE_ROWS + H4_XO_ROWS) * H4_XP * 4 + H4_BFLOATS * 4));
+        // block row 2 i (+ 1) = row (oy0 - 14) / 2 + i of the even- (odd-) row view of the image; zeros outside it.
+        // The box starts at column ox0 - 16: a TMA box has to start on a 16-byte boundary of the tensor.
+        tma_load_3d(sm + OFF_XE, &map_even, bar, ox0 - 16, (oy0 - 14) / 2, img);
+        tma_load_3d(sm + OFF_XO, &map_odd, bar, ox0 - 16, (oy0 - 14) / 2, img);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(sm + OFF_B), "l"(p.bimg), "r"((uint32_t)(H4_BFLOATS * 4)), "r"(bar) : "memory");
     }
     __syncwarp();
-    if (warp == 0 && !(p.dbg & 2)) {
+    if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sm + OFF_TMEM), "r"(128u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    {   // B operands, biases; the gaps that valid rows' zero-weight K lanes reach must hold finite numbers
-        const float4* src = reinterpret_cast<const float4*>(p.bimg);
-        float4* dst = reinterpret_cast<float4*>(h4_smem + OFF_B);
-        for (int i = tid; i < H4_BFLOATS / 4; i += H4_THREADS) dst[i] = __ldg(src + i);
+    {   // biases; the gaps that valid rows' zero-weight K lanes reach must hold finite numbers
         if (tid < 4) {                                                   // static level index: keeps p in constant memory
 #pragma unroll
             for (int l = 0; l < 4; ++l) sBias[4 * l + tid] = __ldg(p.b[l] + tid);
             if (tid < 2) sBias[16 + tid] = __ldg(p.b[4] + tid);
         }
-        if (tid < 16) {
-            reinterpret_cast<float4*>(h4_smem + OFF_XO - 80)[tid < 5 ? tid : 0] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        if (tid >= 32 && tid < 36) reinterpret_cast<float4*>(h4_smem + OFF_P00 - 64)[tid - 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid >= 64 && tid < 68) reinterpret_cast<float4*>(h4_smem + OFF_D2 + D2_BYTES)[tid - 64] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid >= 96 && tid < 100) reinterpret_cast<float4*>(h4_smem + OFF_U2 + U2_BYTES)[tid - 96] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid >= 32 && tid < 37) h4_zero16(sm + OFF_XO - 80 + 16 * (tid - 32));
+        if (tid >= 64 && tid < 68) h4_zero16(sm + OFF_P00 - 64 + 16 * (tid - 64));
     }
     h4_level_sync();
     const uint32_t tmem = *tmem_slot;
@@ -200,7 +204,6 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
     const uint64_t dA0 = make_kmajor_nosw_desc(sm, 16, 128);             // + byte offset / 16
     const uint64_t dB0 = make_kmajor_nosw_desc(sm + OFF_B, 256, 128);    // + 32 per tile
     const uint32_t my_tmem = tmem + ((uint32_t)(quarter * 32) << 16);
-    if (p.stop == 0) { if (!(p.dbg & 1) && tid == 0) mbar_wait(bar, 0); goto done; }
 
     // ================= down_1: x planes -> D1 parity planes
     if (warp < H4_T1) {
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
     }
     mbar_wait(bar + 8, 0);
     tc_fence_after();
+    float4 bias = h4_lds4(sm + OFF_BIAS);
     for (int t = warp >> 2; t < H4_T1; t += 2) {
         uint32_t v[8];
         tc_ld8_nowait(my_tmem + 16u * t, v);
@@ -224,24 +228,19 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
         const int m = t * 128 + quarter * 32 + lane, r = m / H4_POS, q = m - r * H4_POS;
         if (r < H4_D1H) {
             const bool rowin = (unsigned)(hy0 - 6 + r) < (unsigned)(p.H / 2);
-            uint8_t* plane = h4_smem + ((r & 1) ? OFF_P10 : OFF_P00) + ((r >> 1) * H4_POS + q) * 16;
-            const int pbytes = (r & 1) ? P1_BYTES : P0_BYTES;
-            // position q = block columns 4 q .. 4 q + 3 (the block starts at column ox0 - 16: a TMA box must start on a
-            // 16-byte boundary) = D1 columns 2 q - 1 (odd: plane 1, column q - 1) and 2 q (even: plane 0, column q)
-#pragma unroll
-            for (int jj = 0; jj < 2; ++jj) {
-                const int col = 2 * q - 1 + jj;
-                const bool in = rowin && col >= 0 && col < H4_D1W && (unsigned)(hx0 - 6 + col) < (unsigned)(p.W / 2);
-                const float4 o = h4_act4(v + 4 * jj, sBias, p.alpha, in);
-                if (jj) *reinterpret_cast<float4*>(plane) = o;
-                else if (q > 0) *reinterpret_cast<float4*>(plane + pbytes - 16) = o;
-            }
-            if (q == H4_POS - 1) *reinterpret_cast<float4*>(plane + pbytes) = make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t plane = sm + ((r & 1) ? OFF_P10 : OFF_P00) + ((r >> 1) * H4_POS + q) * 16;
+            const uint32_t pbytes = (r & 1) ? P1_BYTES : P0_BYTES;
+            // position q = block columns 4 q .. 4 q + 3 = D1 columns 2 q - 1 (odd: plane 1, column q - 1) and 2 q (even:
+            // plane 0, column q)
+            const int col = 2 * q - 1;
+            const bool in0 = rowin && col >= 0 && (unsigned)(hx0 - 6 + col) < (unsigned)(p.W / 2);
+            const bool in1 = rowin && col + 1 < H4_D1W && (unsigned)(hx0 - 6 + col + 1) < (unsigned)(p.W / 2);
+            if (q > 0) h4_store4(plane + pbytes - 16, v, bias, p.alpha, in0);
+            h4_store4(plane, v + 4, bias, p.alpha, in1);
+            if (q == H4_POS - 1) h4_zero16(plane + pbytes);
         }
     }
     h4_level_sync();
-
-    if (p.stop == 1) goto done;
 
     // ================= down_2: D1 planes -> D2
     if (warp < H4_T2) {
@@ -264,6 +263,7 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
     }
     mbar_wait(bar + 16, 0);
     tc_fence_after();
+    bias = h4_lds4(sm + OFF_BIAS + 16);
     for (int t = warp >> 2; t < H4_T2; t += 2) {
         uint32_t v[4];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -272,12 +272,10 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
         const int m = t * 128 + quarter * 32 + lane, r = m / H4_POS, c = m - r * H4_POS;
         if (r < H4_D2H) {
             const bool in = c < H4_D2W && (unsigned)(qy0 - 2 + r) < (unsigned)(p.H / 4) && (unsigned)(qx0 - 2 + c) < (unsigned)(p.W / 4);
-            *reinterpret_cast<float4*>(h4_smem + OFF_D2 + m * 16) = h4_act4(v, sBias + 4, p.alpha, in);
+            h4_store4(sm + OFF_D2 + m * 16, v, bias, p.alpha, in);
         }
     }
     h4_level_sync();
-
-    if (p.stop == 2) goto done;
 
     // ================= up_2: D2 -> U2 (source position (j, n) -> pixels (2 j + py, 2 n + px))
     if (warp < H4_T3) {
@@ -294,6 +292,7 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
     }
     mbar_wait(bar + 24, 0);
     tc_fence_after();
+    bias = h4_lds4(sm + OFF_BIAS + 32);
     for (int t = warp >> 2; t < H4_T3; t += 2) {
         uint32_t v[16];
         tc_ld16_nowait(my_tmem + 16u * t, v);
@@ -306,15 +305,12 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
 #pragma unroll
                 for (int px = 0; px < 2; ++px) {
                     const bool in = rowin && (unsigned)(hx0 - 2 + 2 * n + px) < (unsigned)(p.W / 2);
-                    *reinterpret_cast<float4*>(h4_smem + OFF_U2 + ((2 * j + py) * H4_PU2 + 2 * n + px) * 16) =
-                        h4_act4(v + 4 * (2 * py + px), sBias + 8, p.alpha, in);
+                    h4_store4(sm + OFF_U2 + ((2 * j + py) * H4_PU2 + 2 * n + px) * 16, v + 4 * (2 * py + px), bias, p.alpha, in);
                 }
             }
         }
     }
     h4_level_sync();
-
-    if (p.stop == 3) goto done;
 
     // ================= up_1: U2 -> U1
     if (warp < H4_T4) {
@@ -331,6 +327,7 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
     }
     mbar_wait(bar + 32, 0);
     tc_fence_after();
+    bias = h4_lds4(sm + OFF_BIAS + 48);
     for (int t = warp >> 2; t < H4_T4; t += 2) {
         uint32_t v[16];
         tc_ld16_nowait(my_tmem + 16u * t, v);
@@ -343,15 +340,12 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
 #pragma unroll
                 for (int px = 0; px < 2; ++px) {
                     const bool in = rowin && (unsigned)(ox0 - 2 + 2 * n + px) < (unsigned)p.W;
-                    *reinterpret_cast<float4*>(h4_smem + OFF_U1 + ((2 * j + py) * H4_PU1 + 2 * n + px) * 16) =
-                        h4_act4(v + 4 * (2 * py + px), sBias + 12, p.alpha, in);
+                    h4_store4(sm + OFF_U1 + ((2 * j + py) * H4_PU1 + 2 * n + px) * 16, v + 4 * (2 * py + px), bias, p.alpha, in);
                 }
             }
         }
     }
     h4_level_sync();
-
-    if (p.stop == 4) goto done;
 
     // ================= end: U1 -> y; tile g = output rows 8 g .. 8 g + 7, lane = output column
     if (warp < H4_T5) {
@@ -376,44 +370,50 @@ __global__ void __launch_bounds__(H4_THREADS, 2) hourglass4_fwd_kernel(const Hou
         tc_wait_ld();
         const int gx = ox0 + c;
         const float b0 = sBias[16], b1 = sBias[17];
-        if (gx < p.W) {
+        float o[16];
+        if (p.act_end == UOCR_ACT_SIGMOID) {                              // one branch, not one per value
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int gy = oy0 + 8 * g + i;
-                if (gy < p.H)
-                    *reinterpret_cast<float2*>(p.y + (((int64_t)img * p.H + gy) * p.W + gx) * 2) =
-                        make_float2(apply_act_fast(__uint_as_float(v[2 * i]) + b0, p.act_end, p.alpha_end),
-                                    apply_act_fast(__uint_as_float(v[2 * i + 1]) + b1, p.act_end, p.alpha_end));
+            for (int i = 0; i < 16; ++i) o[i] = apply_act_fast(__uint_as_float(v[i]) + ((i & 1) ? b1 : b0), UOCR_ACT_SIGMOID, 0.f);
+        } else {
+            const float a = p.act_end == UOCR_ACT_LEAKY ? p.alpha_end : 1.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float t = __uint_as_float(v[i]) + ((i & 1) ? b1 : b0);
+                o[i] = t > 0.f ? t : t * a;
             }
         }
+        if (gx < p.W) {
+            float* dst = p.y + (((int64_t)img * p.H + oy0 + 8 * g) * p.W + gx) * 2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (oy0 + 8 * g + i < p.H) *reinterpret_cast<float2*>(dst + (int64_t)i * p.W * 2) = make_float2(o[2 * i], o[2 * i + 1]);
+        }
     }
-done:
     tc_fence_before();
     __syncthreads();
-    if (warp == 0 && !(p.dbg & 2)) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
 }
 
 }  // namespace
 
-int hourglass4_fwd(const float* x, const float* const* w, const float* const* b, float* y, int64_t n, int64_t h,
-                   int64_t wd, float alpha, int act_end, float alpha_end, cudaStream_t st) {
-    if (h % 4 || wd % 4 || n > 65535 || alpha < 0.f || alpha > 1.f) return UOCR_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
-    CUtensorMap map_even{}, map_odd{};
-    const int dbg0 = getenv("UOCR_HG4_DBG") ? atoi(getenv("UOCR_HG4_DBG")) : 0;
-    const uint64_t dims[3] = {(uint64_t)wd, (uint64_t)((dbg0 & 64) ? h : h / 2), (uint64_t)n};
-    const uint64_t strides[2] = {(uint64_t)wd * ((dbg0 & 64) ? 4 : 8), (uint64_t)wd * h * 4};
-    int dbg = 0; { const char* e = getenv("UOCR_HG4_DBG"); dbg = e ? atoi(e) : 0; }
-    const uint32_t xw = (dbg & 32) ? 160 : H4_XP;
-    const uint32_t box_e[3] = {xw, (uint32_t)H4_XE_ROWS, 1}, box_o[3] = {xw, (uint32_t)H4_XO_ROWS, 1};
-    int rc = (dbg & 16) ? make_tmap_plain_f32(&map_even, x, 3, dims, strides, box_e) : make_tmap_plain_tf32(&map_even, x, 3, dims, strides, box_e);
-    if (rc == UOCR_OK) rc = (dbg & 16) ? make_tmap_plain_f32(&map_odd, x + wd, 3, dims, strides, box_o) : make_tmap_plain_tf32(&map_odd, x + wd, 3, dims, strides, box_o);
-    if (rc != UOCR_OK) return rc;
-    Scratch bimg(st);
-    rc = bimg.alloc(H4_BFLOATS * sizeof(float));
-    if (rc != UOCR_OK) return rc;
-    hourglass4_prep_kernel<<<(H4_BFLOATS + 255) / 256, 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], static_cast<float*>(bimg.ptr));
+static int hourglass4_pack(const float* const* w, float* packed, cudaStream_t st) {
+    hourglass4_prep_kernel<<<(H4_BFLOATS + 255) / 256, 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], packed);
     UOCR_LAUNCHED("hourglass4_prep");
+    return UOCR_OK;
+}
+
+static int hourglass4_run(const float* x, const float* packed, const float* const* b, float* y, int64_t n, int64_t h,
+                          int64_t wd, float alpha, int act_end, float alpha_end, cudaStream_t st) {
+    if (h % 4 || wd % 4 || n > 65535 || alpha < 0.f || alpha > 1.f) return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(packed)) & 15)
+        return UOCR_ERR_UNSUPPORTED;
+    CUtensorMap map_even{}, map_odd{};
+    const uint64_t dims[3] = {(uint64_t)wd, (uint64_t)(h / 2), (uint64_t)n};         // the even / odd rows of the image
+    const uint64_t strides[2] = {(uint64_t)wd * 8, (uint64_t)wd * h * 4};
+    const uint32_t box_e[3] = {(uint32_t)H4_XP, (uint32_t)H4_XE_ROWS, 1}, box_o[3] = {(uint32_t)H4_XP, (uint32_t)H4_XO_ROWS, 1};
+    int rc = make_tmap_plain_tf32(&map_even, x, 3, dims, strides, box_e);
+    if (rc == UOCR_OK) rc = make_tmap_plain_tf32(&map_odd, x + wd, 3, dims, strides, box_o);
+    if (rc != UOCR_OK) return rc;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(hourglass4_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, H4_SMEM);
@@ -421,10 +421,9 @@ int hourglass4_fwd(const float* x, const float* const* w, const float* const* b,
         configured = true;
     }
     Hourglass4Params p{};
-    p.y = y; p.bimg = static_cast<const float*>(bimg.ptr);
+    p.y = y; p.bimg = packed;
     for (int l = 0; l < 5; ++l) p.b[l] = b[l];
     p.H = (int)h; p.W = (int)wd; p.alpha = alpha; p.act_end = act_end; p.alpha_end = alpha_end;
-    { const char* e = getenv("UOCR_HG4_STOP"); p.stop = e ? atoi(e) : -1; e = getenv("UOCR_HG4_DBG"); p.dbg = e ? atoi(e) : 0; p.xw = (int)xw; }
     dim3 grid((unsigned)ceil_div(wd, H4_TW), (unsigned)ceil_div(h, H4_TH), (unsigned)n);
     if (grid.y > 65535) return UOCR_ERR_UNSUPPORTED;
     hourglass4_fwd_kernel<<<grid, H4_THREADS, H4_SMEM, st>>>(p, map_even, map_odd);
@@ -434,15 +433,52 @@ int hourglass4_fwd(const float* x, const float* const* w, const float* const* b,
 
 }  // namespace uocr
 
+using namespace uocr;
+
+static int hourglass4_check(const void* x, const void* y, const float* const* biases, int64_t n, int64_t h, int64_t w,
+                            int act_end) {
+    UOCR_REQUIRE(x && y && biases, "NULL pointer");
+    for (int l = 0; l < 5; ++l) UOCR_REQUIRE(biases[l], "NULL bias pointer (level %d)", l);
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && h < (1 << 30) && w < (1 << 30), "bad dimension");
+    UOCR_REQUIRE(act_end >= UOCR_ACT_NONE && act_end <= UOCR_ACT_SIGMOID, "unknown activation %d", act_end);
+    return UOCR_OK;
+}
+
+extern "C" int uocr_hourglass4_packed_floats(int64_t* floats) {
+    UOCR_REQUIRE(floats, "NULL pointer");
+    *floats = H4_BFLOATS;
+    return UOCR_OK;
+}
+
+extern "C" int uocr_hourglass4_pack(const float* const* weights, float* packed, void* stream) {
+    UOCR_REQUIRE(weights && packed, "NULL pointer");
+    for (int l = 0; l < 5; ++l) UOCR_REQUIRE(weights[l], "NULL weight pointer (level %d)", l);
+    return hourglass4_pack(weights, packed, as_stream(stream));
+}
+
+extern "C" int uocr_hourglass4_fwd_packed(const float* x, const float* packed, const float* const* biases, float* y,
+                                          int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end,
+                                          void* stream) {
+    UOCR_REQUIRE(packed, "NULL pointer");
+    int rc = hourglass4_check(x, y, biases, n, h, w, act_end);
+    if (rc != UOCR_OK) return rc;
+    rc = hourglass4_run(x, packed, biases, y, n, h, w, alpha, act_end, alpha_end, as_stream(stream));
+    if (rc == UOCR_ERR_UNSUPPORTED) set_error("hourglass4_fwd: unsupported geometry (H, W must be multiples of 4)");
+    return rc;
+}
+
 extern "C" int uocr_hourglass4_fwd(const float* x, const float* const* weights, const float* const* biases, float* y,
                                    int64_t n, int64_t h, int64_t w, float alpha, int act_end, float alpha_end,
                                    void* stream) {
-    using namespace uocr;
-    UOCR_REQUIRE(x && y && weights && biases, "NULL pointer");
-    for (int l = 0; l < 5; ++l) UOCR_REQUIRE(weights[l] && biases[l], "NULL weight pointer (level %d)", l);
-    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && h < (1 << 30) && w < (1 << 30), "bad dimension");
-    UOCR_REQUIRE(act_end >= UOCR_ACT_NONE && act_end <= UOCR_ACT_SIGMOID, "unknown activation %d", act_end);
-    const int rc = hourglass4_fwd(x, weights, biases, y, n, h, w, alpha, act_end, alpha_end, as_stream(stream));
+    UOCR_REQUIRE(weights, "NULL pointer");
+    for (int l = 0; l < 5; ++l) UOCR_REQUIRE(weights[l], "NULL weight pointer (level %d)", l);
+    int rc = hourglass4_check(x, y, biases, n, h, w, act_end);
+    if (rc != UOCR_OK) return rc;
+    Scratch packed(as_stream(stream));
+    rc = packed.alloc(H4_BFLOATS * sizeof(float));
+    if (rc != UOCR_OK) return rc;
+    hourglass4_pack(weights, static_cast<float*>(packed.ptr), as_stream(stream));
+    rc = hourglass4_run(x, static_cast<const float*>(packed.ptr), biases, y, n, h, w, alpha, act_end, alpha_end, as_stream(stream));
     if (rc == UOCR_ERR_UNSUPPORTED) set_error("hourglass4_fwd: unsupported geometry (H, W must be multiples of 4)");
     return rc;
 }

@@ -774,6 +774,7 @@ class HourglassFusion:
 
     def __init__(self, prefix):
         p = prefix
+        self._packed = None
         self.chain = [f'{p}/down_1/conv_1', f'{p}/down_1/leaky_relu_1',
                       f'{p}/down_2/conv_1', f'{p}/down_2/leaky_relu_1',
                       f'{p}/up_2/upsample', f'{p}/up_2/conv_block/conv_1', f'{p}/up_2/conv_block/leaky_relu_1',
@@ -843,7 +844,15 @@ class HourglassFusion:
         last.progress_tracker.start_tracking(last.name, 'forward')
         y = DeviceArray((n, h, w, blocks[4][0].out_channels))
         if four:
-            lib.uocr_hourglass4_fwd(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], stream())
+            key = (CP.weights_generation, tuple(conv.w.value.ptr for conv, _ in blocks))
+            if self._packed is None or self._packed[0] != key:         # tensor-core operand image of the five weight tensors
+                count = ctypes.c_int64()
+                lib.uocr_hourglass4_packed_floats(ctypes.byref(count))
+                packed = DeviceArray((count.value,))
+                lib.uocr_hourglass4_pack(wp, packed.ptr, stream())
+                self._packed = (key, packed)
+            lib.uocr_hourglass4_fwd_packed(X.ptr, self._packed[1].ptr, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1],
+                                           stream())
         else:
             lib.uocr_hourglass1_fwd_mode(X.ptr, wp, bp, y.ptr, n, h, w, inner[0][1], end[0], end[1], CP.math_mode, stream())
         last.progress_tracker.stop_tracking(last.name, 'forward')
