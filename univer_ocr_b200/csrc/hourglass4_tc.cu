@@ -43,14 +43,14 @@ constexpr int H4_P0_ROWS = 10, H4_P1_ROWS = 9;    // rows of the even- / odd-row
 constexpr int H4_D2H = 8, H4_D2W = 36;
 constexpr int H4_U2H = 12, H4_U2W = 68, H4_PU2 = 68;
 constexpr int H4_U1H = 20, H4_U1W = 132, H4_PU1 = 132;
-constexpr int H4_T1 = 6, H4_T2 = 3, H4_T3 = 2, H4_T4 = 6, H4_T5 = 2;      // M tiles per level
+constexpr int H4_T1 = 6, H4_T2 = 3, H4_T3 = 2, H4_T4 = 6, H4_T5 = 1;      // M tiles per level
 static_assert(H4_D1H * H4_POS <= H4_T1 * 128 && H4_D2H * H4_POS <= H4_T2 * 128, "tiles cover the positions");
 static_assert((H4_U2H / 2) * H4_POS <= H4_T3 * 128 && (H4_U1H / 2) * H4_PU2 <= H4_T4 * 128, "tiles cover the positions");
 
-// B operand image (floats): [level 1: 5 tiles][level 2: 15][level 3: 6][level 4: 6][level 5: strip 3 x 2 x 38 x 4]
-constexpr int H4_B1 = 0, H4_B2 = 5 * 128, H4_B3 = H4_B2 + 15 * 128, H4_B4 = H4_B3 + 6 * 128, H4_B5 = H4_B4 + 6 * 128;
-constexpr int H4_SROWS = 38;
-constexpr int H4_BFLOATS = H4_B5 + 3 * 2 * H4_SROWS * 4;                   // 5008
+// B operand image (floats): [level 1: 5 tiles][level 2: 13][level 3: 5][level 4: 5][level 5: strip 3 x 2 x 70 x 4]
+constexpr int H4_B1 = 0, H4_B2 = 5 * 128, H4_B3 = H4_B2 + 13 * 128, H4_B4 = H4_B3 + 5 * 128, H4_B5 = H4_B4 + 5 * 128;
+constexpr int H4_SROWS = 70;                      // 32 tile rows + 2 * 19 window positions
+constexpr int H4_BFLOATS = H4_B5 + 3 * 2 * H4_SROWS * 4;                   // 5264
 
 // shared memory (bytes)
 constexpr int OFF_XE = 0;
@@ -100,25 +100,38 @@ __global__ void __launch_bounds__(256) hourglass4_prep_kernel(const float* __res
         if (i < H4_B2) {                          // down_1: tile = ky, k = x column inside the position, n = (pixel jj, co)
             const int ky = tile, jj = n >> 2, co = n & 3, kx = 4 * c + e - 2 * jj;
             if (n < 8 && kx >= 0 && kx < 5) v = w1[(ky * 5 + kx) * 4 + co];
-        } else if (i < H4_B3) {                   // down_2: tile = (row parity, row tap a) x {even cols b 0-1, even cols b 2-3, odd cols b 0-1}
-            const int t = tile - 5, pair = t / 3, sub = t - 3 * pair;
-            const int pr = pair < 3 ? 0 : 1, a = pr ? pair - 3 : pair, pc = sub == 2, b = (sub == 1 ? 2 : 0) + c;
-            const int ky = 2 * a + pr, kx = 2 * b + pc;
-            if (n < 4 && kx < 5) v = w2[((ky * 5 + kx) * 4 + e) * 4 + n];
-        } else {                                  // up_2 / up_1: tile = (source row a, half h), pixel b = 2 h + c, n = (py, px, co)
+        } else if (i < H4_B3) {
+            // down_2: a K chunk is one pixel of one parity plane = (row parity pr, row tap a, column parity pc, column
+            // tap b), kernel tap (2 a + pr, 2 b + pc).  Tiles 2 g, 2 g + 1 of group g = (pr, a): chunks (pc 0, b 0 | pc 0,
+            // b 1) and (pc 0, b 2 | pc 1, b 0); the five left-over chunks (pc 1, b 1) share tiles 10-12 in pairs.
+            const int t = tile - 5;
+            int g, pc, b;
+            if (t < 10) { g = t >> 1; pc = (t & 1) & c; b = (t & 1) ? (c ? 0 : 2) : c; }
+            else { g = 2 * (t - 10) + c; pc = 1; b = 1; }
+            if (g < 5) {
+                const int pr = g < 3 ? 0 : 1, a = pr ? g - 3 : g, ky = 2 * a + pr, kx = 2 * b + pc;
+                if (n < 4) v = w2[((ky * 5 + kx) * 4 + e) * 4 + n];
+            }
+        } else {
+            // up_2 / up_1: a K chunk = source pixel (row a, column b); tiles 0-2: (a, 0 | a, 1), tile 3: (0, 2 | 1, 2),
+            // tile 4: (2, 2 | nothing); n = (py, px, co), weights pre-summed per output parity
             const bool l4 = i >= H4_B4;
             const float* w = l4 ? w4 : w3;
-            const int t = tile - (l4 ? 26 : 20), a = t >> 1, b = 2 * (t & 1) + c;
+            const int t = tile - (l4 ? 23 : 18);
+            const int a = t < 3 ? t : t == 3 ? c : 2, b = t < 3 ? c : 2;
             const int py = n >> 3, px = (n >> 2) & 1, co = n & 3;
-            if (b < 3)
+            if (!(t == 4 && c == 1))
                 for (int ky = 0; ky < 5; ++ky)
                     for (int kx = 0; kx < 5; ++kx)
                         if (fold_hit(py, a, ky) && fold_hit(px, b, kx)) v += w[((ky * 5 + kx) * 4 + e) * 4 + co];
         }
-    } else {                                      // end: strip [k'][c][row v][ci], row v = kernel row 11 - v / 2, channel v & 1
+    } else {
+        // end: strip [k'][c][row v][ci], row v = kernel row 19 - v / 2, channel v & 1; the tile of input row j is the
+        // 32-row window from row 38 - 2 j.  Block [2][1] repeats block [2][0] (kx = 4): the MMA that pairs the kx = 4
+        // chunks of rows j and j + 1 reads its second chunk's window 2 rows lower, i.e. at a positive offset from the first
         const int s = i - H4_B5, e = s & 3, vrow = (s >> 2) % H4_SROWS, c = (s / (4 * H4_SROWS)) & 1, kq = s / (8 * H4_SROWS);
-        const int ky = 11 - (vrow >> 1), kx = 2 * kq + c;
-        if (ky >= 0 && ky < 5 && kx < 5) v = w5[((ky * 5 + kx) * 4 + e) * 2 + (vrow & 1)];
+        const int ky = 19 - (vrow >> 1), kx = kq == 2 ? 4 : 2 * kq + c;
+        if (ky >= 0 && ky < 5) v = w5[((ky * 5 + kx) * 4 + e) * 2 + (vrow & 1)];
     }
     bimg[i] = round_tf32(v);
 }
@@ -246,17 +259,21 @@ __global__ void __launch_bounds__(H4_THREADS, 3) hourglass4_fwd_kernel(const Hou
     if (warp < H4_T2) {
         if (h4_elect()) {
             const uint32_t d = tmem + 16u * warp;
-            int bidx = 0;
+            const uint32_t t0 = sm + 128 * 16 * warp;                    // this tile's first position
+            // group (pr, a): (pc 0: b 0 | b 1), (pc 0: b 2 | pc 1: b 0) -- the second chunk sits in the other plane
 #pragma unroll
-            for (int pr = 0; pr < 2; ++pr)
-#pragma unroll
-                for (int a = 0; a < 3 - pr; ++a) {
-                    const int off = pr ? OFF_P10 : OFF_P00, pbytes = pr ? P1_BYTES : P0_BYTES;
-                    const uint64_t a0 = dA0 + (uint64_t)(off / 16 + a * H4_POS + 128 * warp);
-                    tc_mma_tf32(d, a0, dB0 + (uint64_t)(H4_B2 / 4 + 32 * bidx), idesc, bidx > 0); ++bidx;
-                    tc_mma_tf32(d, a0 + 2, dB0 + (uint64_t)(H4_B2 / 4 + 32 * bidx), idesc, 1); ++bidx;
-                    tc_mma_tf32(d, a0 + (uint64_t)(pbytes / 16), dB0 + (uint64_t)(H4_B2 / 4 + 32 * bidx), idesc, 1); ++bidx;
-                }
+            for (int g = 0; g < 5; ++g) {
+                const int pr = g < 3 ? 0 : 1, a = pr ? g - 3 : g;
+                const uint32_t base = t0 + (pr ? OFF_P10 : OFF_P00) + a * H4_POS * 16, pbytes = pr ? P1_BYTES : P0_BYTES;
+                tc_mma_tf32(d, make_kmajor_nosw_desc(base, 16, 128), dB0 + (uint64_t)(H4_B2 / 4 + 32 * (2 * g)), idesc, g > 0);
+                tc_mma_tf32(d, make_kmajor_nosw_desc(base + 32, pbytes - 32, 128), dB0 + (uint64_t)(H4_B2 / 4 + 32 * (2 * g + 1)), idesc, 1);
+            }
+            // the left-over chunks (pc 1, b 1) of the five groups, two per MMA
+            constexpr int L0 = OFF_P00 + P0_BYTES + 16, L1 = OFF_P10 + P1_BYTES + 16;       // plane pc 1, pixel c + 1
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + L0, H4_POS * 16, 128), dB0 + (uint64_t)(H4_B2 / 4 + 32 * 10), idesc, 1);
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + L0 + 2 * H4_POS * 16, L1 - (L0 + 2 * H4_POS * 16), 128),
+                        dB0 + (uint64_t)(H4_B2 / 4 + 32 * 11), idesc, 1);
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + L1 + H4_POS * 16, 16, 128), dB0 + (uint64_t)(H4_B2 / 4 + 32 * 12), idesc, 1);
             tc_commit(bar + 16);
         }
         __syncwarp();
@@ -280,12 +297,13 @@ __global__ void __launch_bounds__(H4_THREADS, 3) hourglass4_fwd_kernel(const Hou
     // ================= up_2: D2 -> U2 (source position (j, n) -> pixels (2 j + py, 2 n + px))
     if (warp < H4_T3) {
         if (h4_elect()) {
+            const uint32_t d = tmem + 16u * warp, t0 = sm + OFF_D2 + 128 * 16 * warp;
+            // source pixels (a, 0 | a, 1) for the three rows, then the third column: (0, 2 | 1, 2) one row apart, (2, 2 | -)
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    tc_mma_tf32(tmem + 16u * warp, dA0 + (uint64_t)(OFF_D2 / 16 + a * H4_POS + 128 * warp + 2 * h),
-                                dB0 + (uint64_t)(H4_B3 / 4 + 32 * (2 * a + h)), idesc, (a | h) != 0);
+                tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + a * H4_POS * 16, 16, 128), dB0 + (uint64_t)(H4_B3 / 4 + 32 * a), idesc, a > 0);
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + 32, H4_POS * 16, 128), dB0 + (uint64_t)(H4_B3 / 4 + 32 * 3), idesc, 1);
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + 2 * H4_POS * 16 + 32, 16, 128), dB0 + (uint64_t)(H4_B3 / 4 + 32 * 4), idesc, 1);
             tc_commit(bar + 24);
         }
         __syncwarp();
@@ -315,12 +333,13 @@ __global__ void __launch_bounds__(H4_THREADS, 3) hourglass4_fwd_kernel(const Hou
     // ================= up_1: U2 -> U1
     if (warp < H4_T4) {
         if (h4_elect()) {
+            const uint32_t d = tmem + 16u * warp, t0 = sm + OFF_U2 + 128 * 16 * warp;
+            // source pixels (a, 0 | a, 1) for the three rows, then the third column: (0, 2 | 1, 2) one row apart, (2, 2 | -)
 #pragma unroll
             for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    tc_mma_tf32(tmem + 16u * warp, dA0 + (uint64_t)(OFF_U2 / 16 + a * H4_PU2 + 128 * warp + 2 * h),
-                                dB0 + (uint64_t)(H4_B4 / 4 + 32 * (2 * a + h)), idesc, (a | h) != 0);
+                tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + a * H4_PU2 * 16, 16, 128), dB0 + (uint64_t)(H4_B4 / 4 + 32 * a), idesc, a > 0);
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + 32, H4_PU2 * 16, 128), dB0 + (uint64_t)(H4_B4 / 4 + 32 * 3), idesc, 1);
+            tc_mma_tf32(d, make_kmajor_nosw_desc(t0 + 2 * H4_PU2 * 16 + 32, 16, 128), dB0 + (uint64_t)(H4_B4 / 4 + 32 * 4), idesc, 1);
             tc_commit(bar + 32);
         }
         __syncwarp();
@@ -350,13 +369,21 @@ __global__ void __launch_bounds__(H4_THREADS, 3) hourglass4_fwd_kernel(const Hou
     // ================= end: U1 -> y; tile g = output rows 8 g .. 8 g + 7, lane = output column
     if (warp < H4_T5) {
         if (h4_elect()) {
-            const uint64_t dS = make_kmajor_nosw_desc(sm + OFF_B + H4_B5 * 4, H4_SROWS * 16, 128);
+            // one accumulator of N = 16 output rows x 2 channels; input row j: pixels (c, c+1), (c+2, c+3) against the
+            // strip windows of row j, and pixel c + 4 of rows j and j + 1 together (chunks one block row apart)
+            const uint32_t idesc32 = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t sS = sm + OFF_B + H4_B5 * 4;
 #pragma unroll
-            for (int j = 0; j < 12; ++j)
+            for (int j = 0; j < 20; ++j) {
+                const uint32_t row = sm + OFF_U1 + j * H4_PU1 * 16;
 #pragma unroll
-                for (int kq = 0; kq < 3; ++kq)
-                    tc_mma_tf32(tmem + 16u * warp, dA0 + (uint64_t)(OFF_U1 / 16 + (8 * warp + j) * H4_PU1 + 2 * kq),
-                                dS + (uint64_t)(2 * kq * H4_SROWS + 22 - 2 * j), idesc, (j | kq) != 0);
+                for (int kq = 0; kq < 2; ++kq)
+                    tc_mma_tf32(tmem, make_kmajor_nosw_desc(row + 32 * kq, 16, 128),
+                                make_kmajor_nosw_desc(sS + (2 * kq * H4_SROWS + 38 - 2 * j) * 16, H4_SROWS * 16, 128), idesc32, (j | kq) != 0);
+                if (!(j & 1))
+                    tc_mma_tf32(tmem, make_kmajor_nosw_desc(row + 64, H4_PU1 * 16, 128),
+                                make_kmajor_nosw_desc(sS + (4 * H4_SROWS + 38 - 2 * j) * 16, H4_SROWS * 16 - 32, 128), idesc32, 1);
+            }
             tc_commit(bar + 40);
         }
         __syncwarp();
