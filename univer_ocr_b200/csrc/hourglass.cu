@@ -35,16 +35,23 @@ struct HourglassParams {
     int act_end; float alpha_end;
 };
 
+// a level's 25 weights + bias in shared memory: 28 floats, so that every level's slot is 16-byte aligned and a thread
+// fetches it with 7 vector loads (scalar loads of weights were a quarter of the kernel's shared-memory wavefronts)
+constexpr int HG_WSLOT = 28;
+
 template <int TH, int TW>
 struct HG {
     // X block: origin column ox0 - 16 (16-byte aligned for cp.async; the convolution reads from column 2 on),
     // two spare rows for the last 4-row strip of D1
-    static constexpr int XH = TH + 25, XW = TW + 27, XP = (XW + 3 + 3) & ~3, XROWS = XH + 2;
+    static constexpr int XH = TH + 25, XW = TW + 27, XP = (XW + 1 + 3) & ~3, XROWS = XH + 2;
     static constexpr int D1H = TH / 2 + 11, D1W = TW / 2 + 11, D1P = (D1W + 3 + 3) & ~3;
     static constexpr int D2H = TH / 4 + 4, D2W = TW / 4 + 4, D2P = (D2W + 2 + 3 + 3) & ~3;
     static constexpr int U2H = TH / 2 + 4, U2W = TW / 2 + 4, U2P = (U2W + 3 + 3) & ~3;
     static constexpr int U1H = TH + 4, U1W = TW + 4, U1P = (U1W + 3 + 3) & ~3;
-    static constexpr int FLOATS = XROWS * XP + D1H * D1P + D2H * D2P + U2H * U2P + U1H * U1P + 5 * 26 + 2 * 36 + 6;
+    static constexpr int FLOATS = XROWS * XP + D1H * D1P + D2H * D2P + U2H * U2P + U1H * U1P + 5 * HG_WSLOT + 2 * 36 + 6;
+    // FFMA kernel: the U1 block lives in the x block, which is dead after down_1 -- 54.6 KB, 4 CTAs / SM
+    static constexpr int FLOATS_ALIASED = FLOATS - U1H * U1P;
+    static_assert(U1H * U1P <= XROWS * XP, "U1 fits into the x block");
     // tensor-core `end` level (TF32 mode): the U1 block is read as a tcgen05 A operand whose row m is the 8 floats
     // from float 4 m of the block on (rows of the descriptor overlap; `position` m = row m / PPR, columns 4 (m % PPR) ..
     // + 3).  M tiles of 128 positions cover the TH output rows; the last tile's rows run past the block (garbage lanes):
@@ -53,11 +60,11 @@ struct HG {
     static constexpr int END_TILES = (TH * PPR + 127) / 128;
     static constexpr int END_B = 5 * 2 * 16 * 4;                         // B operand: 5 kernel rows x 2 chunks x 16 x 4
     // floats past the end of the U1 block that the last tile's (garbage) rows read: the weights, folded kernels and
-    // barrier behind the block absorb 5 * 26 + 2 * 36 + 6 of them, END_PAD floats of slack the rest.  The B operand
+    // barrier behind the block absorb 5 * HG_WSLOT + 2 * 36 + 6 of them, END_PAD floats of slack the rest.  The B operand
     // lives in the X block, which is dead after down_1: 3 CTAs / SM need <= ~2 KB of extra shared memory per CTA
     // (with the B operand appended the kernel dropped to 2 CTAs / SM and ran 1.5x slower, measured).
     static constexpr int END_OVER = END_TILES * 128 * 4 + 4 * U1P + 8 - U1H * U1P;
-    static constexpr int END_PAD = END_OVER > 208 ? ((END_OVER - 208 + 3) & ~3) : 0;
+    static constexpr int END_PAD = END_OVER > 5 * HG_WSLOT + 78 ? ((END_OVER - (5 * HG_WSLOT + 78) + 3) & ~3) : 0;
     static constexpr int FLOATS_TC = ((FLOATS + 3) & ~3) + END_PAD + 8;
     static_assert(END_B <= XROWS * XP, "the B operand of the tensor-core level reuses the X block");
 };
@@ -70,6 +77,15 @@ __device__ __forceinline__ bool elect_one_hg() {
     return pred != 0;
 }
 
+template <int N4>
+__device__ __forceinline__ void hg_load_weights(const float* __restrict__ src, float* w) {
+#pragma unroll
+    for (int i = 0; i < N4; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+    }
+}
+
 // dst (DH x DW, origin (gy0, gx0) at its resolution, image hl x wl) = act(conv5x5 stride 2 (src) + b); src(2r+ky, 2c+kx).
 // Thread = one output column x R rows: neighbouring lanes read neighbouring 8-byte words (no bank conflicts).  R = 4
 // for the large level; the small one (12 x 36) uses R = 2 so that seven warps share its 222 strips instead of four
@@ -77,10 +93,9 @@ __device__ __forceinline__ bool elect_one_hg() {
 template <int DH, int DW, int DP, int SP, int R>
 __device__ __forceinline__ void hg_down(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ wb,
                                         int gy0, int gx0, int hl, int wl, float alpha) {
-    float w[25];
-#pragma unroll
-    for (int i = 0; i < 25; ++i) w[i] = wb[i];
-    const float bias = wb[25];
+    float w[28];
+    hg_load_weights<7>(wb, w);
+    const float bias = w[25];
     constexpr int STRIPS = (DH + R - 1) / R;
     for (int item = threadIdx.x; item < STRIPS * DW; item += HG_THREADS) {
         const int s = item / DW, c = item - s * DW, r0 = R * s;
@@ -110,6 +125,55 @@ __device__ __forceinline__ void hg_down(const float* __restrict__ src, float* __
     }
 }
 
+// The large stride-2 level (x block -> D1) with 16-byte loads: thread = D1 columns (2 p - 1, 2 p) x R rows.  Column j reads
+// block columns 2 + 2 j + kx (the block starts 16 columns left of the output block, the convolution 14), so the pair's
+// eight inputs are block columns 4 p .. 4 p + 7: two aligned 128-bit loads per input row at lane stride 16 bytes
+// (conflict-free), 2.6 input floats per FMA-column instead of 6 with the one-column-per-thread form above.  R = 5: the
+// 27 x 75 block is 6 strips x 38 pairs = 228 items, one pass of the 256 threads (R = 4 needs a second pass for 10 items).
+// The last strip's rows past DH read beyond the x block's spare rows into the D1 block; they are not stored.
+template <int DH, int DW, int DP, int SP, int R>
+__device__ __forceinline__ void hg_down_pairs(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ wb,
+                                              int gy0, int gx0, int hl, int wl, float alpha) {
+    float w[28];
+    hg_load_weights<7>(wb, w);
+    const float bias = w[25];
+    constexpr int STRIPS = (DH + R - 1) / R, PAIRS = DW / 2 + 1;
+    for (int item = threadIdx.x; item < STRIPS * PAIRS; item += HG_THREADS) {
+        const int s = item / PAIRS, pr = item - s * PAIRS, r0 = R * s;
+        float acc[R][2];
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j][0] = acc[j][1] = bias;
+#pragma unroll
+        for (int rr = 0; rr < 2 * R + 3; ++rr) {
+            const float4* row = reinterpret_cast<const float4*>(src + (2 * r0 + rr) * SP + 4 * pr);
+            const float4 u = row[0], v = row[1];
+            const float in[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int ky = rr - 2 * j;
+                if (ky >= 0 && ky < 5) {
+#pragma unroll
+                    for (int kx = 0; kx < 5; ++kx) {
+                        acc[j][0] = fmaf(w[ky * 5 + kx], in[kx], acc[j][0]);
+                        acc[j][1] = fmaf(w[ky * 5 + kx], in[2 + kx], acc[j][1]);
+                    }
+                }
+            }
+        }
+        const int c1 = 2 * pr, c0 = c1 - 1;
+        const bool in0 = pr > 0 && (unsigned)(gx0 + c0) < (unsigned)wl, in1 = c1 < DW && (unsigned)(gx0 + c1) < (unsigned)wl;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (r0 + j < DH) {
+                const bool rowin = (unsigned)(gy0 + r0 + j) < (unsigned)hl;
+                const float v0 = fmaxf(acc[j][0], acc[j][0] * alpha), v1 = fmaxf(acc[j][1], acc[j][1] * alpha);
+                if (pr > 0) dst[(r0 + j) * DP + c0] = (rowin && in0) ? v0 : 0.f;
+                if (c1 < DW) dst[(r0 + j) * DP + c1] = (rowin && in1) ? v1 : 0.f;
+            }
+        }
+    }
+}
+
 // dst (DH x DW at 2x the source resolution, origin (gy0, gx0) even) = act(conv5x5(upsample2(src)) + b) through the four
 // parity-folded 3 x 3 kernels wf[py][px][a][b]; output rows (2j, 2j+1) x columns (2n, 2n+1) read src(j + a, n + b).
 // Thread = 2 source cells = a 2 x 4 output block (8-byte loads, 16-byte stores at lane stride: conflict-free).
@@ -117,8 +181,7 @@ template <int DH, int DW, int DP, int SP, bool ROUND_TF32 = false>
 __device__ __forceinline__ void hg_up(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ wf,
                                       float bias, int gy0, int gx0, int hl, int wl, float alpha) {
     float w[36];
-#pragma unroll
-    for (int i = 0; i < 36; ++i) w[i] = wf[i];
+    hg_load_weights<9>(wf, w);
     constexpr int GROUPS = (DW + 3) / 4;
     for (int item = threadIdx.x; item < (DH / 2) * GROUPS; item += HG_THREADS) {
         const int j = item / GROUPS, n0 = (item - j * GROUPS) * 2;
@@ -168,7 +231,7 @@ __device__ __forceinline__ void hg_fold(const float* __restrict__ w25, float* __
 }
 
 template <int TH, int TW, bool TMA, bool TC>
-__global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const HourglassParams p,
+__global__ void __launch_bounds__(HG_THREADS, TC ? 3 : 4) hourglass1_fwd_kernel(const HourglassParams p,
                                                                        const __grid_constant__ CUtensorMap map_x) {
     using G = HG<TH, TW>;
     extern __shared__ __align__(128) float hg_smem[];
@@ -176,9 +239,9 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     float* sD1 = sX + G::XROWS * G::XP;
     float* sD2 = sD1 + G::D1H * G::D1P;
     float* sU2 = sD2 + G::D2H * G::D2P;
-    float* sU1 = sU2 + G::U2H * G::U2P;
-    float* sW = sU1 + G::U1H * G::U1P;               // 5 x (25 weights + bias)
-    float* sF = sW + 5 * 26;                         // folded kernels of up_2, up_1
+    float* sU1 = TC ? sU2 + G::U2H * G::U2P : sX;    // FFMA kernel: over the x block (dead after down_1)
+    float* sW = sU2 + G::U2H * G::U2P + (TC ? G::U1H * G::U1P : 0);     // 5 x (25 weights + bias)
+    float* sF = sW + 5 * HG_WSLOT;                   // folded kernels of up_2, up_1
 
     const int ox0 = blockIdx.x * TW, oy0 = blockIdx.y * TH;
     const float* xim = p.x + (int64_t)blockIdx.z * p.H * p.W;
@@ -216,7 +279,7 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     // weights: static level index (a runtime index into p.w[] forces the whole parameter block into local memory)
     if (tid < 26) {
 #pragma unroll
-        for (int l = 0; l < 5; ++l) sW[l * 26 + tid] = tid < 25 ? __ldg(p.w[l] + tid) : __ldg(p.b[l]);
+        for (int l = 0; l < 5; ++l) sW[l * HG_WSLOT + tid] = tid < 25 ? __ldg(p.w[l] + tid) : __ldg(p.b[l]);
     }
     // the two spare rows the last strip of D1 reads must be finite
     for (int i = tid; i < 2 * G::XP; i += HG_THREADS) sX[G::XH * G::XP + i] = 0.f;
@@ -239,10 +302,10 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
     if (!TMA) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     if (TMA) mbar_wait(smem_u32(bar), 0);
-    hg_fold(sW + 2 * 26, sF);
-    hg_fold(sW + 3 * 26, sF + 36);
+    hg_fold(sW + 2 * HG_WSLOT, sF);
+    hg_fold(sW + 3 * HG_WSLOT, sF + 36);
     const int hy0 = oy0 / 2, hx0 = ox0 / 2, qy0 = oy0 / 4, qx0 = ox0 / 4;
-    hg_down<G::D1H, G::D1W, G::D1P, G::XP, 4>(sX + 2, sD1, sW, hy0 - 6, hx0 - 6, p.H / 2, p.W / 2, p.alpha);
+    hg_down_pairs<G::D1H, G::D1W, G::D1P, G::XP, 5>(sX, sD1, sW, hy0 - 6, hx0 - 6, p.H / 2, p.W / 2, p.alpha);
     __syncthreads();
     if (TC) {                                            // the X block is dead: it now holds the `end` level's B operand
         // B[ky][chunk c][n = phase][e]: k = 4 c + e is the float offset inside the A row; output column 4 pos + phase
@@ -253,11 +316,11 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
             sBend[i] = (n < 4 && kx >= 0 && kx < 5) ? round_tf32(__ldg(p.w[4] + ky * 5 + kx)) : 0.f;
         }
     }
-    hg_down<G::D2H, G::D2W, G::D2P, G::D1P, (G::D2H % 2 == 0) ? 2 : 4>(sD1, sD2, sW + 26, qy0 - 2, qx0 - 2, p.H / 4, p.W / 4, p.alpha);
+    hg_down<G::D2H, G::D2W, G::D2P, G::D1P, (G::D2H % 2 == 0) ? 2 : 4>(sD1, sD2, sW + HG_WSLOT, qy0 - 2, qx0 - 2, p.H / 4, p.W / 4, p.alpha);
     __syncthreads();
-    hg_up<G::U2H, G::U2W, G::U2P, G::D2P>(sD2, sU2, sF, sW[2 * 26 + 25], hy0 - 2, hx0 - 2, p.H / 2, p.W / 2, p.alpha);
+    hg_up<G::U2H, G::U2W, G::U2P, G::D2P>(sD2, sU2, sF, sW[2 * HG_WSLOT + 25], hy0 - 2, hx0 - 2, p.H / 2, p.W / 2, p.alpha);
     __syncthreads();
-    hg_up<G::U1H, G::U1W, G::U1P, G::U2P, TC>(sU2, sU1, sF + 36, sW[3 * 26 + 25], oy0 - 2, ox0 - 2, p.H, p.W, p.alpha);
+    hg_up<G::U1H, G::U1W, G::U1P, G::U2P, TC>(sU2, sU1, sF + 36, sW[3 * HG_WSLOT + 25], oy0 - 2, ox0 - 2, p.H, p.W, p.alpha);
     if (TC) {
         // ---- end on the tensor core: y(r, 4 pos + ph) = act_end(b + sum_ky A_ky[m, :] . B_ky[:, ph]), m = r PPR + pos,
         // A_ky[m, k] = U1 block float (r + ky) U1P + 4 pos + k: five tcgen05.mma (128 x 16 x 8, TF32) per M tile straight
@@ -269,7 +332,7 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
         const uint32_t tmem = *tmem_slot;
         const int warp = tid >> 5, lane = tid & 31;
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
-        const float bias = sW[4 * 26 + 25];
+        const float bias = sW[4 * HG_WSLOT + 25];
         constexpr int ROUND = 5;
         // descriptors in 16-byte units: + 128 per M tile (128 positions x 16 B), + U1P / 4 per kernel row; B: + 32 per
         // kernel row (512 B).  One issuing lane per tile, spread over the CTA's warps: a single issuer would spend
@@ -317,26 +380,27 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
         return;
     }
     __syncthreads();
-    // ---- end: y(r, c) = act_end(conv5x5(U1)(r + ky, c + kx) + b); thread = 2 rows x 4 columns (16-byte loads at
-    // lane stride: conflict-free)
+    // ---- end: y(r, c) = act_end(conv5x5(U1)(r + ky, c + kx) + b); thread = 4 rows x 4 columns (16-byte loads at lane
+    // stride: conflict-free; 8 input rows x 32 bytes per 16 outputs, was 6 x 32 per 8), one pass of the 256 threads
     {
-        float w[25];
+        float w[28];
+        hg_load_weights<7>(sW + 4 * HG_WSLOT, w);
+        const float bias = w[25];
+        constexpr int GROUPS = TW / 4, RE = 4;
+        for (int item = tid; item < (TH / RE) * GROUPS; item += HG_THREADS) {
+            const int r = (item / GROUPS) * RE, c0 = (item - (item / GROUPS) * GROUPS) * 4;
+            float acc[RE][4];
 #pragma unroll
-        for (int i = 0; i < 25; ++i) w[i] = sW[4 * 26 + i];
-        const float bias = sW[4 * 26 + 25];
-        constexpr int GROUPS = TW / 4;
-        for (int item = tid; item < (TH / 2) * GROUPS; item += HG_THREADS) {
-            const int r = (item / GROUPS) * 2, c0 = (item - (item / GROUPS) * GROUPS) * 4;
-            float acc[2][4];
+            for (int k = 0; k < RE; ++k)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[0][j] = acc[1][j] = bias;
+                for (int j = 0; j < 4; ++j) acc[k][j] = bias;
 #pragma unroll
-            for (int rr = 0; rr < 6; ++rr) {
+            for (int rr = 0; rr < RE + 4; ++rr) {
                 const float4* row = reinterpret_cast<const float4*>(sU1 + (r + rr) * G::U1P + c0);
                 const float4 u = row[0], v = row[1];
                 const float in[8] = {u.x, u.y, u.z, u.w, v.x, v.y, v.z, v.w};
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < RE; ++k) {
                     const int ky = rr - k;
                     if (ky >= 0 && ky < 5) {
 #pragma unroll
@@ -349,7 +413,7 @@ __global__ void __launch_bounds__(HG_THREADS, 3) hourglass1_fwd_kernel(const Hou
             const int gx = ox0 + c0;
             if (gx < p.W) {                                              // W % 4 == 0: float4 granularity
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
+                for (int k = 0; k < RE; ++k) {
                     const int gy = oy0 + r + k;
                     if (gy < p.H)
                         *reinterpret_cast<float4*>(yim + (int64_t)gy * p.W + gx) =
@@ -367,7 +431,7 @@ template <bool TMA, bool TC>
 static int hourglass1_launch(const HourglassParams& p, const CUtensorMap& map, int64_t n, int64_t h, int64_t wd,
                              cudaStream_t st) {
     constexpr int TH = 32, TW = 128;
-    const size_t smem = sizeof(float) * (TC ? HG<TH, TW>::FLOATS_TC : HG<TH, TW>::FLOATS);
+    const size_t smem = sizeof(float) * (TC ? HG<TH, TW>::FLOATS_TC : HG<TH, TW>::FLOATS_ALIASED);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(hourglass1_fwd_kernel<TH, TW, TMA, TC>,
