@@ -393,6 +393,36 @@ int uocr_label_components(const uint8_t* mask, int32_t* labels, int32_t* counts,
  * (interpreter/interpreter.py:36-38, 125-148, 230, 303, 341, 496-497). */
 int uocr_label_stats(const int32_t* labels, int64_t* stats, int64_t n, int64_t h, int64_t w, int64_t max_labels,
                      void* stream);
+/* ---- the crop stages' selection and resampling (interpreter/interpreter.py:234-523; SciPy's arithmetic, bit for bit:
+ * coordinates in double, every product and sum rounded separately, in ni_interpolation.c's order of operations).
+ * out[n, y, x, k] = image[n, y0 + y, x0 + x, k] * (labels[n, y0 + y, x0 + x] == label): `(image * mask)[:, region_y,
+ * region_x, :]` with mask = the label_layer object `label` (:303-309); labels == NULL: the plain crop (:511). */
+int uocr_crop_masked_f32(const float* image, const int32_t* labels, int32_t label, float* out, int64_t n, int64_t h,
+                         int64_t w, int64_t c, int64_t y0, int64_t x0, int64_t ch, int64_t cw, void* stream);
+/* out[n, y, x] (uint8) = labels[n, y0 + y, x0 + x] == label: `mask[:, region_y, region_x, :]` (:304). */
+int uocr_crop_label_mask(const int32_t* labels, int32_t label, uint8_t* out, int64_t n, int64_t h, int64_t w, int64_t y0,
+                         int64_t x0, int64_t ch, int64_t cw, void* stream);
+/* dst (n, out_h, out_wp, c) = ndimage.zoom(src (n, h, w, c), (1, out_h / h, out_w / w, 1), order=0) in its first out_w
+ * columns, zeros in columns out_w .. out_wp - 1 (the `minimal_width` padding): CropRotateAndZoomLines._func2 (:513-521).
+ * out_h, out_w: int(round(h * zf)), int(round(w * zf)) as ndimage.zoom computes them (host side). */
+int uocr_zoom_nearest_f32(const float* src, float* dst, int64_t n, int64_t h, int64_t w, int64_t c, int64_t out_h,
+                          int64_t out_w, int64_t out_wp, void* stream);
+/* dst (n, out_h, out_w, c) = ndimage.rotate(src (n, h, w, c), angle, axes=(2, 1), order, reshape=True): rotate_array
+ * (:188-192).  matrix (4 doubles, row-major) / offset (2 doubles): HOST pointers to ndimage.rotate's rot_matrix and
+ * offset (input (y, x) = matrix . output (y, x) + offset); order 0 (nearest) or 1 (linear); mode constant, cval 0. */
+int uocr_rotate_f32(const float* src, float* dst, int64_t n, int64_t h, int64_t w, int64_t c, int64_t out_h,
+                    int64_t out_w, const double* matrix, const double* offset, int order, void* stream);
+int uocr_rotate_nearest_u8(const uint8_t* src, uint8_t* dst, int64_t n, int64_t h, int64_t w, int64_t c, int64_t out_h,
+                           int64_t out_w, const double* matrix, const double* offset, void* stream);
+/* box[0..3] (int32, device) = y_min, y_max, x_min, x_max over the non-zero elements of a (n, h, w, c) uint8 array:
+ * ndimage.find_objects(mask)[0] of a boolean array (:230, 303, 341); y_max = -1 when the array is all zero. */
+int uocr_mask_bbox(const uint8_t* mask, int32_t* box, int64_t n, int64_t h, int64_t w, int64_t c, void* stream);
+/* dst[p] = src[p, k] of a (positions, c) uint8 array: one channel of a multi-channel mask, `mask[:, :, :, k:k+1]` (:437-438). */
+int uocr_channel_slice_u8(const uint8_t* src, uint8_t* dst, int64_t positions, int64_t c, int64_t k, void* stream);
+/* mask[n, p, c] (uint8) = x[n, p, c] > mean_p x[n, :, c]: the foreground of label_layer applied to a float map
+ * (`layer > np.mean(layer)`, :16-17).  Workspace as for uocr_threshold_mask. */
+int uocr_above_mean_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
+                         void* stream);
 /* mask[n, p, c] (uint8) = x[n, p, c] > 0.5 * (mean_p x[n, :, c] + max_p x[n, :, c]) over the
  * hw positions of each (image, channel): the `thresholded()` of the crop stages,
  * interpreter/interpreter.py:437-438 (per mask channel) and :549.  Sums in float64, fixed order

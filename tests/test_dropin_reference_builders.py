@@ -61,7 +61,7 @@ def test_reference_builders_construct_the_same_networks_on_the_dropin_package(re
     assert theirs._plan_train == ours._plan_train and theirs._plan_infer == ours._plan_infer
     assert any(step[0] != 'layer' for step in theirs._plan_infer)
     assert type(theirs.infer_fusion) is type(ours.infer_fusion)
-    assert (theirs.infer_fusion is not None) == (name == 'paragraph')
+    assert (theirs.infer_fusion is not None) == (name in ('paragraph', 'line'))    # the two one-kernel hourglass paths
     assert theirs.fused_optimizer() is not None                           # Model.train takes the flat fused update
     if name in ('paragraph', 'line', 'monochrome'):
         assert theirs.get_receptive_fields() == ours.get_receptive_fields()

@@ -1,0 +1,151 @@
+"""GPU parity tests of the crop stages (univer_ocr_b200/stages.py, csrc/stages.cu) against
+scipy.ndimage itself and against the oracle restatement of the reference's stage logic (oracle/np_stages.py, pinned
+against the reference's functions in tests/test_oracle_pin.py).  Everything here is selection / resampling with SciPy's
+own arithmetic: bit-exact."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import np_stages as S
+from tests import stage_cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def nn():
+    import univer_ocr_b200.nn as nn_
+    nn_.CP.use_gpu()
+    return nn_
+
+
+def test_zoom_nearest_matches_scipy(nn):
+    """uocr_zoom_nearest_f32 == ndimage.zoom(a, (1, zf, zf, 1), order=0) (+ the zero padding to minimal_width) through
+    the C ABI: random shapes and factors, incl. the rounding case where the last coordinate lands above in - 1."""
+    from scipy import ndimage
+    from univer_ocr_b200 import stages
+    rng = np.random.default_rng(3)
+    cases = [((1, 21, 197, 2), 16 / 21), ((1, 42, 256, 1), 64 / 42), ((2, 15, 184, 3), 32 / 15), ((1, 1, 1, 1), 3.0),
+             ((1, 7, 5, 1), 1.0)]
+    for t in range(40):
+        h, w, c = int(rng.integers(1, 70)), int(rng.integers(1, 300)), int(rng.integers(1, 4))
+        cases.append(((int(rng.integers(1, 3)), h, w, c), int(rng.integers(1, 64)) / h))
+    for shape, zf in cases:
+        a = rng.uniform(-1, 1, size=shape).astype(np.float32)
+        want = ndimage.zoom(a, (1, zf, zf, 1), order=0)
+        got = stages.zoom_nearest(nn.CP.copy(a), zf).get()
+        assert got.shape == want.shape and np.array_equal(got, want), (shape, zf)
+        padded = stages.zoom_nearest(nn.CP.copy(a), zf, minimal_width=want.shape[2] + 9).get()
+        assert np.array_equal(padded[:, :, :want.shape[2]], want) and not padded[:, :, want.shape[2]:].any()
+
+
+def test_rotate_matches_scipy(nn):
+    """uocr_rotate_f32 (order 0 and 1) and uocr_rotate_nearest_u8 == ndimage.rotate(a, angle, axes=(2, 1), order,
+    reshape=True): random angles, the quarter turns (pure permutations) and 45 degrees (coordinates exactly on .5)."""
+    from scipy import ndimage
+    from univer_ocr_b200 import stages
+    rng = np.random.default_rng(4)
+    for t in range(60):
+        n, h, w, c = int(rng.integers(1, 3)), int(rng.integers(1, 60)), int(rng.integers(1, 90)), int(rng.integers(1, 3))
+        a = rng.uniform(-1, 1, size=(n, h, w, c)).astype(np.float32)
+        angle = float(rng.uniform(0, 180)) if t % 3 else float(rng.choice([0, 90, 180, 270, 45, 135, 30]))
+        for order in (0, 1):
+            want = ndimage.rotate(a, angle, axes=(2, 1), order=order, reshape=True)
+            got = stages.rotate_array(nn.CP.copy(a), angle, good_rotation=bool(order)).get()
+            assert got.shape == want.shape and np.array_equal(got, want), (a.shape, angle, order)
+        m = a[..., :1] > 0
+        want = ndimage.rotate(m, angle, axes=(2, 1), order=0, reshape=True)
+        got = stages.rotate_array(stages._device(m), angle, good_rotation=False).get()
+        assert np.array_equal(got.astype(bool), want)
+    assert stages.rotate_array('untouched', None) == 'untouched'                  # angle None: the array itself
+
+
+def test_crop_bbox_and_above_mean(nn):
+    """uocr_crop_masked_f32 == (image * mask)[:, ry, rx, :] incl. the -0.0 a product leaves under a False mask,
+    uocr_crop_label_mask, uocr_mask_bbox == ndimage.find_objects of the mask (IndexError when empty),
+    uocr_above_mean_mask == arr > mean(arr), uocr_channel_slice_u8."""
+    from scipy import ndimage
+    from univer_ocr_b200 import glue, stages
+    rng = np.random.default_rng(6)
+    pred = (rng.uniform(size=(1, 60, 90, 1)) ** 3).astype(np.float32)
+    fg = pred.astype(np.float64) > pred.astype(np.float64).mean()
+    assert np.array_equal(glue.above_mean(pred).get().astype(bool), fg)
+    labels, objects = stages.label_objects(pred)
+    want_labels, count = ndimage.label(fg)
+    assert len(objects) == count and np.array_equal(labels.get(), want_labels)
+    image = rng.uniform(-1, 1, size=(1, 60, 90, 3)).astype(np.float32)
+    dimage = nn.CP.copy(image)
+    for l in (1, count // 2 + 1, count):
+        mask = want_labels == l
+        ry, rx = objects[l - 1]['slices']
+        assert (ry, rx) == ndimage.find_objects(mask.astype(np.uint8))[0][1:3]
+        want = (image * mask)[:, ry, rx, :]
+        got = stages.crop(dimage, ry, rx, labels, l).get()
+        assert np.array_equal(got, want) and np.array_equal(np.signbit(got), np.signbit(want))
+        assert np.array_equal(stages.crop(dimage, ry, rx).get(), image[:, ry, rx, :])
+        cm = stages.crop_label_mask(labels, l, ry, rx)
+        assert np.array_equal(cm.get().astype(bool), mask[:, ry, rx, :])
+        assert stages.mask_bbox(cm) == (slice(0, ry.stop - ry.start), slice(0, rx.stop - rx.start))
+    whole = stages._device(want_labels == 1)
+    assert stages.mask_bbox(whole) == ndimage.find_objects((want_labels == 1).astype(np.uint8))[0][1:3]
+    with pytest.raises(IndexError):
+        stages.mask_bbox(stages._device(np.zeros((1, 5, 7, 1), bool)))
+    two = (rng.uniform(size=(2, 9, 11, 2)) < 0.5).astype(np.uint8)
+    for k in (0, 1):
+        assert np.array_equal(glue.channel(stages._device(two), k).get(), two[..., k:k + 1])
+    # error convention of the C ABI: a region outside the image
+    from univer_ocr_b200._lib import UocrError, lib
+    out = nn.DeviceArray.empty((1, 4, 4, 3))
+    with pytest.raises(UocrError) as err:
+        lib.uocr_crop_masked_f32(dimage.ptr, None, 0, out.ptr, 1, 60, 90, 3, 58, 0, 4, 4, nn.CP.stream())
+    assert err.value.code == -1 and 'region outside' in str(err.value)
+
+
+def test_crop_rotate_and_zoom_lines_matches_oracle(nn):
+    """stages.CropRotateAndZoomLines (interpreter.py:423-523) == the oracle's serial restatement, for the four reading
+    directions rearrange_lines distinguishes, with and without zoom / padding: same nesting, same shapes, same bits."""
+    from univer_ocr_b200 import stages
+    for direction in (None, 90, 180, 270):
+        m1, a1 = C.line_paragraph(1, direction)
+        m2, a2 = C.line_paragraph(2, direction, lines=2)
+        masks, arrays = [m1, m2], [[a1[0], a2[0]], [a1[1], a2[1]]]
+        for zoomed, minimal in ((32, 200), (32, 1000), (None, 300), (None, None)):
+            want = S.crop_rotate_and_zoom_lines(masks, arrays, zoomed, minimal)
+            got = stages.CropRotateAndZoomLines(8, zoomed, minimal, to_host=True)(masks, arrays)
+            assert len(got) == len(want) == 2
+            for aid in range(2):
+                assert [len(p) for p in got[aid]] == [len(p) for p in want[aid]] == [3, 2]
+                for pid in range(2):
+                    for g, w in zip(got[aid][pid], want[aid][pid]):
+                        assert g.shape == w.shape and np.array_equal(g, w), (direction, zoomed, minimal, aid, pid)
+    # device results by default
+    got = stages.CropRotateAndZoomLines(None, 32, 200)(masks, arrays)
+    assert isinstance(got[0][0][0], nn.DeviceArray) and got[0][0][0].shape[1] == 32
+    # the reference's failure modes: no marks -> IndexError; no reading direction -> UnboundLocalError
+    with pytest.raises(IndexError):
+        stages.CropRotateAndZoomLines(None, 32, 200)([np.zeros((1, 16, 16, 2), np.float32)], [[a1[0][:, :16, :16]]])
+    same = np.zeros((1, 32, 32, 2), np.float32)
+    same[0, 10:12, 4:28, :] = 1.0                             # top and bottom marks coincide: offset 0 in both axes
+    with pytest.raises(UnboundLocalError):
+        stages.CropRotateAndZoomLines(None, 32, 200)([same], [[a1[0][:, :32, :32]]])
+    with pytest.raises(UnboundLocalError):
+        S.crop_rotate_and_zoom_lines([same], [[a1[0][:, :32, :32]]], 32, 200)
+
+
+def test_crop_and_rotate_paragraphs_matches_oracle(nn):
+    """stages.CropAndRotateParagraphs (interpreter.py:234-374) == the oracle's serial restatement: the same paragraphs,
+    the same angles out of the ternary search over nearest-rotated masks, the same straightened crops, bit for bit --
+    with the rotation search and without it."""
+    from univer_ocr_b200 import stages
+    for seed, tilt in ((0, (12.0, -25.0)), (1, (80.0, 3.0))):
+        pred, images = C.paragraph_page(seed, tilt=tilt)
+        for find_rotation in (True, False):
+            want, angles = S.crop_and_rotate_paragraphs(pred, images, find_rotation)
+            stage = stages.CropAndRotateParagraphs(4, find_rotation, to_host=True)
+            got = stage(pred, images)
+            assert stage.angles == angles and len(angles) == 2
+            assert len(got) == len(want) == 2
+            for iid in range(2):
+                for g, w in zip(got[iid], want[iid]):
+                    assert g.shape == w.shape and np.array_equal(g, w), (seed, find_rotation, iid)

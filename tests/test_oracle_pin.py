@@ -246,3 +246,85 @@ def test_live_reference_gradient_suite_subset():
     layer = nn.layers.Convolutional2D((3, 3), 3, 2, padding=1, padding_value=0.5, stride=2)
     assert nn.gradient_check.check_layer_gradient(layer, X)
     assert nn.gradient_check.check_layer_param_gradient(layer, X, 'w')
+
+
+# ---------------------------------------------------------------------------------------------- crop stages (row f4)
+
+def test_stage_resampling_oracle_matches_scipy():
+    """oracle/np_stages.py restates SciPy's zoom (order 0) and rotate (order 0 / 1) arithmetic -- pinned against SciPy
+    itself on random shapes, zoom factors and angles (incl. the quarter turns and the tie-prone 45 degrees): bit-equal."""
+    from scipy import ndimage
+    from oracle import np_stages as S
+    rng = np.random.default_rng(11)
+    for t in range(120):
+        h, w, c = int(rng.integers(1, 70)), int(rng.integers(1, 260)), int(rng.integers(1, 3))
+        a = rng.uniform(0.1, 1, size=(1, h, w, c)).astype(np.float32)
+        zf = int(rng.integers(1, 64)) / h
+        want = ndimage.zoom(a, (1, zf, zf, 1), order=0)
+        got = S.zoom_nearest(a, zf, zf)
+        assert want.shape == got.shape and np.array_equal(want, got), (a.shape, zf)
+    for t in range(120):
+        h, w, c = int(rng.integers(1, 50)), int(rng.integers(1, 80)), int(rng.integers(1, 3))
+        a = rng.uniform(-1, 1, size=(1, h, w, c)).astype(np.float32)
+        angle = float(rng.uniform(0, 180)) if t % 4 else float(rng.choice([0, 90, 180, 270, 45, 30, 60, 120, 135]))
+        for order in (0, 1):
+            want = ndimage.rotate(a, angle, axes=(2, 1), order=order, reshape=True)
+            got = S.rotate(a, angle, order)
+            assert want.shape == got.shape and np.array_equal(want, got), (a.shape, angle, order)
+        m = a[..., :1] > 0
+        assert np.array_equal(ndimage.rotate(m, angle, axes=(2, 1), order=0, reshape=True), S.rotate(m, angle, 0))
+
+
+@needs_ref
+def test_stage_oracle_matches_reference_functions():
+    """The stage restatements of oracle/np_stages.py against the reference's own functions (interpreter.py:
+    label_layer, rearrange_lines, CropRotateAndZoomLines._func1 / _func2, FindObjectHeightInRotated._func,
+    rotate_array) on the synthetic cases of tests/stage_cases.py, all four reading directions.  Boolean masks are cast
+    to uint8 before the reference's find_objects calls (SciPy 1.18 refuses a boolean maximum label)."""
+    import importlib
+    from scipy import ndimage
+    from oracle import np_stages as S
+    from tests import stage_cases as C
+    ref_loader.load_my_model()
+    I = importlib.import_module('web_app.components.interpreter.interpreter')
+
+    def u8(m):
+        return m.astype(np.uint8)
+
+    for direction in (None, 90, 180, 270):
+        mask, arrays = C.line_paragraph(1, direction)
+        top, bottom = S.thresholded(mask[..., 0:1]), S.thresholded(mask[..., 1:2])
+        rt, rb, rrot = I.rearrange_lines(I.label_layer(top), I.label_layer(bottom))
+        ot, ob, orot = S.rearrange_lines(S.label_layer(top), S.label_layer(bottom))
+        assert rrot == orot == direction and len(rt) == len(ot) == 3
+        assert all(np.array_equal(a, b) for a, b in zip(rt, ot)) and all(np.array_equal(a, b) for a, b in zip(rb, ob))
+        for t, b in zip(rt, rb):
+            y, x = I.CropRotateAndZoomLines._func1(u8(t), u8(b))
+            assert (y, x) == S.line_region(t, b)
+            for arr in arrays:
+                for zoomed, minimal in ((32, 200), (32, 1000), (None, 300), (None, None)):
+                    want = I.CropRotateAndZoomLines._func2(arr, y, x, rrot, zoomed, minimal)
+                    got = S.crop_rotate_zoom(arr, y, x, orot, zoomed, minimal)
+                    assert want.shape == got.shape and np.array_equal(want, got)
+    pred, images = C.paragraph_page(0)
+    res, angles = S.crop_and_rotate_paragraphs(pred, images, True)
+    objects = I.label_layer(pred)
+    assert len(objects) == len(angles) == 2
+    for pid, m in enumerate(objects):
+        _, ry, rx, _ = ndimage.find_objects(u8(m))[0]
+        cm = u8(m[:, ry, rx, :])
+        low, high = 0.0, 180.0
+        while high - low > 1.0:                                # CropAndRotateSingleParagraph._func, :318-333
+            a, b = low + (high - low) / 3, high - (high - low) / 3
+            ha, hb = I.FindObjectHeightInRotated._func(cm, a), I.FindObjectHeightInRotated._func(cm, b)
+            assert (ha, hb) == (S.rotated_height(cm, a), S.rotated_height(cm, b))
+            if ha < hb:
+                high = b
+            else:
+                low = a
+        angle = (high + low) / 2
+        assert angle == angles[pid]
+        _, oy, ox, _ = ndimage.find_objects(I.rotate_array(cm, angle, good_rotation=False))[0]
+        for iid, image in enumerate(images):
+            want = I.rotate_array((image * m)[:, ry, rx, :], angle)[:, oy, ox, :]
+            assert np.array_equal(want, res[iid][pid])

@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(kThreads) threshold_partials_kernel(const floa
 }
 
 __global__ void threshold_finalize_kernel(const double* __restrict__ part, double* __restrict__ thr,
-                                          int64_t groups, int blocks, int c, int64_t hw) {
+                                          int64_t groups, int blocks, int c, int64_t hw, int mean_only) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // g = n * c + channel
     if (g >= groups) return;
     const int64_t n = g / c, ch = g % c;
@@ -465,7 +465,7 @@ __global__ void threshold_finalize_kernel(const double* __restrict__ part, doubl
         s += p[0];
         m = fmax(m, p[1]);
     }
-    thr[g] = 0.5 * (s / (double)hw + m);
+    thr[g] = mean_only ? s / (double)hw : 0.5 * (s / (double)hw + m);
 }
 
 __global__ void __launch_bounds__(kThreads) threshold_apply_kernel(const float* __restrict__ x,
@@ -946,8 +946,8 @@ int uocr_threshold_mask_workspace(int64_t n, int64_t c, size_t* bytes) {
     return UOCR_OK;
 }
 
-int uocr_threshold_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
-                        void* stream) {
+static int threshold_mask_impl(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
+                               int mean_only, void* stream) {
     if (n <= 0 || hw <= 0 || c <= 0) return UOCR_OK;
     UOCR_REQUIRE(x && mask && workspace, "NULL pointer");
     UOCR_REQUIRE(c <= kThrMaxC, "threshold_mask supports at most 8 channels");
@@ -959,13 +959,23 @@ int uocr_threshold_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, in
     UOCR_LAUNCHED("threshold_partials");
     const int64_t groups = n * c;
     threshold_finalize_kernel<<<(int)ceil_div(groups, 128), 128, 0, as_stream(stream)>>>(part, thr, groups,
-                                                                                       kThrBlocks, (int)c, hw);
+                                                                                       kThrBlocks, (int)c, hw, mean_only);
     UOCR_LAUNCHED("threshold_finalize");
     const int64_t total = n * hw * c;
     threshold_apply_kernel<<<ew_grid(total, 4), kThreads, 0, as_stream(stream)>>>(x, thr, mask, total, hw * c,
                                                                                 (int)c);
     UOCR_LAUNCHED("threshold_apply");
     return UOCR_OK;
+}
+
+int uocr_threshold_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
+                        void* stream) {
+    return threshold_mask_impl(x, mask, n, hw, c, workspace, 0, stream);
+}
+
+int uocr_above_mean_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,
+                         void* stream) {
+    return threshold_mask_impl(x, mask, n, hw, c, workspace, 1, stream);
 }
 
 }  // extern "C"

@@ -12,8 +12,8 @@ the host link is uint8 masks / hit tables (1 byte per element instead of 8):
     row_max_hits / pred_to_text   interpreter/interpreter.py:595-614  (PredToText._func1)
     label_components / label_layer   interpreter/interpreter.py:16-22  (ndimage.label of the crop stages)
 
-Of the stages between them (row f4) the connected-component labelling runs on the device as well; rotation and zoom
-(`scipy.ndimage.rotate / zoom`) stay on the host.
+The stages between them (row f4: label, crop, rotate, zoom) are in `stages.py`, built on the labelling and statistics
+here.
 """
 import ctypes
 
@@ -59,6 +59,28 @@ def thresholded(arr):
     work = DeviceArray.empty((nbytes.value,), np.uint8)
     lib.uocr_threshold_mask(arr.ptr, mask.ptr, n, hw, c, work.ptr, stream())
     return mask
+
+
+def above_mean(arr):
+    """uint8 mask of `arr > mean(arr)`, the mean taken per (image, channel) over H x W in float64: the foreground
+    `label_layer` labels when it is handed a float map (`interpreter/interpreter.py:16-17`)."""
+    arr = as_device(arr)
+    n, c = arr.shape[0], arr.shape[-1]
+    hw = arr.size // (n * c)
+    mask = DeviceArray.empty(arr.shape, np.uint8)
+    nbytes = ctypes.c_size_t(0)
+    lib.uocr_threshold_mask_workspace(n, c, ctypes.byref(nbytes))
+    work = DeviceArray.empty((nbytes.value,), np.uint8)
+    lib.uocr_above_mean_mask(arr.ptr, mask.ptr, n, hw, c, work.ptr, stream())
+    return mask
+
+
+def channel(mask, k):
+    """`mask[:, :, :, k:k+1]` of a uint8 (N, H, W, C) device mask, contiguous."""
+    n, h, w, c = mask.shape
+    out = DeviceArray.empty((n, h, w, 1), np.uint8)
+    lib.uocr_channel_slice_u8(mask.ptr, out.ptr, n * h * w, c, k, stream())
+    return out
 
 
 def label_components(mask):
