@@ -16,8 +16,9 @@ planes in (`train_data_generator.py:24-37`), thresholded uint8 masks and the Pre
 (`interpreter/interpreter.py:437-447, 596-602`); `e2e.float_out_value` is the all-float32 variant.
 Extra keys of the same JSON line: `train` (BASELINE configs[2]: data-parallel training step, weak scaling
 at 64 tiles per GPU, and `train.global_512` = global batch 512 as the config is written), `fullpage`
-(configs[3]: 64 pages of 2064 x 2064 sharded over the ranks), `roofline`, `cpu_baseline`,
-`cpu_baseline_train`.  Prints ONE JSON line (rank 0).
+(configs[3]: 64 pages of 2064 x 2064 sharded over the ranks), `stages` (the crop stages between the networks on the
+device next to their scipy.ndimage restatement on the host), `roofline`, `cpu_baseline`, `cpu_baseline_train`.
+Prints ONE JSON line (rank 0).
 
 No PyTorch: ranks rendezvous and reduce through libuocr's own NCCL binding (univer_ocr_b200.comm).
 
@@ -428,12 +429,60 @@ def run_b200(args):
         result['train'] = train
     if fullpage is not None:
         result['fullpage'] = fullpage
+    if comm.rank == 0 and not args.no_stages:
+        result['stages'] = measure_stages(nn, lib)
     if comm.rank == 0 and comm.world == 1 and not args.no_cpu_baseline:
         result['cpu_baseline'] = cpu_baseline(budget_s=args.cpu_budget, cores=1)
         result['cpu_baseline_train'] = cpu_baseline(budget_s=args.cpu_budget, cores=1, train=True)
     if comm.rank == 0:
         print(json.dumps(result), flush=True)
     comm.close()
+
+
+def measure_stages(nn, lib):
+    """the crop stages between the sub-networks (interpreter.py:234-523) on one synthetic page tile with
+    two tilted paragraphs and on two cropped paragraphs of three lines each -- device classes (univer_ocr_b200.stages,
+    results stay on the device; the timed region ends with a device synchronise) next to the CPU restatement with
+    scipy.ndimage (oracle/np_stages.py, single process; the reference spreads the same calls over worker processes).
+    Host wall clock: the stages are host-driven object loops around small kernels."""
+    import time
+    from oracle import np_stages
+    from tests import stage_cases
+    from univer_ocr_b200 import stages
+    from univer_ocr_b200._lib import launch_count
+    pred, images = stage_cases.paragraph_page(0, h=PAGE_HW[0], w=PAGE_HW[1])
+    images = images[:1]                                        # PREDICT mode cuts the Monochrome map only
+    lines = [stage_cases.line_paragraph(s, None, h=128, w=512, lines=3) for s in (1, 2)]
+    masks, arrays = [m for m, _ in lines], [[a[0] for _, a in lines]]
+    d_pred, d_images = nn.CP.copy(pred), [nn.CP.copy(i) for i in images]
+    d_masks, d_arrays = [nn.CP.copy(m) for m in masks], [[nn.CP.copy(a) for a in arrays[0]]]
+    para = stages.CropAndRotateParagraphs(None, True)
+    line = stages.CropRotateAndZoomLines(None, 32, 8)
+
+    def device_pass():
+        para(d_pred, d_images)
+        line(d_masks, d_arrays)
+        nn.CP.synchronize()
+    device_pass()
+    n0, reps = launch_count(), 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        device_pass()
+    dev_s = (time.perf_counter() - t0) / reps
+    launches = (launch_count() - n0) // reps
+    t0 = time.perf_counter()
+    want_p, angles = np_stages.crop_and_rotate_paragraphs(pred, images, True)
+    want_l = np_stages.crop_rotate_and_zoom_lines(masks, arrays, 32, 8)
+    cpu_s = time.perf_counter() - t0
+    got_p = stages.CropAndRotateParagraphs(None, True, to_host=True)(d_pred, d_images)
+    got_l = stages.CropRotateAndZoomLines(None, 32, 8, to_host=True)(d_masks, d_arrays)
+    same = (all(np.array_equal(g, w) for g, w in zip(got_p[0], want_p[0]))
+            and all(np.array_equal(g, w) for gp, wp in zip(got_l[0], want_l[0]) for g, w in zip(gp, wp)))
+    return {'metric': 'crop stages per page tile: CropAndRotateParagraphs (rotation search on) + CropRotateAndZoomLines',
+            'workload': '1 page tile %dx%d with 2 tilted paragraphs (1 map cut) + 2 paragraphs 128x512 with 3 lines each, '
+                        'zoomed to height 32' % PAGE_HW,
+            'device_ms': dev_s * 1e3, 'cpu_ms': cpu_s * 1e3, 'cpu_kind': 'port (scipy.ndimage, 1 process)',
+            'gpu_launches': int(launches), 'angles': angles, 'bit_identical_to_cpu': bool(same)}
 
 
 def measure_long_gemm(nn, lib, timer):
@@ -796,6 +845,7 @@ def main():
     ap.add_argument('--no-train', action='store_true', help='skip the training-step measurement')
     ap.add_argument('--no-global512', action='store_true', help='skip the global-batch-512 training measurement')
     ap.add_argument('--no-fullpage', action='store_true', help='skip the full-page (configs[3]) measurement')
+    ap.add_argument('--no-stages', action='store_true', help='skip the crop-stage (row f4) measurement')
     ap.add_argument('--no-gemm-peak', action='store_true', help='skip the long-GEMM TF32 rate measurement')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
