@@ -414,6 +414,13 @@ int uocr_rotate_f32(const float* src, float* dst, int64_t n, int64_t h, int64_t 
                     int64_t out_w, const double* matrix, const double* offset, int order, void* stream);
 int uocr_rotate_nearest_u8(const uint8_t* src, uint8_t* dst, int64_t n, int64_t h, int64_t w, int64_t c, int64_t out_h,
                            int64_t out_w, const double* matrix, const double* offset, void* stream);
+/* spans[2 k], spans[2 k + 1] (int32, device) = first and last output row of the nearest-rotated mask that holds a
+ * non-zero element (INT_MAX, -1 if none), for count = 1 or 2 rotations of the same (n, h, w, c) uint8 mask at once and
+ * without materialising them: FindObjectHeightInRotated._func (:229-232) for both probe angles of one step of the
+ * ternary search (:318-333).  matrices (count x 4), offsets (count x 2), out_shapes (count x 2): HOST arrays as for
+ * uocr_rotate_nearest_u8. */
+int uocr_rotated_row_spans(const uint8_t* mask, int32_t* spans, int64_t n, int64_t h, int64_t w, int64_t c, int count,
+                           const double* matrices, const double* offsets, const int64_t* out_shapes, void* stream);
 /* box[0..3] (int32, device) = y_min, y_max, x_min, x_max over the non-zero elements of a (n, h, w, c) uint8 array:
  * ndimage.find_objects(mask)[0] of a boolean array (:230, 303, 341); y_max = -1 when the array is all zero. */
 int uocr_mask_bbox(const uint8_t* mask, int32_t* box, int64_t n, int64_t h, int64_t w, int64_t c, void* stream);

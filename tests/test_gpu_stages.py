@@ -58,6 +58,17 @@ def test_rotate_matches_scipy(nn):
         want = ndimage.rotate(m, angle, axes=(2, 1), order=0, reshape=True)
         got = stages.rotate_array(stages._device(m), angle, good_rotation=False).get()
         assert np.array_equal(got.astype(bool), want)
+        # the rows the rotated mask spans, read off without materialising it (the angle search's probe)
+        if want.any():
+            rows = np.flatnonzero(want.any(axis=(0, 2, 3)))
+            other = float(rng.uniform(0, 180))
+            want2 = ndimage.rotate(m, other, axes=(2, 1), order=0, reshape=True)
+            if want2.any():
+                rows2 = np.flatnonzero(want2.any(axis=(0, 2, 3)))
+                assert stages.rotated_heights(stages._device(m), (angle, other)) == [rows[-1] - rows[0] + 1,
+                                                                                     rows2[-1] - rows2[0] + 1]
+            assert stages.rotated_heights(stages._device(m), (angle,)) == [rows[-1] - rows[0] + 1]
+            assert stages.rotated_height(stages._device(m), angle) == rows[-1] - rows[0] + 1
     assert stages.rotate_array('untouched', None) == 'untouched'                  # angle None: the array itself
 
 

@@ -120,6 +120,41 @@ __global__ void __launch_bounds__(256) rotate_kernel(const T* __restrict__ src, 
     }
 }
 
+// Rows spanned by the nearest-rotated mask for up to two rotations at once, without materialising them: what
+// FindObjectHeightInRotated._func (interpreter.py:229-232) extracts from rotate_array(mask, angle, good_rotation=False),
+// for the two probe angles of one step of the ternary search (:318-333).
+struct SpanGeoms { RotateGeom g[2]; int oh[2], ow[2]; };
+
+__global__ void row_span_init_kernel(int32_t* __restrict__ spans, int k) {
+    if ((int)threadIdx.x < 2 * k) spans[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
+}
+
+__global__ void __launch_bounds__(256) rotated_row_span_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ spans,
+                                                               int n, int h, int w, int c, const SpanGeoms sg) {
+    const int k = blockIdx.y;
+    const RotateGeom g = sg.g[k];
+    const int oh = sg.oh[k], ow = sg.ow[k];
+    const int64_t total = (int64_t)n * oh * ow * c;
+    int y0 = 0x7fffffff, y1 = -1;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int ch = (int)(i % c);
+        int64_t r = i / c;
+        const int ox = (int)(r % ow); r /= ow;
+        const int oy = (int)(r % oh);
+        const int64_t img = r / oh;
+        double cy, cx;
+        if (rotate_coords(g, oy, ox, h, w, cy, cx)) {
+            const int iy = min((int)floor(__dadd_rn(cy, 0.5)), h - 1), ix = min((int)floor(__dadd_rn(cx, 0.5)), w - 1);
+            if (mask[((img * h + iy) * w + ix) * c + ch]) { y0 = min(y0, oy); y1 = max(y1, oy); }
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        y0 = min(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        y1 = max(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if ((threadIdx.x & 31) == 0 && y1 >= 0) { atomicMin(spans + 2 * k, y0); atomicMax(spans + 2 * k + 1, y1); }
+}
+
 __global__ void mask_bbox_init_kernel(int32_t* __restrict__ box) {
     box[0] = 0x7fffffff; box[1] = -1; box[2] = 0x7fffffff; box[3] = -1;
 }
@@ -241,6 +276,31 @@ int uocr_rotate_nearest_u8(const uint8_t* src, uint8_t* dst, int64_t n, int64_t 
     rotate_kernel<uint8_t, 0><<<stage_grid(total), 256, 0, as_stream(stream)>>>(src, dst, total, (int)h, (int)w, (int)c,
                                                                                (int)out_h, (int)out_w, g);
     UOCR_LAUNCHED("rotate_nearest_u8");
+    return UOCR_OK;
+}
+
+int uocr_rotated_row_spans(const uint8_t* mask, int32_t* spans, int64_t n, int64_t h, int64_t w, int64_t c, int count,
+                           const double* matrices, const double* offsets, const int64_t* out_shapes, void* stream) {
+    UOCR_REQUIRE(mask && spans && matrices && offsets && out_shapes, "NULL pointer");
+    UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && fits32(h) && fits32(w) && fits32(c), "bad dimension");
+    UOCR_REQUIRE(count == 1 || count == 2, "1 or 2 rotations per call, got %d", count);
+    SpanGeoms sg{};
+    int64_t most = 0;
+    for (int k = 0; k < count; ++k) {
+        UOCR_REQUIRE(out_shapes[2 * k] >= 0 && out_shapes[2 * k + 1] >= 0 && fits32(out_shapes[2 * k]) &&
+                     fits32(out_shapes[2 * k + 1]), "bad output shape");
+        sg.g[k] = RotateGeom{matrices[4 * k], matrices[4 * k + 1], matrices[4 * k + 2], matrices[4 * k + 3],
+                             offsets[2 * k], offsets[2 * k + 1]};
+        sg.oh[k] = (int)out_shapes[2 * k]; sg.ow[k] = (int)out_shapes[2 * k + 1];
+        const int64_t total = n * out_shapes[2 * k] * out_shapes[2 * k + 1] * c;
+        if (total > most) most = total;
+    }
+    row_span_init_kernel<<<1, 32, 0, as_stream(stream)>>>(spans, count);
+    UOCR_LAUNCHED("row_span_init");
+    if (most == 0) return UOCR_OK;
+    rotated_row_span_kernel<<<dim3((unsigned)stage_grid(most), (unsigned)count), 256, 0, as_stream(stream)>>>(
+        mask, spans, (int)n, (int)h, (int)w, (int)c, sg);
+    UOCR_LAUNCHED("rotated_row_span");
     return UOCR_OK;
 }
 

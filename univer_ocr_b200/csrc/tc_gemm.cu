@@ -649,24 +649,33 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
                                     apply_act_fast(__uint_as_float(cur[4 * g + 3]) + b4.w, p.act, p.alpha));
                 }
                 __syncwarp();
+                if (vec_ok && ncols == 16) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int rr = 8 * i + sub_r;
-                    const float4 o = stg[rr * 4 + (sub_g ^ ((rr >> 1) & 3))];
-                    if (row0 + rr >= p.M) continue;
-                    float* dst = p.C + (row0 + rr) * p.ldc + c + 4 * sub_g;
-                    if (vec_ok && ncols == 16) {
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = 8 * i + sub_r;
+                        const float4 o = stg[rr * 4 + (sub_g ^ ((rr >> 1) & 3))];
+                        if (row0 + rr >= p.M) continue;
+                        float* dst = p.C + (row0 + rr) * p.ldc + c + 4 * sub_g;
                         if (p.accumulate) {
                             const float4 c4 = *reinterpret_cast<const float4*>(dst);
                             *reinterpret_cast<float4*>(dst) = make_float4(c4.x + o.x, c4.y + o.y, c4.z + o.z, c4.w + o.w);
                         } else {
                             *reinterpret_cast<float4*>(dst) = o;
                         }
-                    } else {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (4 * sub_g + k < ncols) dst[k] = p.accumulate ? dst[k] + ov[k] : ov[k];
+                    }
+                } else {
+                    // rows that are not 16-byte multiples (dense_3: n_out = 162) or a ragged last chunk: scalar stores,
+                    // a half-warp per row -- 16 consecutive floats = 64 contiguous bytes, 2 rows per instruction (the
+                    // float4-shaped form wrote words 16 bytes apart: 16 sectors per instruction instead of 4-6)
+                    const float* sf = reinterpret_cast<const float*>(stg);
+                    const int col = lane & 15;
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = 2 * i + (lane >> 4);
+                        const float o = sf[(rr * 4 + ((col >> 2) ^ ((rr >> 1) & 3))) * 4 + (col & 3)];
+                        if (row0 + rr >= p.M || col >= ncols) continue;
+                        float* dst = p.C + (row0 + rr) * p.ldc + c + col;
+                        *dst = p.accumulate ? *dst + o : o;
                     }
                 }
             };
@@ -717,7 +726,7 @@ static int tc_gemm_tn_persistent_impl(const float* A, int64_t lda, const WindowG
     // (its dgrad), +10 % at 14 tiles per CTA (504 -> 556 TFLOP/s).  UOCR_TC_PAIR = 0 / 1 forces never / always.
     const char* pe = getenv("UOCR_TC_PAIR");
     const int pair_mode = pe ? atoi(pe) : -1;
-    const bool pair_fits = p.nt == 256 && M >= 4096;
+    const bool pair_fits = p.nt == 256 && M >= 4096;            // nt = 128 pairs work but gain nothing (dense_2: 21.5 vs 20.4 us)
     const bool pair = pair_fits && (pair_mode > 0 || (pair_mode < 0 && (K >= 1024 || M * N >= ((int64_t)1 << 25))));
     const size_t a_bytes = TC_BM * TC_BK * 4;
     const size_t b_bytes = (((size_t)(pair ? p.nt / 2 : p.nt) * TC_BK * 4) + 1023) & ~(size_t)1023;

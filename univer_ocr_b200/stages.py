@@ -131,14 +131,33 @@ def rotated_height(mask, angle):
     return region_y.stop - region_y.start
 
 
+def rotated_heights(mask, angles):
+    """`rotated_height` for one or two angles in one launch: the rows each nearest rotation would span, read off the
+    source mask without materialising the rotated copies (uocr_rotated_row_spans)."""
+    n, h, w, c = mask.shape
+    k = len(angles)
+    geoms = [rotate_geometry(h, w, angle) for angle in angles]
+    mats = (ctypes.c_double * (4 * k))(*[v for _, m, _ in geoms for v in m.ravel()])
+    offs = (ctypes.c_double * (2 * k))(*[v for _, _, off in geoms for v in off])
+    shapes = (ctypes.c_int64 * (2 * k))(*[v for shape, _, _ in geoms for v in shape])
+    spans = DeviceArray.empty((2 * k,), np.int32)
+    lib.uocr_rotated_row_spans(mask.ptr, spans.ptr, n, h, w, c, k, mats, offs, shapes, stream())
+    host = spans.get()
+    if (host[1::2] < 0).any():
+        raise IndexError('list index out of range')           # find_objects(all-False)[0]
+    return [int(host[2 * i + 1] - host[2 * i] + 1) for i in range(k)]
+
+
 def find_rotation_angle(mask, EPS=1.0):
     """The ternary search of CropAndRotateSingleParagraph._func (:318-333): the angle in (0, 180) at which the
-    nearest-rotated mask spans the fewest rows; None within EPS of 0 / 180."""
+    nearest-rotated mask spans the fewest rows; None within EPS of 0 / 180.  One launch and one 16-byte read-back per
+    step (both probe angles together)."""
     low, high = 0.0, 180.0
     while high - low > EPS:
         a = low + (high - low) / 3
         b = high - (high - low) / 3
-        if rotated_height(mask, a) < rotated_height(mask, b):
+        height_a, height_b = rotated_heights(mask, (a, b))
+        if height_a < height_b:
             high = b
         else:
             low = a
