@@ -160,3 +160,84 @@ def test_crop_and_rotate_paragraphs_matches_oracle(nn):
             for iid in range(2):
                 for g, w in zip(got[iid], want[iid]):
                     assert g.shape == w.shape and np.array_equal(g, w), (seed, find_rotation, iid)
+
+
+def test_text_pipeline_wiring_matches_oracle_composition(nn):
+    """predict.TextPipeline = the reference's PREDICT model system (my_model/model.py:688-717) on the device.  The four
+    networks are replaced by deterministic stand-ins (so that the comparison is about the wiring, the padding between
+    the stages and the stages themselves, not about TF32 arithmetic at decision thresholds): the same stand-ins composed
+    on the host with the oracle's stages must give the same paragraphs, angles, line crops (bit for bit), class ids and
+    text."""
+    from oracle import np_oracle as O
+    from univer_ocr_b200 import my_model, predict
+    pred, images = C.paragraph_page(3, h=150, w=230)
+    page = images[0]
+
+    def lines_for(shape):                                      # Line stand-in: marks at fixed relative rows
+        _, h, w, _ = shape
+        out = np.zeros((1, h, w, 2), np.float32)
+        for centre in (h // 3, (2 * h) // 3):
+            out[0, centre - 6:centre - 4, 6:w - 6, 0] = 1.0
+            out[0, centre + 4:centre + 6, 6:w - 6, 1] = 1.0
+        return out
+
+    def chars_for(line):                                       # Char stand-in: class from the column's brightness
+        cols = np.asarray(line)[0, :, :, 0].mean(axis=0)
+        out = np.zeros((cols.size, my_model.N_CHARS), np.float32)
+        out[np.arange(cols.size), (cols * 40).astype(int) % my_model.N_CHARS] = 1.0
+        return out
+
+    padded_pred = O.make_divisible_by(pred, 16, 16).astype(np.float32)
+    predictors = {'monochrome': lambda x: x,
+                  'paragraph': lambda x: nn.CP.copy(padded_pred),
+                  'line': lambda x: nn.CP.copy(lines_for(x.shape)),
+                  'char': lambda x: nn.CP.copy(chars_for(x.get()))}
+    chars = [chr(33 + i) for i in range(my_model.N_CHARS)]
+    similar = lambda a, b: a == b                              # noqa: E731
+    got = predict.TextPipeline(predictors=predictors, chars=chars, are_similar=similar)(page)
+    # the same composition on the host
+    x = O.make_divisible_by(page, 16, 16).astype(np.float32)
+    cropped, angles = S.crop_and_rotate_paragraphs(padded_pred, [x], True)
+    cropped = [O.make_divisible_by(t, 16, 16).astype(np.float32) for t in cropped[0]]
+    line_pred = [lines_for(t.shape) for t in cropped]
+    lines = S.crop_rotate_and_zoom_lines(line_pred, [cropped], my_model.CHAR_INPUT_HEIGHT, my_model.CHAR_FIXED_WIDTH)[0]
+    assert got['angles'] == angles and len(angles) == 2
+    assert len(got['cropped_monochrome']) == len(cropped)
+    for g, w in zip(got['cropped_monochrome'], cropped):
+        assert np.array_equal(g.get(), w)
+    assert [len(p) for p in got['cropped_2_monochrome']] == [len(p) for p in lines] == [2, 2]
+    for gp, wp, tp in zip(got['cropped_2_monochrome'], lines, got['text']):
+        for g, w, text in zip(gp, wp, tp):
+            assert g.shape == w.shape and w.shape[1] == my_model.CHAR_INPUT_HEIGHT and np.array_equal(g.get(), w)
+            assert text == O.pred_to_text(chars_for(w), chars, similar) and len(text) > 0
+    ids = predict.TextPipeline(predictors=predictors)(page)['text']
+    assert all(isinstance(v, int) for p in ids for line in p for v in line)
+
+
+def test_text_pipeline_runs_the_networks(nn):
+    """The same pipeline with the real networks (default initialisation, TF32 mode) on a small page: every stage
+    runs, shapes chain (crops padded to multiples of 16, lines zoomed to CHAR_INPUT_HEIGHT), the text nesting follows
+    the paragraphs and lines found.  find_rotation off: with untrained weights the paragraph map is noise and the
+    search would only slow the test."""
+    from univer_ocr_b200 import my_model, predict
+    rng = np.random.default_rng(8)
+    page = rng.uniform(0, 1, size=(1, 90, 120, 1)).astype(np.float32)
+    pipe = predict.TextPipeline(find_rotation=False)
+    mono = pipe.predict('monochrome', nn.CP.copy(np.zeros((1, 96, 128, 1), np.float32)))
+    assert mono.shape == (1, 96, 128, 1)
+    # untrained networks label noise: cap the work by handing the Paragraph stage a clean synthetic map
+    clean = np.zeros((1, 96, 128, 1), np.float32)
+    clean[0, 20:70, 16:110, 0] = 1.0
+    pipe.predictors['paragraph'] = lambda x: nn.CP.copy(clean)
+    marks = np.zeros((1, 64, 96, 2), np.float32)
+    marks[0, 20:22, 8:88, 0] = 1.0
+    marks[0, 40:42, 8:88, 1] = 1.0
+    pipe.predictors['line'] = lambda x: nn.CP.copy(marks[:, :x.shape[1], :x.shape[2]]) if x.shape[1:3] == (64, 96) else None
+    out = pipe(page)
+    assert len(out['cropped_monochrome']) == 1 and out['cropped_monochrome'][0].shape == (1, 64, 96, 1)
+    assert len(out['cropped_2_monochrome'][0]) == 1
+    line = out['cropped_2_monochrome'][0][0]
+    assert line.shape[1] == my_model.CHAR_INPUT_HEIGHT and line.shape[2] >= my_model.CHAR_FIXED_WIDTH
+    pred = out['char_pred'][0][0]
+    assert pred.shape == (line.shape[2], my_model.N_CHARS) and np.isfinite(pred.get()).all()
+    assert isinstance(out['text'][0][0], list)
