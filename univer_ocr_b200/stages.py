@@ -134,37 +134,55 @@ def rotated_height(mask, angle):
 def rotated_heights(mask, angles):
     """`rotated_height` for one or two angles in one launch: the rows each nearest rotation would span, read off the
     source mask without materialising the rotated copies (uocr_rotated_row_spans)."""
-    n, h, w, c = mask.shape
     k = len(angles)
-    geoms = [rotate_geometry(h, w, angle) for angle in angles]
-    mats = (ctypes.c_double * (4 * k))(*[v for _, m, _ in geoms for v in m.ravel()])
-    offs = (ctypes.c_double * (2 * k))(*[v for _, _, off in geoms for v in off])
-    shapes = (ctypes.c_int64 * (2 * k))(*[v for shape, _, _ in geoms for v in shape])
     spans = DeviceArray.empty((2 * k,), np.int32)
-    lib.uocr_rotated_row_spans(mask.ptr, spans.ptr, n, h, w, c, k, mats, offs, shapes, stream())
+    _launch_row_spans(mask, angles, spans, 0)
     host = spans.get()
     if (host[1::2] < 0).any():
         raise IndexError('list index out of range')           # find_objects(all-False)[0]
     return [int(host[2 * i + 1] - host[2 * i] + 1) for i in range(k)]
 
 
+def _launch_row_spans(mask, angles, spans, slot):
+    """Queues uocr_rotated_row_spans for `angles` (1 or 2) of `mask` into spans[slot : slot + 2 * len(angles)]."""
+    n, h, w, c = mask.shape
+    k = len(angles)
+    geoms = [rotate_geometry(h, w, angle) for angle in angles]
+    mats = (ctypes.c_double * (4 * k))(*[v for _, m, _ in geoms for v in m.ravel()])
+    offs = (ctypes.c_double * (2 * k))(*[v for _, _, off in geoms for v in off])
+    shapes = (ctypes.c_int64 * (2 * k))(*[v for shape, _, _ in geoms for v in shape])
+    lib.uocr_rotated_row_spans(mask.ptr, spans.ptr + 4 * slot, n, h, w, c, k, mats, offs, shapes, stream())
+
+
+def find_rotation_angles(masks, EPS=1.0):
+    """The ternary search of CropAndRotateSingleParagraph._func (:318-333) for several paragraph masks in lockstep: the
+    angle in (0, 180) at which each nearest-rotated mask spans the fewest rows; None within EPS of 0 / 180.  Every mask
+    takes the same number of steps (the interval shrinks by a third per step whatever the comparison says), so one step
+    is one launch per mask (both probe angles, `uocr_rotated_row_spans`) and ONE read-back for all of them."""
+    low, high = [0.0] * len(masks), [180.0] * len(masks)
+    spans = DeviceArray.empty((4 * max(len(masks), 1),), np.int32)
+    while masks and high[0] - low[0] > EPS:
+        probes = []
+        for i, mask in enumerate(masks):
+            a = low[i] + (high[i] - low[i]) / 3
+            b = high[i] - (high[i] - low[i]) / 3
+            probes.append((a, b))
+            _launch_row_spans(mask, (a, b), spans, 4 * i)
+        host = spans.get()
+        for i, (a, b) in enumerate(probes):
+            y0a, y1a, y0b, y1b = (int(v) for v in host[4 * i:4 * i + 4])
+            if y1a < 0 or y1b < 0:
+                raise IndexError('list index out of range')       # find_objects(all-False)[0]
+            if y1a - y0a < y1b - y0b:
+                high[i] = b
+            else:
+                low[i] = a
+    angles = [(h + l) / 2 for l, h in zip(low, high)]
+    return [angle if EPS <= angle <= 180.0 - EPS else None for angle in angles]
+
+
 def find_rotation_angle(mask, EPS=1.0):
-    """The ternary search of CropAndRotateSingleParagraph._func (:318-333): the angle in (0, 180) at which the
-    nearest-rotated mask spans the fewest rows; None within EPS of 0 / 180.  One launch and one 16-byte read-back per
-    step (both probe angles together)."""
-    low, high = 0.0, 180.0
-    while high - low > EPS:
-        a = low + (high - low) / 3
-        b = high - (high - low) / 3
-        height_a, height_b = rotated_heights(mask, (a, b))
-        if height_a < height_b:
-            high = b
-        else:
-            low = a
-    angle = (high + low) / 2
-    if not EPS <= angle <= 180.0 - EPS:
-        angle = None
-    return angle
+    return find_rotation_angles([mask], EPS)[0]
 
 
 class CropAndRotateParagraphs:
@@ -179,25 +197,26 @@ class CropAndRotateParagraphs:
         self.workers_count, self.find_rotation, self.EPS, self.to_host = workers_count, find_rotation, EPS, to_host
         self.angles = []                                       # of the last call, per paragraph (None: not rotated)
 
-    def _single(self, labels, label, obj, images):
-        region_y, region_x = obj['slices']
-        mask = crop_label_mask(labels, label, region_y, region_x)
-        arrays = [crop(image, region_y, region_x, labels, label) for image in images]
-        angle = find_rotation_angle(mask, self.EPS) if self.find_rotation else None
-        self.angles.append(angle)
-        rotated_mask = rotate_array(mask, angle, good_rotation=False)
-        out_y, out_x = mask_bbox(rotated_mask)
-        return [crop(rotate_array(arr, angle), out_y, out_x) for arr in arrays]
-
     def __call__(self, masks, images):
         images = [_device(image) for image in images]
         labels, objects = label_objects(masks)
-        self.angles = []
-        result = [[None for _ in objects] for _ in images]
+        # per paragraph: the object's mask and the masked maps, cut to its box (CropAndRotateSingleParagraph._run, :300-309)
+        cut = []
         for paragraph_id, obj in enumerate(objects):
-            res = self._single(labels, paragraph_id + 1, obj, images)
-            for image_id in range(len(images)):
-                result[image_id][paragraph_id] = res[image_id].get() if self.to_host else res[image_id]
+            region_y, region_x = obj['slices']
+            mask = crop_label_mask(labels, paragraph_id + 1, region_y, region_x)
+            cut.append((mask, [crop(image, region_y, region_x, labels, paragraph_id + 1) for image in images]))
+        # ._func (:312-343): the angle (all paragraphs searched in lockstep), the rotated mask's box, the rotated maps cut to it
+        if self.find_rotation:
+            self.angles = find_rotation_angles([mask for mask, _ in cut], self.EPS)
+        else:
+            self.angles = [None] * len(cut)
+        result = [[None for _ in objects] for _ in images]
+        for paragraph_id, ((mask, arrays), angle) in enumerate(zip(cut, self.angles)):
+            out_y, out_x = mask_bbox(rotate_array(mask, angle, good_rotation=False))
+            for image_id, arr in enumerate(arrays):
+                res = crop(rotate_array(arr, angle), out_y, out_x)
+                result[image_id][paragraph_id] = res.get() if self.to_host else res
         return result
 
 
