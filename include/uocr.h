@@ -321,6 +321,15 @@ int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t
  * through library scratch.  w_kmajor: optional cached K-major copy (n_out, width*c) of W's weight rows, may be NULL. */
 int uocr_window_fc_fwd(const float* x, const float* w, const float* w_kmajor, float* y, int64_t n, int64_t wd,
                        int64_t c, int32_t width, int64_t n_out, int act, float alpha, int math_mode, void* stream);
+/* y (batch, n_out) = act1([x, 1] . W1) extended by 1, times W2: two FullyConnected layers with an activation between
+ * them in one call (make_dense_block, my_model/model.py:251-262: dense_2 + LeakyRelu + dense_3; layers.py:335-347 twice +
+ * :390-401).  W1: (n_in + 1, n_hidden), W2: (n_hidden + 1, n_out), bias rows last; w1_kmajor / w2_kmajor: optional cached
+ * K-major copies of the weight rows.  In TF32 mode with n_hidden == 128, n_in % 32 == 0, 16 <= n_out <= 256 and
+ * batch >= 128 one tcgen05 kernel keeps the hidden tile in shared memory (written by the first epilogue in the operand
+ * layout the second GEMM reads); otherwise the two layers run one after the other through library scratch. */
+int uocr_fc_chain2_fwd(const float* x, const float* w1, const float* w1_kmajor, const float* w2, const float* w2_kmajor,
+                       float* y, int64_t batch, int64_t n_in, int64_t n_hidden, int64_t n_out, int act1, float alpha1,
+                       int math_mode, void* stream);
 int uocr_fc_fwd_kmajor(const float* x, const float* w, const float* w_kmajor, float* y, int64_t batch, int64_t n_in,
                        int64_t n_out, int act, float alpha, int math_mode, void* stream);
 /* dx = dy . W[:-1]^T (skipped when dx == NULL); dw (+)= [x, 1]^T . dy.  replaces: layers.py:341-347 */

@@ -507,3 +507,62 @@ def test_line_model_uses_the_one_kernel_path(nn):
         nn.CP.set_math_mode('tf32')
     assert 0.05 < ref.mean() < 0.95
     close_tf32(np.asarray(y3, dtype=np.float64), np.asarray(ref, dtype=np.float64), 'line model fused vs fp32', tol=1e-3)
+
+
+@pytest.mark.parametrize('batch,n_in,n_hidden,n_out,mode', [
+    (16384, 1024, 128, 162, 'tf32'),     # Char dense_2 + leaky_relu_2 + dense_3 at batch 64: the one-kernel path
+    (1000, 1024, 128, 162, 'tf32'),      # ragged last tile
+    (4096, 64, 128, 16, 'tf32'), (640, 256, 128, 256, 'tf32'), (777, 128, 128, 200, 'tf32'),
+    (300, 96, 64, 30, 'tf32'),           # hidden width the kernel is not built for: two GEMMs inside the library
+    (200, 50, 128, 162, 'tf32'),         # n_in % 32 != 0: likewise
+    (300, 1024, 128, 162, 'fp32'),       # FP32 check mode: likewise, FFMA
+])
+def test_fc_chain_vs_oracle(nn, batch, n_in, n_hidden, n_out, mode):
+    """uocr_fc_chain2_fwd: FullyConnected + LeakyRelu + FullyConnected (make_dense_block, my_model/model.py:251-262) in
+    one call vs the float64 oracle (layers.py:335-347 twice); the one-kernel path keeps the hidden tile in shared memory
+    in the tensor-core operand layout.  TF32: 1e-3 of the output range per GEMM -> 2e-3; FP32: 1e-4."""
+    from univer_ocr_b200._lib import ACT_LEAKY, MATH_FP32, MATH_TF32, lib
+    rng = np.random.default_rng(batch + n_in + n_out)
+    X = f32(rng.standard_normal((batch, n_in)))
+    W1 = f32(rng.standard_normal((n_in + 1, n_hidden)) / np.sqrt(n_in))
+    W2 = f32(rng.standard_normal((n_hidden + 1, n_out)) / np.sqrt(n_hidden))
+    want = O.fc_fwd(O.leaky_relu_fwd(O.fc_fwd(X, W1), 0.01), W2)
+    dX, dW1, dW2 = nn.CP.copy(X), nn.CP.copy(W1), nn.CP.copy(W2)
+    y = nn.DeviceArray.full((batch, n_out), -7.0)
+    for kmajor in (False, True):
+        w1t = w2t = None
+        if kmajor:
+            w1t, w2t = nn.DeviceArray((n_hidden, n_in)), nn.DeviceArray((n_out, n_hidden))
+            lib.uocr_weights_to_kmajor(dW1.ptr, w1t.ptr, n_in, n_hidden, nn.CP.stream())
+            lib.uocr_weights_to_kmajor(dW2.ptr, w2t.ptr, n_hidden, n_out, nn.CP.stream())
+        lib.uocr_fc_chain2_fwd(dX.ptr, dW1.ptr, w1t.ptr if kmajor else None, dW2.ptr, w2t.ptr if kmajor else None, y.ptr,
+                               batch, n_in, n_hidden, n_out, ACT_LEAKY, 0.01, MATH_TF32 if mode == 'tf32' else MATH_FP32,
+                               nn.CP.stream())
+        got = np.asarray(y.get(), dtype=np.float64)
+        if mode == 'tf32':
+            close_tf32(got, want, f'fc chain {(batch, n_in, n_hidden, n_out)} kmajor={kmajor}', tol=2e-3)
+        else:
+            assert np.abs(got - want).max() <= 1e-4 * np.abs(want).max()
+
+
+def test_char_head_runs_as_two_launches(nn):
+    """Inference plan of make_char in TF32 mode: window batching + Flatten + dense_1 + LeakyRelu is one GEMM, dense_2 +
+    LeakyRelu + dense_3 one kernel -- 5 launches for the whole network -- and agrees with the layer-by-layer plan."""
+    from oracle import np_models
+    from univer_ocr_b200 import my_model
+    from univer_ocr_b200._lib import launch_count
+    shape = (64, 32, 256, 1)
+    w0 = np_models.golden_weights('char', 5)
+    X = nn.CP.copy(f32(np.random.default_rng(1).uniform(size=shape)))
+    nn.CP.set_math_mode('tf32')
+    model = my_model.make_char(shape)
+    model.set_weights({k: {n: v.tolist() for n, v in p.items()} for k, p in w0.items()})
+    assert [s[0] for s in model._plan_infer] == ['conv', 'conv', 'conv', 'winfc', 'fcchain']
+    fused = model.predict(X)[0].get()
+    n0 = launch_count()
+    model.predict(X)
+    assert launch_count() - n0 == 5
+    model.fusion = False
+    model.initialize(model.input_shapes)
+    plain = model.predict(X)[0].get()
+    assert np.abs(fused - plain).max() <= 2e-3 * np.abs(plain).max()

@@ -139,6 +139,23 @@ int uocr_window_fc_fwd(const float* x, const float* w, const float* w_kmajor, fl
     return fc_fwd_impl((const float*)win.ptr, w, w_kmajor, y, n * wd, (int64_t)width * c, n_out, act, alpha, math_mode, stream);
 }
 
+int uocr_fc_chain2_fwd(const float* x, const float* w1, const float* w1_kmajor, const float* w2, const float* w2_kmajor,
+                       float* y, int64_t batch, int64_t n_in, int64_t n_hidden, int64_t n_out, int act1, float alpha1,
+                       int math_mode, void* stream) {
+    UOCR_REQUIRE(x && w1 && w2 && y, "NULL pointer");
+    UOCR_REQUIRE(batch > 0 && n_in > 0 && n_hidden > 0 && n_out > 0, "non-positive dimension");
+    UOCR_REQUIRE(act1 >= UOCR_ACT_NONE && act1 <= UOCR_ACT_SIGMOID, "unknown activation %d", act1);
+    cudaStream_t st = as_stream(stream);
+    int rc = fc_chain2_fwd_fast(math_mode, x, w1, w1_kmajor, w2, w2_kmajor, y, batch, n_in, n_hidden, n_out, act1, alpha1, st);
+    if (rc != UOCR_ERR_UNSUPPORTED) return rc;
+    Scratch hidden(st);                                   // any other geometry / FP32 mode: the two layers one after the other
+    rc = hidden.alloc(sizeof(float) * (size_t)batch * n_hidden);
+    if (rc) return rc;
+    rc = fc_fwd_impl(x, w1, w1_kmajor, (float*)hidden.ptr, batch, n_in, n_hidden, act1, alpha1, math_mode, stream);
+    if (rc) return rc;
+    return fc_fwd_impl((const float*)hidden.ptr, w2, w2_kmajor, y, batch, n_hidden, n_out, UOCR_ACT_NONE, 0.f, math_mode, stream);
+}
+
 int uocr_fc_fwd(const float* x, const float* w, float* y, int64_t batch, int64_t n_in, int64_t n_out,
                 int act, float alpha, int math_mode, void* stream) {
     return fc_fwd_impl(x, w, nullptr, y, batch, n_in, n_out, act, alpha, math_mode, stream);

@@ -21,6 +21,9 @@ int sgemm_fp32(const GemmArgs& p, bool ta, bool tb, int splitk, cudaStream_t st)
 // tensor-core paths: UOCR_ERR_UNSUPPORTED when math_mode / shape has no tcgen05 kernel
 int fc_fwd_fast(int math_mode, const float* x, const float* w, const float* w_kmajor /* may be NULL */, float* y,
                 int64_t batch, int64_t n_in, int64_t n_out, int act, float alpha, cudaStream_t st);
+// FullyConnected (hidden width 128) + activation + FullyConnected as one tensor-core kernel (tc_gemm.cu: fc_chain2_kernel)
+int fc_chain2_fwd_fast(int math_mode, const float* x, const float* w1, const float* w1t, const float* w2, const float* w2t,
+                       float* y, int64_t batch, int64_t k1, int64_t n1, int64_t n2, int act1, float alpha1, cudaStream_t st);
 int fc_window_fwd_fast(int math_mode, const float* x, const float* w, const float* w_kmajor, float* y, int64_t n,
                        int64_t wd, int64_t c, int width, int64_t n_out, int act, float alpha, cudaStream_t st);
 int weights_to_kmajor(const float* w, float* wt, int64_t k_rows, int64_t n_cols, cudaStream_t st);

@@ -1477,4 +1477,218 @@ int conv3x3_pair_tc(const float* x, const float* w1, const float* b1, const floa
     UOCR_LAUNCHED("conv3x3_pair_tc");
     return UOCR_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Two FullyConnected layers in one kernel (inference): y = (act1(x . W1 + b1)) . W2 + b2 for a hidden width of 128
+// (Char dense_2 + LeakyRelu + dense_3, my_model/model.py:251-304; nn/layers/layers.py:335-347).  Per 128-row tile:
+//   GEMM 1  the usual TMA -> 128B-swizzled ring -> tcgen05.mma pipeline over K1, accumulator 1 in TMEM columns 0..127
+//   middle  the four epilogue warps read accumulator 1 (lane = row), add b1, apply act1, round to TF32 and write the
+//           128 x 128 hidden tile INTO SHARED MEMORY IN THE OPERAND LAYOUT the next MMA reads (K-major rows of 128
+//           bytes, 16-byte chunks XOR-swizzled with the row like a SWIZZLE_128B TMA box): it never goes to HBM
+//   GEMM 2  the producer warp simply keeps going: W2's four K blocks travel through the same ring (one per stage);
+//           A = the hidden tile, accumulator 2 in TMEM columns 128..
+//   last    accumulator 2 + b2 is staged in the (now idle) ring as packed rows of n2 floats and leaves as one linear,
+//           16-byte-coalesced copy -- a tile's rows are contiguous in y even when n2 = 162 is not a multiple of 4
+// Saves the hidden matrix's round trip (2 x 8.4 MB at batch 16384), one launch, and dense_3's operand loads.
+// ------------------------------------------------------------------------------------------
+constexpr int FC2_HID = 128;              // hidden width = N of GEMM 1 = K of GEMM 2
+constexpr int FC2_STAGES = 4;
+constexpr int FC2_STAGE_BYTES = 2 * TC_BM * TC_BK * 4;                    // A 16 KB + B 16 KB; a W2 block uses <= 32 KB of it
+
+struct Fc2Params {
+    float* y; int64_t M; int n2, nt2, num_kb1;
+    const float* b1; const float* b2;
+    int act1; float alpha1;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) fc_chain2_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                  const __grid_constant__ CUtensorMap map_w1,
+                                                                  const __grid_constant__ CUtensorMap map_w2,
+                                                                  const Fc2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_hid = smem + FC2_STAGES * FC2_STAGE_BYTES;                  // 4 K blocks x 16 KB, 1024-aligned
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_hid + 4 * TC_BM * TC_BK * 4);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + FC2_STAGES;
+    uint64_t* acc1_full = bars + 2 * FC2_STAGES;
+    uint64_t* hid_full = acc1_full + 1;
+    uint64_t* acc2_full = acc1_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 3);
+    float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);               // b1[128], b2[nt2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+    const int m_rows = (int)min((int64_t)TC_BM, p.M - m0);
+    const int total_kb = p.num_kb1 + FC2_HID / TC_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FC2_STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+        mbar_init(smem_u32(acc1_full), 1);
+        mbar_init(smem_u32(hid_full), 128);
+        mbar_init(smem_u32(acc2_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < FC2_HID + p.nt2; i += TC_THREADS)
+        s_bias[i] = i < FC2_HID ? __ldg(p.b1 + i) : (i - FC2_HID < p.n2 ? __ldg(p.b2 + i - FC2_HID) : 0.f);
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: K1 / 32 blocks of (x, W1), then the 4 blocks of W2 =====================
+        if (lane == 0) {
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int s = kb % FC2_STAGES;
+                mbar_wait(smem_u32(&empty[s]), ((kb / FC2_STAGES) & 1) ^ 1);
+                const uint32_t sa = smem_u32(smem + (size_t)s * FC2_STAGE_BYTES), bar = smem_u32(&full[s]);
+                if (kb < p.num_kb1) {
+                    mbar_arrive_expect_tx(bar, (uint32_t)FC2_STAGE_BYTES);
+                    tma_load_2d(sa, &map_x, bar, kb * TC_BK, (int)m0);
+                    tma_load_2d(sa + TC_BM * TC_BK * 4, &map_w1, bar, kb * TC_BK, 0);
+                } else {
+                    mbar_arrive_expect_tx(bar, (uint32_t)p.nt2 * TC_BK * 4);
+                    tma_load_2d(sa, &map_w2, bar, (kb - p.num_kb1) * TC_BK, 0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FC2_HID >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.nt2 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int s = kb % FC2_STAGES;
+                if (kb == p.num_kb1) {                         // GEMM 1 is complete; GEMM 2 needs the hidden tile
+                    tc_commit(smem_u32(acc1_full));
+                    mbar_wait(smem_u32(hid_full), 0);
+                }
+                mbar_wait(smem_u32(&full[s]), (kb / FC2_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)s * FC2_STAGE_BYTES);
+                if (kb < p.num_kb1) {
+                    const uint64_t da = make_kmajor_sw128_desc(sa), db = make_kmajor_sw128_desc(sa + TC_BM * TC_BK * 4);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc1, (kb > 0 || k > 0) ? 1u : 0u);
+                } else {
+                    const int j = kb - p.num_kb1;
+                    const uint64_t da = make_kmajor_sw128_desc(smem_u32(s_hid + (size_t)j * TC_BM * TC_BK * 4));
+                    const uint64_t db = make_kmajor_sw128_desc(sa);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; ++k)
+                        tc_mma_tf32(tmem_base + FC2_HID, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc2, (j > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(smem_u32(&empty[s]));
+            }
+            tc_commit(smem_u32(acc2_full));
+        }
+    } else {
+        // ===================== epilogue warps (lane quarter q, row r of the tile) =====================
+        const int q = warp & 3, r = q * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        mbar_wait(smem_u32(acc1_full), 0);
+        tc_fence_after();
+        for (int j = 0; j < FC2_HID / TC_BK; ++j) {
+            float v[32];
+            tc_ld_32x32(lane_base + (uint32_t)(j * TC_BK), v);
+            uint8_t* row = s_hid + (size_t)j * TC_BM * TC_BK * 4 + (size_t)r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float t = apply_act_fast(v[4 * c + e] + s_bias[j * TC_BK + 4 * c + e], p.act1, p.alpha1);
+                    o[e] = (__float_as_uint(t) + 0x1000u) & 0xffffe000u;      // TF32, round to nearest
+                }
+                *reinterpret_cast<uint4*>(row + ((c ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // generic writes -> the MMA's async-proxy reads
+        mbar_arrive(smem_u32(hid_full));
+        // ---- accumulator 2 -> packed rows in the idle ring -> one linear copy
+        mbar_wait(smem_u32(acc2_full), 0);
+        tc_fence_after();
+        float* stage = reinterpret_cast<float*>(smem);
+        for (int c0 = 0; c0 < p.nt2; c0 += 32) {
+            float v[32];
+            tc_ld_32x32(lane_base + (uint32_t)(FC2_HID + c0), v);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+                if (c0 + e < p.n2) stage[r * p.n2 + c0 + e] = v[e] + s_bias[FC2_HID + c0 + e];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = threadIdx.x - 64;                                      // 0..127
+        const int64_t count = (int64_t)m_rows * p.n2;
+        float* dst = p.y + m0 * p.n2;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            const int64_t quads = count >> 2;
+            for (int64_t i = t; i < quads; i += 128)
+                reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(stage)[i];
+            for (int64_t i = (quads << 2) + t; i < count; i += 128) dst[i] = stage[i];
+        } else {
+            for (int64_t i = t; i < count; i += 128) dst[i] = stage[i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// y (batch, n2) = act1([x, 1] . W1) . W2[:-1] + W2[-1];  W1: (k1 + 1, 128), W2: (129, n2); w1t / w2t: K-major copies
+int fc_chain2_fwd_fast(int math_mode, const float* x, const float* w1, const float* w1t, const float* w2, const float* w2t,
+                       float* y, int64_t batch, int64_t k1, int64_t n1, int64_t n2, int act1, float alpha1, cudaStream_t st) {
+    if (math_mode != UOCR_MATH_TF32 || !encode_tiled()) return UOCR_ERR_UNSUPPORTED;
+    if (n1 != FC2_HID || k1 % TC_BK || k1 < TC_BK || n2 < 16 || n2 > 256 || batch < 128 || batch > 0x7fffffff) return UOCR_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return UOCR_ERR_UNSUPPORTED;
+    Scratch t1(st), t2(st);
+    if (!w1t) {
+        int rc = t1.alloc(sizeof(float) * n1 * k1);
+        if (rc) return rc;
+        rc = transpose_async(w1, (float*)t1.ptr, (int)k1, (int)n1, n1, k1, st);
+        if (rc) return rc;
+        w1t = (const float*)t1.ptr;
+    }
+    if (!w2t) {
+        int rc = t2.alloc(sizeof(float) * n2 * n1);
+        if (rc) return rc;
+        rc = transpose_async(w2, (float*)t2.ptr, (int)n1, (int)n2, n2, n1, st);
+        if (rc) return rc;
+        w2t = (const float*)t2.ptr;
+    }
+    Fc2Params p{};
+    p.y = y; p.M = batch; p.n2 = (int)n2; p.nt2 = (int)(((n2 + 15) / 16) * 16); p.num_kb1 = (int)(k1 / TC_BK);
+    p.b1 = w1 + k1 * n1; p.b2 = w2 + n1 * n2; p.act1 = act1; p.alpha1 = alpha1;
+    CUtensorMap mx, m1, m2;
+    const uint64_t dx[2] = {(uint64_t)k1, (uint64_t)batch}, sx[1] = {(uint64_t)k1 * 4};
+    const uint32_t bx[2] = {TC_BK, TC_BM};
+    int rc = make_tmap(&mx, x, 2, dx, sx, bx);
+    if (rc) return rc;
+    const uint64_t d1[2] = {(uint64_t)k1, (uint64_t)n1}, s1[1] = {(uint64_t)k1 * 4};
+    const uint32_t b1[2] = {TC_BK, (uint32_t)FC2_HID};
+    rc = make_tmap(&m1, w1t, 2, d1, s1, b1);
+    if (rc) return rc;
+    const uint64_t d2[2] = {(uint64_t)n1, (uint64_t)n2}, s2[1] = {(uint64_t)n1 * 4};
+    const uint32_t b2[2] = {TC_BK, (uint32_t)p.nt2};
+    rc = make_tmap(&m2, w2t, 2, d2, s2, b2);
+    if (rc) return rc;
+    const size_t smem = 1024 + (size_t)FC2_STAGES * FC2_STAGE_BYTES + 4 * TC_BM * TC_BK * 4 + (2 * FC2_STAGES + 3) * 8 + 16 +
+                        (FC2_HID + p.nt2) * sizeof(float) + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fc_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        configured = true;
+    }
+    fc_chain2_kernel<<<(unsigned)ceil_div(batch, TC_BM), TC_THREADS, smem, st>>>(mx, m1, m2, p);
+    UOCR_LAUNCHED("fc_chain2");
+    return UOCR_OK;
+}
 }  // namespace uocr

@@ -259,8 +259,20 @@ class Model(BaseModel):
                             a2_name = self._sole_consumer(c2_name) if not training else None
                             a2 = _act_code(self.layers[a2_name]) if a2_name is not None else None
                             pair = (c2_name, a2_name if a2 is not None else None)
+                    chain = None
+                    if (not training and type(conv) is FullyConnected and act_name is not None
+                            and conv.n_output == self.FC_CHAIN_HIDDEN):
+                        # inference: FullyConnected(-> 128) + activation + FullyConnected as one kernel whose hidden
+                        # tile stays in shared memory (uocr_fc_chain2_fwd): Char dense_2 + leaky_relu_2 + dense_3
+                        nxt = self._sole_consumer(act_name)
+                        if nxt is not None and type(self.layers[nxt]) is FullyConnected:
+                            after = self._sole_consumer(nxt)
+                            if after is None or _act_code(self.layers[after]) is None:
+                                chain = nxt
                     if pair is not None:
                         step = ('pair', conv_name, act_name, pair[0], pair[1])
+                    elif chain is not None:
+                        step = ('fcchain', conv_name, act_name, chain)
                     elif ups is not None or act_name is not None:
                         step = ('conv', ups, conv_name, act_name)
             if (step is None and self.fusion and not training and type(layer) is Conv2DToBatchedFixedWidthed
@@ -324,6 +336,8 @@ class Model(BaseModel):
                 self._run_fused_conv(step, value_of, outputs, training, clear_grads)
             elif kind == 'winfc':
                 self._run_winfc(step, value_of, outputs)
+            elif kind == 'fcchain':
+                self._run_fcchain(step, value_of, outputs)
             else:
                 if clear_grads:                                    # reference :188, for every member of the fused pair
                     for member in step[1:]:
@@ -390,6 +404,28 @@ class Model(BaseModel):
         for nm in names:
             outputs[nm] = None
         outputs[names[-1]] = y
+
+    FC_CHAIN_HIDDEN = 128                                # hidden width the two-layer kernel is built for
+
+    def _run_fcchain(self, step, value_of, outputs):
+        """Inference only: FullyConnected -> activation -> FullyConnected (uocr_fc_chain2_fwd; any geometry or math mode
+        the one-kernel path does not cover runs as two GEMMs inside the library)."""
+        _, fc1_name, act_name, fc2_name = step
+        X = as_device(value_of(self.relations[fc1_name][0]))
+        fc1, fc2 = self.layers[fc1_name], self.layers[fc2_name]
+        assert len(X.shape) == 2 and X.shape[1] == fc1.n_input, f'{fc1_name}: expected (batch, {fc1.n_input}), got {X.shape}'
+        act, alpha = _act_code(self.layers[act_name])
+        fc2.progress_tracker.start_tracking(fc2.name, 'forward')
+        y = DeviceArray((X.shape[0], fc2.n_output))
+        tf32 = CP.math_mode == MATH_TF32
+        w1t = _kmajor_copy(fc1, fc1.w.value, fc1.n_input, fc1.n_output) if tf32 else None
+        w2t = _kmajor_copy(fc2, fc2.w.value, fc2.n_input, fc2.n_output) if tf32 else None
+        lib.uocr_fc_chain2_fwd(X.ptr, fc1.w.value.ptr, w1t.ptr if w1t is not None else None, fc2.w.value.ptr,
+                               w2t.ptr if w2t is not None else None, y.ptr, X.shape[0], fc1.n_input, fc1.n_output,
+                               fc2.n_output, act, float(alpha), CP.math_mode, stream())
+        fc2.progress_tracker.stop_tracking(fc2.name, 'forward')
+        outputs[fc1_name] = outputs[act_name] = None
+        outputs[fc2_name] = y
 
     def _run_pair(self, step, value_of, outputs, training=False):
         _, c1_name, a1_name, c2_name, a2_name = step
