@@ -809,8 +809,13 @@ int tc_gemm_mn_atomic(const float* At, int64_t lda, const float* B, int64_t ldb,
     p.nt = N >= 256 ? 256 : (int)(((N + 31) / 32) * 32);
     p.act = UOCR_ACT_NONE; p.atomic = 1;
     const int64_t tiles = ceil_div(M, TC_BM) * ceil_div(N, p.nt);
-    int64_t splits = (148 * 2 + tiles - 1) / tiles;
-    if (splits > p.num_kb / 4) splits = p.num_kb / 4;          // >= 4 K blocks per CTA
+    // split K so that tiles x splits is about ONE wave of CTAs and every CTA owns >= 8 K blocks: the partial tiles meet in
+    // atomicAdds, and two waves of shorter CTAs (the first version) doubled that traffic for nothing -- measured on the
+    // Char head's weight gradients (tools/trainprof.py): dense_1 0.185 -> 0.149 ms, dense_2 0.105 -> 0.097, dense_3
+    // (one tile, 128-way contention) 0.085 -> 0.071
+    int64_t splits = (148 + tiles - 1) / tiles;
+    static const int min_kb = env_int("UOCR_TC_WGRAD_MIN_KB", 8);
+    if (splits > p.num_kb / min_kb) splits = p.num_kb / min_kb;
     if (splits < 1) splits = 1;
     if (splits > 65535) splits = 65535;
     p.kb_per_split = (int)ceil_div(p.num_kb, splits);
@@ -949,11 +954,57 @@ static int colsum_async(const float* src, int64_t rows, int cols, float* out, in
     return UOCR_OK;
 }
 
+// dst (rows, cols_pad) = src (rows, cols) with zeros in the pad columns: operands whose row pitch is not a multiple of
+// 16 bytes (Char dense_3: n_out = 162) cannot be fetched by TMA as they are
+__global__ void __launch_bounds__(256) pad_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows,
+                                                       int cols, int cols_pad) {
+    const int64_t total = rows * cols_pad;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t r = i / cols_pad;
+        const int c = (int)(i - r * cols_pad);
+        dst[i] = c < cols ? src[r * cols + c] : 0.f;
+    }
+}
+
+static int pad_cols_async(const float* src, float* dst, int64_t rows, int cols, int cols_pad, cudaStream_t st) {
+    const int64_t blocks = ceil_div(rows * cols_pad, 256 * 4);
+    pad_cols_kernel<<<(unsigned)(blocks < 148 * 8 ? (blocks > 0 ? blocks : 1) : 148 * 8), 256, 0, st>>>(src, dst, rows, cols, cols_pad);
+    UOCR_LAUNCHED("pad_cols");
+    return UOCR_OK;
+}
+
 int fc_bwd_fast(int math_mode, const float* x, const float* w, const float* dy, float* dx, float* dw,
                 int64_t batch, int64_t n_in, int64_t n_out, int accumulate, cudaStream_t st) {
     if (math_mode != UOCR_MATH_TF32) return UOCR_ERR_UNSUPPORTED;
-    if (n_out % 4 || n_in % 4 || batch < 128 || n_out < 32 || n_in < 32 || !encode_tiled())
+    if (n_in % 4 || batch < 128 || n_out < 32 || n_in < 32 || !encode_tiled())
         return UOCR_ERR_UNSUPPORTED;
+    if (n_out % 4) {
+        // Char dense_3 (n_out = 162): dy and W padded to a 16-byte row pitch in scratch (zero columns contribute
+        // nothing), then the same two tensor-core GEMMs; was 0.099 ms on the FP32 SGEMM path
+        if (n_out > 0x7fffffff - 4) return UOCR_ERR_UNSUPPORTED;
+        const int n_pad = (int)((n_out + 3) & ~(int64_t)3);
+        Scratch dyp(st), wp(st);
+        int rc = dyp.alloc(sizeof(float) * (size_t)batch * n_pad);
+        if (rc) return rc;
+        rc = pad_cols_async(dy, (float*)dyp.ptr, batch, (int)n_out, n_pad, st);
+        if (rc) return rc;
+        if (dx) {
+            rc = wp.alloc(sizeof(float) * (size_t)n_in * n_pad);
+            if (rc) return rc;
+            rc = pad_cols_async(w, (float*)wp.ptr, n_in, (int)n_out, n_pad, st);
+            if (rc) return rc;
+            rc = tc_gemm_tn((const float*)dyp.ptr, n_pad, (const float*)wp.ptr, n_pad, dx, n_in, batch, n_in, n_pad, nullptr,
+                            UOCR_ACT_NONE, 0.f, 0, st);
+            if (rc) return rc;
+        }
+        if (!accumulate) {
+            cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (n_in + 1) * n_out, st);
+            if (e != cudaSuccess) { set_error("memset: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+        }
+        rc = tc_gemm_mn_atomic(x, n_in, (const float*)dyp.ptr, n_pad, dw, n_out, n_in, n_out, batch, st);
+        if (rc) return rc;
+        return colsum_async(dy, batch, (int)n_out, dw + n_in * n_out, 1, st);
+    }
     // dx = dy . W[:-1]^T : A = dy (batch, n_out) K-major; B^T = W[:-1] (n_in, n_out) is already K-major
     if (dx) {
         int rc = tc_gemm_tn(dy, n_out, w, n_out, dx, n_in, batch, n_in, n_out, nullptr, UOCR_ACT_NONE, 0.f, 0, st);
