@@ -241,3 +241,18 @@ def test_text_pipeline_runs_the_networks(nn):
     pred = out['char_pred'][0][0]
     assert pred.shape == (line.shape[2], my_model.N_CHARS) and np.isfinite(pred.get()).all()
     assert isinstance(out['text'][0][0], list)
+
+
+def test_stages_with_nothing_to_cut(nn):
+    """A constant Paragraph map has no pixel above its mean: no objects, empty result lists (one per image), like the
+    reference's label_layer -> {} -> [[] for image in images]; the pipeline then returns no text."""
+    from univer_ocr_b200 import predict, stages
+    flat = np.full((1, 48, 64, 1), 0.25, np.float32)
+    images = [np.ones((1, 48, 64, 1), np.float32), np.ones((1, 48, 64, 2), np.float32)]
+    assert stages.CropAndRotateParagraphs()(flat, images) == [[], []]
+    want, angles = S.crop_and_rotate_paragraphs(flat, images, True)
+    assert want == [[], []] and angles == []
+    assert stages.CropRotateAndZoomLines(None, 32, 8)([], [[], []]) == [[], []]
+    pipe = predict.TextPipeline(predictors={'monochrome': lambda x: x, 'paragraph': lambda x: nn.CP.copy(flat)})
+    out = pipe(np.zeros((1, 40, 60, 1), np.float32))
+    assert out['text'] == [] and out['angles'] == []
