@@ -429,7 +429,11 @@ int uocr_rotate_nearest_u8(const uint8_t* src, uint8_t* dst, int64_t n, int64_t 
  * ternary search (:318-333).  matrices (count x 4), offsets (count x 2), out_shapes (count x 2): HOST arrays as for
  * uocr_rotate_nearest_u8. */
 int uocr_rotated_row_spans(const uint8_t* mask, int32_t* spans, int64_t n, int64_t h, int64_t w, int64_t c, int count,
-                           const double* matrices, const double* offsets, const int64_t* out_shapes, void* stream);
+                           const double* matrices, const double* offsets, const int64_t* out_shapes, int reset,
+                           void* stream);
+/* spans[0 .. 2 count) = (INT_MAX, -1) pairs: the state uocr_rotated_row_spans accumulates into.  reset != 0 in that
+ * call does it for the call's own pairs; a caller that probes many (mask, step) slots resets the whole table once. */
+int uocr_row_spans_reset(int32_t* spans, int64_t count, void* stream);
 /* box[0..3] (int32, device) = y_min, y_max, x_min, x_max over the non-zero elements of a (n, h, w, c) uint8 array:
  * ndimage.find_objects(mask)[0] of a boolean array (:230, 303, 341); y_max = -1 when the array is all zero. */
 int uocr_mask_bbox(const uint8_t* mask, int32_t* box, int64_t n, int64_t h, int64_t w, int64_t c, void* stream);

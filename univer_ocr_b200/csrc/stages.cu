@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256) rotate_kernel(const T* __restrict__ src, 
 struct SpanGeoms { RotateGeom g[2]; int oh[2], ow[2]; };
 
 __global__ void row_span_init_kernel(int32_t* __restrict__ spans, int k) {
-    if ((int)threadIdx.x < 2 * k) spans[threadIdx.x] = (threadIdx.x & 1) ? -1 : 0x7fffffff;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * k) spans[i] = (i & 1) ? -1 : 0x7fffffff;
 }
 
 __global__ void __launch_bounds__(256) rotated_row_span_kernel(const uint8_t* __restrict__ mask, int32_t* __restrict__ spans,
@@ -279,8 +280,17 @@ int uocr_rotate_nearest_u8(const uint8_t* src, uint8_t* dst, int64_t n, int64_t 
     return UOCR_OK;
 }
 
+int uocr_row_spans_reset(int32_t* spans, int64_t count, void* stream) {
+    UOCR_REQUIRE(spans, "NULL pointer");
+    UOCR_REQUIRE(count > 0 && count <= (1 << 20), "bad count");
+    row_span_init_kernel<<<(unsigned)ceil_div(2 * count, 256), 256, 0, as_stream(stream)>>>(spans, (int)count);
+    UOCR_LAUNCHED("row_span_init");
+    return UOCR_OK;
+}
+
 int uocr_rotated_row_spans(const uint8_t* mask, int32_t* spans, int64_t n, int64_t h, int64_t w, int64_t c, int count,
-                           const double* matrices, const double* offsets, const int64_t* out_shapes, void* stream) {
+                           const double* matrices, const double* offsets, const int64_t* out_shapes, int reset,
+                           void* stream) {
     UOCR_REQUIRE(mask && spans && matrices && offsets && out_shapes, "NULL pointer");
     UOCR_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && fits32(h) && fits32(w) && fits32(c), "bad dimension");
     UOCR_REQUIRE(count == 1 || count == 2, "1 or 2 rotations per call, got %d", count);
@@ -295,8 +305,10 @@ int uocr_rotated_row_spans(const uint8_t* mask, int32_t* spans, int64_t n, int64
         const int64_t total = n * out_shapes[2 * k] * out_shapes[2 * k + 1] * c;
         if (total > most) most = total;
     }
-    row_span_init_kernel<<<1, 32, 0, as_stream(stream)>>>(spans, count);
-    UOCR_LAUNCHED("row_span_init");
+    if (reset) {
+        row_span_init_kernel<<<1, 256, 0, as_stream(stream)>>>(spans, count);
+        UOCR_LAUNCHED("row_span_init");
+    }
     if (most == 0) return UOCR_OK;
     rotated_row_span_kernel<<<dim3((unsigned)stage_grid(most), (unsigned)count), 256, 0, as_stream(stream)>>>(
         mask, spans, (int)n, (int)h, (int)w, (int)c, sg);

@@ -29,17 +29,33 @@ from .nn.gpu import DeviceArray, as_device, stream
 
 # ---------------------------------------------------------------------------------------------- resampling primitives
 
+_special = None
+_corners = {}
+
+
 def rotate_geometry(h, w, angle):
     """Output plane shape, matrix and offset of `ndimage.rotate(..., axes=(2, 1), reshape=True)` for an (h, w) plane
-    (scipy/ndimage/_interpolation.py: rotate): input (y, x) = matrix @ output (y, x) + offset."""
-    from scipy import special
-    c, s = float(special.cosdg(angle)), float(special.sindg(angle))
+    (scipy/ndimage/_interpolation.py: rotate): input (y, x) = matrix @ output (y, x) + offset.  The two matrix products
+    stay NumPy's (`@`, i.e. the BLAS rounding SciPy itself gets); everything around them is scalar Python arithmetic
+    -- the angle search calls this four times per step and 30 us of array bookkeeping per call was most of its time."""
+    global _special
+    if _special is None:
+        from scipy import special as _special_module
+        _special = _special_module
+    c, s = float(_special.cosdg(angle)), float(_special.sindg(angle))
     m = np.array([[c, s], [-s, c]], dtype=np.float64)
-    out_bounds = m @ np.array([[0, 0, h, h], [0, w, 0, w]], dtype=np.float64)
-    out_shape = (np.ptp(out_bounds, axis=1) + 0.5).astype(int)
-    out_center = m @ ((out_shape - 1) / 2)
-    in_center = (np.array([h, w]) - 1) / 2
-    return (int(out_shape[0]), int(out_shape[1])), m, in_center - out_center
+    corners = _corners.get((h, w))
+    if corners is None:
+        corners = _corners[(h, w)] = np.array([[0, 0, h, h], [0, w, 0, w]], dtype=np.float64)
+        if len(_corners) > 4096:
+            _corners.clear()
+    bounds = (m @ corners).tolist()
+    # (np.ptp(out_bounds, axis=1) + 0.5).astype(int): max - min per row, + 0.5, truncated
+    oh = int((max(bounds[0]) - min(bounds[0])) + 0.5)
+    ow = int((max(bounds[1]) - min(bounds[1])) + 0.5)
+    centre = (m @ np.array([(oh - 1) / 2, (ow - 1) / 2], dtype=np.float64)).tolist()
+    offset = np.array([(h - 1) / 2 - centre[0], (w - 1) / 2 - centre[1]], dtype=np.float64)
+    return (oh, ow), m, offset
 
 
 def _device(array, dtype=None):
@@ -143,7 +159,7 @@ def rotated_heights(mask, angles):
     return [int(host[2 * i + 1] - host[2 * i] + 1) for i in range(k)]
 
 
-def _launch_row_spans(mask, angles, spans, slot):
+def _launch_row_spans(mask, angles, spans, slot, reset=True):
     """Queues uocr_rotated_row_spans for `angles` (1 or 2) of `mask` into spans[slot : slot + 2 * len(angles)]."""
     n, h, w, c = mask.shape
     k = len(angles)
@@ -151,7 +167,8 @@ def _launch_row_spans(mask, angles, spans, slot):
     mats = (ctypes.c_double * (4 * k))(*[v for _, m, _ in geoms for v in m.ravel()])
     offs = (ctypes.c_double * (2 * k))(*[v for _, _, off in geoms for v in off])
     shapes = (ctypes.c_int64 * (2 * k))(*[v for shape, _, _ in geoms for v in shape])
-    lib.uocr_rotated_row_spans(mask.ptr, spans.ptr + 4 * slot, n, h, w, c, k, mats, offs, shapes, stream())
+    lib.uocr_rotated_row_spans(mask.ptr, spans.ptr + 4 * slot, n, h, w, c, k, mats, offs, shapes, 1 if reset else 0,
+                               stream())
 
 
 def find_rotation_angles(masks, EPS=1.0):
@@ -160,15 +177,26 @@ def find_rotation_angles(masks, EPS=1.0):
     takes the same number of steps (the interval shrinks by a third per step whatever the comparison says), so one step
     is one launch per mask (both probe angles, `uocr_rotated_row_spans`) and ONE read-back for all of them."""
     low, high = [0.0] * len(masks), [180.0] * len(masks)
-    spans = DeviceArray.empty((4 * max(len(masks), 1),), np.int32)
+    steps, width = 0, 180.0
+    while width > EPS:                                        # every mask takes the same number of steps
+        width, steps = width - width / 3, steps + 1          # (an upper bound is enough: the table is only sized by it)
+    steps += 2
+    per_step = 4 * max(len(masks), 1)
+    table = DeviceArray.empty((steps * per_step,), np.int32)
+    lib.uocr_row_spans_reset(table.ptr, steps * per_step // 2, stream())
+    host = np.empty(per_step, np.int32)
+    step = 0
     while masks and high[0] - low[0] > EPS:
+        assert step < steps
         probes = []
         for i, mask in enumerate(masks):
             a = low[i] + (high[i] - low[i]) / 3
             b = high[i] - (high[i] - low[i]) / 3
             probes.append((a, b))
-            _launch_row_spans(mask, (a, b), spans, 4 * i)
-        host = spans.get()
+            _launch_row_spans(mask, (a, b), table, step * per_step + 4 * i, reset=False)
+        lib.uocr_memcpy_d2h(host.ctypes.data, table.ptr + 4 * step * per_step, host.nbytes, stream())
+        lib.uocr_stream_sync(stream())
+        step += 1
         for i, (a, b) in enumerate(probes):
             y0a, y1a, y0b, y1b = (int(v) for v in host[4 * i:4 * i + 4])
             if y1a < 0 or y1b < 0:
