@@ -439,6 +439,9 @@ int uocr_row_spans_reset(int32_t* spans, int64_t count, void* stream);
 int uocr_mask_bbox(const uint8_t* mask, int32_t* box, int64_t n, int64_t h, int64_t w, int64_t c, void* stream);
 /* dst[p] = src[p, k] of a (positions, c) uint8 array: one channel of a multi-channel mask, `mask[:, :, :, k:k+1]` (:437-438). */
 int uocr_channel_slice_u8(const uint8_t* src, uint8_t* dst, int64_t positions, int64_t c, int64_t k, void* stream);
+/* dst[k, p] = src[p, k]: all channels of a (positions, c) uint8 array as c contiguous planes, so that the top / bottom
+ * marks of a Line mask are labelled as two images of one uocr_label_components call (:437-447). */
+int uocr_channel_planes_u8(const uint8_t* src, uint8_t* dst, int64_t positions, int64_t c, void* stream);
 /* mask[n, p, c] (uint8) = x[n, p, c] > mean_p x[n, :, c]: the foreground of label_layer applied to a float map
  * (`layer > np.mean(layer)`, :16-17).  Workspace as for uocr_threshold_mask. */
 int uocr_above_mean_mask(const float* x, uint8_t* mask, int64_t n, int64_t hw, int64_t c, void* workspace,

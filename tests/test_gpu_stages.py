@@ -105,6 +105,8 @@ def test_crop_bbox_and_above_mean(nn):
     two = (rng.uniform(size=(2, 9, 11, 2)) < 0.5).astype(np.uint8)
     for k in (0, 1):
         assert np.array_equal(glue.channel(stages._device(two), k).get(), two[..., k:k + 1])
+    planes = glue.channel_planes(stages._device(two[:1])).get()
+    assert planes.shape == (2, 9, 11, 1) and np.array_equal(planes[:, :, :, 0], np.moveaxis(two[0], -1, 0))
     # error convention of the C ABI: a region outside the image
     from univer_ocr_b200._lib import UocrError, lib
     out = nn.DeviceArray.empty((1, 4, 4, 3))

@@ -185,6 +185,15 @@ __global__ void __launch_bounds__(256) channel_slice_u8_kernel(const uint8_t* __
         dst[i] = src[i * c + k];
 }
 
+__global__ void __launch_bounds__(256) channel_planes_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                int64_t positions, int c) {
+    const int64_t total = positions * c;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int64_t k = i / positions, p = i - k * positions;             // writes are contiguous per plane
+        dst[i] = src[p * c + k];
+    }
+}
+
 inline int stage_grid(int64_t total) {
     const int64_t blocks = ceil_div(total, 256);
     return (int)(blocks < 148 * 16 ? (blocks > 0 ? blocks : 1) : 148 * 16);
@@ -322,6 +331,15 @@ int uocr_channel_slice_u8(const uint8_t* src, uint8_t* dst, int64_t positions, i
     if (positions == 0) return UOCR_OK;
     channel_slice_u8_kernel<<<stage_grid(positions), 256, 0, as_stream(stream)>>>(src, dst, positions, (int)c, (int)k);
     UOCR_LAUNCHED("channel_slice_u8");
+    return UOCR_OK;
+}
+
+int uocr_channel_planes_u8(const uint8_t* src, uint8_t* dst, int64_t positions, int64_t c, void* stream) {
+    UOCR_REQUIRE(src && dst, "NULL pointer");
+    UOCR_REQUIRE(positions >= 0 && c > 0 && fits32(c), "bad dimension");
+    if (positions == 0) return UOCR_OK;
+    channel_planes_u8_kernel<<<stage_grid(positions * c), 256, 0, as_stream(stream)>>>(src, dst, positions, (int)c);
+    UOCR_LAUNCHED("channel_planes_u8");
     return UOCR_OK;
 }
 

@@ -83,6 +83,16 @@ def channel(mask, k):
     return out
 
 
+def channel_planes(mask):
+    """(1, H, W, C) uint8 device mask -> (C, H, W, 1): the channels as separate images (`mask[:, :, :, k:k+1]` for every
+    k at once), e.g. to label the top and bottom marks of a Line mask in one `label_components` call."""
+    n, h, w, c = mask.shape
+    assert n == 1, f'expected one image, got {n}'
+    out = DeviceArray.empty((c, h, w, 1), np.uint8)
+    lib.uocr_channel_planes_u8(mask.ptr, out.ptr, h * w, c, stream())
+    return out
+
+
 def label_components(mask):
     """Connected components of every image of a uint8 mask (N, H, W) or (N, H, W, 1) -> (labels int32 of the same
     shape, counts int32 (N,)), both on the device: foreground = strictly above the image's mean, 4-neighbourhood,

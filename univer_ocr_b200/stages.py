@@ -318,8 +318,8 @@ class CropRotateAndZoomLines:
             mask = _device(mask)
             _, h, w, _ = mask.shape
             marks = glue.thresholded(mask)                     # per channel: arr > 0.5 * (mean + max)
-            _, top = label_objects(glue.channel(marks, 0))
-            _, bottom = label_objects(glue.channel(marks, 1))
+            # label_layer(top), label_layer(bottom): the two channels as two images of one labelling call
+            top, bottom = glue.label_stats(*glue.label_components(glue.channel_planes(marks)))
             tops, bottoms, rotation = rearrange_lines(top, bottom, h, w)
             for array_id in range(len(arrays)):
                 result[array_id].append([])
