@@ -258,3 +258,32 @@ def test_stages_with_nothing_to_cut(nn):
     pipe = predict.TextPipeline(predictors={'monochrome': lambda x: x, 'paragraph': lambda x: nn.CP.copy(flat)})
     out = pipe(np.zeros((1, 40, 60, 1), np.float32))
     assert out['text'] == [] and out['angles'] == []
+
+
+def test_stages_match_reference_golden(nn):
+    """The device stage classes against tests/golden/stages.npz, i.e. against what the UNMODIFIED reference's own
+    functions returned for the same seeded inputs (tests/golden/make_stage_golden.py): zoomed line crops in all four
+    reading directions, paragraph angles, straightened paragraph crops -- bit for bit."""
+    import os
+    from univer_ocr_b200 import stages
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'stages.npz'))
+    for direction in (None, 90, 180, 270):
+        mask, arrays = C.line_paragraph(1, direction)
+        tag = f'lines_{direction}'
+        got = stages.CropRotateAndZoomLines(8, 32, 200, to_host=True)([mask], [[a] for a in arrays])
+        assert len(got[0][0]) == int(gold[f'{tag}__count'])
+        for lid in range(len(got[0][0])):
+            for aid in range(2):
+                want = gold[f'{tag}__line{lid}_array{aid}']
+                assert got[aid][0][lid].shape == want.shape and np.array_equal(got[aid][0][lid], want)
+    for seed, tilt in ((0, (12.0, -25.0)), (1, (80.0, 3.0))):
+        pred, images = C.paragraph_page(seed, tilt=tilt)
+        tag = f'page_{seed}'
+        stage = stages.CropAndRotateParagraphs(4, True, to_host=True)
+        got = stage(pred, images)
+        assert len(stage.angles) == int(gold[f'{tag}__count'])
+        for pid, angle in enumerate(stage.angles):
+            assert angle == float(gold[f'{tag}__angle{pid}'])
+            for iid in range(2):
+                want = gold[f'{tag}__par{pid}_image{iid}']
+                assert got[iid][pid].shape == want.shape and np.array_equal(got[iid][pid], want)

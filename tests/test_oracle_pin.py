@@ -328,3 +328,30 @@ def test_stage_oracle_matches_reference_functions():
         for iid, image in enumerate(images):
             want = I.rotate_array((image * m)[:, ry, rx, :], angle)[:, oy, ox, :]
             assert np.array_equal(want, res[iid][pid])
+
+
+def test_stage_oracle_matches_reference_golden():
+    """oracle/np_stages.py against tests/golden/stages.npz -- outputs of the UNMODIFIED reference's crop-stage functions
+    (tests/golden/make_stage_golden.py) on the seeded cases of tests/stage_cases.py: line boxes, zoomed line crops in
+    all four reading directions, paragraph angles and straightened paragraph crops, bit for bit."""
+    import os
+    from oracle import np_stages as S
+    from tests import stage_cases as C
+    gold = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'stages.npz'))
+    for direction in (None, 90, 180, 270):
+        mask, arrays = C.line_paragraph(1, direction)
+        tag = f'lines_{direction}'
+        got = S.crop_rotate_and_zoom_lines([mask], [[a] for a in arrays], 32, 200)
+        assert len(got[0][0]) == int(gold[f'{tag}__count']) == 3
+        for lid in range(3):
+            for aid in range(2):
+                assert np.array_equal(got[aid][0][lid], gold[f'{tag}__line{lid}_array{aid}'])
+    for seed, tilt in ((0, (12.0, -25.0)), (1, (80.0, 3.0))):
+        pred, images = C.paragraph_page(seed, tilt=tilt)
+        tag = f'page_{seed}'
+        got, angles = S.crop_and_rotate_paragraphs(pred, images, True)
+        assert len(angles) == int(gold[f'{tag}__count']) == 2
+        for pid in range(2):
+            assert angles[pid] == float(gold[f'{tag}__angle{pid}'])
+            for iid in range(2):
+                assert np.array_equal(got[iid][pid], gold[f'{tag}__par{pid}_image{iid}'])
