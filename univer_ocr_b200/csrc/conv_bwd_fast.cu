@@ -648,8 +648,8 @@ static SmallWgradPlan plan_small_wgrad(const ConvGeom& g) {
     else if (k33 && g.cin % 4 == 0 && g.cout == 1) set(4, 1, 4, 16);
     else if (k55s1 && g.cin == 1 && g.cout == 1) set(1, 1, 8, 16);
     else if (k55s2 && g.cin == 1 && g.cout == 1) set(1, 1, 4, 4);      // 4 rows per thread: 4x the CTAs of R = 16, the loop is latency-bound
-    else if (k55s2 && g.cin == 1 && g.cout % 2 == 0) set(1, 2, 4, 8);
-    else if (k55s2 && g.cin == 4) set(4, 1, 4, 8);
+    else if (k55s2 && g.cin == 1 && g.cout % 2 == 0) set(1, 2, 4, 2);      // Line down_1, down_2: two rows per thread --
+    else if (k55s2 && g.cin == 4) set(4, 1, 4, 2);                         // 64 CTAs at R = 8 left most SMs idle (0.066 ms)
     else if (k55s1 && g.cin == 4) set(4, 1, 4, 8);
     else if (k53 && g.cin == 1 && g.cout % 4 == 0) set(1, 4, 4, 7);
     return p;
@@ -743,8 +743,8 @@ int conv_wgrad_fast(const ConvGeom& g, int math_mode, const float* x, const floa
     else if (g.ups != 1) return UOCR_ERR_UNSUPPORTED;      // only the kernel above reads an upsampled input
     else if (g.kw == 5 && g.sh == 1 && g.cin == 1) rc = launch_small_wgrad<5, 5, 1, 1, 1, 1, 1, 8, 16>(g, x, dy, ws, nblk, chunks, st);
     else if (g.kw == 5 && g.sh == 2 && g.cin == 1 && p.cot == 1) rc = launch_small_wgrad<5, 5, 2, 2, 1, 1, 1, 4, 4>(g, x, dy, ws, nblk, chunks, st);
-    else if (g.kw == 5 && g.sh == 2 && g.cin == 1 && p.cot == 2) rc = launch_small_wgrad<5, 5, 2, 2, 1, 1, 2, 4, 8>(g, x, dy, ws, nblk, chunks, st);
-    else if (g.kw == 5 && g.sh == 2 && g.cin == 4) rc = launch_small_wgrad<5, 5, 2, 2, 4, 4, 1, 4, 8>(g, x, dy, ws, nblk, chunks, st);
+    else if (g.kw == 5 && g.sh == 2 && g.cin == 1 && p.cot == 2) rc = launch_small_wgrad<5, 5, 2, 2, 1, 1, 2, 4, 2>(g, x, dy, ws, nblk, chunks, st);
+    else if (g.kw == 5 && g.sh == 2 && g.cin == 4) rc = launch_small_wgrad<5, 5, 2, 2, 4, 4, 1, 4, 2>(g, x, dy, ws, nblk, chunks, st);
     else if (g.kw == 5 && g.sh == 1 && g.cin == 4) rc = launch_small_wgrad<5, 5, 1, 1, 4, 4, 1, 4, 8>(g, x, dy, ws, nblk, chunks, st);
     else if (g.kw == 3 && g.kh == 5 && g.cin == 1) rc = launch_small_wgrad<5, 3, 2, 1, 1, 1, 4, 4, 7>(g, x, dy, ws, nblk, chunks, st);
     if (rc) return rc;
