@@ -108,6 +108,21 @@ def test_conv_tf32(nn, shape, cin, cout, ks, pad, st):
     close_tf32(layer.b.grad, odb, 'db')
 
 
+def test_conv_slab_multicast_cluster_variant(nn, monkeypatch):
+    """UOCR_CONV_SLAB_MC=1: the two x-blocks of a 256-pixel output row as a thread-block cluster that shares the weight
+    chunks by TMA multicast (csrc/tc_gemm.cu: tc_conv_slab_kernel<true>; slower than the plain kernel, off by default, kept
+    as a measured negative result) -- same results as the oracle at Char conv_2 / conv_3 geometry."""
+    monkeypatch.setenv('UOCR_CONV_SLAB_MC', '1')
+    rng = np.random.default_rng(99)
+    for (n, h, w) in ((64, 14, 256), (3, 5, 256)):
+        X = f32(rng.standard_normal((n, h, w, 64)))
+        wt = f32(rng.standard_normal((5, 3, 64, 64)) / np.sqrt(15 * 64))
+        b = f32(rng.standard_normal(64))
+        layer = nn.layers.Convolutional2D((5, 3), 64, 64, padding=(0, 1), stride=(2, 1), w=wt, b=b)
+        y = layer.forward(X)[0]
+        close_tf32(y, O.conv2d_fwd(X, wt, b, (0, 1), 0.0, (2, 1)), f'multicast slab {(n, h, w)}')
+
+
 def test_char_model_tf32_matches_fp32(nn):
     """Whole Char sub-network (inference plan: conv + LeakyRelu epilogues on the tensor-core
     kernels) in TF32 mode vs FP32 check mode: predictions within 2e-3 of max|logit|."""

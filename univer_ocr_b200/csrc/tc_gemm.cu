@@ -1097,6 +1097,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_off(uint32_t smem_add
     return d;
 }
 
+// MC: the two CTAs of a cluster are the two x-blocks of one output row.  They need the same weight chunks, so each
+// fetches HALF of every chunk (cout / 2 rows, map_b's box) and multicasts it to both; a stage is refilled only when the
+// MMAs of BOTH CTAs have released it (empty[] counts 2, the commits are multicast).  Halves the weight traffic through
+// L2, which was 57 % of this kernel's operand bytes.
+template <bool MC>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                      const __grid_constant__ CUtensorMap map_b,
                                                                      const SlabParams p) {
@@ -1120,7 +1125,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __gri
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), 1);
+            mbar_init(smem_u32(&empty[s]), MC ? 2 : 1);
         }
         mbar_init(smem_u32(tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1131,9 +1136,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __gri
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all();             // the peer's barriers exist before anything is multicast to them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -1148,8 +1155,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __gri
                 for (int xb = 0; xb < xb_live; ++xb)
                     tma_load_4d(sa + (uint32_t)xb * p.slab_bytes, &map_a, bar, cb * TC_BK, cx_base + xb * TC_BM - p.pw,
                                 oy * p.sh + ky - p.ph, cn);
-                for (int kx = 0; kx < p.kw; ++kx)
-                    tma_load_2d(sb + (uint32_t)kx * p.b_bytes, &map_b, bar, ((ky * p.kw + kx) * p.cblocks + cb) * TC_BK, 0);
+                for (int kx = 0; kx < p.kw; ++kx) {
+                    const int k0 = ((ky * p.kw + kx) * p.cblocks + cb) * TC_BK;
+                    if (MC)                  // rows [rank * cout / 2, ..) of the chunk, to both CTAs
+                        tma_load_2d_mc(sb + (uint32_t)kx * p.b_bytes + rank * (p.b_bytes / 2), &map_b, bar, k0,
+                                       (int)rank * (p.nt / 2), (uint16_t)3);
+                    else
+                        tma_load_2d(sb + (uint32_t)kx * p.b_bytes, &map_b, bar, k0, 0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -1173,7 +1186,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __gri
                             tc_mma_tf32(tmem_base + (uint32_t)(xb * p.nt), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc,
                                         (it > 0 || kx > 0 || k > 0) ? 1u : 0u);
                     }
-                tc_commit(smem_u32(&empty[s]));
+                if (MC) tc_commit_mc(smem_u32(&empty[s]), (uint16_t)3);
+                else tc_commit(smem_u32(&empty[s]));
             }
             tc_commit(smem_u32(tmem_full));
         }
@@ -1205,7 +1219,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_slab_kernel(const __gri
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all();             // the peer's last commits arrive on this CTA's barriers: do not exit before them
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1248,18 +1263,38 @@ static int conv_fwd_tc_slab(const ConvGeom& g, const float* x, const float* wt /
     const uint32_t ba[4] = {TC_BK, box_rows, 1, 1};
     int rc = make_tmap(&ma, x, 4, da, sa, ba);
     if (rc) return rc;
+    // UOCR_CONV_SLAB_MC=1: two x-blocks per output row (Char: wo = 256) run as a cluster and share the weight fetches by
+    // TMA multicast.  A measured NEGATIVE result, off by default: conv_2 44.7 -> 48.5 us, the step 0.379 -> 0.386 ms.
+    // Halving the weight traffic through L2 (57 % of the operand bytes) buys nothing because the kernel is not held up by
+    // L2 bytes but by per-CTA latency at 2 stages, and the shared stages make the two CTAs of a cluster wait for each
+    // other (a stage is refilled only when both have released it).
+    const int mc_env = env_int("UOCR_CONV_SLAB_MC", 0);
+    const bool mc = mc_env && p.xb == 1 && xtiles == 2 && g.wo == 2 * TC_BM && (p.b_bytes / 2) % 1024 == 0;
     const uint64_t db[2] = {(uint64_t)K, (uint64_t)g.cout}, sb[1] = {(uint64_t)K * 4};
-    const uint32_t bb[2] = {TC_BK, (uint32_t)g.cout};
+    const uint32_t bb[2] = {TC_BK, (uint32_t)(mc ? g.cout / 2 : g.cout)};
     rc = make_tmap(&mb, wt, 2, db, sb, bb);
     if (rc) return rc;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv_slab_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_conv_slab_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(xtiles, p.xb), (unsigned)g.ho, (unsigned)g.n);
-    tc_conv_slab_kernel<<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+    if (mc) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_slab_kernel<true>, ma, mb, p);
+        if (e != cudaSuccess) { set_error("cluster launch: %s", cudaGetErrorString(e)); return UOCR_ERR_CUDA; }
+    } else {
+        tc_conv_slab_kernel<false><<<grid, TC_THREADS, smem, st>>>(ma, mb, p);
+    }
     UOCR_LAUNCHED("tc_conv_slab_tf32");
     return UOCR_OK;
 }
